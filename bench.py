@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Benchmark of the candidate-view scoring hot path (BASELINE.json metric: candidate views scored/sec).
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA engine (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host CPU cores
+
+A step = one pass of the hot path over one batch of synthetic candidate views: configs[1] of
+BASELINE.json (Object scene, 512 hemisphere views x 80x60 rays, 64+128 samples, random-init
+reference NeRF x2), in reference-parity mode (frequency encoding + 8x256 NeRF + NeurAR head --
+the only scorer the reference implements).  With N ranks every rank scores
+its own 512-view block (weak scaling) and the per-view scores are all-gathered over NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_EVAL = 1187072.0
+V_PER_RANK, IMG_H, IMG_W, FOCAL = 512, 60, 80, 60.0
+NEAR, FAR = 0.5, 6.0
+S_C, S_I = 64, 128
+EVALS_PER_RAY = S_C + (S_C + S_I)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_workload(rank):
+    from oracle import evpp_oracle as O          # only used for the synthetic pose generator + weights
+    torch.manual_seed(0)
+    c = O.init_nerf_state_dict()
+    f = O.init_nerf_state_dict()
+    views = O.hemisphere_views(V_PER_RANK, seed=rank)
+    poses = torch.Tensor(np.asarray(O.views_to_poses(views)))[:, :3, :4].contiguous()
+    return c, f, views, poses
+
+
+def cpu_reference_rate(c, f, views, seconds_budget=20.0, max_views=8):
+    """Times the oracle port (== the reference's render() + sum(beta^2)/R, bit-identical on CPU) on a
+    bounded sample of the same workload with all host threads."""
+    from oracle import evpp_oracle as O
+    K = O.make_K(IMG_H, IMG_W, FOCAL)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    poses = O.views_to_poses(views)
+    t0 = time.time()
+    with torch.no_grad():
+        O.score_views(poses[:1], IMG_H, IMG_W, K, NEAR, FAR, c, f)
+    t1 = time.time() - t0
+    nv = int(max(1, min(max_views, seconds_budget // max(t1, 1e-3))))
+    t0 = time.time()
+    with torch.no_grad():
+        O.score_views(poses[:nv], IMG_H, IMG_W, K, NEAR, FAR, c, f)
+    dt = time.time() - t0
+    return nv / dt, threads, f"{nv} of {V_PER_RANK} views x {IMG_W}x{IMG_H} rays, 64+128 samples, {dt:.1f} s wall (1 warm-up view {t1:.1f} s)"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import evpp_oracle as O
+    c, f, views, _ = make_workload(0)
+    K = O.make_K(IMG_H, IMG_W, FOCAL)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    poses = O.views_to_poses(views)
+    per_step = 1                                             # bounded sample: 1 view (4800 rays) per step
+    times = []
+    with torch.no_grad():
+        for s in range(args.warmup + args.steps):
+            t0 = time.time()
+            O.score_views(poses[s % 8:s % 8 + per_step], IMG_H, IMG_W, K, NEAR, FAR, c, f)
+            if s >= args.warmup:
+                times.append(time.time() - t0)
+    ms = 1e3 * float(np.mean(times))
+    val = per_step / (ms / 1e3)
+    kind = "port"
+    line = {"impl": "reference", "metric": "candidate views scored/sec", "value": val, "unit": "views/s",
+            "rays_per_s": val * IMG_H * IMG_W, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world, "host CPU, torch fp32"),
+            "cpu_baseline": {"value": val, "unit": "views/s", "cores": threads, "kind": kind,
+                             "sample": f"{per_step} view(s) x {IMG_W}x{IMG_H} rays per step of the {V_PER_RANK}-view workload; oracle port, bit-identical to the reference's render() on CPU (oracle/make_golden.py)"},
+            "e2e": {"value": val, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world, engine_desc):
+    return {"workload": f"BASELINE configs[1] Object scene: {V_PER_RANK} hemisphere candidate views x {IMG_W}x{IMG_H} rays per GPU, "
+                        f"{S_C}+{S_I} samples/ray ({EVALS_PER_RAY} MLP evals/ray), reference-parity scorer "
+                        "(freq. encoding + 8x256 NeRF + NeurAR uncertainty head, random-init seed 0)",
+            "views_per_gpu": V_PER_RANK, "rays_per_view": IMG_H * IMG_W, "near": NEAR, "far": FAR,
+            "parallelism": f"views sharded over {world} GPU(s), all_gather of scores", "engine": engine_desc,
+            "l2": "per-step working set (~14 GB of streamed ray/sample intermediates) exceeds L2; 256 MB L2 flush between timed steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="evpp_b200")
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import evpp_b200
+    from evpp_b200 import dist as edist
+    from evpp_b200.run_nerf import _intrinsics
+    from __graft_entry__ import build
+    if local_rank == 0:
+        build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    dev = torch.device("cuda", local_rank)
+    c, f, views, poses_host = make_workload(rank)
+    K = np.array([[FOCAL, 0, 0.5 * IMG_W], [0, FOCAL, 0.5 * IMG_H], [0, 0, 1]])
+    fx, fy, cx, cy = _intrinsics(K)
+    eng = evpp_b200.Engine(device=local_rank, n_samples=S_C, n_importance=S_I, near=NEAR, far=FAR,
+                           white_bkgd=True, precision=args.precision)
+    eng.load_weights(0, c)
+    eng.load_weights(1, f)
+    poses_dev = poses_host.to(dev)
+    poses_pinned = poses_host.pin_memory()
+    scores_pinned = torch.empty(V_PER_RANK, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    V_total = V_PER_RANK * world
+
+    def step_device():
+        s = eng.score_views(poses_dev, IMG_H, IMG_W, fx, fy, cx, cy)
+        if world > 1:
+            s = edist.gather_scores(s, V_total, rank, world)
+        return s
+
+    def step_e2e():
+        s = eng.score_views_host(poses_pinned, IMG_H, IMG_W, fx, fy, cx, cy, out=scores_pinned)
+        if world > 1:
+            s = edist.gather_scores(s.to(dev, non_blocking=True), V_total, rank, world).cpu()
+        return s
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            eng.set_profiling(True)
+        l0, e0 = eng.counters()
+        total_ms, wall = 0.0, 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev0.record()
+            fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            wall += time.perf_counter() - t0
+            total_ms += ev0.elapsed_time(ev1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l1, e1 = eng.counters()
+        t = torch.tensor([total_ms, wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item() / steps, t[1].item() / steps, (l1 - l0), (e1 - e0)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, _, launches, evals = timed(step_device, args.steps, args.warmup, profile=True)
+    mlp_ms, mlp_launches, mlp_evals = eng.mlp_time()
+    eng.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    _, ms_e2e_wall, _, _ = timed(step_e2e, max(2, min(args.steps, 3)), 1)
+
+    if rank == 0:
+        sustained, burst, src = peaks()
+        value = V_total / (ms_dev / 1e3)
+        e2e_val = V_total / (ms_e2e_wall / 1e3)
+        flops_per_launch = FLOP_PER_EVAL * mlp_evals / max(1, mlp_launches)
+        avg_launch_ms = mlp_ms / max(1, mlp_launches)
+        achieved = flops_per_launch / (avg_launch_ms / 1e3) / 1e12 if avg_launch_ms > 0 else 0.0
+        tensor = args.precision != "fp32"
+        line = {"metric": "candidate views scored/sec", "value": value, "unit": "views/s",
+                "rays_per_s": value * IMG_H * IMG_W, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp16": "f16 operands, f32 accumulate (tcgen05)", "bf16": "bf16 operands, f32 accumulate (tcgen05)",
+                          "fp32": "f32"}[args.precision],
+                "data": "synthetic", "config": workload_config(world, f"evpp_b200 CUDA engine, precision={args.precision}"),
+                "e2e": {"value": e2e_val, "unit": "views/s", "h2d_bytes_per_step": int(V_PER_RANK * 12 * 4),
+                        "d2h_bytes_per_step": int(V_PER_RANK * 4), "ms_per_step": ms_e2e_wall,
+                        "api": "Engine.score_views_host == evpp_score_views_host (pinned host poses in, host scores out)"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                             "frac": achieved / sustained, "traffic": None, "peak_source": f"{src} bf16_tflops_sustained",
+                             "kernel": "mlp_tc_kernel (fused encode + NeRF MLP)" if tensor else "mlp_simt_kernel (fp32 FFMA; tensor peak shown for scale only)",
+                             "flop_per_launch": flops_per_launch, "avg_launch_ms": avg_launch_ms,
+                             "mlp_share_of_step": mlp_ms / (ms_dev * args.steps) if ms_dev > 0 else None},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_reference_rate(c, f, views)
+            line["cpu_baseline"] = {"value": v, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,68 @@
+// Shared declarations of the evpp_b200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/evpp_b200.h"
+
+namespace evpp {
+
+// ---- fixed architecture of the reference NeRF (run_nerf_helpers.py:78-134, nerf_configs.py) ----
+constexpr int kW = 256;          // netwidth
+constexpr int kD = 8;            // netdepth
+constexpr int kSkip = 4;         // skips=[4]
+constexpr int kLpos = 10;        // multires
+constexpr int kLdir = 4;         // multires_views
+constexpr int kEmbPos = 63;      // 3 + 3*2*10
+constexpr int kEmbDir = 27;      // 3 + 3*2*4
+constexpr int kWv = 128;         // W/2 view branch
+constexpr int kOut = 5;          // r,g,b,sigma,beta
+constexpr double kFlopPerEval = 1187072.0;
+
+// ---- fp32 (exact) MLP weight stream: 8 KB chunks of [kc][N] fp32, see mlp_simt.cu -------------
+constexpr int kSimtChunkFloats = 2048;
+// chunk counts per layer: L0 64/8=8, L1-4 32 each, L5 (64+256)/8=40, L6-7 32, feature 32,
+// views (256+32)/16=18
+constexpr int kSimtChunksTotal = 8 + 4 * 32 + 40 + 2 * 32 + 32 + 18;
+
+struct SimtWeights {          // device pointers
+  const float* stream;        // [kSimtChunksTotal][2048]
+  const float* bias;          // [8*256 + 256(feature) + 128(views)]
+  const float* head_w;        // alpha [256], rgb [3][128], unc [128]  -> 256 + 384 + 128
+  const float* head_b;        // alpha, r, g, b, unc -> 5
+};
+
+// ---- tcgen05 MLP weight image (fp16 or bf16), see mlp_tc.cu ------------------------------------
+struct TcWeights {
+  const void* image;          // pre-tiled, pre-swizzled B operand slices, streamed with cp.async.bulk
+  const float* bias;          // same layout as SimtWeights::bias
+  const float* head_b;        // 5
+  int dtype;                  // EVPP_PREC_FP16 / EVPP_PREC_BF16
+};
+
+struct RayBatch {             // device pointers of one chunk
+  const float* rays_o;        // [n,3]
+  const float* rays_d;        // [n,3]
+  const float* viewdirs;      // [n,3]
+  const float* z;             // [n,S]
+  int n;
+  int S;
+};
+
+// launchers (each returns the number of kernels launched)
+int launch_mlp_simt(const SimtWeights& w, const RayBatch& rb, float* raw, cudaStream_t st);
+int launch_mlp_simt_points(const SimtWeights& w, const float* pts, const float* dirs, int64_t M, float* out,
+                           cudaStream_t st);
+int launch_mlp_tc(const TcWeights& w, const RayBatch& rb, float* raw, int num_sms, cudaStream_t st);
+int launch_mlp_tc_points(const TcWeights& w, const float* pts, const float* dirs, int64_t M, float* out,
+                         int num_sms, cudaStream_t st);
+size_t tc_weight_image_bytes();
+// host-side repack of one network: fills `image` (tc_weight_image_bytes()) from fp32 state_dict tensors
+void tc_pack_weights(const std::vector<std::vector<float>>& tensors, int dtype, std::vector<uint8_t>& image);
+int tc_configure();   // sets kernel attributes; returns cudaError_t as int
+
+}  // namespace evpp

@@ -1,0 +1,610 @@
+// C ABI of the evpp_b200 engine (see include/evpp_b200.h): handle, weight snapshot, chunked
+// orchestration of the per-ray pipeline
+//   get_rays -> coarse z -> MLP(coarse) -> composite+resample -> MLP(fine) -> composite+beta^2
+//   -> per-view reduction
+// on the caller's stream.  There is deliberately no CPU path: without an sm_100 device every entry
+// point fails with EVPP_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "sampling.cuh"
+
+using namespace evpp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(EVPP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                  __LINE__);                                                                        \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) return (int)e;
+    bytes = need;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct NetWeights {
+  bool loaded = false;
+  DevBuf simt_stream, bias, head_w, head_b, tc_image[3];   // tc_image indexed by precision (1,2)
+  bool tc_ready[3] = {false, false, false};
+  std::vector<std::vector<float>> host;                   // fp32 state_dict tensors (for lazy tc repack)
+};
+
+}  // namespace
+
+struct evpp_handle {
+  int device = 0;
+  int num_sms = 148;
+  evpp_config cfg{};
+  int Sc = 64, Ni = 128, Sf = 192;
+  NetWeights net[2];
+  DevBuf t_vals, u_vals;
+  // chunk workspace
+  int chunk_cap = 0;
+  DevBuf rays_o, rays_d, viewdirs, z_c, raw_c, z_f, raw_f;
+  DevBuf beta2, st_c2w, st_pix, st_scores;
+  // stage capture
+  bool capture = false;
+  DevBuf w_c, cdf, inds, zs;
+  int last_n = 0;
+  // counters / profiling
+  int64_t launches = 0, evals = 0;
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::vector<int64_t> prof_evals;
+  double prof_ms = 0.0;
+  int64_t prof_launches = 0, prof_total_evals = 0;
+};
+
+namespace {
+
+// torch.linspace on CPU (fp32): step = (end-start)/(steps-1); first half start + step*i, second
+// half end - step*(steps-1-i), each with a fused multiply-add (verified against torch 2.11).
+std::vector<float> torch_linspace(float start, float end, int steps) {
+  std::vector<float> v(steps);
+  if (steps == 1) { v[0] = start; return v; }
+  const float step = (end - start) / (float)(steps - 1);
+  const int half = steps / 2;
+  for (int i = 0; i < steps; ++i)
+    v[i] = i < half ? std::fmaf(step, (float)i, start) : std::fmaf(-step, (float)(steps - i - 1), end);
+  return v;
+}
+
+const int kTensorSizes[26] = {
+    256 * 63, 256, 256 * 256, 256, 256 * 256, 256, 256 * 256, 256, 256 * 256, 256, 256 * 319, 256,
+    256 * 256, 256, 256 * 256, 256, 128 * 283, 128, 256 * 256, 256, 1 * 256, 1, 3 * 128, 3, 1 * 128, 1};
+
+int ensure_workspace(evpp_handle* h, int cap) {
+  if (cap <= h->chunk_cap) return 0;
+  const size_t c = (size_t)cap;
+  int e = 0;
+  e |= h->rays_o.ensure(c * 3 * 4);
+  e |= h->rays_d.ensure(c * 3 * 4);
+  e |= h->viewdirs.ensure(c * 3 * 4);
+  e |= h->z_c.ensure(c * h->Sc * 4);
+  e |= h->raw_c.ensure(c * h->Sc * 5 * 4);
+  if (h->Ni > 0) {
+    e |= h->z_f.ensure(c * h->Sf * 4);
+    e |= h->raw_f.ensure(c * h->Sf * 5 * 4);
+  }
+  if (h->capture) {
+    e |= h->w_c.ensure(c * h->Sc * 4);
+    e |= h->cdf.ensure(c * (h->Sc - 1) * 4);
+    e |= h->inds.ensure(c * (h->Ni > 0 ? h->Ni : 1) * 4);
+    e |= h->zs.ensure(c * (h->Ni > 0 ? h->Ni : 1) * 4);
+  }
+  if (e) return fail(EVPP_ERR_CUDA, "workspace allocation for %d rays failed: %s", cap,
+                     cudaGetErrorString(cudaGetLastError()));
+  h->chunk_cap = cap;
+  return 0;
+}
+
+int ensure_tc(evpp_handle* h, int which, int prec) {
+  NetWeights& nw = h->net[which];
+  if (nw.tc_ready[prec]) return 0;
+  std::vector<uint8_t> image;
+  tc_pack_weights(nw.host, prec, image);
+  if (nw.tc_image[prec].ensure(image.size())) return fail(EVPP_ERR_CUDA, "tc weight image alloc failed");
+  CUDA_TRY(cudaMemcpy(nw.tc_image[prec].p, image.data(), image.size(), cudaMemcpyHostToDevice));
+  int e = tc_configure();
+  if (e) return fail(EVPP_ERR_CUDA, "tcgen05 kernel configuration failed: %s", cudaGetErrorString((cudaError_t)e));
+  nw.tc_ready[prec] = true;
+  return 0;
+}
+
+SimtWeights simt_of(const NetWeights& nw) {
+  return SimtWeights{nw.simt_stream.as<float>(), nw.bias.as<float>(), nw.head_w.as<float>(), nw.head_b.as<float>()};
+}
+TcWeights tc_of(const NetWeights& nw, int prec) {
+  return TcWeights{nw.tc_image[prec].p, nw.bias.as<float>(), nw.head_b.as<float>(), prec};
+}
+
+int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw, cudaStream_t st) {
+  NetWeights& nw = h->net[which];
+  if (!nw.loaded) return fail(EVPP_ERR_STATE, "weights of net %d not loaded (evpp_load_nerf_weights)", which);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profiling) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+  }
+  int nl = 0;
+  if (prec == EVPP_PREC_FP32) {
+    nl = launch_mlp_simt(simt_of(nw), rb, raw, st);
+  } else {
+    int rc = ensure_tc(h, which, prec);
+    if (rc) return rc;
+    nl = launch_mlp_tc(tc_of(nw, prec), rb, raw, h->num_sms, st);
+    if (nl < 0) return fail(EVPP_ERR_CUDA, "tcgen05 MLP launch failed");
+  }
+  if (h->profiling) {
+    cudaEventRecord(e1, st);
+    h->prof_events.emplace_back(e0, e1);
+    h->prof_evals.push_back((int64_t)rb.n * rb.S);
+  }
+  h->launches += nl;
+  h->evals += (int64_t)rb.n * rb.S;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// One chunk of rays already in h->rays_*: coarse pass, resample, fine pass, composite.
+int render_chunk(evpp_handle* h, int n, float near_plane, float far_plane, int prec, const evpp_render_out* out,
+                 long long off, float* beta2, cudaStream_t st) {
+  const int Sc = h->Sc, Ni = h->Ni, Sf = h->Sf;
+  h->launches += launch_coarse_z(h->t_vals.as<float>(), n, Sc, near_plane, far_plane, h->cfg.lindisp,
+                                 h->z_c.as<float>(), st);
+  RayBatch rb{h->rays_o.as<float>(), h->rays_d.as<float>(), h->viewdirs.as<float>(), h->z_c.as<float>(), n, Sc};
+  int rc = run_mlp(h, EVPP_NET_COARSE, prec, rb, h->raw_c.as<float>(), st);
+  if (rc) return rc;
+  CompositeOut co{};
+  if (Ni > 0) {
+    if (out) {
+      co.rgb = out->rgb0 ? out->rgb0 + off * 3 : nullptr;
+      co.disp = out->disp0 ? out->disp0 + off : nullptr;
+      co.acc = out->acc0 ? out->acc0 + off : nullptr;
+      co.depth = out->depth0 ? out->depth0 + off : nullptr;
+      co.unc = out->unc0 ? out->unc0 + off * Sc : nullptr;
+      co.z_std = out->z_std ? out->z_std + off : nullptr;
+    }
+    co.weights = h->capture ? h->w_c.as<float>() : nullptr;
+    h->launches += launch_coarse_resample(
+        h->raw_c.as<float>(), h->z_c.as<float>(), h->rays_d.as<float>(), h->u_vals.as<float>(), n, Sc, Ni,
+        h->cfg.white_bkgd, co, h->z_f.as<float>(), h->capture ? h->cdf.as<float>() : nullptr,
+        h->capture ? h->inds.as<int32_t>() : nullptr, h->capture ? h->zs.as<float>() : nullptr, st);
+    RayBatch rf{h->rays_o.as<float>(), h->rays_d.as<float>(), h->viewdirs.as<float>(), h->z_f.as<float>(), n, Sf};
+    rc = run_mlp(h, EVPP_NET_FINE, prec, rf, h->raw_f.as<float>(), st);
+    if (rc) return rc;
+  }
+  const float* raw = Ni > 0 ? h->raw_f.as<float>() : h->raw_c.as<float>();
+  const float* z = Ni > 0 ? h->z_f.as<float>() : h->z_c.as<float>();
+  const int S = Ni > 0 ? Sf : Sc;
+  CompositeOut cf{};
+  if (out) {
+    cf.rgb = out->rgb ? out->rgb + off * 3 : nullptr;
+    cf.disp = out->disp ? out->disp + off : nullptr;
+    cf.acc = out->acc ? out->acc + off : nullptr;
+    cf.depth = out->depth ? out->depth + off : nullptr;
+    cf.unc = out->unc ? out->unc + off * S : nullptr;
+    if (out->raw)
+      CUDA_TRY(cudaMemcpyAsync(out->raw + off * S * 5, raw, (size_t)n * S * 5 * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (Ni == 0 && h->capture) cf.weights = h->w_c.as<float>();
+  cf.beta2 = beta2;
+  h->launches += launch_composite(raw, z, h->rays_d.as<float>(), n, S, h->cfg.white_bkgd, cf, st);
+  h->last_n = n;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int check_device_ok(int device) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(EVPP_ERR_NO_DEVICE, "no CUDA device visible; evpp_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= count) return fail(EVPP_ERR_INVALID, "device ordinal %d out of range (%d devices)", device, count);
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (major != 10)
+    return fail(EVPP_ERR_NO_DEVICE, "device %d has compute capability %d.x; this build is sm_100a only", device, major);
+  return 0;
+}
+
+int score_views_device(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx,
+                       float cy, const int32_t* pix_idx, int R, float* scores, int prec, cudaStream_t st) {
+  if (V < 0 || H <= 0 || W <= 0) return fail(EVPP_ERR_INVALID, "bad V/H/W");
+  if (V == 0) return 0;
+  if (!pix_idx) R = H * W;
+  if (R <= 0) return fail(EVPP_ERR_INVALID, "R must be positive when pix_idx is given");
+  const long long N = (long long)V * R;
+  const int cap = (int)std::min<long long>(N, h->cfg.max_chunk_rays);
+  int rc = ensure_workspace(h, cap);
+  if (rc) return rc;
+  if (h->beta2.ensure((size_t)N * 4)) return fail(EVPP_ERR_CUDA, "beta2 buffer alloc failed");
+  for (long long g0 = 0; g0 < N; g0 += cap) {
+    const int n = (int)std::min<long long>(cap, N - g0);
+    h->launches += launch_get_rays(c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, g0, n, h->rays_o.as<float>(),
+                                   h->rays_d.as<float>(), h->viewdirs.as<float>(), st);
+    rc = render_chunk(h, n, h->cfg.near_plane, h->cfg.far_plane, prec, nullptr, 0, h->beta2.as<float>() + g0, st);
+    if (rc) return rc;
+  }
+  h->launches += launch_view_reduce(h->beta2.as<float>(), V, R, scores, st);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* evpp_last_error(void) { return g_err.c_str(); }
+int evpp_abi_version(void) { return EVPP_ABI_VERSION; }
+
+int evpp_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < count; ++d) {
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d);
+    if (major == 10) ++ok;
+  }
+  return ok;
+}
+
+int evpp_create(int device_ordinal, const evpp_config* cfg, evpp_handle** out) {
+  if (!cfg || !out) return fail(EVPP_ERR_INVALID, "null cfg/out");
+  *out = nullptr;
+  int rc = check_device_ok(device_ordinal);
+  if (rc) return rc;
+  if (cfg->n_samples < 4 || cfg->n_samples > kMaxSc)
+    return fail(EVPP_ERR_INVALID, "n_samples %d out of range [4,%d]", cfg->n_samples, kMaxSc);
+  if (cfg->n_importance < 0 || cfg->n_importance + cfg->n_samples > kMaxSf)
+    return fail(EVPP_ERR_INVALID, "n_samples+n_importance %d exceeds %d", cfg->n_importance + cfg->n_samples, kMaxSf);
+  if (cfg->precision < 0 || cfg->precision > 2) return fail(EVPP_ERR_INVALID, "bad precision %d", cfg->precision);
+  CUDA_TRY(cudaSetDevice(device_ordinal));
+  evpp_handle* h = new evpp_handle();
+  h->device = device_ordinal;
+  h->cfg = *cfg;
+  if (h->cfg.max_chunk_rays <= 0) h->cfg.max_chunk_rays = 131072;
+  h->Sc = cfg->n_samples;
+  h->Ni = cfg->n_importance;
+  h->Sf = h->Sc + h->Ni;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device_ordinal);
+  auto t = torch_linspace(0.f, 1.f, h->Sc);
+  auto u = torch_linspace(0.f, 1.f, h->Ni > 0 ? h->Ni : 1);
+  if (h->t_vals.ensure(t.size() * 4) || h->u_vals.ensure(u.size() * 4)) {
+    delete h;
+    return fail(EVPP_ERR_CUDA, "table alloc failed");
+  }
+  cudaMemcpy(h->t_vals.p, t.data(), t.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(h->u_vals.p, u.data(), u.size() * 4, cudaMemcpyHostToDevice);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(EVPP_ERR_CUDA, "create: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return 0;
+}
+
+int evpp_destroy(evpp_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& pr : h->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (int i = 0; i < 2; ++i) {
+    NetWeights& nw = h->net[i];
+    nw.simt_stream.release(); nw.bias.release(); nw.head_w.release(); nw.head_b.release();
+    for (auto& b : nw.tc_image) b.release();
+  }
+  for (DevBuf* b : {&h->t_vals, &h->u_vals, &h->rays_o, &h->rays_d, &h->viewdirs, &h->z_c, &h->raw_c, &h->z_f,
+                    &h->raw_f, &h->beta2, &h->st_c2w, &h->st_pix, &h->st_scores, &h->w_c, &h->cdf, &h->inds, &h->zs})
+    b->release();
+  delete h;
+  return 0;
+}
+
+int evpp_load_nerf_weights(evpp_handle* h, int which, const float* packed, const int64_t* offsets, int n) {
+  if (!h || !packed || !offsets) return fail(EVPP_ERR_INVALID, "null argument");
+  if (which != 0 && which != 1) return fail(EVPP_ERR_INVALID, "which_net must be 0 (coarse) or 1 (fine)");
+  if (n != 26) return fail(EVPP_ERR_INVALID, "expected 26 state_dict tensors (NeRF D=8,W=256,use_viewdirs), got %d", n);
+  CUDA_TRY(cudaSetDevice(h->device));
+  NetWeights& nw = h->net[which];
+  nw.host.assign(26, {});
+  for (int i = 0; i < 26; ++i) {
+    if (offsets[i] < 0) return fail(EVPP_ERR_INVALID, "negative offset for tensor %d", i);
+    nw.host[i].resize(kTensorSizes[i]);
+    CUDA_TRY(cudaMemcpy(nw.host[i].data(), packed + offsets[i], (size_t)kTensorSizes[i] * 4, cudaMemcpyDefault));
+    for (float v : nw.host[i])
+      if (!std::isfinite(v)) return fail(EVPP_ERR_INVALID, "non-finite weight in tensor %d", i);
+  }
+  // ---- fp32 stream: per layer [K_padded][N] (input-major), chunked in 2048 floats -------------
+  std::vector<float> stream((size_t)kSimtChunksTotal * kSimtChunkFloats, 0.f);
+  size_t pos = 0;
+  auto put = [&](const std::vector<float>& Wt, int N, int in_dim, int in_begin, int in_count, int k_pad) {
+    // appends rows k=0..k_pad-1: row k = W[:, in_begin+k] (zero if k >= in_count)
+    for (int k = 0; k < k_pad; ++k) {
+      if (k < in_count)
+        for (int o = 0; o < N; ++o) stream[pos + (size_t)k * N + o] = Wt[(size_t)o * in_dim + in_begin + k];
+    }
+    pos += (size_t)k_pad * N;
+  };
+  put(nw.host[0], 256, 63, 0, 63, 64);
+  for (int l = 1; l <= 4; ++l) put(nw.host[2 * l], 256, 256, 0, 256, 256);
+  put(nw.host[10], 256, 319, 0, 63, 64);      // skip layer: cat[input_pts(63), h(256)]
+  put(nw.host[10], 256, 319, 63, 256, 256);
+  put(nw.host[12], 256, 256, 0, 256, 256);
+  put(nw.host[14], 256, 256, 0, 256, 256);
+  put(nw.host[18], 256, 256, 0, 256, 256);    // feature_linear
+  put(nw.host[16], 128, 283, 0, 256, 256);    // views_linears.0: cat[feature(256), dirs(27)]
+  put(nw.host[16], 128, 283, 256, 27, 32);
+  if (pos != stream.size()) return fail(EVPP_ERR_INVALID, "internal: weight stream size mismatch");
+  std::vector<float> bias(10 * 256, 0.f);
+  for (int l = 0; l < 8; ++l) memcpy(&bias[l * 256], nw.host[2 * l + 1].data(), 256 * 4);
+  memcpy(&bias[8 * 256], nw.host[19].data(), 256 * 4);
+  memcpy(&bias[9 * 256], nw.host[17].data(), 128 * 4);
+  std::vector<float> head_w(256 + 384 + 128), head_b(8, 0.f);
+  memcpy(&head_w[0], nw.host[20].data(), 256 * 4);
+  memcpy(&head_w[256], nw.host[22].data(), 384 * 4);
+  memcpy(&head_w[640], nw.host[24].data(), 128 * 4);
+  head_b[0] = nw.host[21][0];
+  head_b[1] = nw.host[23][0]; head_b[2] = nw.host[23][1]; head_b[3] = nw.host[23][2];
+  head_b[4] = nw.host[25][0];
+  if (nw.simt_stream.ensure(stream.size() * 4) || nw.bias.ensure(bias.size() * 4) ||
+      nw.head_w.ensure(head_w.size() * 4) || nw.head_b.ensure(head_b.size() * 4))
+    return fail(EVPP_ERR_CUDA, "weight buffer alloc failed");
+  CUDA_TRY(cudaMemcpy(nw.simt_stream.p, stream.data(), stream.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(nw.bias.p, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(nw.head_w.p, head_w.data(), head_w.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(nw.head_b.p, head_b.data(), head_b.size() * 4, cudaMemcpyHostToDevice));
+  for (bool& b : nw.tc_ready) b = false;
+  nw.loaded = true;
+  if (h->cfg.precision != EVPP_PREC_FP32) {
+    int rc = ensure_tc(h, which, h->cfg.precision);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int evpp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx,
+                     float cy, const int32_t* pix_idx, int R, float* scores, void* stream) {
+  if (!h || !c2w || !scores) return fail(EVPP_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return score_views_device(h, c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, scores, h->cfg.precision,
+                            (cudaStream_t)stream);
+}
+
+static int score_host_impl(evpp_handle* h, const float* c2w_host, int V, int H, int W, float fx, float fy,
+                           float cx, float cy, const int32_t* pix_host, int R, float* scores_host, int prec,
+                           cudaStream_t st) {
+  if (V == 0) return 0;
+  if (h->st_c2w.ensure((size_t)V * 12 * 4) || h->st_scores.ensure((size_t)V * 4))
+    return fail(EVPP_ERR_CUDA, "staging alloc failed");
+  CUDA_TRY(cudaMemcpyAsync(h->st_c2w.p, c2w_host, (size_t)V * 12 * 4, cudaMemcpyHostToDevice, st));
+  const int32_t* pix_dev = nullptr;
+  if (pix_host) {
+    if (h->st_pix.ensure((size_t)V * R * 4)) return fail(EVPP_ERR_CUDA, "staging alloc failed");
+    CUDA_TRY(cudaMemcpyAsync(h->st_pix.p, pix_host, (size_t)V * R * 4, cudaMemcpyHostToDevice, st));
+    pix_dev = h->st_pix.as<int32_t>();
+  }
+  int rc = score_views_device(h, h->st_c2w.as<float>(), V, H, W, fx, fy, cx, cy, pix_dev, R,
+                              h->st_scores.as<float>(), prec, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(scores_host, h->st_scores.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int evpp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int H, int W, float fx, float fy,
+                          float cx, float cy, const int32_t* pix_idx_host, int R, float* scores_host,
+                          void* stream) {
+  if (!h || !c2w_host || !scores_host) return fail(EVPP_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return score_host_impl(h, c2w_host, V, H, W, fx, fy, cx, cy, pix_idx_host, R, scores_host, h->cfg.precision,
+                         (cudaStream_t)stream);
+}
+
+int evpp_rescore_views_fp32(evpp_handle* h, const float* c2w_host, const int32_t* view_ids, int K, int H, int W,
+                            float fx, float fy, float cx, float cy, const int32_t* pix_idx_host, int R,
+                            float* scores_host, void* stream) {
+  if (!h || !c2w_host || !view_ids || !scores_host) return fail(EVPP_ERR_INVALID, "null argument");
+  if (K <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  std::vector<float> poses((size_t)K * 12);
+  std::vector<int32_t> pix;
+  if (pix_idx_host) pix.resize((size_t)K * R);
+  for (int k = 0; k < K; ++k) {
+    if (view_ids[k] < 0) return fail(EVPP_ERR_INVALID, "negative view id");
+    memcpy(&poses[(size_t)k * 12], c2w_host + (size_t)view_ids[k] * 12, 48);
+    if (pix_idx_host) memcpy(&pix[(size_t)k * R], pix_idx_host + (size_t)view_ids[k] * R, (size_t)R * 4);
+  }
+  return score_host_impl(h, poses.data(), K, H, W, fx, fy, cx, cy, pix_idx_host ? pix.data() : nullptr, R,
+                         scores_host, EVPP_PREC_FP32, (cudaStream_t)stream);
+}
+
+int evpp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, int64_t N, float near_plane,
+                     float far_plane, int precision, const evpp_render_out* out, void* stream) {
+  if (!h || !out) return fail(EVPP_ERR_INVALID, "null argument");
+  if (N < 0) return fail(EVPP_ERR_INVALID, "negative N");
+  if (N == 0) return 0;
+  if (!rays_o || !rays_d) return fail(EVPP_ERR_INVALID, "null rays");
+  if (precision < 0) precision = h->cfg.precision;
+  if (precision > 2) return fail(EVPP_ERR_INVALID, "bad precision");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cap = (int)std::min<int64_t>(N, h->cfg.max_chunk_rays);
+  int rc = ensure_workspace(h, cap);
+  if (rc) return rc;
+  for (int64_t g0 = 0; g0 < N; g0 += cap) {
+    const int n = (int)std::min<int64_t>(cap, N - g0);
+    CUDA_TRY(cudaMemcpyAsync(h->rays_o.p, rays_o + g0 * 3, (size_t)n * 12, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->rays_d.p, rays_d + g0 * 3, (size_t)n * 12, cudaMemcpyDeviceToDevice, st));
+    // viewdirs = rays_d / ||rays_d|| (run_nerf.py:165-171): reuse the ray kernel's normalisation
+    h->launches += launch_normalize_dirs(h->rays_d.as<float>(), n, h->viewdirs.as<float>(), st);
+    rc = render_chunk(h, n, near_plane, far_plane, precision, out, g0, nullptr, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int evpp_get_rays(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx, float cy,
+                  const int32_t* pix_idx, int R, float* rays_o, float* rays_d, float* viewdirs, void* stream) {
+  if (!h || !c2w) return fail(EVPP_ERR_INVALID, "null argument");
+  if (!pix_idx) R = H * W;
+  const long long N = (long long)V * R;
+  if (N <= 0) return 0;
+  if (N > 0x7fffffffLL) return fail(EVPP_ERR_INVALID, "too many rays for one call");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->launches += launch_get_rays(c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, 0, (int)N, rays_o, rays_d, viewdirs,
+                                 (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int evpp_mlp_forward(evpp_handle* h, int which, int precision, const float* pts, const float* dirs, int64_t M,
+                     float* out, void* stream) {
+  if (!h || !pts || !dirs || !out) return fail(EVPP_ERR_INVALID, "null argument");
+  if (which != 0 && which != 1) return fail(EVPP_ERR_INVALID, "bad net");
+  if (M <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  NetWeights& nw = h->net[which];
+  if (!nw.loaded) return fail(EVPP_ERR_STATE, "weights of net %d not loaded", which);
+  if (precision < 0) precision = h->cfg.precision;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == EVPP_PREC_FP32) {
+    h->launches += launch_mlp_simt_points(simt_of(nw), pts, dirs, M, out, st);
+  } else if (precision <= 2) {
+    int rc = ensure_tc(h, which, precision);
+    if (rc) return rc;
+    int nl = launch_mlp_tc_points(tc_of(nw, precision), pts, dirs, M, out, h->num_sms, st);
+    if (nl < 0) return fail(EVPP_ERR_CUDA, "tcgen05 MLP launch failed");
+    h->launches += nl;
+  } else {
+    return fail(EVPP_ERR_INVALID, "bad precision");
+  }
+  h->evals += M;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int evpp_set_stage_capture(evpp_handle* h, int enabled) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  h->capture = enabled != 0;
+  h->chunk_cap = 0;   // force (re)allocation of the capture buffers
+  return 0;
+}
+
+int evpp_stage_dump(evpp_handle* h, int stage, void* out, int64_t* count, void* stream) {
+  if (!h || !count) return fail(EVPP_ERR_INVALID, "null argument");
+  const int64_t n = h->last_n;
+  const void* src = nullptr;
+  int64_t cnt = 0;
+  switch (stage) {
+    case EVPP_STAGE_Z_COARSE: src = h->z_c.p; cnt = n * h->Sc; break;
+    case EVPP_STAGE_RAW_COARSE: src = h->raw_c.p; cnt = n * h->Sc * 5; break;
+    case EVPP_STAGE_W_COARSE: src = h->w_c.p; cnt = n * h->Sc; break;
+    case EVPP_STAGE_CDF: src = h->cdf.p; cnt = n * (h->Sc - 1); break;
+    case EVPP_STAGE_INDS: src = h->inds.p; cnt = n * h->Ni; break;
+    case EVPP_STAGE_Z_SAMPLES: src = h->zs.p; cnt = n * h->Ni; break;
+    case EVPP_STAGE_Z_FINE: src = h->z_f.p; cnt = n * h->Sf; break;
+    default: return fail(EVPP_ERR_INVALID, "unknown stage %d", stage);
+  }
+  *count = cnt;
+  if (!out) return 0;
+  if (!src) return fail(EVPP_ERR_STATE, "stage %d not captured (evpp_set_stage_capture before rendering)", stage);
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(out, src, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, int V, int dirs_per_location,
+                    float* norm_scores, int32_t* best_dir, int32_t* winner_view, void* stream) {
+  if (!h || !scores) return fail(EVPP_ERR_INVALID, "null argument");
+  if (dirs_per_location <= 0 || V <= 0 || V % dirs_per_location)
+    return fail(EVPP_ERR_INVALID, "V (%d) must be a positive multiple of dirs_per_location (%d)", V, dirs_per_location);
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->launches += launch_select_nbv(scores, weight, V, dirs_per_location, norm_scores, best_dir, winner_view,
+                                   (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int evpp_get_counters(evpp_handle* h, int64_t* kernel_launches, int64_t* mlp_evals) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  if (kernel_launches) *kernel_launches = h->launches;
+  if (mlp_evals) *mlp_evals = h->evals;
+  return 0;
+}
+
+int evpp_set_profiling(evpp_handle* h, int enabled) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  h->profiling = enabled != 0;
+  for (auto& pr : h->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  h->prof_events.clear();
+  h->prof_evals.clear();
+  h->prof_ms = 0.0;
+  h->prof_launches = 0;
+  h->prof_total_evals = 0;
+  return 0;
+}
+
+int evpp_get_mlp_time_ms(evpp_handle* h, double* total_ms, int64_t* launches, int64_t* evals) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (size_t i = 0; i < h->prof_events.size(); ++i) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second));
+    h->prof_ms += ms;
+    h->prof_launches += 1;
+    h->prof_total_evals += h->prof_evals[i];
+    cudaEventDestroy(h->prof_events[i].first);
+    cudaEventDestroy(h->prof_events[i].second);
+  }
+  h->prof_events.clear();
+  h->prof_evals.clear();
+  if (total_ms) *total_ms = h->prof_ms;
+  if (launches) *launches = h->prof_launches;
+  if (evals) *evals = h->prof_total_evals;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+"""Python face of the C-ABI engine: owns an evpp_handle, moves torch tensors across the boundary.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EvppConfig, EvppRenderOut, check, PRECISIONS
+
+STATE_DICT_KEYS = [f"pts_linears.{i}.{p}" for i in range(8) for p in ("weight", "bias")] + \
+    [f"{n}.{p}" for n in ("views_linears.0", "feature_linear", "alpha_linear", "rgb_linear", "uncertainty_linear")
+     for p in ("weight", "bias")]
+STATE_DICT_SHAPES = [(256, 63), (256,)] + [(256, 256), (256,)] * 4 + [(256, 319), (256,)] + [(256, 256), (256,)] * 2 + \
+    [(128, 283), (128,), (256, 256), (256,), (1, 256), (1,), (3, 128), (3,), (1, 128), (1,)]
+
+STAGES = {"z_coarse": (0, torch.float32), "raw_coarse": (1, torch.float32), "weights_coarse": (2, torch.float32),
+          "cdf": (3, torch.float32), "inds": (4, torch.int32), "z_samples": (5, torch.float32),
+          "z_fine": (6, torch.float32)}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    """One evpp_handle on one GPU.  Calls on one Engine must be serialised by the caller."""
+
+    def __init__(self, device=0, n_samples=64, n_importance=128, near=0.5, far=80.0, white_bkgd=True,
+                 lindisp=False, precision="fp16", max_chunk_rays=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.EvppError(-4, "no CUDA device visible; evpp_b200 has no CPU fallback")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.precision = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        self.cfg = EvppConfig(n_samples, n_importance, near, far, int(bool(white_bkgd)), int(bool(lindisp)),
+                              self.precision, max_chunk_rays)
+        self.n_samples, self.n_importance = n_samples, n_importance
+        self.S_f = n_samples + n_importance
+        self._h = C.c_void_p()
+        check(self.lib.evpp_create(self.device.index, C.byref(self.cfg), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.evpp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights (Controller.copy_model, nerf.py:718-757) -------------------------------------------
+    def load_weights(self, which, state_dict):
+        """which: 0/'coarse' (network_fn) or 1/'fine' (network_fine); state_dict: reference NeRF keys."""
+        which = {"coarse": 0, "fine": 1}.get(which, which)
+        if hasattr(state_dict, "state_dict"):
+            state_dict = state_dict.state_dict()
+        flat, offsets, off = [], [], 0
+        for k, shape in zip(STATE_DICT_KEYS, STATE_DICT_SHAPES):
+            if k not in state_dict:
+                raise KeyError(f"state_dict lacks {k} (expected reference NeRF(D=8,W=256,use_viewdirs=True))")
+            t = state_dict[k].detach().to("cpu", torch.float32).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{k}: shape {tuple(t.shape)} != {shape}")
+            flat.append(t.reshape(-1))
+            offsets.append(off)
+            off += t.numel()
+        packed = torch.cat(flat).contiguous()
+        offs = np.asarray(offsets, dtype=np.int64)
+        check(self.lib.evpp_load_nerf_weights(self._h, which, C.c_void_p(packed.data_ptr()),
+                                              offs.ctypes.data_as(C.c_void_p), len(offsets)))
+
+    # ---- scoring (Controller.get_uncertainty, nerf.py:266-309) -------------------------------------
+    def score_views(self, c2w, H, W, fx, fy, cx, cy, pix_idx=None):
+        """c2w: cuda float32 [V,3,4]; pix_idx: cuda int32 [V,R] or None.  Returns cuda float32 [V]."""
+        c2w = c2w.to(self.device, torch.float32).contiguous()
+        V = c2w.shape[0]
+        R = 0
+        if pix_idx is not None:
+            pix_idx = pix_idx.to(self.device, torch.int32).contiguous()
+            R = pix_idx.shape[1]
+        scores = torch.empty(V, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_score_views(self._h, _ptr(c2w), V, H, W, fx, fy, cx, cy, _ptr(pix_idx), R,
+                                            _ptr(scores), _stream_ptr(self.device)))
+        return scores
+
+    def score_views_host(self, c2w_host, H, W, fx, fy, cx, cy, pix_idx_host=None, out=None):
+        """HOST in / HOST out (pinned torch CPU tensors recommended).  Synchronises."""
+        assert c2w_host.device.type == "cpu" and c2w_host.dtype == torch.float32 and c2w_host.is_contiguous()
+        V = c2w_host.shape[0]
+        R = 0
+        if pix_idx_host is not None:
+            assert pix_idx_host.dtype == torch.int32 and pix_idx_host.is_contiguous()
+            R = pix_idx_host.shape[1]
+        if out is None:
+            out = torch.empty(V, dtype=torch.float32).pin_memory()
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_score_views_host(self._h, _ptr(c2w_host), V, H, W, fx, fy, cx, cy,
+                                                 _ptr(pix_idx_host), R, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def rescore_views_fp32(self, c2w_host, view_ids, H, W, fx, fy, cx, cy, pix_idx_host=None):
+        ids = torch.as_tensor(np.asarray(view_ids), dtype=torch.int32).contiguous()
+        R = 0 if pix_idx_host is None else pix_idx_host.shape[1]
+        out = torch.empty(len(ids), dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_rescore_views_fp32(self._h, _ptr(c2w_host), _ptr(ids), len(ids), H, W, fx, fy, cx,
+                                                   cy, _ptr(pix_idx_host), R, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    # ---- rendering (render / render_rays, run_nerf.py:131-196, 391-509) -----------------------------
+    def render_rays(self, rays_o, rays_d, near, far, precision=None, want=("rgb", "disp", "acc", "depth", "unc"),
+                    capture_stages=False):
+        rays_o = rays_o.to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        rays_d = rays_d.to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        N = rays_o.shape[0]
+        S = self.S_f if self.n_importance > 0 else self.n_samples
+        shapes = {"rgb": (N, 3), "disp": (N,), "acc": (N,), "depth": (N,), "unc": (N, S), "raw": (N, S, 5),
+                  "rgb0": (N, 3), "disp0": (N,), "acc0": (N,), "depth0": (N,), "unc0": (N, self.n_samples),
+                  "z_std": (N,)}
+        outs = {k: torch.empty(shapes[k], device=self.device, dtype=torch.float32) for k in want}
+        ro = EvppRenderOut(**{k: (outs[k].data_ptr() if k in outs else None) for k in shapes})
+        prec = self.precision if precision is None else (PRECISIONS[precision] if isinstance(precision, str) else precision)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_set_stage_capture(self._h, int(capture_stages)))
+            check(self.lib.evpp_render_rays(self._h, _ptr(rays_o), _ptr(rays_d), N, float(near), float(far), prec,
+                                            C.byref(ro), _stream_ptr(self.device)))
+        return outs
+
+    def stage(self, name):
+        sid, dt = STAGES[name]
+        cnt = C.c_int64(0)
+        check(self.lib.evpp_stage_dump(self._h, sid, C.c_void_p(0), C.byref(cnt), C.c_void_p(0)))
+        out = torch.empty(cnt.value, device=self.device, dtype=dt)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_stage_dump(self._h, sid, _ptr(out), C.byref(cnt), _stream_ptr(self.device)))
+        return out
+
+    def get_rays(self, c2w, H, W, fx, fy, cx, cy, pix_idx=None):
+        c2w = c2w.to(self.device, torch.float32).contiguous()
+        V = c2w.shape[0]
+        R = H * W
+        if pix_idx is not None:
+            pix_idx = pix_idx.to(self.device, torch.int32).contiguous()
+            R = pix_idx.shape[1]
+        o = torch.empty(V * R, 3, device=self.device)
+        d = torch.empty_like(o)
+        vd = torch.empty_like(o)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_get_rays(self._h, _ptr(c2w), V, H, W, fx, fy, cx, cy, _ptr(pix_idx), R, _ptr(o),
+                                         _ptr(d), _ptr(vd), _stream_ptr(self.device)))
+        return o, d, vd
+
+    def mlp_forward(self, which, pts, dirs, precision=None):
+        which = {"coarse": 0, "fine": 1}.get(which, which)
+        pts = pts.to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        dirs = dirs.to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        out = torch.empty(pts.shape[0], 5, device=self.device)
+        prec = self.precision if precision is None else (PRECISIONS[precision] if isinstance(precision, str) else precision)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_mlp_forward(self._h, which, prec, _ptr(pts), _ptr(dirs), pts.shape[0], _ptr(out),
+                                            _stream_ptr(self.device)))
+        return out
+
+    def select_nbv(self, scores, weight=None, dirs_per_location=1):
+        scores = scores.to(self.device, torch.float32).contiguous()
+        V = scores.shape[0]
+        L = V // dirs_per_location
+        if weight is not None:
+            weight = weight.to(self.device, torch.float32).contiguous()
+        norm = torch.empty(L, device=self.device)
+        best = torch.empty(L, device=self.device, dtype=torch.int32)
+        win = torch.empty(1, device=self.device, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_select_nbv(self._h, _ptr(scores), _ptr(weight), V, dirs_per_location, _ptr(norm),
+                                           _ptr(best), _ptr(win), _stream_ptr(self.device)))
+        return norm, best, win
+
+    # ---- counters -----------------------------------------------------------------------------------
+    def counters(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(self.lib.evpp_get_counters(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_profiling(self, on):
+        check(self.lib.evpp_set_profiling(self._h, int(on)))
+
+    def mlp_time(self):
+        ms, n, ev = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        check(self.lib.evpp_get_mlp_time_ms(self._h, C.byref(ms), C.byref(n), C.byref(ev)))
+        return ms.value, n.value, ev.value

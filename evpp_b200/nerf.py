@@ -1,0 +1,80 @@
+"""Drop-in for the scoring seam of the reference's ``Controller`` (nerfServer/core/nerf.py:73):
+``get_uncertainty(poses)`` (:266-309), ``get_surface_points`` (:325-351), ``get_rays_depth``
+(:353-392) and the weight hand-off ``copy_model`` (:718-757).  The training loop, image store
+and HTTP glue of the reference Controller are out of scope."""
+import numpy as np
+import torch
+
+from .engine import Engine
+from .run_nerf import _intrinsics
+
+
+class Controller:
+    def __init__(self, H=400, W=400, focal=300.0, near=0.5, far=80.0, N_samples=64, N_importance=128,
+                 white_bkgd=True, device=0, precision="fp16", sample_num=1000, max_chunk_rays=0):
+        """Defaults are the live constants: views.py:21-23 (H, W, focal), nerf.py:100-101 (near, far),
+        config.txt:10-13, nerf.py:276 (sample_num)."""
+        self.H, self.W, self.focal = H, W, focal
+        self.K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])   # nerf.py:112-116
+        self.near, self.far = near, far
+        self.sample_num = sample_num
+        self.engine = Engine(device=device, n_samples=N_samples, n_importance=N_importance, near=near, far=far,
+                             white_bkgd=white_bkgd, precision=precision, max_chunk_rays=max_chunk_rays)
+        self.uncertainty_kargs = None
+
+    def copy_model(self, network_fn, network_fine=None):
+        """Snapshot the (training) networks into the scorer; never aliases their parameters."""
+        self.engine.load_weights(0, network_fn)
+        self.engine.load_weights(1, network_fine if network_fine is not None else network_fn)
+        self.uncertainty_kargs = [{"engine": self.engine, "device": self.engine.device}]
+
+    def _pixel_subset(self, V):
+        if self.sample_num is None:
+            return None
+        n = self.H * self.W
+        # nerf.py:287 -- one np.random.choice per pose from numpy's global RNG
+        return np.stack([np.random.choice(n, size=[self.sample_num], replace=False) for _ in range(V)]).astype(np.int32)
+
+    def get_uncertainty(self, poses, pix_idx=None):
+        """poses: list/array [V,4,4] (views.get_pose).  Returns a cuda float32 tensor [V] with
+        sum over rays and the 192 fine samples of beta^2, divided by rays per view (nerf.py:307-309)."""
+        if self.uncertainty_kargs is None:
+            raise TypeError("'NoneType' object is not subscriptable (weights not handed off: call copy_model)")
+        poses = torch.Tensor(np.asarray(poses, dtype=np.float64))[:, :3, :4].contiguous()   # fp64 -> fp32, nerf.py:278
+        V = poses.shape[0]
+        if pix_idx is None:
+            pix_idx = self._pixel_subset(V)
+        fx, fy, cx, cy = _intrinsics(self.K)
+        pix_t = None if pix_idx is None else torch.as_tensor(np.ascontiguousarray(pix_idx, dtype=np.int32))
+        scores = self.engine.score_views_host(poses, self.H, self.W, fx, fy, cx, cy, pix_t)
+        return scores.to(self.engine.device)
+
+    def _render(self, rays_o, rays_d):
+        return self.engine.render_rays(rays_o, rays_d, self.near, self.far, want=("rgb", "depth"))
+
+    def get_surface_points(self, location, radius, step):
+        """nerf.py:325-351: sphere of rays from ``location``; keep hits with near < depth < radius."""
+        rays_d = []
+        for u in np.arange(0, 2 * np.pi, step):
+            for v in np.arange(0, np.pi, step):
+                rays_d.append([np.cos(u), np.sin(u) * np.cos(v), np.sin(u) * np.sin(v)])
+        rays_d = torch.Tensor(rays_d).to(self.engine.device)
+        rays_o = torch.Tensor(location).to(self.engine.device).expand(rays_d.shape).contiguous()
+        o = self._render(rays_o, rays_d)
+        depth = o["depth"].clone()
+        depth[torch.mean(o["rgb"], -1) * 255 > 250] = 0
+        points = rays_o + rays_d * depth[..., None]
+        points = points[depth < radius]
+        depth = depth[depth < radius]
+        return points[depth > self.near]
+
+    def get_rays_depth(self, locations, dirs):
+        """nerf.py:353-392: depth along arbitrary rays; white pixels and depth<near -> 0."""
+        rays_o = torch.Tensor(locations).reshape(-1, 3)
+        rays_d = torch.Tensor(dirs).reshape(-1, 3)
+        sh = torch.Tensor(dirs).shape
+        o = self._render(rays_o, rays_d)
+        depth = o["depth"].clone()
+        depth[torch.mean(o["rgb"], -1) * 255 > 250] = 0
+        depth[depth < self.near] = 0
+        return depth.reshape(sh[:-1])

@@ -1,0 +1,107 @@
+"""Drop-in for the renderer seam of the reference: same names, argument meaning and return
+structure as nerfServer/core/run_nerf.py (render, :131-196) and run_nerf_helpers.py (get_rays,
+:173-182), backed by the CUDA engine instead of PyTorch ops.
+
+Supported configuration = what the server runs at inference (nerf.py:727-752): ndc=False,
+use_viewdirs=True, perturb=0, raw_noise_std=0.  Anything else raises (no silent fallback).
+"""
+import numpy as np
+import torch
+
+from .engine import Engine
+
+_ENGINE_CACHE = {}
+
+
+def get_pose(location, u, v):
+    """c2w from position + pitch u + yaw v; same matrix as nerfServer/core/views.py:141-150."""
+    su, cu, sv, cv = np.sin(u), np.cos(u), np.sin(v), np.cos(v)
+    return [[cv, sv * su, -sv * cu, location[0]],
+            [0, cu, su, location[1]],
+            [-sv, cv * su, -cv * cu, location[2]],
+            [0, 0, 0, 1]]
+
+
+def _intrinsics(K):
+    return float(np.float32(K[0][0])), float(np.float32(K[1][1])), float(np.float32(K[0][2])), float(np.float32(K[1][2]))
+
+
+def make_render_kwargs(network_fn, network_fine, N_samples=64, N_importance=128, white_bkgd=True, lindisp=False,
+                       device=0, precision="fp16", near=0.5, far=80.0, max_chunk_rays=0):
+    """Counterpart of create_nerf's render_kwargs_test (run_nerf.py:316-333) / copy_model's kwargs
+    (nerf.py:727-752): snapshots both networks into an Engine and returns the kwargs dict that
+    ``render(**kwargs)`` consumes.  network_fn / network_fine: reference NeRF modules or state_dicts."""
+    eng = Engine(device=device, n_samples=N_samples, n_importance=N_importance, near=near, far=far,
+                 white_bkgd=white_bkgd, lindisp=lindisp, precision=precision, max_chunk_rays=max_chunk_rays)
+    eng.load_weights(0, network_fn)
+    eng.load_weights(1, network_fine if network_fine is not None else network_fn)
+    return {"network_query_fn": None, "perturb": False, "N_importance": N_importance, "network_fine": network_fine,
+            "N_samples": N_samples, "network_fn": network_fn, "use_viewdirs": True, "white_bkgd": white_bkgd,
+            "raw_noise_std": 0., "device": eng.device, "ndc": False, "lindisp": lindisp, "engine": eng}
+
+
+def _engine_from_kwargs(kwargs, near, far):
+    eng = kwargs.get("engine")
+    if eng is not None:
+        return eng
+    net, fine = kwargs.get("network_fn"), kwargs.get("network_fine")
+    if net is None:
+        raise ValueError("render(): kwargs need 'engine' (make_render_kwargs) or 'network_fn'")
+    dev = kwargs.get("device", 0)
+    dev = dev.index if isinstance(dev, torch.device) else dev
+    key = (id(net), id(fine), kwargs.get("N_samples", 64), kwargs.get("N_importance", 128),
+           bool(kwargs.get("white_bkgd", False)), bool(kwargs.get("lindisp", False)), dev)
+    if key not in _ENGINE_CACHE:
+        kw = make_render_kwargs(net, fine, N_samples=key[2], N_importance=key[3], white_bkgd=key[4], lindisp=key[5],
+                                device=dev or 0, near=near, far=far)
+        _ENGINE_CACHE[key] = kw["engine"]
+    return _ENGINE_CACHE[key]
+
+
+def get_rays(H, W, K, c2w, dev=None, engine=None):
+    """Same contract as run_nerf_helpers.get_rays: returns rays_o, rays_d of shape [H,W,3]."""
+    if engine is None:
+        raise ValueError("get_rays needs engine= (the CUDA engine that generates the rays)")
+    c2w = torch.as_tensor(np.asarray(c2w.cpu() if torch.is_tensor(c2w) else c2w), dtype=torch.float32)[:3, :4]
+    fx, fy, cx, cy = _intrinsics(K)
+    o, d, _ = engine.get_rays(c2w[None].contiguous(), H, W, fx, fy, cx, cy)
+    return o.reshape(H, W, 3), d.reshape(H, W, 3)
+
+
+def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, dev=None, **kwargs):
+    """Render rays.  Signature and return value of run_nerf.render (run_nerf.py:131-196):
+    returns [rgb_map, disp_map, acc_map, uncertainty_map, depth_map, extras_dict] with extras
+    holding raw (if retraw), rgb0, disp0, acc0, uncertainty_map0, depth_map0, z_std.
+    ``chunk`` is accepted for compatibility; the engine chunks internally."""
+    if ndc:
+        raise NotImplementedError("ndc=True (LLFF forward-facing) is not on the scoring path (nerf.py:745 sets ndc=False)")
+    if not use_viewdirs:
+        raise NotImplementedError("use_viewdirs=False: the reference's networks are built with use_viewdirs=True (config.txt:9)")
+    if kwargs.get("perturb", 0.) not in (0., False) or kwargs.get("raw_noise_std", 0.) not in (0., False):
+        raise NotImplementedError("perturb / raw_noise_std are training-time options (nerf.py:750-751 zeroes them)")
+    if c2w_staticcam is not None:
+        raise NotImplementedError("c2w_staticcam is a visualisation-only option")
+    eng = _engine_from_kwargs(kwargs, near, far)
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, K, c2w, engine=eng)
+    else:
+        rays_o, rays_d = rays
+    sh = tuple(rays_d.shape)
+    want = ["rgb", "disp", "acc", "depth", "unc"]
+    if eng.n_importance > 0:
+        want += ["rgb0", "disp0", "acc0", "depth0", "unc0", "z_std"]
+    if kwargs.get("retraw", False):
+        want.append("raw")
+    o = eng.render_rays(rays_o, rays_d, near, far, precision=kwargs.get("precision"), want=tuple(want))
+
+    def rs(t):
+        return t.reshape(sh[:-1] + tuple(t.shape[1:]))
+
+    extras = {}
+    if "raw" in o:
+        extras["raw"] = rs(o["raw"])
+    if eng.n_importance > 0:
+        extras.update({"rgb0": rs(o["rgb0"]), "disp0": rs(o["disp0"]), "acc0": rs(o["acc0"]),
+                       "uncertainty_map0": rs(o["unc0"]), "depth_map0": rs(o["depth0"]), "z_std": rs(o["z_std"])})
+    return [rs(o["rgb"]), rs(o["disp"]), rs(o["acc"]), rs(o["unc"]), rs(o["depth"]), extras]

@@ -1,0 +1,169 @@
+/*
+ * evpp_b200 -- C ABI of the B200-native candidate-view scoring engine.
+ *
+ * The reference (small-zeng/EVPP) has no FFI layer; its seam for this path is two Python
+ * call signatures:
+ *   render(H, W, K, chunk, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam, dev, **kwargs)
+ *        nerfServer/core/run_nerf.py:131-196
+ *   Controller.get_uncertainty(self, poses) -> Tensor[V]
+ *        nerfServer/core/nerf.py:266-323
+ * Each entry point below names the reference code it replaces.  All functions return 0 on
+ * success and a negative evpp_status on failure; evpp_last_error() returns a thread-local,
+ * NUL-terminated description of the last failure on the calling thread.
+ *
+ * Pointers documented "device" are CUDA device pointers owned by the caller (e.g. PyTorch
+ * tensors); "host" pointers are ordinary (ideally pinned) host memory.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  The engine keeps its
+ * workspace per handle: calls on ONE handle must be serialised by the caller; different
+ * handles are independent (the Django server of the reference is thread-per-request,
+ * nerfServer/core/views.py:79 -- use one handle per request thread or a lock).
+ */
+#ifndef EVPP_B200_H_
+#define EVPP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVPP_ABI_VERSION 1
+
+typedef enum evpp_status {
+  EVPP_OK = 0,
+  EVPP_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  EVPP_ERR_CUDA = -2,      /* a CUDA runtime call or kernel failed */
+  EVPP_ERR_STATE = -3,     /* e.g. weights not loaded */
+  EVPP_ERR_NO_DEVICE = -4  /* no usable sm_100 device: there is NO CPU fallback */
+} evpp_status;
+
+typedef enum evpp_precision {
+  EVPP_PREC_FP32 = 0,  /* fp32 FFMA MLP (exact mode; used for the top-K re-score)            */
+  EVPP_PREC_FP16 = 1,  /* tcgen05.mma kind::f16, fp16 operands, fp32 accumulation in TMEM   */
+  EVPP_PREC_BF16 = 2   /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulation in TMEM   */
+} evpp_precision;
+
+typedef enum evpp_net { EVPP_NET_COARSE = 0, EVPP_NET_FINE = 1 } evpp_net;
+
+/* Mirrors the reference's flags: nerfServer/config.txt:6-13, core/nerf_configs.py:17-58,
+ * Controller.near/far nerfServer/core/nerf.py:100-101. */
+typedef struct evpp_config {
+  int32_t n_samples;       /* N_samples (64)                                   */
+  int32_t n_importance;    /* N_importance (128; 0 = coarse only)              */
+  float   near_plane;      /* Controller.near (0.5)                            */
+  float   far_plane;       /* Controller.far (80 live, 6 offline)              */
+  int32_t white_bkgd;      /* white_bkgd (1)                                   */
+  int32_t lindisp;         /* lindisp (0)                                      */
+  int32_t precision;       /* evpp_precision of the bulk pass                  */
+  int32_t max_chunk_rays;  /* rays per internal chunk (0 = default 131072)     */
+} evpp_config;
+
+typedef struct evpp_handle evpp_handle;
+
+const char* evpp_last_error(void);
+int evpp_abi_version(void);
+
+/* Number of CUDA devices usable by the engine (compute capability 10.x). */
+int evpp_device_count(void);
+
+/* Replaces create_nerf's model construction (run_nerf.py:244-341) for inference. */
+int evpp_create(int device_ordinal, const evpp_config* cfg, evpp_handle** out);
+int evpp_destroy(evpp_handle* h);
+
+/* Replaces Controller.copy_model (nerf.py:718-757): snapshot one network's weights.
+ * `packed` (host or device memory) holds the fp32 tensors of NeRF.state_dict() in its
+ * own order (run_nerf_helpers.py:90-104): pts_linears.{0..7}.{weight,bias},
+ * views_linears.0, feature_linear, alpha_linear, rgb_linear, uncertainty_linear;
+ * weight = [out,in] row-major.  offsets[i] = element offset of tensor i in `packed`,
+ * n_tensors must be 26.  The engine keeps its own repacked copies. */
+int evpp_load_nerf_weights(evpp_handle* h, int which_net, const float* packed,
+                           const int64_t* offsets, int n_tensors);
+
+/* Replaces Controller.get_uncertainty (nerf.py:266-309) = get_rays (run_nerf_helpers.py:
+ * 173-182) + render (run_nerf.py:131-196) + sum(beta^2)/R.
+ *   c2w      device [V,3,4] fp32 camera-to-world (views.get_pose, views.py:141-150)
+ *   pix_idx  device [V,R] int32 flat pixel indices j*W+i, or NULL = full H*W grid (R ignored)
+ *   scores   device [V] fp32 out */
+int evpp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy,
+                     float cx, float cy, const int32_t* pix_idx, int R, float* scores,
+                     void* stream);
+
+/* Same with HOST buffers (what the HTTP view nerfServer/core/views.py:94-113 holds):
+ * host->device copy of poses / pixel indices and device->host copy of the scores included. */
+int evpp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int H, int W, float fx,
+                          float fy, float cx, float cy, const int32_t* pix_idx_host, int R,
+                          float* scores_host, void* stream);
+
+/* Re-score a subset of views with the fp32 (exact) MLP regardless of cfg.precision; used to
+ * make the arg-max of plannerServer_{Object,Room}/core/interface.py:115-116 identical to the fp32
+ * reference.  view_ids: host [K] indices into c2w; scores_host: host [K] out. */
+int evpp_rescore_views_fp32(evpp_handle* h, const float* c2w_host, const int32_t* view_ids, int K,
+                            int H, int W, float fx, float fy, float cx, float cy,
+                            const int32_t* pix_idx_host, int R, float* scores_host, void* stream);
+
+/* Replaces render(rays=...) / batchify_rays / render_rays (run_nerf.py:116-196, 391-509) with
+ * use_viewdirs=True, ndc=False, perturb=0, raw_noise_std=0.  All device pointers; any output
+ * may be NULL.  S_f = n_samples + n_importance (or n_samples when n_importance == 0).
+ *   rgb [N,3] disp [N] acc [N] depth [N] unc [N,S_f] (= raw[...,4], 'uncertainty_map')
+ *   raw [N,S_f,5]; coarse-pass extras rgb0 [N,3] disp0 acc0 depth0 [N] unc0 [N,n_samples];
+ *   z_std [N] */
+typedef struct evpp_render_out {
+  float* rgb; float* disp; float* acc; float* depth; float* unc; float* raw;
+  float* rgb0; float* disp0; float* acc0; float* depth0; float* unc0; float* z_std;
+} evpp_render_out;
+
+int evpp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, int64_t N,
+                     float near_plane, float far_plane, int precision,
+                     const evpp_render_out* out, void* stream);
+
+/* get_rays (run_nerf_helpers.py:173-182) + viewdir normalisation (run_nerf.py:170).
+ * device out: rays_o/rays_d/viewdirs [V*R,3] (any may be NULL). */
+int evpp_get_rays(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy,
+                  float cx, float cy, const int32_t* pix_idx, int R, float* rays_o, float* rays_d,
+                  float* viewdirs, void* stream);
+
+/* The MLP alone: embed (run_nerf_helpers.py:22-55) + NeRF.forward (:108-134) on explicit
+ * points.  pts/dirs device [M,3] (dirs already normalised), out device [M,5] =
+ * [r,g,b,sigma_raw,beta]. M is padded internally. */
+int evpp_mlp_forward(evpp_handle* h, int which_net, int precision, const float* pts,
+                     const float* dirs, int64_t M, float* out, void* stream);
+
+/* Per-stage dumps of the LAST evpp_render_rays call's final chunk, for parity tests
+ * (SURVEY.md appendix B).  `out` is a device buffer of at least *count elements
+ * (call with out == NULL to query count).  Stages: */
+typedef enum evpp_stage {
+  EVPP_STAGE_Z_COARSE = 0,   /* float [n,n_samples]                 */
+  EVPP_STAGE_RAW_COARSE = 1, /* float [n,n_samples,5]               */
+  EVPP_STAGE_W_COARSE = 2,   /* float [n,n_samples] weights         */
+  EVPP_STAGE_CDF = 3,        /* float [n,n_samples-1]               */
+  EVPP_STAGE_INDS = 4,       /* int32 [n,n_importance] searchsorted */
+  EVPP_STAGE_Z_SAMPLES = 5,  /* float [n,n_importance]              */
+  EVPP_STAGE_Z_FINE = 6      /* float [n,S_f] sorted                */
+} evpp_stage;
+/* Enable (1) / disable (0) allocation and filling of the capture-only stages (W_COARSE, CDF,
+ * INDS, Z_SAMPLES). Off by default. */
+int evpp_set_stage_capture(evpp_handle* h, int enabled);
+int evpp_stage_dump(evpp_handle* h, int stage, void* out, int64_t* count, void* stream);
+
+/* Next-best-view selection tail (plannerServer_Object/core/vpp.py:199-220 +
+ * interface.py:115-116): score*=weight (NULL = 1), per-location max over consecutive groups
+ * of dirs_per_location views, normalise by the global max, arg-max (highest index on exact
+ * ties).  Device in/out; norm_scores [V/dirs_per_location] and best_dir [same, int32] may be
+ * NULL; winner_view (device int32[1]) receives the index into the V input views. */
+int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, int V,
+                    int dirs_per_location, float* norm_scores, int32_t* best_dir,
+                    int32_t* winner_view, void* stream);
+
+/* Counters since handle creation: kernels launched by this library and algorithmic MLP
+ * evaluations issued (for bench.py's gpu_launches and roofline accounting). */
+int evpp_get_counters(evpp_handle* h, int64_t* kernel_launches, int64_t* mlp_evals);
+
+/* Average duration in ms of the MLP kernel launches recorded (CUDA events on the launching
+ * stream) since the last reset; enable with evpp_set_profiling(h, 1). Synchronises. */
+int evpp_set_profiling(evpp_handle* h, int enabled);
+int evpp_get_mlp_time_ms(evpp_handle* h, double* total_ms, int64_t* launches, int64_t* evals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVPP_B200_H_ */

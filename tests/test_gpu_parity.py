@@ -1,0 +1,289 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs and against the committed reference-generated golden fixtures.
+
+Tolerances (SURVEY.md appendix B / BASELINE.json north_star): integer and index work bit-exact;
+fp32 path 1e-5-class; tensor-core (fp16/bf16 operand, fp32 accumulate) path: per-view score within
+1e-3 relative, next-best view identical."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import evpp_oracle as O
+
+pytestmark = pytest.mark.gpu
+TC_PRECISIONS = ["fp16", "bf16"]
+
+
+def _intr(K):
+    return float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+
+
+# ---------------------------------------------------------------- rays (a1, a2) ----------------
+@pytest.mark.parametrize("H,W,focal", [(6, 8, 6.0), (30, 40, 30.0), (96, 128, 96.0), (400, 400, 300.0)])
+def test_get_rays_bit_exact(engine_factory, H, W, focal):
+    eng = engine_factory()
+    K = O.make_K(H, W, focal)
+    views = O.hemisphere_views(5, seed=7)
+    poses = torch.Tensor(np.asarray(O.views_to_poses(views)))[:, :3, :4].contiguous()
+    o, d, vd = eng.get_rays(poses.cuda(), H, W, *_intr(K))
+    ref = O.build_view_rays(O.views_to_poses(views), H, W, K)
+    assert torch.equal(o.cpu(), ref[0])
+    assert torch.equal(d.cpu(), ref[1])                      # bit-exact ray directions
+    vref = ref[1] / torch.norm(ref[1], dim=-1, keepdim=True)
+    assert (vd.cpu() - vref).abs().max() <= 1.2e-7           # <= 1 ulp
+    # pixel subset (nerf.py:284-290) -> exact same rows
+    rng = np.random.RandomState(1)
+    pix = np.stack([rng.choice(H * W, size=17, replace=False) for _ in range(5)]).astype(np.int32)
+    o2, d2, _ = eng.get_rays(poses.cuda(), H, W, *_intr(K), pix_idx=torch.from_numpy(pix).cuda())
+    ref2 = O.build_view_rays(O.views_to_poses(views), H, W, K, pix)
+    assert torch.equal(d2.cpu(), ref2[1]) and torch.equal(o2.cpu(), ref2[0])
+
+
+# ---------------------------------------------------------------- MLP (a6, a7) ----------------
+def test_mlp_fp32_known_answers(engine_factory):
+    g = load_golden("mlp_kat.npz")
+    eng = engine_factory()
+    y = eng.mlp_forward(0, torch.from_numpy(g["pts"]), torch.from_numpy(g["dirs"]), precision="fp32").cpu().numpy()
+    np.testing.assert_allclose(y, g["out"], rtol=3e-5, atol=3e-6)
+
+
+def test_mlp_fp32_large_coordinates(engine_factory, weights):
+    """far=80 live bounds: sin/cos arguments up to ~4e4 need accurate range reduction."""
+    torch.manual_seed(3)
+    pts = (torch.rand(1000, 3) - 0.5) * 160
+    dirs = torch.nn.functional.normalize(torch.randn(1000, 3), dim=-1)
+    x = torch.cat([O.embed(pts, 10), O.embed(dirs, 4)], -1)
+    with torch.no_grad():
+        ref = O.nerf_forward(weights["spread"][1], x).numpy()
+    y = engine_factory("spread").mlp_forward(1, pts, dirs, precision="fp32").cpu().numpy()
+    np.testing.assert_allclose(y, ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("prec", TC_PRECISIONS)
+def test_mlp_tensor_core_vs_oracle(engine_factory, weights, prec):
+    torch.manual_seed(4)
+    M = 128 * 37 + 5   # ragged tail
+    pts = (torch.rand(M, 3) - 0.5) * 10
+    dirs = torch.nn.functional.normalize(torch.randn(M, 3), dim=-1)
+    x = torch.cat([O.embed(pts, 10), O.embed(dirs, 4)], -1)
+    with torch.no_grad():
+        ref = O.nerf_forward(weights["plain"][0], x).numpy()
+    y = engine_factory().mlp_forward(0, pts, dirs, precision=prec).cpu().numpy()
+    tol = 4e-3 if prec == "fp16" else 3e-2
+    err = np.abs(y - ref).max(0) / (np.abs(ref).max(0) + 1e-6)
+    assert (err < tol).all(), err
+    assert np.isfinite(y).all()
+
+
+# ---------------------------------------------------------------- full render, per stage --------
+@pytest.mark.parametrize("variant", ["plain", "spread"])
+def test_render_fp32_matches_reference_golden(engine_factory, variant):
+    g = load_golden(f"render_small_{variant}.npz")
+    eng = engine_factory(variant)
+    ro, rd = torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"])
+    out = eng.render_rays(ro, rd, float(g["near"]), float(g["far"]), precision="fp32", capture_stages=True,
+                          want=("rgb", "disp", "acc", "depth", "unc", "raw", "rgb0", "disp0", "acc0", "depth0",
+                                "unc0", "z_std"))
+    n = ro.shape[0]
+    z_c = eng.stage("z_coarse").cpu().reshape(n, 64).numpy()
+    assert np.array_equal(z_c, g["st_z_coarse"])                               # coarse z bit-exact
+    raw_c = eng.stage("raw_coarse").cpu().reshape(n, 64, 5).numpy()
+    np.testing.assert_allclose(raw_c, g["st_raw_coarse"], rtol=1e-4, atol=2e-5)
+    w_c = eng.stage("weights_coarse").cpu().reshape(n, 64).numpy()
+    np.testing.assert_allclose(w_c, g["st_weights_coarse"], atol=1e-5)
+    # resample: indices are bit-exact given the engine's own cdf ...
+    cdf = eng.stage("cdf").cpu().reshape(n, 63)
+    inds = eng.stage("inds").cpu().reshape(n, 128)
+    u = torch.linspace(0., 1., 128).expand(n, 128).contiguous()
+    assert torch.equal(torch.searchsorted(cdf, u, right=True).int(), inds)
+    # ... and vs the reference differ only where a cdf entry moved by rounding
+    flip = (inds.numpy() != g["st_inds"]).mean()
+    assert flip < 5e-3, flip
+    z_f = eng.stage("z_fine").cpu().reshape(n, 192).numpy()
+    assert (np.diff(z_f, axis=1) >= 0).all()                                    # sortedness
+    rows_ok = (inds.numpy() == g["st_inds"]).all(1)
+    np.testing.assert_allclose(z_f[rows_ok], g["st_z_fine"][rows_ok], atol=1e-4 * (float(g["far"]) - float(g["near"])))
+    np.testing.assert_allclose(out["unc"].cpu().numpy()[rows_ok], g["unc"][rows_ok], rtol=1e-3)
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), g["rgb"], atol=2e-4)
+    np.testing.assert_allclose(out["acc"].cpu().numpy(), g["acc"], atol=2e-4)
+    np.testing.assert_allclose(out["depth"].cpu().numpy(), g["depth"], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(out["disp"].cpu().numpy(), g["disp"], rtol=2e-3)
+    np.testing.assert_allclose(out["rgb0"].cpu().numpy(), g["rgb0"], atol=1e-4)
+    np.testing.assert_allclose(out["depth0"].cpu().numpy(), g["depth0"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(out["unc0"].cpu().numpy(), g["unc0"], rtol=1e-4)
+    np.testing.assert_allclose(out["z_std"].cpu().numpy(), g["z_std"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(out["raw"].cpu().numpy()[rows_ok], g["raw"][rows_ok], rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("variant", ["plain", "spread"])
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("fp16", 1e-3), ("bf16", 1e-3)])
+def test_scores_match_reference_golden(engine_factory, variant, prec, tol):
+    g = load_golden(f"render_small_{variant}.npz")
+    eng = engine_factory(variant, precision=prec)
+    H, W = int(g["H"]), int(g["W"])
+    K = O.make_K(H, W, float(g["focal"]))
+    poses = torch.Tensor(g["poses"])[:, :3, :4].contiguous()
+    s = eng.score_views(poses.cuda(), H, W, *_intr(K)).cpu().numpy()
+    np.testing.assert_allclose(s, g["uncers"], rtol=tol)
+
+
+@pytest.mark.parametrize("variant", ["plain", "spread"])
+@pytest.mark.parametrize("prec,tol", [("fp32", 5e-5), ("fp16", 1e-3), ("bf16", 1e-3)])
+def test_scores_far80_pixel_subset(engine_factory, variant, prec, tol):
+    """Live bounds near 0.5 / far 80 (nerf.py:100-101) and an explicit pixel subset (nerf.py:284-290),
+    through the HOST-buffer entry point."""
+    g = load_golden(f"score_far80_{variant}.npz")
+    eng = engine_factory(variant, precision=prec, far=80.0)
+    H, W = int(g["H"]), int(g["W"])
+    K = O.make_K(H, W, float(g["focal"]))
+    poses = torch.Tensor(g["poses"])[:, :3, :4].contiguous()
+    s = eng.score_views_host(poses, H, W, *_intr(K), pix_idx_host=torch.from_numpy(g["pix"]).contiguous()).numpy()
+    np.testing.assert_allclose(s, g["uncers"], rtol=tol)
+
+
+# ---------------------------------------------------------------- config 1: scores + NBV --------
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+def test_config1_scores_and_identical_nbv(engine_factory, prec):
+    from evpp_b200 import planner
+    g = load_golden("config1_spread.npz")
+    eng = engine_factory("spread", precision=prec)
+    H, W = int(g["H"]), int(g["W"])
+    K = O.make_K(H, W, float(g["focal"]))
+    res = planner.score_and_select(eng, g["views"], H, W, K, dirs_per_location=1, topk=8)
+    np.testing.assert_allclose(res["scores"], g["uncers"], rtol=1e-3)
+    assert res["winner"] == int(g["win"])
+    # GPU-side selection kernel agrees with the host tail
+    norm, best, win = eng.select_nbv(torch.from_numpy(res["scores"]).float(), None, 1)
+    assert int(win.item()) == int(g["win"])
+    assert abs(float(norm.max().item()) - 1.0) < 1e-6
+
+
+def test_plain_weights_tight_margin_nbv(engine_factory, weights):
+    """Random-init scores differ by <1% between views: the fp32 re-score of the top-K must make
+    the fp16 pipeline pick the oracle's view ('arg-max identity')."""
+    from evpp_b200 import planner
+    H, W = 12, 16
+    K = O.make_K(H, W, 12.0)
+    views = O.hemisphere_views(24, seed=11)
+    c, f = weights["plain"]
+    with torch.no_grad():
+        ref = O.score_views(O.views_to_poses(views), H, W, K, 0.5, 6.0, c, f).numpy()
+    _, _, win_ref = O.select_nbv(views, ref, 1)
+    for prec in ("fp32", "fp16"):
+        res = planner.score_and_select(engine_factory("plain", precision=prec), views, H, W, K, 1, topk=8)
+        np.testing.assert_allclose(res["scores"], ref, rtol=1e-3)
+        assert res["winner"] == win_ref, (prec, res["margin"])
+
+
+# ---------------------------------------------------------------- drop-in API ------------------
+def test_render_and_controller_drop_in(engine_factory, weights):
+    import evpp_b200
+    g = load_golden("render_small_spread.npz")
+    c, f = weights["spread"]
+    kw = evpp_b200.make_render_kwargs(c, f, precision="fp32", near=0.5, far=6.0)
+    H, W = int(g["H"]), int(g["W"])
+    K = O.make_K(H, W, float(g["focal"]))
+    rays = torch.stack([torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"])], 0)
+    rgb, disp, acc, unc, depth, extras = evpp_b200.render(H, W, K, chunk=1024 * 32, rays=rays, near=0.5, far=6.0,
+                                                          retraw=True, dev=None, **kw)
+    assert unc.shape == (rays.shape[1], 192) and extras["raw"].shape == (rays.shape[1], 192, 5)
+    assert set(extras) == {"raw", "rgb0", "disp0", "acc0", "uncertainty_map0", "depth_map0", "z_std"}
+    np.testing.assert_allclose(rgb.cpu().numpy(), g["rgb"], atol=2e-4)
+    # full-image branch (c2w=...), run_nerf.py:158-160
+    p = torch.Tensor(g["poses"])[0, :3, :4]
+    rgb2, *_ = evpp_b200.render(H, W, K, c2w=p, near=0.5, far=6.0, ndc=False, use_viewdirs=True, **kw)
+    assert rgb2.shape == (H, W, 3)
+    np.testing.assert_allclose(rgb2.reshape(-1, 3).cpu().numpy(), g["rgb"][:H * W], atol=2e-4)
+    # Controller.get_uncertainty (nerf.py:266-309)
+    ctl = evpp_b200.Controller(H=H, W=W, focal=float(g["focal"]), near=0.5, far=6.0, precision="fp32", sample_num=None)
+    with pytest.raises(TypeError):
+        ctl.get_uncertainty(g["poses"])          # reference raises TypeError when kwargs are None (nerf.py:396-398)
+    ctl.copy_model(c, f)
+    s = ctl.get_uncertainty(g["poses"])
+    assert s.is_cuda and s.shape == (6,)
+    np.testing.assert_allclose(s.cpu().numpy(), g["uncers"], rtol=2e-5)
+    # live pixel-subset protocol: same numpy RNG stream -> same pixels as the reference would draw
+    ctl.sample_num = 10
+    np.random.seed(0)
+    s1 = ctl.get_uncertainty(g["poses"]).cpu().numpy()
+    np.random.seed(0)
+    pix = np.stack([np.random.choice(H * W, size=[10], replace=False) for _ in range(6)])
+    with torch.no_grad():
+        ref = O.score_views(g["poses"], H, W, K, 0.5, 6.0, c, f, pix_idx=pix).numpy()
+    np.testing.assert_allclose(s1, ref, rtol=2e-5)
+    d = ctl.get_rays_depth(g["rays_o"][:7], g["rays_d"][:7])
+    assert d.shape == (7,)
+    pts = ctl.get_surface_points([0.0, 1.0, 0.0], 4.0, 0.8)
+    assert pts.ndim == 2 and pts.shape[1] == 3
+
+
+# ---------------------------------------------------------------- edge cases -------------------
+def test_edge_cases(engine_factory):
+    eng = engine_factory()
+    K = O.make_K(3, 5, 4.0)
+    # empty input
+    assert eng.score_views(torch.zeros(0, 3, 4).cuda(), 3, 5, *_intr(K)).numel() == 0
+    out = eng.render_rays(torch.zeros(0, 3), torch.zeros(0, 3), 0.5, 6.0)
+    assert out["rgb"].shape == (0, 3)
+    # single ray, ragged (n*S not a multiple of the tile) and axis-parallel directions
+    ro = torch.zeros(3, 3)
+    rd = torch.eye(3)
+    o = eng.render_rays(ro, rd, 0.5, 6.0, precision="fp32")
+    assert torch.isfinite(o["rgb"]).all() and torch.isfinite(o["depth"]).all()
+    # chunking does not change results
+    small = engine_factory(max_chunk_rays=7)
+    poses = torch.Tensor(np.asarray(O.views_to_poses(O.circle_views(4))))[:, :3, :4].contiguous().cuda()
+    a = eng.score_views(poses, 3, 5, *_intr(K))
+    b = small.score_views(poses, 3, 5, *_intr(K))
+    assert torch.equal(a, b)
+    # coarse-only configuration (N_importance=0)
+    co = engine_factory(n_importance=0)
+    s = co.score_views(poses, 3, 5, *_intr(K))
+    assert s.shape == (4,) and torch.isfinite(s).all()
+
+
+def test_zero_density_resample_branch(engine_factory, weights):
+    """All-zero coarse weights -> pdf is uniform 1e-5 (helpers:218) -> samples = bin mids' lerp."""
+    from evpp_b200 import Engine
+    c, f = weights["plain"]
+    c2 = {k: v.clone() for k, v in c.items()}
+    c2["alpha_linear.weight"].zero_()
+    c2["alpha_linear.bias"].fill_(-1.0)          # relu(sigma)=0 everywhere
+    eng = Engine(device=0, near=0.5, far=6.0, precision="fp32")
+    eng.load_weights(0, c2)
+    eng.load_weights(1, f)
+    ro = torch.zeros(5, 3)
+    rd = torch.nn.functional.normalize(torch.randn(5, 3), dim=-1)
+    eng.render_rays(ro, rd, 0.5, 6.0, capture_stages=True)
+    zs = eng.stage("z_samples").cpu().reshape(5, 128)
+    batch = torch.cat([ro, rd, torch.full((5, 1), 0.5), torch.full((5, 1), 6.0), rd], -1)
+    st = {}
+    with torch.no_grad():
+        O.render_rays(batch, c2, f, stages=st)
+    np.testing.assert_allclose(zs.numpy(), st["z_samples"][0].numpy(), atol=2e-5)
+    assert torch.equal(eng.stage("inds").cpu().reshape(5, 128), st["inds"][0].int())
+    eng.close()
+
+
+# ---------------------------------------------------------------- size-independent properties ---
+def test_full_size_properties(engine_factory, weights):
+    """Object-scene shape (80x60 rays/view): sharding invariance, permutation equivariance and
+    per-view independence of the score -- properties that hold at any size."""
+    eng = engine_factory("spread", precision="fp16")
+    H, W = 60, 80
+    K = O.make_K(H, W, 60.0)
+    views = O.hemisphere_views(16, seed=0)
+    poses = torch.Tensor(np.asarray(O.views_to_poses(views)))[:, :3, :4].contiguous().cuda()
+    s = eng.score_views(poses, H, W, *_intr(K))
+    perm = torch.randperm(16)
+    sp = eng.score_views(poses[perm].contiguous(), H, W, *_intr(K))
+    assert torch.equal(sp, s[perm.cuda()])                                   # equivariant, bit-exact
+    s_a = eng.score_views(poses[:5].contiguous(), H, W, *_intr(K))
+    s_b = eng.score_views(poses[5:].contiguous(), H, W, *_intr(K))
+    assert torch.equal(torch.cat([s_a, s_b]), s)                             # shards == whole
+    # 3 of the 16 views against the oracle at full ray count
+    c, f = weights["spread"]
+    with torch.no_grad():
+        ref = O.score_views(O.views_to_poses(views[:3]), H, W, K, 0.5, 6.0, c, f).numpy()
+    np.testing.assert_allclose(s[:3].cpu().numpy(), ref, rtol=1e-3)

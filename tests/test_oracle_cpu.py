@@ -1,0 +1,115 @@
+"""CPU tests (-m "not gpu"): the oracle restatement against the committed golden fixtures (which
+were produced by the UNMODIFIED reference, oracle/make_golden.py) and, when /root/reference is
+present, against the reference itself."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import evpp_oracle as O
+from oracle import ref_import
+
+
+def test_weight_init_matches_reference_checksum(weights):
+    g = load_golden("weights_seed0_checksum.npz")
+    c, f = weights["plain"]
+    assert list(c.keys()) == [str(k) for k in g["keys"]] == O.nerf_state_dict_keys()
+    sums = np.array([float(v.double().sum()) for v in c.values()])
+    np.testing.assert_allclose(sums, g["sums"], rtol=0, atol=1e-9)
+    assert np.array_equal(c["pts_linears.0.weight"][:4, :8].numpy(), g["first"])
+    assert np.array_equal(f["pts_linears.0.weight"][:4, :8].numpy(), g["fine_first"])
+    n_params = sum(v.numel() for v in c.values())
+    assert n_params == 595973
+
+
+def test_mlp_known_answers(weights):
+    g = load_golden("mlp_kat.npz")
+    x = torch.cat([O.embed(torch.from_numpy(g["pts"]), 10), O.embed(torch.from_numpy(g["dirs"]), 4)], -1)
+    np.testing.assert_allclose(x.numpy(), g["emb"], rtol=0, atol=2e-6)   # libm vs SLEEF sin/cos across CPUs
+    with torch.no_grad():
+        y = O.nerf_forward(weights["plain"][0], torch.from_numpy(g["emb"]))
+    np.testing.assert_allclose(y.numpy(), g["out"], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("variant", ["plain", "spread"])
+def test_render_small_matches_reference_golden(weights, variant):
+    g = load_golden(f"render_small_{variant}.npz")
+    c, f = weights[variant]
+    H, W = int(g["H"]), int(g["W"])
+    K = O.make_K(H, W, float(g["focal"]))
+    rays = O.build_view_rays(g["poses"], H, W, K)
+    assert np.array_equal(rays[0].numpy(), g["rays_o"])
+    np.testing.assert_allclose(rays[1].numpy(), g["rays_d"], rtol=0, atol=1e-7)
+    stages = {}
+    with torch.no_grad():
+        uncers = O.score_views(g["poses"], H, W, K, float(g["near"]), float(g["far"]), c, f, stages=stages)
+        out = O.render(H, W, K, rays=rays, near=float(g["near"]), far=float(g["far"]), sd_coarse=c, sd_fine=f)
+    # same machine -> bit-exact; other CPUs differ by BLAS blocking / vector width only
+    np.testing.assert_allclose(uncers.numpy(), g["uncers"], rtol=2e-5)
+    np.testing.assert_allclose(out[0].numpy(), g["rgb"], atol=2e-5)
+    np.testing.assert_allclose(out[4].numpy(), g["depth"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(out[3].numpy(), g["unc"], rtol=1e-4)
+    z = torch.cat(stages["z_coarse"], 0).numpy()
+    assert np.array_equal(z, g["st_z_coarse"])
+    inds = torch.cat(stages["inds"], 0).numpy()
+    assert (inds != g["st_inds"]).mean() < 2e-3   # identical unless a cdf entry moved by an ulp
+
+
+@pytest.mark.parametrize("variant", ["plain", "spread"])
+def test_score_far80_pixel_subset(weights, variant):
+    g = load_golden(f"score_far80_{variant}.npz")
+    c, f = weights[variant]
+    H, W = int(g["H"]), int(g["W"])
+    K = O.make_K(H, W, float(g["focal"]))
+    with torch.no_grad():
+        uncers = O.score_views(g["poses"], H, W, K, 0.5, 80.0, c, f, pix_idx=g["pix"])
+    np.testing.assert_allclose(uncers.numpy(), g["uncers"], rtol=5e-5)
+
+
+def test_select_nbv_semantics():
+    g = load_golden("config1_spread.npz")
+    data, nbv, win = O.select_nbv(g["views"], g["uncers"], dirs_per_location=1)
+    assert win == int(g["win"]) == int(np.argmax(g["uncers"]))
+    assert data[:, 5].max() == 1.0
+    # grouped: per-location max then arg-max; ties -> highest index
+    views = np.zeros((6, 5)); views[:, 0] = np.arange(6)
+    data, nbv, win = O.select_nbv(views, [1, 5, 2, 5, 5, 1], dirs_per_location=3)
+    assert win == 3 and data.shape == (2, 6)        # loc0 best=idx1 (5), loc1 best=idx3 (first max); tie -> last location
+    clip = O.depth_clip_object(np.array([1.0, 3.0, 5.0]))
+    np.testing.assert_allclose(clip, [np.exp(-4.0), 1.0, np.exp(-4.0)])
+
+
+def test_get_pose_is_rotation():
+    for (u, v) in [(0.1, 0.2), (-1.2, 3.0), (np.pi / 2, -2.0)]:
+        P = np.array(O.get_pose([1, 2, 3], u, v))
+        Rm = P[:3, :3]
+        np.testing.assert_allclose(Rm @ Rm.T, np.eye(3), atol=1e-12)
+        assert list(P[:3, 3]) == [1, 2, 3]
+
+
+def test_workload_generators():
+    assert O.circle_views(32).shape == (32, 5)
+    v = O.hemisphere_views(512)
+    assert v.shape == (512, 5) and (v[:, 1] >= 1.0).all()
+    r = O.room_views(4096)
+    assert r.shape == (4096, 5)
+    assert np.array_equal(r, O.room_views(4096))     # seeded
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_oracle_bit_exact_vs_reference(weights):
+    H, R = ref_import.load()
+    c, f = weights["spread"]
+    kwargs = ref_import.make_reference_kwargs(H, R, c, f)
+    Hi, Wi = 5, 7
+    K = O.make_K(Hi, Wi, 6.0)
+    poses = O.views_to_poses(O.hemisphere_views(3, seed=4))
+    rays = O.build_view_rays(poses, Hi, Wi, K)
+    with torch.no_grad():
+        ref = R.render(Hi, Wi, K, chunk=32768, rays=rays, near=0.5, far=80.0, retraw=True,
+                       dev=torch.device("cpu"), **kwargs)
+        mine = O.render(Hi, Wi, K, rays=rays, near=0.5, far=80.0, sd_coarse=c, sd_fine=f)
+    for a, b in zip(ref[:5], mine[:5]):
+        assert torch.equal(a, b)
+    for k in ref[5]:
+        assert torch.equal(ref[5][k], mine[5][k]), k
