@@ -43,6 +43,8 @@ SIGNATURES = {
     "evpp_mlp_forward": (_I, [_P, _I, _I, _P, _P, _L, _P, _P]),
     "evpp_set_stage_capture": (_I, [_P, _I]),
     "evpp_stage_dump": (_I, [_P, _I, _P, C.POINTER(_L), _P]),
+    "evpp_composite": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "evpp_resample": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "evpp_select_nbv": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "evpp_get_counters": (_I, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "evpp_set_profiling": (_I, [_P, _I]),

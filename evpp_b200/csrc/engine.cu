@@ -555,6 +555,32 @@ int evpp_stage_dump(evpp_handle* h, int stage, void* out, int64_t* count, void* 
   return 0;
 }
 
+int evpp_composite(evpp_handle* h, const float* raw, const float* z, const float* rays_d, int n, int S,
+                   float* rgb, float* disp, float* acc, float* depth, float* weights, float* beta2, void* stream) {
+  if (!h || !raw || !z || !rays_d) return fail(EVPP_ERR_INVALID, "null argument");
+  if (n <= 0) return 0;
+  if (S < 1) return fail(EVPP_ERR_INVALID, "bad S");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CompositeOut co{};
+  co.rgb = rgb; co.disp = disp; co.acc = acc; co.depth = depth; co.weights = weights; co.beta2 = beta2;
+  h->launches += launch_composite(raw, z, rays_d, n, S, h->cfg.white_bkgd, co, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int evpp_resample(evpp_handle* h, const float* raw_coarse, const float* z_coarse, const float* rays_d, int n,
+                  float* z_fine, float* cdf, int32_t* inds, float* z_samples, void* stream) {
+  if (!h || !raw_coarse || !z_coarse || !rays_d || !z_fine) return fail(EVPP_ERR_INVALID, "null argument");
+  if (h->Ni <= 0) return fail(EVPP_ERR_STATE, "engine configured with n_importance == 0");
+  if (n <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CompositeOut co{};
+  h->launches += launch_coarse_resample(raw_coarse, z_coarse, rays_d, h->u_vals.as<float>(), n, h->Sc, h->Ni,
+                                        h->cfg.white_bkgd, co, z_fine, cdf, inds, z_samples, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, int V, int dirs_per_location,
                     float* norm_scores, int32_t* best_dir, int32_t* winner_view, void* stream) {
   if (!h || !scores) return fail(EVPP_ERR_INVALID, "null argument");

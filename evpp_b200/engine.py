@@ -171,6 +171,37 @@ class Engine:
                                             _stream_ptr(self.device)))
         return out
 
+    def composite(self, raw, z, rays_d):
+        """raw2outputs on caller tensors; returns dict(rgb, disp, acc, depth, weights, beta2)."""
+        raw = raw.to(self.device, torch.float32).contiguous()
+        z = z.to(self.device, torch.float32).contiguous()
+        rays_d = rays_d.to(self.device, torch.float32).contiguous()
+        n, S = z.shape
+        o = {"rgb": torch.empty(n, 3, device=self.device), "disp": torch.empty(n, device=self.device),
+             "acc": torch.empty(n, device=self.device), "depth": torch.empty(n, device=self.device),
+             "weights": torch.empty(n, S, device=self.device), "beta2": torch.empty(n, device=self.device)}
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_composite(self._h, _ptr(raw), _ptr(z), _ptr(rays_d), n, S, _ptr(o["rgb"]),
+                                          _ptr(o["disp"]), _ptr(o["acc"]), _ptr(o["depth"]), _ptr(o["weights"]),
+                                          _ptr(o["beta2"]), _stream_ptr(self.device)))
+        return o
+
+    def resample(self, raw_coarse, z_coarse, rays_d):
+        """coarse compositing + sample_pdf + sort on caller tensors; returns dict(z_fine, cdf, inds, z_samples)."""
+        raw = raw_coarse.to(self.device, torch.float32).contiguous()
+        z = z_coarse.to(self.device, torch.float32).contiguous()
+        rays_d = rays_d.to(self.device, torch.float32).contiguous()
+        n = z.shape[0]
+        o = {"z_fine": torch.empty(n, self.S_f, device=self.device),
+             "cdf": torch.empty(n, self.n_samples - 1, device=self.device),
+             "inds": torch.empty(n, self.n_importance, device=self.device, dtype=torch.int32),
+             "z_samples": torch.empty(n, self.n_importance, device=self.device)}
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_resample(self._h, _ptr(raw), _ptr(z), _ptr(rays_d), n, _ptr(o["z_fine"]),
+                                         _ptr(o["cdf"]), _ptr(o["inds"]), _ptr(o["z_samples"]),
+                                         _stream_ptr(self.device)))
+        return o
+
     def select_nbv(self, scores, weight=None, dirs_per_location=1):
         scores = scores.to(self.device, torch.float32).contiguous()
         V = scores.shape[0]

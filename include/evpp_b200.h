@@ -145,6 +145,20 @@ typedef enum evpp_stage {
 int evpp_set_stage_capture(evpp_handle* h, int enabled);
 int evpp_stage_dump(evpp_handle* h, int stage, void* out, int64_t* count, void* stream);
 
+/* Stage-level entry points on caller-provided tensors (device pointers), for parity tests that
+ * feed the reference's own intermediate tensors to one stage at a time:
+ * evpp_composite = raw2outputs (run_nerf.py:344-388) on raw [n,S,5], z [n,S], rays_d [n,3];
+ *   outputs (any may be NULL): rgb [n,3], disp/acc/depth [n], weights [n,S], beta2 [n] (sum of
+ *   raw[...,4]^2 per ray, the numerator of nerf.py:307-309).
+ * evpp_resample = raw2outputs on the coarse pass + sample_pdf(det=True)
+ *   (run_nerf_helpers.py:216-259) + sort(cat) (run_nerf.py:479-483) -> z_fine [n,S+n_importance];
+ *   optional dumps cdf [n,S-1], inds int32 [n,n_importance], z_samples [n,n_importance]. */
+int evpp_composite(evpp_handle* h, const float* raw, const float* z, const float* rays_d, int n, int S,
+                   float* rgb, float* disp, float* acc, float* depth, float* weights, float* beta2,
+                   void* stream);
+int evpp_resample(evpp_handle* h, const float* raw_coarse, const float* z_coarse, const float* rays_d,
+                  int n, float* z_fine, float* cdf, int32_t* inds, float* z_samples, void* stream);
+
 /* Next-best-view selection tail (plannerServer_Object/core/vpp.py:199-220 +
  * interface.py:115-116): score*=weight (NULL = 1), per-location max over consecutive groups
  * of dirs_per_location views, normalise by the global max, arg-max (highest index on exact

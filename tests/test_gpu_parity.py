@@ -103,7 +103,10 @@ def test_render_fp32_matches_reference_golden(engine_factory, variant):
     z_f = eng.stage("z_fine").cpu().reshape(n, 192).numpy()
     assert (np.diff(z_f, axis=1) >= 0).all()                                    # sortedness
     rows_ok = (inds.numpy() == g["st_inds"]).all(1)
-    np.testing.assert_allclose(z_f[rows_ok], g["st_z_fine"][rows_ok], atol=1e-4 * (float(g["far"]) - float(g["near"])))
+    # fine z's inherit the coarse weights' RELATIVE error amplified by ~62 bins (tiny random-init
+    # densities make 1e-6 absolute raw differences 1e-4 relative); the stage-isolated check with
+    # identical inputs is test_sampling_stages_on_reference_tensors
+    np.testing.assert_allclose(z_f[rows_ok], g["st_z_fine"][rows_ok], atol=4e-3)
     np.testing.assert_allclose(out["unc"].cpu().numpy()[rows_ok], g["unc"][rows_ok], rtol=1e-3)
     np.testing.assert_allclose(out["rgb"].cpu().numpy(), g["rgb"], atol=2e-4)
     np.testing.assert_allclose(out["acc"].cpu().numpy(), g["acc"], atol=2e-4)
@@ -114,6 +117,29 @@ def test_render_fp32_matches_reference_golden(engine_factory, variant):
     np.testing.assert_allclose(out["unc0"].cpu().numpy(), g["unc0"], rtol=1e-4)
     np.testing.assert_allclose(out["z_std"].cpu().numpy(), g["z_std"], rtol=1e-3, atol=1e-4)
     np.testing.assert_allclose(out["raw"].cpu().numpy()[rows_ok], g["raw"][rows_ok], rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("variant", ["plain", "spread"])
+def test_sampling_stages_on_reference_tensors(engine_factory, variant):
+    """Compositing, inverse-cdf resampling and the merge-sort fed with the REFERENCE's own coarse /
+    fine raw tensors: integer indices bit-exact, everything else at rounding level."""
+    g = load_golden(f"render_small_{variant}.npz")
+    eng = engine_factory(variant)
+    rd = torch.from_numpy(g["rays_d"])
+    r = eng.resample(torch.from_numpy(g["st_raw_coarse"]), torch.from_numpy(g["st_z_coarse"]), rd)
+    assert np.array_equal(r["inds"].cpu().numpy(), g["st_inds"])                 # searchsorted indices bit-exact
+    np.testing.assert_allclose(r["cdf"].cpu().numpy(), g["st_cdf"], rtol=0, atol=2.5e-7)
+    np.testing.assert_allclose(r["z_samples"].cpu().numpy(), g["st_z_samples"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(r["z_fine"].cpu().numpy(), g["st_z_fine"], rtol=0, atol=2e-5)
+    c = eng.composite(torch.from_numpy(g["raw"]), torch.from_numpy(g["st_z_fine"]), rd)
+    np.testing.assert_allclose(c["weights"].cpu().numpy(), g["st_weights_fine"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(c["rgb"].cpu().numpy(), g["rgb"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(c["depth"].cpu().numpy(), g["depth"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(c["acc"].cpu().numpy(), g["acc"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(c["disp"].cpu().numpy(), g["disp"], rtol=1e-5)
+    V = len(g["uncers"])
+    score = c["beta2"].double().reshape(V, -1).sum(-1) / (g["rays_o"].shape[0] // V)
+    np.testing.assert_allclose(score.cpu().numpy(), g["uncers"], rtol=2e-6)
 
 
 @pytest.mark.parametrize("variant", ["plain", "spread"])
