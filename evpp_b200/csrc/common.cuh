@@ -4,6 +4,8 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -36,12 +38,20 @@ struct SimtWeights {          // device pointers
   const float* head_b;        // alpha, r, g, b, unc -> 5
 };
 
-// ---- tcgen05 MLP weight image (fp16 or bf16), see mlp_tc.cu ------------------------------------
+// ---- tcgen05 MLP (fp16 or bf16 operands), see mlp_tc.cu ------------------------------------------
+struct TcConsts {             // fp32 epilogue constants, passed to the kernel by value (constant bank)
+  float bias[10][256];        // pts_linears 0..7, feature_linear (8), views_linears.0 (9, first 128)
+  float w_alpha[256];
+  float w_rgb[3][128];
+  float w_unc[128];
+  float head_b[8];            // alpha, r, g, b, uncertainty
+};
 struct TcWeights {
-  const void* image;          // pre-tiled, pre-swizzled B operand slices, streamed with cp.async.bulk
-  const float* bias;          // same layout as SimtWeights::bias
-  const float* head_b;        // 5
+  const void* image;          // device: pre-tiled, pre-swizzled B-operand K-blocks, streamed with cp.async.bulk
+  const TcConsts* consts;     // host
   int dtype;                  // EVPP_PREC_FP16 / EVPP_PREC_BF16
+  float* dbg;                 // optional device [M,256] dump of one layer's activations (parity tests)
+  int dbg_layer;
 };
 
 struct RayBatch {             // device pointers of one chunk
@@ -62,7 +72,8 @@ int launch_mlp_tc_points(const TcWeights& w, const float* pts, const float* dirs
                          int num_sms, cudaStream_t st);
 size_t tc_weight_image_bytes();
 // host-side repack of one network: fills `image` (tc_weight_image_bytes()) from fp32 state_dict tensors
-void tc_pack_weights(const std::vector<std::vector<float>>& tensors, int dtype, std::vector<uint8_t>& image);
+void tc_pack_weights(const std::vector<std::vector<float>>& tensors, int dtype, std::vector<uint8_t>& image,
+                     TcConsts& consts);
 int tc_configure();   // sets kernel attributes; returns cudaError_t as int
 
 }  // namespace evpp

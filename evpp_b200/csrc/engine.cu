@@ -63,6 +63,7 @@ struct NetWeights {
   bool loaded = false;
   DevBuf simt_stream, bias, head_w, head_b, tc_image[3];   // tc_image indexed by precision (1,2)
   bool tc_ready[3] = {false, false, false};
+  TcConsts tc_consts{};
   std::vector<std::vector<float>> host;                   // fp32 state_dict tensors (for lazy tc repack)
 };
 
@@ -139,7 +140,7 @@ int ensure_tc(evpp_handle* h, int which, int prec) {
   NetWeights& nw = h->net[which];
   if (nw.tc_ready[prec]) return 0;
   std::vector<uint8_t> image;
-  tc_pack_weights(nw.host, prec, image);
+  tc_pack_weights(nw.host, prec, image, nw.tc_consts);
   if (nw.tc_image[prec].ensure(image.size())) return fail(EVPP_ERR_CUDA, "tc weight image alloc failed");
   CUDA_TRY(cudaMemcpy(nw.tc_image[prec].p, image.data(), image.size(), cudaMemcpyHostToDevice));
   int e = tc_configure();
@@ -151,8 +152,8 @@ int ensure_tc(evpp_handle* h, int which, int prec) {
 SimtWeights simt_of(const NetWeights& nw) {
   return SimtWeights{nw.simt_stream.as<float>(), nw.bias.as<float>(), nw.head_w.as<float>(), nw.head_b.as<float>()};
 }
-TcWeights tc_of(const NetWeights& nw, int prec) {
-  return TcWeights{nw.tc_image[prec].p, nw.bias.as<float>(), nw.head_b.as<float>(), prec};
+TcWeights tc_of(const NetWeights& nw, int prec, float* dbg = nullptr, int dbg_layer = -1) {
+  return TcWeights{nw.tc_image[prec].p, &nw.tc_consts, prec, dbg, dbg_layer};
 }
 
 int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw, cudaStream_t st) {
@@ -171,7 +172,7 @@ int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw,
     int rc = ensure_tc(h, which, prec);
     if (rc) return rc;
     nl = launch_mlp_tc(tc_of(nw, prec), rb, raw, h->num_sms, st);
-    if (nl < 0) return fail(EVPP_ERR_CUDA, "tcgen05 MLP launch failed");
+    if (nl < 0) return fail(EVPP_ERR_CUDA, "tcgen05 MLP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (h->profiling) {
     cudaEventRecord(e1, st);
@@ -499,8 +500,8 @@ int evpp_get_rays(evpp_handle* h, const float* c2w, int V, int H, int W, float f
   return 0;
 }
 
-int evpp_mlp_forward(evpp_handle* h, int which, int precision, const float* pts, const float* dirs, int64_t M,
-                     float* out, void* stream) {
+static int mlp_forward_impl(evpp_handle* h, int which, int precision, const float* pts, const float* dirs,
+                            int64_t M, float* out, int dbg_layer, float* dbg, void* stream) {
   if (!h || !pts || !dirs || !out) return fail(EVPP_ERR_INVALID, "null argument");
   if (which != 0 && which != 1) return fail(EVPP_ERR_INVALID, "bad net");
   if (M <= 0) return 0;
@@ -510,12 +511,13 @@ int evpp_mlp_forward(evpp_handle* h, int which, int precision, const float* pts,
   if (precision < 0) precision = h->cfg.precision;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == EVPP_PREC_FP32) {
+    if (dbg) return fail(EVPP_ERR_INVALID, "layer dumps exist for the tensor-core path only");
     h->launches += launch_mlp_simt_points(simt_of(nw), pts, dirs, M, out, st);
   } else if (precision <= 2) {
     int rc = ensure_tc(h, which, precision);
     if (rc) return rc;
-    int nl = launch_mlp_tc_points(tc_of(nw, precision), pts, dirs, M, out, h->num_sms, st);
-    if (nl < 0) return fail(EVPP_ERR_CUDA, "tcgen05 MLP launch failed");
+    int nl = launch_mlp_tc_points(tc_of(nw, precision, dbg, dbg_layer), pts, dirs, M, out, h->num_sms, st);
+    if (nl < 0) return fail(EVPP_ERR_CUDA, "tcgen05 MLP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += nl;
   } else {
     return fail(EVPP_ERR_INVALID, "bad precision");
@@ -523,6 +525,17 @@ int evpp_mlp_forward(evpp_handle* h, int which, int precision, const float* pts,
   h->evals += M;
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+int evpp_mlp_forward(evpp_handle* h, int which, int precision, const float* pts, const float* dirs, int64_t M,
+                     float* out, void* stream) {
+  return mlp_forward_impl(h, which, precision, pts, dirs, M, out, -1, nullptr, stream);
+}
+
+int evpp_mlp_layer_dump(evpp_handle* h, int which, int precision, const float* pts, const float* dirs, int64_t M,
+                        int layer, float* out, float* acts, void* stream) {
+  if (layer < 0 || layer > 9 || !acts) return fail(EVPP_ERR_INVALID, "layer must be 0..9 and acts non-null");
+  return mlp_forward_impl(h, which, precision, pts, dirs, M, out, layer, acts, stream);
 }
 
 int evpp_set_stage_capture(evpp_handle* h, int enabled) {

@@ -1,9 +1,581 @@
-// placeholder (replaced by the tcgen05 kernel)
+// Fused positional encoding + NeRF/NeurAR MLP on the 5th-generation tensor cores (sm_100a).
+// Replaces Embedder.embed (run_nerf_helpers.py:22-55), run_network (run_nerf.py:84-113) and
+// NeRF.forward (run_nerf_helpers.py:108-134) of the reference for the bulk (fp16 / bf16 operand,
+// fp32 accumulate) pass.  The fp32 twin is mlp_simt.cu.
+//
+// One persistent CTA per SM (optionally clusters of C CTAs sharing the weight stream by bulk-copy
+// multicast).  A CTA owns one 128-row tile at a time:
+//
+//   shared memory   A[4]   4 x 16 KB   current activations h (128 rows x 256 ch), as four K-blocks of
+//                                      64 channels, K-major, 128-byte swizzle (UMMA canonical layout)
+//                   X      16 KB       the 63-ch position embedding (layers 0 and 5), later the 27-ch
+//                                      direction embedding (view layer), same layout
+//                   ring   4 x 32 KB   weight K-blocks W[:, 64k..64k+63] ([N rows x 128 B], pre-swizzled
+//                                      on the host) streamed from L2 with cp.async.bulk + mbarrier
+//   tensor memory   acc[2] 2 x 256 col fp32 accumulators (128 lanes x 256 columns), layer l -> acc[l&1]
+//
+//   warp 0  (1 lane)  weight producer: 39 bulk copies per tile through the 4-stage ring
+//   warp 1  (1 lane)  tcgen05.mma issuer: D[128 x N] += A[128 x 16] * W[N x 16]^T, 4 per K-block
+//   warps 4-11        encode the tile, then per layer drain the accumulator with tcgen05.ld, add bias,
+//                     ReLU, convert and store the next layer's A operand K-block by K-block; the MMA
+//                     warp starts layer l+1 on K-block k as soon as that block is written, i.e. the
+//                     epilogue of layer l overlaps the MMAs of layer l+1 (which go to the other
+//                     accumulator).  alpha / rgb / uncertainty heads are fp32 FFMA in the epilogue.
+//
+// Activations never leave the SM; per row the kernel reads 4 B (z) and writes 20 B.
 #include "common.cuh"
+
 namespace evpp {
-int launch_mlp_tc(const TcWeights&, const RayBatch&, float*, int, cudaStream_t) { return -1; }
-int launch_mlp_tc_points(const TcWeights&, const float*, const float*, int64_t, float*, int, cudaStream_t) { return -1; }
-size_t tc_weight_image_bytes() { return 16; }
-void tc_pack_weights(const std::vector<std::vector<float>>&, int, std::vector<uint8_t>& image) { image.assign(16, 0); }
-int tc_configure() { return 0; }
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
+constexpr int kStages = 4;
+constexpr int kStageBytes = 32768;
+constexpr int kBlkBytes = 16384;          // 128 rows x 128 B
+constexpr int kLayers = 10;               // pts_linears 0..7, feature_linear (8), views_linears.0 (9)
+constexpr int kOffX = 4 * kBlkBytes;
+constexpr int kOffRing = kOffX + kBlkBytes;
+constexpr int kOffMisc = kOffRing + kStages * kStageBytes;
+
+struct Misc {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t acc_full[2];
+  uint64_t a_ready[4];
+  uint64_t x_ready;
+  uint32_t tmem_base;
+  uint32_t pad_;
+  float partial[kTileM][8];               // head partial sums of the upper column half
+};
+constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc) + 1024;   // + alignment slack
+
+// per-tile weight stream: number of 64-wide K-blocks per layer and their size
+__host__ __device__ constexpr int layer_has_x(int l) { return l == 0 || l == 5 || l == 9; }
+__host__ __device__ constexpr int layer_h_blocks(int l) { return l == 0 ? 0 : 4; }
+__host__ __device__ constexpr int layer_n(int l) { return l == 9 ? 128 : 256; }
+constexpr size_t kImageBytes = (size_t)34 * 32768 + (size_t)5 * 16384;
+
+// ---------------------------------------------------------------- PTX helpers --------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+          "r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(bar), "h"(mask)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, M=128, K=16, kind::f16 (fp16 or bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout_type SWIZZLE_128B=2 [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format f32 (1) [4,6), a/b format [7,10)/[10,13)
+// (0 = f16, 1 = bf16), K-major A and B, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(bool bf16, int n) {
+  return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (BF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+// byte offset of 16-byte chunk `ch` (8 channels) of row `row` inside a swizzled 16 KB K-block
+__device__ __forceinline__ uint32_t sw128(int row, int ch) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4));
+}
+
+// Frequency encoding of one coordinate triple by angle doubling from an accurate sincosf at the
+// base frequency: the 2^k-th octave carries <= 2^k ulp-level phase error (<= 6e-5 at k = 9), below
+// the 2.4e-4 rounding step of the 16-bit operand it is converted to.
+template <bool BF16, int L>
+__device__ __forceinline__ void encode_store(const float (&p)[3], uint32_t row_base, int row, int nchunks) {
+  float e[64];
+  e[0] = p[0]; e[1] = p[1]; e[2] = p[2];
+  float s[3], c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sincosf(p[i], &s[i], &c[i]);
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      e[3 + l * 6 + i] = s[i];
+      e[3 + l * 6 + 3 + i] = c[i];
+      const float s2 = 2.f * s[i] * c[i];
+      const float c2 = fmaf(-2.f * s[i], s[i], 1.f);
+      s[i] = s2; c[i] = c2;
+    }
+  }
+#pragma unroll
+  for (int k = 3 + 6 * L; k < 64; ++k) e[k] = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    if (ch < nchunks) {
+      st_shared_v4(row_base + ((ch ^ (row & 7)) << 4), pack2<BF16>(e[ch * 8 + 0], e[ch * 8 + 1]),
+                   pack2<BF16>(e[ch * 8 + 2], e[ch * 8 + 3]), pack2<BF16>(e[ch * 8 + 4], e[ch * 8 + 5]),
+                   pack2<BF16>(e[ch * 8 + 6], e[ch * 8 + 7]));
+    }
+  }
+}
+
+struct TcArgs {
+  const uint8_t* image;
+  RayBatch rb;
+  const float* pts;
+  const float* dirs;
+  long long M;
+  float* out;
+  float* dbg;        // optional [M,256] dump of the activations written by layer dbg_layer
+  int dbg_layer;
+  int tiles_per_cta;
+};
+
+template <bool BF16, bool RAYS, int C>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcArgs args) {
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  Misc& misc = *reinterpret_cast<Misc*>(smem_gen + kOffMisc);
+  const uint32_t sA = smem_base, sX = smem_base + kOffX, sRing = smem_base + kOffRing;
+  const uint32_t bar_full = smem_u32(&misc.full[0]), bar_empty = smem_u32(&misc.empty[0]);
+  const uint32_t bar_acc = smem_u32(&misc.acc_full[0]), bar_a = smem_u32(&misc.a_ready[0]);
+  const uint32_t bar_x = smem_u32(&misc.x_ready);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = C > 1 ? cluster_ctarank() : 0u;
+  const uint16_t mc_mask = (uint16_t)((1u << C) - 1u);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, C);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_acc + 8, 1);
+    for (int k = 0; k < 4; ++k) mbar_init(bar_a + 8 * k, kEpiThreads);
+    mbar_init(bar_x, kEpiThreads);
+    fence_barrier_init();
+  }
+  if (warp == 1) {   // TMEM: all 512 columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc.tmem_base)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (C > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = misc.tmem_base;
+
+  const int ntile_iters = args.tiles_per_cta;
+  const long long ntiles = (args.M + kTileM - 1) / kTileM;
+
+  if (warp == 0) {
+    // ================= weight producer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < ntile_iters; ++it) {
+        const uint8_t* src = args.image;
+        for (int l = 0; l < kLayers; ++l) {
+          const int nblk = layer_has_x(l) + layer_h_blocks(l);
+          const uint32_t bytes = (uint32_t)layer_n(l) * 128u;
+          for (int b = 0; b < nblk; ++b) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            mbar_expect_tx(bar_full + 8 * stage, bytes);
+            if (C == 1) {
+              bulk_g2s(sRing + stage * kStageBytes, src, bytes, bar_full + 8 * stage);
+            } else {
+              const uint32_t part = bytes / C;
+              bulk_g2s_mcast(sRing + stage * kStageBytes + cta_rank * part, src + cta_rank * part, part,
+                             bar_full + 8 * stage, mc_mask);
+            }
+            src += bytes;
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0, x_phase = 0;
+      for (int it = 0; it < ntile_iters; ++it) {
+        for (int l = 0; l < kLayers; ++l) {
+          const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 256u;
+          const uint32_t idesc = make_idesc(BF16, layer_n(l));
+          uint32_t accumulate = 0;
+          if (layer_has_x(l)) {
+            if (l != 5) { mbar_wait(bar_x, x_phase); x_phase ^= 1u; }   // layer 5 re-reads layer 0's embedding
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const int ksteps = l == 9 ? 2 : 4;
+            for (int k = 0; k < ksteps; ++k) {
+              umma_f16(d_tmem, make_desc(sX + k * 32), make_desc(sRing + stage * kStageBytes + k * 32), idesc,
+                       accumulate);
+              accumulate = 1;
+            }
+            if (C == 1) umma_commit(bar_empty + 8 * stage); else umma_commit_mcast(bar_empty + 8 * stage, mc_mask);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          for (int kb = 0; kb < layer_h_blocks(l); ++kb) {
+            mbar_wait(bar_a + 8 * kb, a_phase);
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(d_tmem, make_desc(sA + kb * kBlkBytes + k * 32),
+                       make_desc(sRing + stage * kStageBytes + k * 32), idesc, accumulate);
+              accumulate = 1;
+            }
+            if (C == 1) umma_commit(bar_empty + 8 * stage); else umma_commit_mcast(bar_empty + 8 * stage, mc_mask);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          if (l >= 1) a_phase ^= 1u;
+          umma_commit(bar_acc + 8 * (l & 1));
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= encode + epilogue warps =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int hf = (warp - 4) >> 2;         // which 32-column half of every 64-column chunk
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t acc_phase[2] = {0u, 0u};
+    for (int it = 0; it < ntile_iters; ++it) {
+      const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+      const long long m = tile * kTileM + row;
+      const bool valid = tile < ntiles && m < args.M;
+      float p[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 1.f};
+      if (valid) {
+        if (RAYS) {
+          const long long ray = m / args.rb.S;
+          const float z = args.rb.z[m];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            p[c] = __fadd_rn(args.rb.rays_o[ray * 3 + c], __fmul_rn(args.rb.rays_d[ray * 3 + c], z));
+            dv[c] = args.rb.viewdirs[ray * 3 + c];
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { p[c] = args.pts[m * 3 + c]; dv[c] = args.dirs[m * 3 + c]; }
+        }
+      }
+      // X <- position embedding (the previous tile's view-layer MMAs, the last readers of X, completed
+      // before that tile's final accumulator wait)
+      if (hf == 0) encode_store<BF16, kLpos>(p, sX + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128), row, 8);
+      fence_proxy_async();
+      mbar_arrive(bar_x);
+
+      float alpha = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+#pragma unroll 1
+      for (int l = 0; l < kLayers; ++l) {
+        const int ab = l & 1;
+        mbar_wait(bar_acc + 8 * ab, acc_phase[ab]);
+        acc_phase[ab] ^= 1u;
+        tc_fence_after();
+        if (l == 5) {   // layer 5's MMAs are done with the position embedding: X <- direction embedding
+          if (hf == 1) encode_store<BF16, kLdir>(dv, sX + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128), row, 4);
+          fence_proxy_async();
+          mbar_arrive(bar_x);
+        }
+        const int nchunks = l == 9 ? 2 : 4;
+#pragma unroll 1
+        for (int kb = 0; kb < nchunks; ++kb) {
+          const int c0 = kb * 64 + hf * 32;
+          uint32_t r[32];
+          tmem_ld32(t_lane + (uint32_t)(ab * 256 + c0), r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(r[j]) + cst.bias[l][c0 + j];
+            if (l != 8) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (args.dbg && l == args.dbg_layer && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) args.dbg[m * 256 + c0 + j] = v[j];
+          }
+          if (l == 7) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) alpha = fmaf(v[j], cst.w_alpha[c0 + j], alpha);
+          }
+          if (l < 9) {
+            const uint32_t rb_ = sA + (uint32_t)(kb * kBlkBytes) + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int ch = hf * 4 + g;
+              st_shared_v4(rb_ + ((ch ^ (row & 7)) << 4), pack2<BF16>(v[g * 8 + 0], v[g * 8 + 1]),
+                           pack2<BF16>(v[g * 8 + 2], v[g * 8 + 3]), pack2<BF16>(v[g * 8 + 4], v[g * 8 + 5]),
+                           pack2<BF16>(v[g * 8 + 6], v[g * 8 + 7]));
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar_a + 8 * kb);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              h0 = fmaf(v[j], cst.w_rgb[0][c0 + j], h0);
+              h1 = fmaf(v[j], cst.w_rgb[1][c0 + j], h1);
+              h2 = fmaf(v[j], cst.w_rgb[2][c0 + j], h2);
+              h3 = fmaf(v[j], cst.w_unc[c0 + j], h3);
+            }
+          }
+        }
+      }
+      // ---- heads: combine the two column halves, add biases, exp on the uncertainty ----
+      tc_fence_before();
+      if (hf == 1) {
+        misc.partial[row][0] = h0; misc.partial[row][1] = h1; misc.partial[row][2] = h2;
+        misc.partial[row][3] = alpha; misc.partial[row][4] = h3;
+      }
+      epi_bar_sync();
+      if (hf == 0 && valid) {
+        float* o = args.out + m * 5;
+        o[0] = h0 + misc.partial[row][0] + cst.head_b[1];
+        o[1] = h1 + misc.partial[row][1] + cst.head_b[2];
+        o[2] = h2 + misc.partial[row][2] + cst.head_b[3];
+        o[3] = alpha + misc.partial[row][3] + cst.head_b[0];
+        o[4] = expf(h3 + misc.partial[row][4] + cst.head_b[4]);   // run_nerf_helpers.py:128-129
+      }
+      epi_bar_sync();   // partial[] is free again
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (C > 1) cluster_sync_all();   // peers may still multicast into / commit to this CTA until here
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+template <bool BF16, bool RAYS, int C>
+cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStream_t st) {
+  auto kern = mlp_tc_kernel<BF16, RAYS, C>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, cst, a);
+}
+
+int g_cluster = 1;   // CTAs sharing one weight stream (1, 2 or 4); EVPP_TC_CLUSTER overrides
+
+template <bool RAYS>
+int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
+  if (a.M <= 0) return 0;
+  static bool env_read = false;
+  if (!env_read) {
+    if (const char* e = getenv("EVPP_TC_CLUSTER")) {
+      const int c = atoi(e);
+      if (c == 1 || c == 2 || c == 4) g_cluster = c;
+    }
+    env_read = true;
+  }
+  const int C = g_cluster;
+  const long long ntiles = (a.M + kTileM - 1) / kTileM;
+  long long grid = ntiles < num_sms ? ntiles : num_sms;
+  grid = (grid + C - 1) / C * C;
+  if (grid > num_sms) grid = num_sms / C * C;
+  a.tiles_per_cta = (int)((ntiles + grid - 1) / grid);
+  a.image = reinterpret_cast<const uint8_t*>(w.image);
+  a.dbg = w.dbg;
+  a.dbg_layer = w.dbg_layer;
+  const bool bf = w.dtype == EVPP_PREC_BF16;
+  cudaError_t e;
+#define EVPP_TC_DISPATCH(CC)                                                           \
+  e = bf ? launch_one<true, RAYS, CC>(*w.consts, a, (int)grid, st)                     \
+         : launch_one<false, RAYS, CC>(*w.consts, a, (int)grid, st)
+  if (C == 4) { EVPP_TC_DISPATCH(4); }
+  else if (C == 2) { EVPP_TC_DISPATCH(2); }
+  else { EVPP_TC_DISPATCH(1); }
+#undef EVPP_TC_DISPATCH
+  return e == cudaSuccess ? 1 : -1;
+}
+
+template <typename T>
+T to_op(float v);
+template <>
+__half to_op<__half>(float v) { return __float2half_rn(v); }
+template <>
+__nv_bfloat16 to_op<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Appends one pre-swizzled K-block: n_rows x 64 channels; channel k of row n = W[n*in_dim + col0 + k]
+// for k < count, else 0.  Layout = what make_desc()/SWIZZLE_128B expects (see sw128()).
+template <typename T>
+void put_block(std::vector<uint8_t>& img, const std::vector<float>& W, int n_rows, int in_dim, int col0, int count) {
+  const size_t base = img.size();
+  img.resize(base + (size_t)n_rows * 128, 0);
+  for (int n = 0; n < n_rows; ++n)
+    for (int k = 0; k < 64; ++k) {
+      const float v = k < count ? W[(size_t)n * in_dim + col0 + k] : 0.f;
+      const T hv = to_op<T>(v);
+      const size_t off = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
+      memcpy(&img[base + off], &hv, 2);
+    }
+}
+
+template <typename T>
+void pack_image(const std::vector<std::vector<float>>& t, std::vector<uint8_t>& img) {
+  img.clear();
+  img.reserve(kImageBytes);
+  put_block<T>(img, t[0], 256, 63, 0, 63);                                   // layer 0 : X
+  for (int l = 1; l <= 4; ++l)
+    for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[2 * l], 256, 256, kb * 64, 64);
+  put_block<T>(img, t[10], 256, 319, 0, 63);                                 // layer 5 : X part of cat[pts, h]
+  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[10], 256, 319, 63 + kb * 64, 64);
+  for (int l = 6; l <= 7; ++l)
+    for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[2 * l], 256, 256, kb * 64, 64);
+  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[18], 256, 256, kb * 64, 64);   // feature_linear
+  put_block<T>(img, t[16], 128, 283, 256, 27);                               // views : direction part
+  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[16], 128, 283, kb * 64, 64);   // views : feature part
+}
+
+}  // namespace
+
+size_t tc_weight_image_bytes() { return kImageBytes; }
+
+void tc_pack_weights(const std::vector<std::vector<float>>& t, int dtype, std::vector<uint8_t>& image, TcConsts& c) {
+  if (dtype == EVPP_PREC_BF16) pack_image<__nv_bfloat16>(t, image); else pack_image<__half>(t, image);
+  memset(&c, 0, sizeof(c));
+  for (int l = 0; l < 8; ++l) memcpy(c.bias[l], t[2 * l + 1].data(), 256 * 4);
+  memcpy(c.bias[8], t[19].data(), 256 * 4);
+  memcpy(c.bias[9], t[17].data(), 128 * 4);
+  memcpy(c.w_alpha, t[20].data(), 256 * 4);
+  memcpy(c.w_rgb, t[22].data(), 384 * 4);
+  memcpy(c.w_unc, t[24].data(), 128 * 4);
+  c.head_b[0] = t[21][0];
+  c.head_b[1] = t[23][0]; c.head_b[2] = t[23][1]; c.head_b[3] = t[23][2];
+  c.head_b[4] = t[25][0];
+}
+
+int tc_configure() { return 0; }   // attributes are set lazily per instantiation in launch_one
+
+int launch_mlp_tc(const TcWeights& w, const RayBatch& rb, float* raw, int num_sms, cudaStream_t st) {
+  TcArgs a{};
+  a.rb = rb;
+  a.M = (long long)rb.n * rb.S;
+  a.out = raw;
+  return launch_any<true>(w, a, num_sms, st);
+}
+
+int launch_mlp_tc_points(const TcWeights& w, const float* pts, const float* dirs, int64_t M, float* out,
+                         int num_sms, cudaStream_t st) {
+  TcArgs a{};
+  a.pts = pts;
+  a.dirs = dirs;
+  a.M = (long long)M;
+  a.out = out;
+  return launch_any<false>(w, a, num_sms, st);
+}
+
+}  // namespace evpp

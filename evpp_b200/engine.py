@@ -171,6 +171,19 @@ class Engine:
                                             _stream_ptr(self.device)))
         return out
 
+    def mlp_layer_dump(self, which, pts, dirs, layer, precision="fp16"):
+        """Tensor-core MLP + fp32 dump of the activations layer `layer` produces; returns (out [M,5], acts [M,256])."""
+        which = {"coarse": 0, "fine": 1}.get(which, which)
+        pts = pts.to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        dirs = dirs.to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        out = torch.empty(pts.shape[0], 5, device=self.device)
+        acts = torch.zeros(pts.shape[0], 256, device=self.device)
+        prec = PRECISIONS[precision] if isinstance(precision, str) else precision
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_mlp_layer_dump(self._h, which, prec, _ptr(pts), _ptr(dirs), pts.shape[0], int(layer),
+                                               _ptr(out), _ptr(acts), _stream_ptr(self.device)))
+        return out, acts
+
     def composite(self, raw, z, rays_d):
         """raw2outputs on caller tensors; returns dict(rgb, disp, acc, depth, weights, beta2)."""
         raw = raw.to(self.device, torch.float32).contiguous()

@@ -128,6 +128,13 @@ int evpp_get_rays(evpp_handle* h, const float* c2w, int V, int H, int W, float f
 int evpp_mlp_forward(evpp_handle* h, int which_net, int precision, const float* pts,
                      const float* dirs, int64_t M, float* out, void* stream);
 
+/* Same, and additionally dumps the fp32 activations one layer of the tensor-core path hands to the
+ * next (after bias / ReLU, before the 16-bit conversion): layer 0..7 = pts_linears (run_nerf_helpers.py:
+ * 111-116), 8 = feature_linear (:119), 9 = views_linears.0 (:122-124, 128 wide).  acts: device
+ * [M,256] (layer 9 fills the first 128 columns of each row).  Parity-test hook. */
+int evpp_mlp_layer_dump(evpp_handle* h, int which_net, int precision, const float* pts, const float* dirs,
+                        int64_t M, int layer, float* out, float* acts, void* stream);
+
 /* Per-stage dumps of the LAST evpp_render_rays call's final chunk, for parity tests
  * (SURVEY.md appendix B).  `out` is a device buffer of at least *count elements
  * (call with out == NULL to query count).  Stages: */
