@@ -76,12 +76,12 @@ class ClockSampler:
 
 
 def make_workload(rank):
-    from oracle import evpp_oracle as O          # only used for the synthetic pose generator + weights
+    from evpp_b200 import synthetic as S
     torch.manual_seed(0)
-    c = O.init_nerf_state_dict()
-    f = O.init_nerf_state_dict()
-    views = O.hemisphere_views(V_PER_RANK, seed=rank)
-    poses = torch.Tensor(np.asarray(O.views_to_poses(views)))[:, :3, :4].contiguous()
+    c = S.init_nerf_state_dict()
+    f = S.init_nerf_state_dict()
+    views = S.hemisphere_views(V_PER_RANK, seed=rank)
+    poses = torch.Tensor(np.asarray(S.views_to_poses(views)))[:, :3, :4].contiguous()
     return c, f, views, poses
 
 

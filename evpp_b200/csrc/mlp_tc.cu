@@ -31,13 +31,14 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = 8;
 constexpr int kStages = 4;
 constexpr int kStageBytes = 32768;
 constexpr int kBlkBytes = 16384;          // 128 rows x 128 B
 constexpr int kLayers = 10;               // pts_linears 0..7, feature_linear (8), views_linears.0 (9)
 constexpr int kOffX = 4 * kBlkBytes;
-constexpr int kOffRing = kOffX + kBlkBytes;
+constexpr int kOffXD = kOffX + kBlkBytes;
+constexpr int kOffRing = kOffXD + kBlkBytes;
 constexpr int kOffMisc = kOffRing + kStages * kStageBytes;
 
 struct Misc {
@@ -46,9 +47,9 @@ struct Misc {
   uint64_t acc_full[2];
   uint64_t a_ready[4];
   uint64_t x_ready;
+  uint64_t xd_ready;
   uint32_t tmem_base;
   uint32_t pad_;
-  float partial[kTileM][8];               // head partial sums of the upper column half
 };
 constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc) + 1024;   // + alignment slack
 
@@ -225,17 +226,144 @@ struct TcArgs {
   int tiles_per_cta;
 };
 
-template <bool BF16, bool RAYS, int C>
+struct RowData {     // what one epilogue thread knows about its row of the current tile
+  float p[3];
+  float dv[3];
+  long long m;
+  bool valid;
+};
+
+template <bool RAYS>
+__device__ __forceinline__ void load_row(const TcArgs& args, long long tile, long long ntiles, int row, RowData& rd) {
+  rd.m = tile * kTileM + row;
+  rd.valid = tile < ntiles && rd.m < args.M;
+  rd.p[0] = rd.p[1] = rd.p[2] = 0.f;
+  rd.dv[0] = rd.dv[1] = 0.f; rd.dv[2] = 1.f;
+  if (rd.valid) {
+    if (RAYS) {
+      const long long ray = rd.m / args.rb.S;
+      const float z = args.rb.z[rd.m];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        // pts = rays_o + rays_d * z (run_nerf.py:466), product and sum rounded separately like ATen
+        rd.p[c] = __fadd_rn(args.rb.rays_o[ray * 3 + c], __fmul_rn(args.rb.rays_d[ray * 3 + c], z));
+        rd.dv[c] = args.rb.viewdirs[ray * 3 + c];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { rd.p[c] = args.pts[rd.m * 3 + c]; rd.dv[c] = args.dirs[rd.m * 3 + c]; }
+    }
+  }
+}
+
+// two fp32 adds in one instruction (sm_100 packed fp32 pipe)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 c;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(c.x), "=f"(c.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return c;
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t relu2(uint32_t v) {   // max(x, 0) on a packed pair; commutes with the rounding
+  if (BF16) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&v);
+    x = __hmax2(x, __floats2bfloat162_rn(0.f, 0.f));
+    return *reinterpret_cast<uint32_t*>(&x);
+  } else {
+    __half2 x = *reinterpret_cast<__half2*>(&v);
+    x = __hmax2(x, __floats2half2_rn(0.f, 0.f));
+    return *reinterpret_cast<uint32_t*>(&x);
+  }
+}
+
+// Drains one layer's accumulator.  KIND 0: ReLU layer -> next A operand; 1: layer 7 (ReLU + alpha head);
+// 2: feature_linear (no ReLU); 3: view layer (ReLU + rgb / uncertainty heads, nothing stored).
+// The TMEM load of chunk k+1 is in flight while chunk k is converted and stored.
+template <bool BF16, int KIND, bool DBG>
+__device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& args, int l, uint32_t t_acc, int hf,
+                                            int row, int lane, uint32_t sA_row, uint32_t bar_a, const RowData& rd,
+                                            float& alpha, float (&hd)[4]) {
+  constexpr int NCH = KIND == 3 ? 2 : 4;
+  uint32_t r[2][32];
+  tmem_ld32(t_acc + (uint32_t)(hf * 32), r[0]);
+#pragma unroll
+  for (int kb = 0; kb < NCH; ++kb) {
+    tmem_ld_wait();
+    if (kb + 1 < NCH) tmem_ld32(t_acc + (uint32_t)((kb + 1) * 64 + hf * 32), r[(kb + 1) & 1]);
+    const int c0 = kb * 64 + hf * 32;
+    const float2* b2 = reinterpret_cast<const float2*>(&cst.bias[l][c0]);
+    float2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      v[j] = add2(make_float2(__uint_as_float(r[kb & 1][2 * j]), __uint_as_float(r[kb & 1][2 * j + 1])), b2[j]);
+    if (KIND == 1 || KIND == 3 || DBG) {
+      if (KIND != 2) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); }
+      }
+    }
+    if (DBG) {
+      if (l == args.dbg_layer && rd.valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          args.dbg[rd.m * 256 + c0 + 2 * j] = v[j].x;
+          args.dbg[rd.m * 256 + c0 + 2 * j + 1] = v[j].y;
+        }
+      }
+    }
+    if (KIND == 1) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        alpha = fmaf(v[j].x, cst.w_alpha[c0 + 2 * j], alpha);
+        alpha = fmaf(v[j].y, cst.w_alpha[c0 + 2 * j + 1], alpha);
+      }
+    }
+    if (KIND == 3) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float x = e ? v[j].y : v[j].x;
+          const int c = c0 + 2 * j + e;
+          hd[0] = fmaf(x, cst.w_rgb[0][c], hd[0]);
+          hd[1] = fmaf(x, cst.w_rgb[1][c], hd[1]);
+          hd[2] = fmaf(x, cst.w_rgb[2][c], hd[2]);
+          hd[3] = fmaf(x, cst.w_unc[c], hd[3]);
+        }
+      }
+    } else {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        pk[j] = pack2<BF16>(v[j].x, v[j].y);
+        if (KIND == 0 && !DBG) pk[j] = relu2<BF16>(pk[j]);
+      }
+      const uint32_t rb_ = sA_row + (uint32_t)(kb * kBlkBytes);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        st_shared_v4(rb_ + (uint32_t)(((hf * 4 + g) ^ (row & 7)) << 4), pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2],
+                     pk[g * 4 + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a + 8 * kb);
+    }
+  }
+}
+
+template <bool BF16, bool RAYS, int C, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcArgs args) {
-  extern __shared__ uint8_t smem_dyn[];
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
   Misc& misc = *reinterpret_cast<Misc*>(smem_gen + kOffMisc);
-  const uint32_t sA = smem_base, sX = smem_base + kOffX, sRing = smem_base + kOffRing;
+  float* partial = reinterpret_cast<float*>(smem_gen);   // [128][8] head partial sums, aliases A block 0
+  const uint32_t sA = smem_base, sX = smem_base + kOffX, sXD = smem_base + kOffXD, sRing = smem_base + kOffRing;
   const uint32_t bar_full = smem_u32(&misc.full[0]), bar_empty = smem_u32(&misc.empty[0]);
   const uint32_t bar_acc = smem_u32(&misc.acc_full[0]), bar_a = smem_u32(&misc.a_ready[0]);
-  const uint32_t bar_x = smem_u32(&misc.x_ready);
+  const uint32_t bar_x = smem_u32(&misc.x_ready), bar_xd = smem_u32(&misc.xd_ready);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = C > 1 ? cluster_ctarank() : 0u;
@@ -248,8 +376,9 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
     }
     mbar_init(bar_acc, 1);
     mbar_init(bar_acc + 8, 1);
-    for (int k = 0; k < 4; ++k) mbar_init(bar_a + 8 * k, kEpiThreads);
-    mbar_init(bar_x, kEpiThreads);
+    for (int k = 0; k < 4; ++k) mbar_init(bar_a + 8 * k, kEpiWarps);
+    mbar_init(bar_x, kEpiWarps);
+    mbar_init(bar_xd, kEpiWarps);
     fence_barrier_init();
   }
   if (warp == 1) {   // TMEM: all 512 columns (one CTA per SM)
@@ -295,19 +424,22 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0, x_phase = 0;
+      uint32_t stage = 0, phase = 0, a_phase = 0, x_phase = 0, xd_phase = 0;
       for (int it = 0; it < ntile_iters; ++it) {
         for (int l = 0; l < kLayers; ++l) {
           const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 256u;
           const uint32_t idesc = make_idesc(BF16, layer_n(l));
           uint32_t accumulate = 0;
           if (layer_has_x(l)) {
-            if (l != 5) { mbar_wait(bar_x, x_phase); x_phase ^= 1u; }   // layer 5 re-reads layer 0's embedding
+            // layers 0 and 5 read the position embedding (X), the view layer the direction embedding (XD)
+            if (l == 0) { mbar_wait(bar_x, x_phase); x_phase ^= 1u; }
+            if (l == 9) { mbar_wait(bar_xd, xd_phase); xd_phase ^= 1u; }
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
             const int ksteps = l == 9 ? 2 : 4;
+            const uint32_t xa = l == 9 ? sXD : sX;
             for (int k = 0; k < ksteps; ++k) {
-              umma_f16(d_tmem, make_desc(sX + k * 32), make_desc(sRing + stage * kStageBytes + k * 32), idesc,
+              umma_f16(d_tmem, make_desc(xa + k * 32), make_desc(sRing + stage * kStageBytes + k * 32), idesc,
                        accumulate);
               accumulate = 1;
             }
@@ -337,105 +469,70 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int hf = (warp - 4) >> 2;         // which 32-column half of every 64-column chunk
     const int row = q * 32 + lane;
+    const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t acc_phase[2] = {0u, 0u};
-    for (int it = 0; it < ntile_iters; ++it) {
-      const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
-      const long long m = tile * kTileM + row;
-      const bool valid = tile < ntiles && m < args.M;
-      float p[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 1.f};
-      if (valid) {
-        if (RAYS) {
-          const long long ray = m / args.rb.S;
-          const float z = args.rb.z[m];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            p[c] = __fadd_rn(args.rb.rays_o[ray * 3 + c], __fmul_rn(args.rb.rays_d[ray * 3 + c], z));
-            dv[c] = args.rb.viewdirs[ray * 3 + c];
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) { p[c] = args.pts[m * 3 + c]; dv[c] = args.dirs[m * 3 + c]; }
-        }
-      }
-      // X <- position embedding (the previous tile's view-layer MMAs, the last readers of X, completed
-      // before that tile's final accumulator wait)
-      if (hf == 0) encode_store<BF16, kLpos>(p, sX + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128), row, 8);
+    RowData cur, nxt;
+    load_row<RAYS>(args, (long long)blockIdx.x, ntiles, row, cur);
+    if (hf == 0) {
+      encode_store<BF16, kLpos>(cur.p, sX + row_off, row, 8);
       fence_proxy_async();
-      mbar_arrive(bar_x);
-
-      float alpha = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_x);
+    for (int it = 0; it < ntile_iters; ++it) {
+      float alpha = 0.f;
+      float hd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int l = 0; l < kLayers; ++l) {
         const int ab = l & 1;
         mbar_wait(bar_acc + 8 * ab, acc_phase[ab]);
         acc_phase[ab] ^= 1u;
         tc_fence_after();
-        if (l == 5) {   // layer 5's MMAs are done with the position embedding: X <- direction embedding
-          if (hf == 1) encode_store<BF16, kLdir>(dv, sX + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128), row, 4);
-          fence_proxy_async();
-          mbar_arrive(bar_x);
-        }
-        const int nchunks = l == 9 ? 2 : 4;
-#pragma unroll 1
-        for (int kb = 0; kb < nchunks; ++kb) {
-          const int c0 = kb * 64 + hf * 32;
-          uint32_t r[32];
-          tmem_ld32(t_lane + (uint32_t)(ab * 256 + c0), r);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = __uint_as_float(r[j]) + cst.bias[l][c0 + j];
-            if (l != 8) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (args.dbg && l == args.dbg_layer && valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) args.dbg[m * 256 + c0 + j] = v[j];
-          }
-          if (l == 7) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) alpha = fmaf(v[j], cst.w_alpha[c0 + j], alpha);
-          }
-          if (l < 9) {
-            const uint32_t rb_ = sA + (uint32_t)(kb * kBlkBytes) + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int ch = hf * 4 + g;
-              st_shared_v4(rb_ + ((ch ^ (row & 7)) << 4), pack2<BF16>(v[g * 8 + 0], v[g * 8 + 1]),
-                           pack2<BF16>(v[g * 8 + 2], v[g * 8 + 3]), pack2<BF16>(v[g * 8 + 4], v[g * 8 + 5]),
-                           pack2<BF16>(v[g * 8 + 6], v[g * 8 + 7]));
-            }
+        const uint32_t t_acc = t_lane + (uint32_t)(ab * 256);
+        if (l == 9)      drain_layer<BF16, 3, DBG>(cst, args, l, t_acc, hf, row, lane, sA + row_off, bar_a, cur, alpha, hd);
+        else if (l == 8) drain_layer<BF16, 2, DBG>(cst, args, l, t_acc, hf, row, lane, sA + row_off, bar_a, cur, alpha, hd);
+        else if (l == 7) drain_layer<BF16, 1, DBG>(cst, args, l, t_acc, hf, row, lane, sA + row_off, bar_a, cur, alpha, hd);
+        else             drain_layer<BF16, 0, DBG>(cst, args, l, t_acc, hf, row, lane, sA + row_off, bar_a, cur, alpha, hd);
+        // The epilogue warps now idle until the next layer's MMAs finish: use the window to stage operands.
+        if (l == 0) {
+          // XD <- direction embedding of this tile (the previous tile's view-layer MMAs, its last readers,
+          // completed before that tile's final accumulator wait)
+          if (hf == 1) {
+            encode_store<BF16, kLdir>(cur.dv, sXD + row_off, row, 4);
             fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(bar_a + 8 * kb);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              h0 = fmaf(v[j], cst.w_rgb[0][c0 + j], h0);
-              h1 = fmaf(v[j], cst.w_rgb[1][c0 + j], h1);
-              h2 = fmaf(v[j], cst.w_rgb[2][c0 + j], h2);
-              h3 = fmaf(v[j], cst.w_unc[c0 + j], h3);
-            }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_xd);
+        } else if (l == 5) {
+          // X <- position embedding of the NEXT tile (layer 5's MMAs were the last readers of this tile's)
+          load_row<RAYS>(args, (long long)blockIdx.x + (long long)(it + 1) * gridDim.x,
+                         it + 1 < ntile_iters ? ntiles : 0, row, nxt);
+          if (hf == 0) {
+            encode_store<BF16, kLpos>(nxt.p, sX + row_off, row, 8);
+            fence_proxy_async();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_x);
         }
       }
       // ---- heads: combine the two column halves, add biases, exp on the uncertainty ----
-      tc_fence_before();
       if (hf == 1) {
-        misc.partial[row][0] = h0; misc.partial[row][1] = h1; misc.partial[row][2] = h2;
-        misc.partial[row][3] = alpha; misc.partial[row][4] = h3;
+        float* pr = partial + row * 8;
+        pr[0] = hd[0]; pr[1] = hd[1]; pr[2] = hd[2]; pr[3] = alpha; pr[4] = hd[3];
       }
       epi_bar_sync();
-      if (hf == 0 && valid) {
-        float* o = args.out + m * 5;
-        o[0] = h0 + misc.partial[row][0] + cst.head_b[1];
-        o[1] = h1 + misc.partial[row][1] + cst.head_b[2];
-        o[2] = h2 + misc.partial[row][2] + cst.head_b[3];
-        o[3] = alpha + misc.partial[row][3] + cst.head_b[0];
-        o[4] = expf(h3 + misc.partial[row][4] + cst.head_b[4]);   // run_nerf_helpers.py:128-129
+      if (hf == 0 && cur.valid) {
+        const float* pr = partial + row * 8;
+        float* o = args.out + cur.m * 5;
+        o[0] = hd[0] + pr[0] + cst.head_b[1];
+        o[1] = hd[1] + pr[1] + cst.head_b[2];
+        o[2] = hd[2] + pr[2] + cst.head_b[3];
+        o[3] = alpha + pr[3] + cst.head_b[0];
+        o[4] = expf(hd[3] + pr[4] + cst.head_b[4]);   // run_nerf_helpers.py:128-129
       }
-      epi_bar_sync();   // partial[] is free again
+      epi_bar_sync();   // partial[] (A block 0) is rewritten by the next tile's layer-0 epilogue
+      cur = nxt;
     }
   }
 
@@ -448,9 +545,9 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   }
 }
 
-template <bool BF16, bool RAYS, int C>
+template <bool BF16, bool RAYS, int C, bool DBG>
 cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStream_t st) {
-  auto kern = mlp_tc_kernel<BF16, RAYS, C>;
+  auto kern = mlp_tc_kernel<BF16, RAYS, C, DBG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -468,7 +565,7 @@ cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStrea
   return cudaLaunchKernelEx(&cfg, kern, cst, a);
 }
 
-int g_cluster = 1;   // CTAs sharing one weight stream (1, 2 or 4); EVPP_TC_CLUSTER overrides
+int g_cluster = 1;   // CTAs sharing one weight stream (1 or 2); EVPP_TC_CLUSTER overrides
 
 template <bool RAYS>
 int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
@@ -477,7 +574,7 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   if (!env_read) {
     if (const char* e = getenv("EVPP_TC_CLUSTER")) {
       const int c = atoi(e);
-      if (c == 1 || c == 2 || c == 4) g_cluster = c;
+      if (c == 1 || c == 2) g_cluster = c;
     }
     env_read = true;
   }
@@ -492,12 +589,14 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   a.dbg_layer = w.dbg_layer;
   const bool bf = w.dtype == EVPP_PREC_BF16;
   cudaError_t e;
-#define EVPP_TC_DISPATCH(CC)                                                           \
-  e = bf ? launch_one<true, RAYS, CC>(*w.consts, a, (int)grid, st)                     \
-         : launch_one<false, RAYS, CC>(*w.consts, a, (int)grid, st)
-  if (C == 4) { EVPP_TC_DISPATCH(4); }
-  else if (C == 2) { EVPP_TC_DISPATCH(2); }
-  else { EVPP_TC_DISPATCH(1); }
+#define EVPP_TC_DISPATCH(CC, DD)                                                       \
+  e = bf ? launch_one<true, RAYS, CC, DD>(*w.consts, a, (int)grid, st)                 \
+         : launch_one<false, RAYS, CC, DD>(*w.consts, a, (int)grid, st)
+  if (a.dbg) {
+    if (RAYS) return -1;
+    EVPP_TC_DISPATCH(1, !RAYS);
+  } else if (C == 2) { EVPP_TC_DISPATCH(2, false); }
+  else { EVPP_TC_DISPATCH(1, false); }
 #undef EVPP_TC_DISPATCH
   return e == cudaSuccess ? 1 : -1;
 }
