@@ -42,6 +42,7 @@ SIGNATURES = {
     "evpp_get_rays": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P, _P, _P]),
     "evpp_mlp_forward": (_I, [_P, _I, _I, _P, _P, _L, _P, _P]),
     "evpp_mlp_layer_dump": (_I, [_P, _I, _I, _P, _P, _L, _I, _P, _P, _P]),
+    "evpp_mlp_trace": (_I, [_P, _I, _I, _P, _P, _L, _P, _P, _P]),
     "evpp_set_stage_capture": (_I, [_P, _I]),
     "evpp_stage_dump": (_I, [_P, _I, _P, C.POINTER(_L), _P]),
     "evpp_composite": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),

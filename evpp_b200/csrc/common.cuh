@@ -52,6 +52,7 @@ struct TcWeights {
   int dtype;                  // EVPP_PREC_FP16 / EVPP_PREC_BF16
   float* dbg;                 // optional device [M,256] dump of one layer's activations (parity tests)
   int dbg_layer;
+  long long* trace;           // optional device [128] clock64 stamps of one tile's pipeline (diagnostics)
 };
 
 struct RayBatch {             // device pointers of one chunk

@@ -152,8 +152,8 @@ int ensure_tc(evpp_handle* h, int which, int prec) {
 SimtWeights simt_of(const NetWeights& nw) {
   return SimtWeights{nw.simt_stream.as<float>(), nw.bias.as<float>(), nw.head_w.as<float>(), nw.head_b.as<float>()};
 }
-TcWeights tc_of(const NetWeights& nw, int prec, float* dbg = nullptr, int dbg_layer = -1) {
-  return TcWeights{nw.tc_image[prec].p, &nw.tc_consts, prec, dbg, dbg_layer};
+TcWeights tc_of(const NetWeights& nw, int prec, float* dbg = nullptr, int dbg_layer = -1, long long* trace = nullptr) {
+  return TcWeights{nw.tc_image[prec].p, &nw.tc_consts, prec, dbg, dbg_layer, trace};
 }
 
 int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw, cudaStream_t st) {
@@ -407,7 +407,9 @@ int evpp_load_nerf_weights(evpp_handle* h, int which, const float* packed, const
 
 int evpp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx,
                      float cy, const int32_t* pix_idx, int R, float* scores, void* stream) {
-  if (!h || !c2w || !scores) return fail(EVPP_ERR_INVALID, "null argument");
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  if (V == 0) return 0;   // empty candidate list: nothing to score (empty tensors carry null pointers)
+  if (!c2w || !scores) return fail(EVPP_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
   return score_views_device(h, c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, scores, h->cfg.precision,
                             (cudaStream_t)stream);
@@ -437,7 +439,9 @@ static int score_host_impl(evpp_handle* h, const float* c2w_host, int V, int H, 
 int evpp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int H, int W, float fx, float fy,
                           float cx, float cy, const int32_t* pix_idx_host, int R, float* scores_host,
                           void* stream) {
-  if (!h || !c2w_host || !scores_host) return fail(EVPP_ERR_INVALID, "null argument");
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  if (V == 0) return 0;
+  if (!c2w_host || !scores_host) return fail(EVPP_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
   return score_host_impl(h, c2w_host, V, H, W, fx, fy, cx, cy, pix_idx_host, R, scores_host, h->cfg.precision,
                          (cudaStream_t)stream);
@@ -501,7 +505,8 @@ int evpp_get_rays(evpp_handle* h, const float* c2w, int V, int H, int W, float f
 }
 
 static int mlp_forward_impl(evpp_handle* h, int which, int precision, const float* pts, const float* dirs,
-                            int64_t M, float* out, int dbg_layer, float* dbg, void* stream) {
+                            int64_t M, float* out, int dbg_layer, float* dbg, void* stream,
+                            long long* trace = nullptr) {
   if (!h || !pts || !dirs || !out) return fail(EVPP_ERR_INVALID, "null argument");
   if (which != 0 && which != 1) return fail(EVPP_ERR_INVALID, "bad net");
   if (M <= 0) return 0;
@@ -516,7 +521,7 @@ static int mlp_forward_impl(evpp_handle* h, int which, int precision, const floa
   } else if (precision <= 2) {
     int rc = ensure_tc(h, which, precision);
     if (rc) return rc;
-    int nl = launch_mlp_tc_points(tc_of(nw, precision, dbg, dbg_layer), pts, dirs, M, out, h->num_sms, st);
+    int nl = launch_mlp_tc_points(tc_of(nw, precision, dbg, dbg_layer, trace), pts, dirs, M, out, h->num_sms, st);
     if (nl < 0) return fail(EVPP_ERR_CUDA, "tcgen05 MLP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += nl;
   } else {
@@ -536,6 +541,14 @@ int evpp_mlp_layer_dump(evpp_handle* h, int which, int precision, const float* p
                         int layer, float* out, float* acts, void* stream) {
   if (layer < 0 || layer > 9 || !acts) return fail(EVPP_ERR_INVALID, "layer must be 0..9 and acts non-null");
   return mlp_forward_impl(h, which, precision, pts, dirs, M, out, layer, acts, stream);
+}
+
+int evpp_mlp_trace(evpp_handle* h, int which, int precision, const float* pts, const float* dirs, int64_t M,
+                   float* out, int64_t* trace, void* stream) {
+  if (!trace) return fail(EVPP_ERR_INVALID, "null trace buffer");
+  if (precision == EVPP_PREC_FP32) return fail(EVPP_ERR_INVALID, "the pipeline trace exists for the tensor-core path only");
+  return mlp_forward_impl(h, which, precision, pts, dirs, M, out, -1, nullptr, stream,
+                          reinterpret_cast<long long*>(trace));
 }
 
 int evpp_set_stage_capture(evpp_handle* h, int enabled) {

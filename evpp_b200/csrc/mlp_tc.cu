@@ -30,16 +30,24 @@ namespace evpp {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
-constexpr int kStages = 4;
+constexpr int kEpiWarps = 16;              // 4 per TMEM lane quarter
+constexpr int kColSplit = kEpiWarps / 4;   // warps sharing one 64-column chunk of a row quarter
+constexpr int kColsPerWarp = 64 / kColSplit;
+constexpr int kThreads = 32 * (kEpiWarps + 2);
+// Warp roles: 0..kEpiWarps-1 epilogue (TMEM lane quarter = warp & 3); the two control warps get the HIGHEST
+// warp ids because the SM's issue arbiter favours high warp ids: the MMA issuer must never wait for an
+// issue slot behind busy epilogue warps.
+constexpr int kProducerWarp = kEpiWarps;
+constexpr int kMmaWarp = kEpiWarps + 1;
+constexpr int kStages = 6;
 constexpr int kStageBytes = 32768;
 constexpr int kBlkBytes = 16384;          // 128 rows x 128 B
 constexpr int kLayers = 10;               // pts_linears 0..7, feature_linear (8), views_linears.0 (9)
-constexpr int kOffX = 4 * kBlkBytes;
-constexpr int kOffXD = kOffX + kBlkBytes;
-constexpr int kOffRing = kOffXD + kBlkBytes;
-constexpr int kOffMisc = kOffRing + kStages * kStageBytes;
+constexpr int kOffX = 0;                             // position embedding: 128 rows x 128 B, 128-byte swizzle
+constexpr int kOffXD = kOffX + kBlkBytes;            // direction embedding: 128 rows x 64 B, 64-byte swizzle
+constexpr int kOffRing = kOffXD + kBlkBytes / 2;
+constexpr int kOffBias = kOffRing + kStages * kStageBytes;   // fp32 bias[10][256]
+constexpr int kOffMisc = kOffBias + kLayers * 256 * 4;
 
 struct Misc {
   uint64_t full[kStages];
@@ -51,7 +59,8 @@ struct Misc {
   uint32_t tmem_base;
   uint32_t pad_;
 };
-constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc) + 1024;   // + alignment slack
+constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc);
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 
 // per-tile weight stream: number of 64-wide K-blocks per layer and their size
 __host__ __device__ constexpr int layer_has_x(int l) { return l == 0 || l == 5 || l == 9; }
@@ -77,7 +86,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
@@ -126,12 +135,34 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in tensor memory (lane = row, 8 columns = 16 packed 16-bit channels)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
 // layout_type SWIZZLE_128B=2 [61,64))
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// same for 64-byte rows (32 channels): 64-byte swizzle (layout_type 4), 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format f32 (1) [4,6), a/b format [7,10)/[10,13)
 // (0 = f16, 1 = bf16), K-major A and B, N>>3 [17,23), M>>4 [24,29)
@@ -151,11 +182,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -184,7 +224,7 @@ __device__ __forceinline__ uint32_t sw128(int row, int ch) {
 // Frequency encoding of one coordinate triple by angle doubling from an accurate sincosf at the
 // base frequency: the 2^k-th octave carries <= 2^k ulp-level phase error (<= 6e-5 at k = 9), below
 // the 2.4e-4 rounding step of the 16-bit operand it is converted to.
-template <bool BF16, int L>
+template <bool BF16, int L, bool SW64>
 __device__ __forceinline__ void encode_store(const float (&p)[3], uint32_t row_base, int row, int nchunks) {
   float e[64];
   e[0] = p[0]; e[1] = p[1]; e[2] = p[2];
@@ -207,7 +247,8 @@ __device__ __forceinline__ void encode_store(const float (&p)[3], uint32_t row_b
 #pragma unroll
   for (int ch = 0; ch < 8; ++ch) {
     if (ch < nchunks) {
-      st_shared_v4(row_base + ((ch ^ (row & 7)) << 4), pack2<BF16>(e[ch * 8 + 0], e[ch * 8 + 1]),
+      const int sw = SW64 ? (ch ^ ((row >> 1) & 3)) : (ch ^ (row & 7));
+      st_shared_v4(row_base + (sw << 4), pack2<BF16>(e[ch * 8 + 0], e[ch * 8 + 1]),
                    pack2<BF16>(e[ch * 8 + 2], e[ch * 8 + 3]), pack2<BF16>(e[ch * 8 + 4], e[ch * 8 + 5]),
                    pack2<BF16>(e[ch * 8 + 6], e[ch * 8 + 7]));
     }
@@ -224,7 +265,19 @@ struct TcArgs {
   float* dbg;        // optional [M,256] dump of the activations written by layer dbg_layer
   int dbg_layer;
   int tiles_per_cta;
+  long long* trace;  // optional [128] clock64 stamps of CTA 0's third tile (DBG kernels only)
+  int flags;         // EVPP_TC_FLAGS: timing experiments only (1: skip proxy fence, 2: skip bias) -- wrong results
 };
+
+__device__ __forceinline__ long long clk() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
+#define EVPP_TRACE(idx)                                                              \
+  do {                                                                               \
+    if (DBG && args.trace && blockIdx.x == 0 && it == 2) args.trace[(idx)] = clk();  \
+  } while (0)
 
 struct RowData {     // what one epilogue thread knows about its row of the current tile
   float p[3];
@@ -280,34 +333,47 @@ __device__ __forceinline__ uint32_t relu2(uint32_t v) {   // max(x, 0) on a pack
 
 // Drains one layer's accumulator.  KIND 0: ReLU layer -> next A operand; 1: layer 7 (ReLU + alpha head);
 // 2: feature_linear (no ReLU); 3: view layer (ReLU + rgb / uncertainty heads, nothing stored).
-// The TMEM load of chunk k+1 is in flight while chunk k is converted and stored.
+// A warp owns kColsPerWarp columns of each 64-column chunk of its 32 rows; the TMEM load of chunk k+1 is in
+// flight while chunk k is converted and stored.
 template <bool BF16, int KIND, bool DBG>
-__device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& args, int l, uint32_t t_acc, int hf,
-                                            int row, int lane, uint32_t sA_row, uint32_t bar_a, const RowData& rd,
+__device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& args, const float* bias_l, int l,
+                                            uint32_t t_acc, int hf, int lane, uint32_t bar_a, const RowData& rd,
                                             float& alpha, float (&hd)[4]) {
   constexpr int NCH = KIND == 3 ? 2 : 4;
-  uint32_t r[2][32];
-  tmem_ld32(t_acc + (uint32_t)(hf * 32), r[0]);
+  constexpr int NC = kColsPerWarp;   // 16
+  uint32_t r[2][NC];
+  tmem_ld16(t_acc + (uint32_t)(hf * NC), r[0]);
 #pragma unroll
   for (int kb = 0; kb < NCH; ++kb) {
     tmem_ld_wait();
-    if (kb + 1 < NCH) tmem_ld32(t_acc + (uint32_t)((kb + 1) * 64 + hf * 32), r[(kb + 1) & 1]);
-    const int c0 = kb * 64 + hf * 32;
-    const float2* b2 = reinterpret_cast<const float2*>(&cst.bias[l][c0]);
-    float2 v[16];
+    if (DBG && kb == 0 && lane == 0 && args.trace && blockIdx.x == 0 && args.trace[127] == 2 && (threadIdx.x >> 5) == 0)
+      args.trace[90 + l] = clk();
+    if (kb + 1 < NCH) tmem_ld16(t_acc + (uint32_t)((kb + 1) * 64 + hf * NC), r[(kb + 1) & 1]);
+    const int c0 = kb * 64 + hf * NC;
+    float2 v[NC / 2];
+    if (args.flags & 2) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      v[j] = add2(make_float2(__uint_as_float(r[kb & 1][2 * j]), __uint_as_float(r[kb & 1][2 * j + 1])), b2[j]);
-    if (KIND == 1 || KIND == 3 || DBG) {
-      if (KIND != 2) {
+      for (int j = 0; j < NC / 2; ++j)
+        v[j] = make_float2(__uint_as_float(r[kb & 1][2 * j]), __uint_as_float(r[kb & 1][2 * j + 1]));
+    } else {
+      const float4* b4 = reinterpret_cast<const float4*>(bias_l + c0);   // shared memory, warp-uniform address
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); }
+      for (int j = 0; j < NC / 4; ++j) {
+        const float4 b = b4[j];
+        v[2 * j] = add2(make_float2(__uint_as_float(r[kb & 1][4 * j]), __uint_as_float(r[kb & 1][4 * j + 1])),
+                        make_float2(b.x, b.y));
+        v[2 * j + 1] = add2(make_float2(__uint_as_float(r[kb & 1][4 * j + 2]), __uint_as_float(r[kb & 1][4 * j + 3])),
+                            make_float2(b.z, b.w));
       }
+    }
+    if (KIND == 1 || KIND == 3 || (DBG && KIND != 2)) {
+#pragma unroll
+      for (int j = 0; j < NC / 2; ++j) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); }
     }
     if (DBG) {
       if (l == args.dbg_layer && rd.valid) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < NC / 2; ++j) {
           args.dbg[rd.m * 256 + c0 + 2 * j] = v[j].x;
           args.dbg[rd.m * 256 + c0 + 2 * j + 1] = v[j].y;
         }
@@ -315,14 +381,14 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
     }
     if (KIND == 1) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < NC / 2; ++j) {
         alpha = fmaf(v[j].x, cst.w_alpha[c0 + 2 * j], alpha);
         alpha = fmaf(v[j].y, cst.w_alpha[c0 + 2 * j + 1], alpha);
       }
     }
     if (KIND == 3) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < NC / 2; ++j) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const float x = e ? v[j].y : v[j].x;
@@ -334,20 +400,25 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
         }
       }
     } else {
-      uint32_t pk[16];
+      // next layer's A operand, written IN PLACE over the accumulator columns this thread just read:
+      // channels c0..c0+15 of this row -> 8 packed columns at c0 (k-step c0/16 of the next layer's TS MMAs)
+      uint32_t pk[NC / 2];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < NC / 2; ++j) {
         pk[j] = pack2<BF16>(v[j].x, v[j].y);
         if (KIND == 0 && !DBG) pk[j] = relu2<BF16>(pk[j]);
       }
-      const uint32_t rb_ = sA_row + (uint32_t)(kb * kBlkBytes);
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        st_shared_v4(rb_ + (uint32_t)(((hf * 4 + g) ^ (row & 7)) << 4), pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2],
-                     pk[g * 4 + 3]);
-      fence_proxy_async();
+      if (DBG && kb == 0 && lane == 0 && args.trace && blockIdx.x == 0 && args.trace[127] == 2 && (threadIdx.x >> 5) == 0)
+        args.trace[116 + l] = clk();   // 116..125 (overlaps warp-15 slots 116..119 for l<4: print only one)
+      tmem_st8(t_acc + (uint32_t)c0, pk);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a + 8 * kb);
+      if (DBG && kb == 0 && lane == 0 && args.trace && blockIdx.x == 0 && args.trace[127] == 2) {
+        if ((threadIdx.x >> 5) == 0) args.trace[100 + l] = clk();
+        if ((threadIdx.x >> 5) == kEpiWarps - 1) args.trace[110 + l] = clk();
+      }
     }
   }
 }
@@ -356,11 +427,15 @@ template <bool BF16, bool RAYS, int C, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
-  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  const uint32_t smem_base = smem_u32(smem_dyn);
+  if (smem_base & 1023u) __trap();   // the 128-byte swizzle atoms need 1024-byte aligned blocks
+  uint8_t* smem_gen = smem_dyn;
   Misc& misc = *reinterpret_cast<Misc*>(smem_gen + kOffMisc);
-  float* partial = reinterpret_cast<float*>(smem_gen);   // [128][8] head partial sums, aliases A block 0
-  const uint32_t sA = smem_base, sX = smem_base + kOffX, sXD = smem_base + kOffXD, sRing = smem_base + kOffRing;
+  float* partial = reinterpret_cast<float*>(smem_gen + kOffXD);   // [128][kColSplit-1][5] head partial sums; aliases XD,
+                                                                   // which is idle between the view layer and the next tile
+  float* bias_s = reinterpret_cast<float*>(smem_gen + kOffBias);
+  for (int i = threadIdx.x; i < kLayers * 256; i += kThreads) bias_s[i] = cst.bias[i >> 8][i & 255];
+  const uint32_t sX = smem_base + kOffX, sXD = smem_base + kOffXD, sRing = smem_base + kOffRing;
   const uint32_t bar_full = smem_u32(&misc.full[0]), bar_empty = smem_u32(&misc.empty[0]);
   const uint32_t bar_acc = smem_u32(&misc.acc_full[0]), bar_a = smem_u32(&misc.a_ready[0]);
   const uint32_t bar_x = smem_u32(&misc.x_ready), bar_xd = smem_u32(&misc.xd_ready);
@@ -381,7 +456,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
     mbar_init(bar_xd, kEpiWarps);
     fence_barrier_init();
   }
-  if (warp == 1) {   // TMEM: all 512 columns (one CTA per SM)
+  if (warp == kMmaWarp) {   // TMEM: all 512 columns (one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc.tmem_base)),
                  "r"(512)
                  : "memory");
@@ -396,7 +471,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   const int ntile_iters = args.tiles_per_cta;
   const long long ntiles = (args.M + kTileM - 1) / kTileM;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ================= weight producer =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -404,7 +479,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
         const uint8_t* src = args.image;
         for (int l = 0; l < kLayers; ++l) {
           const int nblk = layer_has_x(l) + layer_h_blocks(l);
-          const uint32_t bytes = (uint32_t)layer_n(l) * 128u;
+          const uint32_t bytes = (args.flags & 16) ? 1024u : (uint32_t)layer_n(l) * 128u;   // 16: timing experiment
           for (int b = 0; b < nblk; ++b) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             mbar_expect_tx(bar_full + 8 * stage, bytes);
@@ -415,21 +490,23 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
               bulk_g2s_mcast(sRing + stage * kStageBytes + cta_rank * part, src + cta_rank * part, part,
                              bar_full + 8 * stage, mc_mask);
             }
-            src += bytes;
+            src += (uint32_t)layer_n(l) * 128u;
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, a_phase = 0, x_phase = 0, xd_phase = 0;
       for (int it = 0; it < ntile_iters; ++it) {
         for (int l = 0; l < kLayers; ++l) {
           const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 256u;
+          const uint32_t a_tmem = tmem + (uint32_t)((l & 1) ^ 1) * 256u;
           const uint32_t idesc = make_idesc(BF16, layer_n(l));
           uint32_t accumulate = 0;
+          EVPP_TRACE(l * 4 + 0);
           if (layer_has_x(l)) {
             // layers 0 and 5 read the position embedding (X), the view layer the direction embedding (XD)
             if (l == 0) { mbar_wait(bar_x, x_phase); x_phase ^= 1u; }
@@ -439,8 +516,8 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
             const int ksteps = l == 9 ? 2 : 4;
             const uint32_t xa = l == 9 ? sXD : sX;
             for (int k = 0; k < ksteps; ++k) {
-              umma_f16(d_tmem, make_desc(xa + k * 32), make_desc(sRing + stage * kStageBytes + k * 32), idesc,
-                       accumulate);
+              umma_f16(d_tmem, l == 9 ? make_desc_sw64(xa + k * 32) : make_desc(xa + k * 32),
+                       make_desc(sRing + stage * kStageBytes + k * 32), idesc, accumulate);
               accumulate = 1;
             }
             if (C == 1) umma_commit(bar_empty + 8 * stage); else umma_commit_mcast(bar_empty + 8 * stage, mc_mask);
@@ -448,12 +525,16 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
           }
           for (int kb = 0; kb < layer_h_blocks(l); ++kb) {
             mbar_wait(bar_a + 8 * kb, a_phase);
+            if (kb == 0) EVPP_TRACE(80 + l);
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
+            if (kb == 0) EVPP_TRACE(l * 4 + 1);
+            if (kb == 3) EVPP_TRACE(l * 4 + 2);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_f16(d_tmem, make_desc(sA + kb * kBlkBytes + k * 32),
-                       make_desc(sRing + stage * kStageBytes + k * 32), idesc, accumulate);
+              // A = the previous layer's activations, packed in place in the other accumulator region
+              umma_f16_ts(d_tmem, a_tmem + (uint32_t)(kb * 64 + k * 16),
+                          make_desc(sRing + stage * kStageBytes + k * 32), idesc, accumulate);
               accumulate = 1;
             }
             if (C == 1) umma_commit(bar_empty + 8 * stage); else umma_commit_mcast(bar_empty + 8 * stage, mc_mask);
@@ -461,13 +542,14 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
           }
           if (l >= 1) a_phase ^= 1u;
           umma_commit(bar_acc + 8 * (l & 1));
+          EVPP_TRACE(l * 4 + 3);
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ================= encode + epilogue warps =================
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int hf = (warp - 4) >> 2;         // which 32-column half of every 64-column chunk
+    const int hf = warp >> 2;         // which kColsPerWarp-column slice of every 64-column chunk
     const int row = q * 32 + lane;
     const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
@@ -475,12 +557,13 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
     RowData cur, nxt;
     load_row<RAYS>(args, (long long)blockIdx.x, ntiles, row, cur);
     if (hf == 0) {
-      encode_store<BF16, kLpos>(cur.p, sX + row_off, row, 8);
+      encode_store<BF16, kLpos, false>(cur.p, sX + row_off, row, 8);
       fence_proxy_async();
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_x);
     for (int it = 0; it < ntile_iters; ++it) {
+      if (DBG && args.trace && blockIdx.x == 0 && threadIdx.x == 0) args.trace[127] = it;
       float alpha = 0.f;
       float hd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -489,17 +572,19 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
         mbar_wait(bar_acc + 8 * ab, acc_phase[ab]);
         acc_phase[ab] ^= 1u;
         tc_fence_after();
+        if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 0);
         const uint32_t t_acc = t_lane + (uint32_t)(ab * 256);
-        if (l == 9)      drain_layer<BF16, 3, DBG>(cst, args, l, t_acc, hf, row, lane, sA + row_off, bar_a, cur, alpha, hd);
-        else if (l == 8) drain_layer<BF16, 2, DBG>(cst, args, l, t_acc, hf, row, lane, sA + row_off, bar_a, cur, alpha, hd);
-        else if (l == 7) drain_layer<BF16, 1, DBG>(cst, args, l, t_acc, hf, row, lane, sA + row_off, bar_a, cur, alpha, hd);
-        else             drain_layer<BF16, 0, DBG>(cst, args, l, t_acc, hf, row, lane, sA + row_off, bar_a, cur, alpha, hd);
+        if (l == 9)      drain_layer<BF16, 3, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, cur, alpha, hd);
+        else if (l == 8) drain_layer<BF16, 2, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, cur, alpha, hd);
+        else if (l == 7) drain_layer<BF16, 1, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, cur, alpha, hd);
+        else             drain_layer<BF16, 0, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, cur, alpha, hd);
+        if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 1);
         // The epilogue warps now idle until the next layer's MMAs finish: use the window to stage operands.
         if (l == 0) {
           // XD <- direction embedding of this tile (the previous tile's view-layer MMAs, its last readers,
           // completed before that tile's final accumulator wait)
           if (hf == 1) {
-            encode_store<BF16, kLdir>(cur.dv, sXD + row_off, row, 4);
+            encode_store<BF16, kLdir, true>(cur.dv, sXD + (uint32_t)(row * 64), row, 4);
             fence_proxy_async();
           }
           __syncwarp();
@@ -509,29 +594,36 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
           load_row<RAYS>(args, (long long)blockIdx.x + (long long)(it + 1) * gridDim.x,
                          it + 1 < ntile_iters ? ntiles : 0, row, nxt);
           if (hf == 0) {
-            encode_store<BF16, kLpos>(nxt.p, sX + row_off, row, 8);
+            encode_store<BF16, kLpos, false>(nxt.p, sX + row_off, row, 8);
             fence_proxy_async();
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_x);
         }
+        if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 2);
       }
       // ---- heads: combine the two column halves, add biases, exp on the uncertainty ----
-      if (hf == 1) {
-        float* pr = partial + row * 8;
+      if (hf != 0) {
+        float* pr = partial + (row * (kColSplit - 1) + hf - 1) * 5;
         pr[0] = hd[0]; pr[1] = hd[1]; pr[2] = hd[2]; pr[3] = alpha; pr[4] = hd[3];
       }
       epi_bar_sync();
       if (hf == 0 && cur.valid) {
-        const float* pr = partial + row * 8;
+        float t[5] = {hd[0], hd[1], hd[2], alpha, hd[3]};
+#pragma unroll
+        for (int k = 0; k < kColSplit - 1; ++k) {
+          const float* pr = partial + (row * (kColSplit - 1) + k) * 5;
+#pragma unroll
+          for (int e = 0; e < 5; ++e) t[e] += pr[e];
+        }
         float* o = args.out + cur.m * 5;
-        o[0] = hd[0] + pr[0] + cst.head_b[1];
-        o[1] = hd[1] + pr[1] + cst.head_b[2];
-        o[2] = hd[2] + pr[2] + cst.head_b[3];
-        o[3] = alpha + pr[3] + cst.head_b[0];
-        o[4] = expf(hd[3] + pr[4] + cst.head_b[4]);   // run_nerf_helpers.py:128-129
+        o[0] = t[0] + cst.head_b[1];
+        o[1] = t[1] + cst.head_b[2];
+        o[2] = t[2] + cst.head_b[3];
+        o[3] = t[3] + cst.head_b[0];
+        o[4] = expf(t[4] + cst.head_b[4]);   // run_nerf_helpers.py:128-129
       }
-      epi_bar_sync();   // partial[] (A block 0) is rewritten by the next tile's layer-0 epilogue
+      epi_bar_sync();   // partial[] (XD) is rewritten in the next tile's layer-0 window
       cur = nxt;
     }
   }
@@ -539,7 +631,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   tc_fence_before();
   __syncthreads();
   if (C > 1) cluster_sync_all();   // peers may still multicast into / commit to this CTA until here
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
@@ -587,12 +679,14 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   a.image = reinterpret_cast<const uint8_t*>(w.image);
   a.dbg = w.dbg;
   a.dbg_layer = w.dbg_layer;
+  a.trace = w.trace;
+  if (const char* e = getenv("EVPP_TC_FLAGS")) a.flags = atoi(e);
   const bool bf = w.dtype == EVPP_PREC_BF16;
   cudaError_t e;
 #define EVPP_TC_DISPATCH(CC, DD)                                                       \
   e = bf ? launch_one<true, RAYS, CC, DD>(*w.consts, a, (int)grid, st)                 \
          : launch_one<false, RAYS, CC, DD>(*w.consts, a, (int)grid, st)
-  if (a.dbg) {
+  if (a.dbg || a.trace) {
     if (RAYS) return -1;
     EVPP_TC_DISPATCH(1, !RAYS);
   } else if (C == 2) { EVPP_TC_DISPATCH(2, false); }

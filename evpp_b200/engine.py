@@ -184,6 +184,19 @@ class Engine:
                                                _ptr(out), _ptr(acts), _stream_ptr(self.device)))
         return out, acts
 
+    def mlp_trace(self, which, pts, dirs, precision="fp16"):
+        """Tensor-core MLP + SM-clock stamps of one tile's pipeline (see evpp_mlp_trace); returns int64 [128]."""
+        which = {"coarse": 0, "fine": 1}.get(which, which)
+        pts = pts.to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        dirs = dirs.to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        out = torch.empty(pts.shape[0], 5, device=self.device)
+        trace = torch.zeros(128, device=self.device, dtype=torch.int64)
+        prec = PRECISIONS[precision] if isinstance(precision, str) else precision
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_mlp_trace(self._h, which, prec, _ptr(pts), _ptr(dirs), pts.shape[0], _ptr(out),
+                                          _ptr(trace), _stream_ptr(self.device)))
+        return trace
+
     def composite(self, raw, z, rays_d):
         """raw2outputs on caller tensors; returns dict(rgb, disp, acc, depth, weights, beta2)."""
         raw = raw.to(self.device, torch.float32).contiguous()

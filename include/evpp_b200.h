@@ -135,6 +135,13 @@ int evpp_mlp_forward(evpp_handle* h, int which_net, int precision, const float* 
 int evpp_mlp_layer_dump(evpp_handle* h, int which_net, int precision, const float* pts, const float* dirs,
                         int64_t M, int layer, float* out, float* acts, void* stream);
 
+/* Diagnostics: runs the tensor-core MLP like evpp_mlp_forward and records SM-clock stamps of the third
+ * tile processed by CTA 0 into trace (device int64[128]): [4l+0..3] = MMA issuer at layer l (layer start,
+ * first K-block issued, last K-block issued, accumulator committed); [40+3l+0..2] = epilogue warp at layer
+ * l (accumulator ready, all chunks stored, staging window done).  Needs M >= 3 * 128 * #SMs rows. */
+int evpp_mlp_trace(evpp_handle* h, int which_net, int precision, const float* pts, const float* dirs,
+                   int64_t M, float* out, int64_t* trace, void* stream);
+
 /* Per-stage dumps of the LAST evpp_render_rays call's final chunk, for parity tests
  * (SURVEY.md appendix B).  `out` is a device buffer of at least *count elements
  * (call with out == NULL to query count).  Stages: */

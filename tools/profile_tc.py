@@ -18,7 +18,11 @@ eng = evpp_b200.Engine(device=0, precision=prec, near=0.5, far=6.0)
 eng.load_weights(0, c)
 eng.load_weights(1, f)
 poses = torch.Tensor(np.asarray(S.views_to_poses(S.hemisphere_views(V, seed=0))))[:, :3, :4].contiguous().cuda()
-for _ in range(2):
+import time
+for i in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     s = eng.score_views(poses, H, W, focal, focal, 0.5 * W, 0.5 * H)
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    print(f"iter {i}: {1e3 * (time.perf_counter() - t0):.2f} ms for {V} views -> {V / (time.perf_counter() - t0):.1f} views/s")
 print("scores", s[:4].cpu().numpy(), "launches", eng.counters())

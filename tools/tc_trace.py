@@ -1,0 +1,33 @@
+"""GPU-box diagnostic: timeline (SM clocks) of one tile through the tcgen05 MLP pipeline."""
+import os
+import sys
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import evpp_b200                      # noqa: E402
+from evpp_b200 import synthetic as S  # noqa: E402
+
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp16"
+torch.manual_seed(0)
+c = S.init_nerf_state_dict()
+eng = evpp_b200.Engine(device=0, precision=prec, near=0.5, far=6.0)
+eng.load_weights(0, c)
+eng.load_weights(1, c)
+M = 148 * 128 * 6
+pts = (torch.rand(M, 3) - 0.5) * 10
+dirs = torch.nn.functional.normalize(torch.randn(M, 3), dim=-1)
+for _ in range(2):
+    t = eng.mlp_trace(0, pts, dirs, precision=prec).cpu().numpy()
+t0 = t[0]
+print("layer | MMA: start  first-issue  last-issue  commit | EPI: acc-ready  stored  window-done   (cycles from the tile's layer-0 start)")
+for l in range(10):
+    m = t[4 * l:4 * l + 4] - t0
+    e = t[40 + 3 * l:40 + 3 * l + 3] - t0
+    print(f"{l:5d} | {m[0]:8d} {m[1]:8d} {m[2]:8d} {m[3]:8d} | {e[0]:8d} {e[1]:8d} {e[2]:8d}")
+print("layer | EPI chunk-0 arrive: warp0  warp15 | MMA: a_ready[0] seen, first issue   (relative to that layer's input accumulator becoming ready)")
+for l in range(1, 10):
+    base = t[40 + 3 * (l - 1)]
+    print(f"{l:5d} | {t[100 + l - 1] - base:8d} {t[110 + l - 1] - base:8d} | {t[80 + l] - base:8d} {t[4 * l + 1] - base:8d}"
+          f" | warp0: first ld done {t[90 + l - 1] - base:6d}, before st {t[116 + l - 1] - base:6d}")
+print("tile total (layer-0 start -> layer-9 stored):", t[40 + 28] - t0)
