@@ -266,7 +266,6 @@ struct TcArgs {
   int dbg_layer;
   int tiles_per_cta;
   long long* trace;  // optional [128] clock64 stamps of CTA 0's third tile (DBG kernels only)
-  int flags;         // EVPP_TC_FLAGS: timing experiments only (1: skip proxy fence, 2: skip bias) -- wrong results
 };
 
 __device__ __forceinline__ long long clk() {
@@ -346,25 +345,17 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
 #pragma unroll
   for (int kb = 0; kb < NCH; ++kb) {
     tmem_ld_wait();
-    if (DBG && kb == 0 && lane == 0 && args.trace && blockIdx.x == 0 && args.trace[127] == 2 && (threadIdx.x >> 5) == 0)
-      args.trace[90 + l] = clk();
     if (kb + 1 < NCH) tmem_ld16(t_acc + (uint32_t)((kb + 1) * 64 + hf * NC), r[(kb + 1) & 1]);
     const int c0 = kb * 64 + hf * NC;
     float2 v[NC / 2];
-    if (args.flags & 2) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias_l + c0);   // shared memory, warp-uniform address
 #pragma unroll
-      for (int j = 0; j < NC / 2; ++j)
-        v[j] = make_float2(__uint_as_float(r[kb & 1][2 * j]), __uint_as_float(r[kb & 1][2 * j + 1]));
-    } else {
-      const float4* b4 = reinterpret_cast<const float4*>(bias_l + c0);   // shared memory, warp-uniform address
-#pragma unroll
-      for (int j = 0; j < NC / 4; ++j) {
-        const float4 b = b4[j];
-        v[2 * j] = add2(make_float2(__uint_as_float(r[kb & 1][4 * j]), __uint_as_float(r[kb & 1][4 * j + 1])),
-                        make_float2(b.x, b.y));
-        v[2 * j + 1] = add2(make_float2(__uint_as_float(r[kb & 1][4 * j + 2]), __uint_as_float(r[kb & 1][4 * j + 3])),
-                            make_float2(b.z, b.w));
-      }
+    for (int j = 0; j < NC / 4; ++j) {
+      const float4 b = b4[j];
+      v[2 * j] = add2(make_float2(__uint_as_float(r[kb & 1][4 * j]), __uint_as_float(r[kb & 1][4 * j + 1])),
+                      make_float2(b.x, b.y));
+      v[2 * j + 1] = add2(make_float2(__uint_as_float(r[kb & 1][4 * j + 2]), __uint_as_float(r[kb & 1][4 * j + 3])),
+                          make_float2(b.z, b.w));
     }
     if (KIND == 1 || KIND == 3 || (DBG && KIND != 2)) {
 #pragma unroll
@@ -408,17 +399,11 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
         pk[j] = pack2<BF16>(v[j].x, v[j].y);
         if (KIND == 0 && !DBG) pk[j] = relu2<BF16>(pk[j]);
       }
-      if (DBG && kb == 0 && lane == 0 && args.trace && blockIdx.x == 0 && args.trace[127] == 2 && (threadIdx.x >> 5) == 0)
-        args.trace[116 + l] = clk();   // 116..125 (overlaps warp-15 slots 116..119 for l<4: print only one)
       tmem_st8(t_acc + (uint32_t)c0, pk);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a + 8 * kb);
-      if (DBG && kb == 0 && lane == 0 && args.trace && blockIdx.x == 0 && args.trace[127] == 2) {
-        if ((threadIdx.x >> 5) == 0) args.trace[100 + l] = clk();
-        if ((threadIdx.x >> 5) == kEpiWarps - 1) args.trace[110 + l] = clk();
-      }
     }
   }
 }
@@ -479,7 +464,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
         const uint8_t* src = args.image;
         for (int l = 0; l < kLayers; ++l) {
           const int nblk = layer_has_x(l) + layer_h_blocks(l);
-          const uint32_t bytes = (args.flags & 16) ? 1024u : (uint32_t)layer_n(l) * 128u;   // 16: timing experiment
+          const uint32_t bytes = (uint32_t)layer_n(l) * 128u;
           for (int b = 0; b < nblk; ++b) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             mbar_expect_tx(bar_full + 8 * stage, bytes);
@@ -490,7 +475,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
               bulk_g2s_mcast(sRing + stage * kStageBytes + cta_rank * part, src + cta_rank * part, part,
                              bar_full + 8 * stage, mc_mask);
             }
-            src += (uint32_t)layer_n(l) * 128u;
+            src += bytes;
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -525,7 +510,6 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
           }
           for (int kb = 0; kb < layer_h_blocks(l); ++kb) {
             mbar_wait(bar_a + 8 * kb, a_phase);
-            if (kb == 0) EVPP_TRACE(80 + l);
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
             if (kb == 0) EVPP_TRACE(l * 4 + 1);
@@ -563,7 +547,6 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_x);
     for (int it = 0; it < ntile_iters; ++it) {
-      if (DBG && args.trace && blockIdx.x == 0 && threadIdx.x == 0) args.trace[127] = it;
       float alpha = 0.f;
       float hd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -680,7 +663,6 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   a.dbg = w.dbg;
   a.dbg_layer = w.dbg_layer;
   a.trace = w.trace;
-  if (const char* e = getenv("EVPP_TC_FLAGS")) a.flags = atoi(e);
   const bool bf = w.dtype == EVPP_PREC_BF16;
   cudaError_t e;
 #define EVPP_TC_DISPATCH(CC, DD)                                                       \

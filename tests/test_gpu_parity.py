@@ -110,9 +110,12 @@ def test_render_fp32_matches_reference_golden(engine_factory, variant):
     np.testing.assert_allclose(out["unc"].cpu().numpy()[rows_ok], g["unc"][rows_ok], rtol=1e-3)
     # composited maps: tight on rays whose 128 importance samples landed in the same bins as the
     # reference's, looser on the few rays where a searchsorted index flipped (a sample moved a bin)
-    np.testing.assert_allclose(out["rgb"].cpu().numpy()[rows_ok], g["rgb"][rows_ok], atol=5e-4)
-    np.testing.assert_allclose(out["acc"].cpu().numpy()[rows_ok], g["acc"][rows_ok], atol=5e-4)
-    np.testing.assert_allclose(out["depth"].cpu().numpy()[rows_ok], g["depth"][rows_ok], rtol=5e-4, atol=5e-4)
+    # ('plain' = un-spread random init: near-zero densities make alpha = 1-exp(-x) ill-conditioned, see
+    # test_sampling_stages_on_reference_tensors)
+    t = 2e-4 if variant == "spread" else 2e-3
+    np.testing.assert_allclose(out["rgb"].cpu().numpy()[rows_ok], g["rgb"][rows_ok], atol=t)
+    np.testing.assert_allclose(out["acc"].cpu().numpy()[rows_ok], g["acc"][rows_ok], atol=t)
+    np.testing.assert_allclose(out["depth"].cpu().numpy()[rows_ok], g["depth"][rows_ok], rtol=t, atol=t)
     np.testing.assert_allclose(out["disp"].cpu().numpy()[rows_ok], g["disp"][rows_ok], rtol=2e-3)
     np.testing.assert_allclose(out["rgb"].cpu().numpy(), g["rgb"], atol=2e-3)
     np.testing.assert_allclose(out["acc"].cpu().numpy(), g["acc"], atol=2e-3)
@@ -132,21 +135,28 @@ def test_sampling_stages_on_reference_tensors(engine_factory, variant):
     eng = engine_factory(variant)
     rd = torch.from_numpy(g["rays_d"])
     r = eng.resample(torch.from_numpy(g["st_raw_coarse"]), torch.from_numpy(g["st_z_coarse"]), rd)
-    # searchsorted indices: bit-exact, except where the reference's own cdf sits within one fp32 ulp of
-    # the query u (its value there depends on the summation order of torch.sum on the host ISA, e.g. the
-    # last query u == 1.0 against cdf[-1] ~ 1.0); those knife-edge entries may differ by one bin.
+    # Conditioning of this stage: alpha = 1 - exp(-relu(sigma)*dist) is evaluated in fp32 as the reference
+    # does (run_nerf.py:358), so for the near-zero densities of the un-spread random init ('plain') a 1-ulp
+    # difference between the GPU's and the host libm's expf moves alpha by ~6e-8 ABSOLUTE = ~1e-3 relative,
+    # and the cdf built from weights+1e-5 by up to ~1e-5.  With realistic densities ('spread') everything
+    # is at rounding level.  torch.sum's summation order (host-ISA dependent) adds 1 ulp on the pdf norm.
+    cdf_tol = 5e-7 if variant == "spread" else 2e-5
+    np.testing.assert_allclose(r["cdf"].cpu().numpy(), g["st_cdf"], rtol=0, atol=cdf_tol)
+    # searchsorted indices: bit-exact, except where the reference's own cdf sits within cdf_tol of the query
+    # u (e.g. the last query u == 1.0 against cdf[-1] ~ 1.0): those knife-edge entries may move by one bin.
     inds, ref_inds = r["inds"].cpu().numpy(), g["st_inds"]
     diff = inds != ref_inds
     assert diff.mean() < 2e-3, diff.mean()
     if diff.any():
         rows, cols = np.nonzero(diff)
         assert (np.abs(inds[rows, cols].astype(np.int64) - ref_inds[rows, cols]) == 1).all()
-        u = np.linspace(0., 1., 128, dtype=np.float32)
+        u = torch.linspace(0., 1., 128).numpy()
         edge = g["st_cdf"][rows, np.minimum(inds[rows, cols], ref_inds[rows, cols])]
-        assert (np.abs(edge - u[cols]) <= 2.5e-7).all()
-    np.testing.assert_allclose(r["cdf"].cpu().numpy(), g["st_cdf"], rtol=0, atol=2.5e-7)
-    np.testing.assert_allclose(r["z_samples"].cpu().numpy(), g["st_z_samples"], rtol=0, atol=2e-5)
-    np.testing.assert_allclose(r["z_fine"].cpu().numpy(), g["st_z_fine"], rtol=0, atol=2e-5)
+        assert (np.abs(edge - u[cols]) <= cdf_tol).all()
+    # a cdf error e moves an inverse-cdf sample by e / pdf-density (<= ~6 m per unit cdf here)
+    z_tol = 2e-5 if variant == "spread" else 2e-4
+    np.testing.assert_allclose(r["z_samples"].cpu().numpy(), g["st_z_samples"], rtol=0, atol=z_tol)
+    np.testing.assert_allclose(r["z_fine"].cpu().numpy(), g["st_z_fine"], rtol=0, atol=z_tol)
     c = eng.composite(torch.from_numpy(g["raw"]), torch.from_numpy(g["st_z_fine"]), rd)
     np.testing.assert_allclose(c["weights"].cpu().numpy(), g["st_weights_fine"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(c["rgb"].cpu().numpy(), g["rgb"], rtol=0, atol=2e-6)

@@ -25,9 +25,4 @@ for l in range(10):
     m = t[4 * l:4 * l + 4] - t0
     e = t[40 + 3 * l:40 + 3 * l + 3] - t0
     print(f"{l:5d} | {m[0]:8d} {m[1]:8d} {m[2]:8d} {m[3]:8d} | {e[0]:8d} {e[1]:8d} {e[2]:8d}")
-print("layer | EPI chunk-0 arrive: warp0  warp15 | MMA: a_ready[0] seen, first issue   (relative to that layer's input accumulator becoming ready)")
-for l in range(1, 10):
-    base = t[40 + 3 * (l - 1)]
-    print(f"{l:5d} | {t[100 + l - 1] - base:8d} {t[110 + l - 1] - base:8d} | {t[80 + l] - base:8d} {t[4 * l + 1] - base:8d}"
-          f" | warp0: first ld done {t[90 + l - 1] - base:6d}, before st {t[116 + l - 1] - base:6d}")
 print("tile total (layer-0 start -> layer-9 stored):", t[40 + 28] - t0)

@@ -49,7 +49,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 
 // PIPE: 0 = loads only, 1 = loads + a concurrent stream of 128x256x16 MMAs into columns 0..255 (loads read 256..511)
 template <int SHAPE, int PIPE>
-__global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long long* cycles, uint32_t* sink, int n_mma) {
+__global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long long* cycles, uint32_t* sink, int n_mma, int mma_mode, int with_st) {
   __shared__ uint32_t tmem_base_s;
   __shared__ uint64_t mma_bar;
   extern __shared__ __align__(1024) uint8_t ops[];   // 16 KB A + 32 KB B (contents irrelevant, zeroed)
@@ -73,11 +73,24 @@ __global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long 
   long long t_mma = 0;
   if (PIPE == 1 && warp == 16) {
     if ((threadIdx.x & 31) == 0) {
-      const uint32_t idesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-      for (int i = 0; i < n_mma; ++i) {
-        const uint64_t ad = make_desc(smem_u32(ops) + (i & 3) * 32), bd = make_desc(smem_u32(ops) + 16384 + (i & 3) * 32);
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                     ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(1));
+      if (mma_mode == 0) {
+        const uint32_t idesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+        for (int i = 0; i < n_mma; ++i) {
+          const uint64_t ad = make_desc(smem_u32(ops) + (i & 3) * 32), bd = make_desc(smem_u32(ops) + 16384 + (i & 3) * 32);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(1));
+        }
+      } else {
+        // TS mode: N = 128 (mode 1) or 256 (mode 2); A = packed columns 256..383, D = columns 0..255
+        const uint32_t n = mma_mode == 1 ? 128u : 256u;
+        const uint32_t idesc = (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+        for (int i = 0; i < n_mma; ++i) {
+          const uint64_t bd = make_desc(smem_u32(ops) + 16384 + (i & 3) * 32);
+          const uint32_t a = tmem + 256 + (i & 7) * 16;
+          const uint32_t d = tmem + (mma_mode == 1 ? ((i >> 3) & 1) * 128 : 0);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                       ::"r"(d), "r"(a), "l"(bd), "r"(idesc), "r"(1));
+        }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar)));
       asm volatile("{\n\t.reg .pred P1;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra D;\n\tbra W;\n\tD:\n\t}"
@@ -86,8 +99,8 @@ __global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long 
       cycles[148 + blockIdx.x] = t_mma;
     }
   }
-  const uint32_t col_base = PIPE == 1 ? 256u : 0u;
-  const uint32_t col_mask = PIPE == 1 ? 255u : 511u;
+  const uint32_t col_base = PIPE == 1 ? (mma_mode ? 384u : 256u) : 0u;
+  const uint32_t col_mask = PIPE == 1 ? (mma_mode ? 127u : 255u) : 511u;
   if (warp < nwarps) {
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int cols_per = SHAPE == 32 ? 32 : (SHAPE == 16 ? 16 : 32);
@@ -97,7 +110,12 @@ __global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long 
         acc ^= do_ld<256>(tmem + lane_base + col);
         acc ^= do_ld<256>(tmem + lane_base + (16u << 16) + col);
       } else {
-        acc ^= do_ld<SHAPE>(tmem + lane_base + col);
+        const uint32_t v = do_ld<SHAPE>(tmem + lane_base + col);
+        acc ^= v;
+        if (with_st) {   // store 8 packed columns back in place, like the MLP epilogue
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(tmem + lane_base + col), "r"(v));
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
       }
     }
   }
@@ -110,7 +128,7 @@ __global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long 
 }
 
 template <int SHAPE, int PIPE>
-void run(int nwarps, const char* name, int iters = 4096) {
+void run(int nwarps, const char* name, int mma_mode = 0, int with_st = 0, int iters = 4096) {
   long long* cyc; uint32_t* sink;
   cudaMalloc(&cyc, 296 * 8); cudaMalloc(&sink, 4);
   cudaMemset(cyc, 0, 296 * 8);
@@ -118,13 +136,13 @@ void run(int nwarps, const char* name, int iters = 4096) {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152);
   const double bytes = (double)iters * nwarps * 32 * (SHAPE == 16 ? 16 : 32) * 4;
   // size the MMA stream to last about as long as the loads would at ~60 B/cycle (128 cycles per MMA)
-  const int n_mma = PIPE ? (int)(bytes / 60.0 / 128.0) : 0;
-  k<<<148, 544, 49152>>>(iters, nwarps, cyc, sink, n_mma);
-  k<<<148, 544, 49152>>>(iters, nwarps, cyc, sink, n_mma);
+  const int n_mma = PIPE ? (int)(bytes / 200.0 / (mma_mode == 1 ? 64.0 : 128.0)) : 0;
+  k<<<148, 544, 49152>>>(iters, nwarps, cyc, sink, n_mma, mma_mode, with_st);
+  k<<<148, 544, 49152>>>(iters, nwarps, cyc, sink, n_mma, mma_mode, with_st);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[296];
   cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
-  printf("%-12s %s warps=%2d  %s  ld cycles=%lld -> %.1f B/cycle/SM", name, PIPE ? "+MMA" : "    ", nwarps, cudaGetErrorString(e), h[0],
+  printf("%-12s %s mode=%d st=%d warps=%2d  %s  ld cycles=%lld -> %.1f B/cycle/SM", name, PIPE ? "+MMA" : "    ", mma_mode, with_st, nwarps, cudaGetErrorString(e), h[0],
          bytes / (double)h[0]);
   if (PIPE) printf("   | %d MMAs in %lld cycles = %.1f cycles/MMA", n_mma, h[148], (double)h[148] / n_mma);
   printf("\n");
@@ -132,9 +150,12 @@ void run(int nwarps, const char* name, int iters = 4096) {
 }
 
 int main() {
-  for (int w : {4, 8, 16}) run<16, 0>(w, "32x32b.x16");
-  for (int w : {4, 8, 16}) run<32, 0>(w, "32x32b.x32");
-  for (int w : {4, 8, 16}) run<16, 1>(w, "32x32b.x16");
-  for (int w : {4, 8, 16}) run<32, 1>(w, "32x32b.x32");
+  run<16, 1>(16, "32x32b.x16", 0, 0);   // SS N=256 + loads
+  run<16, 1>(16, "32x32b.x16", 2, 0);   // TS N=256 + loads
+  run<16, 1>(16, "32x32b.x16", 2, 1);   // TS N=256 + loads + stores
+  run<16, 1>(16, "32x32b.x16", 1, 0);   // TS N=128 + loads
+  run<16, 1>(16, "32x32b.x16", 1, 1);   // TS N=128 + loads + stores
+  run<16, 1>(4, "32x32b.x16", 1, 1);
+  run<16, 1>(1, "32x32b.x16", 1, 1);
   return 0;
 }
