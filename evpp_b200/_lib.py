@@ -48,6 +48,10 @@ SIGNATURES = {
     "evpp_composite": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "evpp_resample": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "evpp_select_nbv": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "evpp_tsdf_set_volume": (_I, [_P, _P, _P, _P, _P, _F, _P, _P, _F, _F, _F, _F]),
+    "evpp_tsdf_render_rays": (_I, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
+    "evpp_tsdf_score_views": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P, _P]),
+    "evpp_tsdf_score_views_host": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P, _P]),
     "evpp_get_counters": (_I, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "evpp_set_profiling": (_I, [_P, _I]),
     "evpp_get_mlp_time_ms": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_L), C.POINTER(_L)]),

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "sampling.cuh"
+#include "tsdf.cuh"
 
 using namespace evpp;
 
@@ -84,6 +85,10 @@ struct evpp_handle {
   bool capture = false;
   DevBuf w_c, cdf, inds, zs;
   int last_n = 0;
+  // stage-1 TSDF scorer
+  bool tsdf_ready = false;
+  TsdfVolume tsdf{};
+  DevBuf tsdf_state, tsdf_nray, tsdf_t, tsdf_ro, tsdf_rd, tsdf_u, tsdf_d, tsdf_vu, tsdf_vd;
   // counters / profiling
   int64_t launches = 0, evals = 0;
   bool profiling = false;
@@ -337,7 +342,9 @@ int evpp_destroy(evpp_handle* h) {
     for (auto& b : nw.tc_image) b.release();
   }
   for (DevBuf* b : {&h->t_vals, &h->u_vals, &h->rays_o, &h->rays_d, &h->viewdirs, &h->z_c, &h->raw_c, &h->z_f,
-                    &h->raw_f, &h->beta2, &h->st_c2w, &h->st_pix, &h->st_scores, &h->w_c, &h->cdf, &h->inds, &h->zs})
+                    &h->raw_f, &h->beta2, &h->st_c2w, &h->st_pix, &h->st_scores, &h->w_c, &h->cdf, &h->inds, &h->zs,
+                    &h->tsdf_state, &h->tsdf_nray, &h->tsdf_t, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d,
+                    &h->tsdf_vu, &h->tsdf_vd})
     b->release();
   delete h;
   return 0;
@@ -616,6 +623,112 @@ int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, in
   h->launches += launch_select_nbv(scores, weight, V, dirs_per_location, norm_scores, best_dir, winner_view,
                                    (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage-1 TSDF occupancy ray-cast scorer (plannerServer_*/core/tsdf_gpu.py)
+// ---------------------------------------------------------------------------------------------------
+int evpp_tsdf_set_volume(evpp_handle* h, const float* state, const float* nray, const int32_t* dims,
+                         const float* origin, float voxel_size, const float* aabb_min, const float* aabb_max,
+                         float near_plane, float far_plane, float c_unknown, float c_surface) {
+  if (!h || !state || !nray || !dims || !origin || !aabb_min || !aabb_max) return fail(EVPP_ERR_INVALID, "null argument");
+  if (dims[0] < 2 || dims[1] < 2 || dims[2] < 2) return fail(EVPP_ERR_INVALID, "volume dims must be >= 2");
+  if (!(voxel_size > 0.f) || !(far_plane > near_plane)) return fail(EVPP_ERR_INVALID, "bad voxel size / bounds");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long n = (long long)dims[0] * dims[1] * dims[2];
+  const int S = (int)(((double)far_plane - (double)near_plane) / (double)voxel_size) + 1;   // tsdf_gpu.py:41
+  if (S < 2 || S > 4096) return fail(EVPP_ERR_INVALID, "sample count %d out of range", S);
+  DevBuf tmp;
+  if (tmp.ensure((size_t)n * 4) || h->tsdf_state.ensure((size_t)n) || h->tsdf_nray.ensure((size_t)n * 4) ||
+      h->tsdf_t.ensure((size_t)S * 4))
+    return fail(EVPP_ERR_CUDA, "TSDF volume allocation failed");
+  CUDA_TRY(cudaMemcpy(tmp.p, state, (size_t)n * 4, cudaMemcpyDefault));
+  CUDA_TRY(cudaMemcpy(h->tsdf_nray.p, nray, (size_t)n * 4, cudaMemcpyDefault));
+  h->launches += launch_tsdf_pack_state(tmp.as<float>(), n, h->tsdf_state.as<uint8_t>(), nullptr);
+  CUDA_TRY(cudaDeviceSynchronize());
+  tmp.release();
+  auto t = torch_linspace(0.f, 1.f, S);
+  CUDA_TRY(cudaMemcpy(h->tsdf_t.p, t.data(), (size_t)S * 4, cudaMemcpyHostToDevice));
+  TsdfVolume& v = h->tsdf;
+  v.state = h->tsdf_state.as<uint8_t>();
+  v.nray = h->tsdf_nray.as<float>();
+  v.t_vals = h->tsdf_t.as<float>();
+  for (int c = 0; c < 3; ++c) { v.dim[c] = dims[c]; v.origin[c] = origin[c]; v.amin[c] = aabb_min[c]; v.amax[c] = aabb_max[c]; }
+  v.voxel = voxel_size;
+  v.near_plane = near_plane;
+  v.far_plane = far_plane;
+  v.n_samples = S;
+  v.c_unknown = c_unknown;
+  v.c_surface = c_surface;
+  h->tsdf_ready = true;
+  return 0;
+}
+
+int evpp_tsdf_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, int64_t N, float* uncer,
+                          float* depth, int32_t* n_unknown, int32_t* first_hit, int32_t* voxel_idx, void* stream) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  if (N == 0) return 0;
+  if (N < 0 || N > 0x7fffffffLL) return fail(EVPP_ERR_INVALID, "bad ray count");
+  if (!rays_o || !rays_d) return fail(EVPP_ERR_INVALID, "null rays");
+  if (!h->tsdf_ready) return fail(EVPP_ERR_STATE, "no TSDF state volume (evpp_tsdf_set_volume)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->launches += launch_tsdf_march(h->tsdf, rays_o, rays_d, (int)N, uncer, depth, n_unknown, first_hit, voxel_idx,
+                                   (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int evpp_tsdf_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx,
+                          float cy, const int32_t* pix_idx, int R, float* view_uncer, float* view_depth,
+                          void* stream) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  if (V == 0) return 0;
+  if (!c2w || !view_uncer || !view_depth) return fail(EVPP_ERR_INVALID, "null argument");
+  if (V < 0 || H <= 0 || W <= 0) return fail(EVPP_ERR_INVALID, "bad V/H/W");
+  if (!h->tsdf_ready) return fail(EVPP_ERR_STATE, "no TSDF state volume (evpp_tsdf_set_volume)");
+  if (!pix_idx) R = H * W;
+  if (R <= 0) return fail(EVPP_ERR_INVALID, "R must be positive when pix_idx is given");
+  const long long N = (long long)V * R;
+  if (N > 0x7fffffffLL) return fail(EVPP_ERR_INVALID, "too many rays for one call");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->tsdf_ro.ensure((size_t)N * 12) || h->tsdf_rd.ensure((size_t)N * 12) || h->tsdf_u.ensure((size_t)N * 4) ||
+      h->tsdf_d.ensure((size_t)N * 4))
+    return fail(EVPP_ERR_CUDA, "TSDF ray workspace allocation failed");
+  h->launches += launch_get_rays(c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, 0, (int)N, h->tsdf_ro.as<float>(),
+                                 h->tsdf_rd.as<float>(), nullptr, st);
+  h->launches += launch_tsdf_march(h->tsdf, h->tsdf_ro.as<float>(), h->tsdf_rd.as<float>(), (int)N, h->tsdf_u.as<float>(),
+                                   h->tsdf_d.as<float>(), nullptr, nullptr, nullptr, st);
+  h->launches += launch_tsdf_view_reduce(h->tsdf_u.as<float>(), h->tsdf_d.as<float>(), V, R, h->tsdf.near_plane,
+                                         h->tsdf.far_plane, view_uncer, view_depth, st);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int evpp_tsdf_score_views_host(evpp_handle* h, const float* c2w_host, int V, int H, int W, float fx, float fy,
+                               float cx, float cy, const int32_t* pix_idx_host, int R, float* view_uncer_host,
+                               float* view_depth_host, void* stream) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  if (V == 0) return 0;
+  if (!c2w_host || !view_uncer_host || !view_depth_host) return fail(EVPP_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->st_c2w.ensure((size_t)V * 48) || h->tsdf_vu.ensure((size_t)V * 4) || h->tsdf_vd.ensure((size_t)V * 4))
+    return fail(EVPP_ERR_CUDA, "staging alloc failed");
+  CUDA_TRY(cudaMemcpyAsync(h->st_c2w.p, c2w_host, (size_t)V * 48, cudaMemcpyHostToDevice, st));
+  const int32_t* pix_dev = nullptr;
+  if (pix_idx_host) {
+    if (h->st_pix.ensure((size_t)V * R * 4)) return fail(EVPP_ERR_CUDA, "staging alloc failed");
+    CUDA_TRY(cudaMemcpyAsync(h->st_pix.p, pix_idx_host, (size_t)V * R * 4, cudaMemcpyHostToDevice, st));
+    pix_dev = h->st_pix.as<int32_t>();
+  }
+  int rc = evpp_tsdf_score_views(h, h->st_c2w.as<float>(), V, H, W, fx, fy, cx, cy, pix_dev, R, h->tsdf_vu.as<float>(),
+                                 h->tsdf_vd.as<float>(), stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(view_uncer_host, h->tsdf_vu.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(view_depth_host, h->tsdf_vd.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
 

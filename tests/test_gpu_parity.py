@@ -345,3 +345,65 @@ def test_full_size_properties(engine_factory, weights):
     with torch.no_grad():
         ref = O.score_views(O.views_to_poses(views[:3]), H, W, K, 0.5, 6.0, c, f).numpy()
     np.testing.assert_allclose(s[:3].cpu().numpy(), ref, rtol=1e-3)
+
+
+# ---------------------------------------------------------------- stage-1 TSDF scorer (a13 / f1) ---
+def _tsdf_with_state(g):
+    import evpp_b200
+    from oracle import tsdf_oracle as T
+    state, nray = T.synthetic_state_volume(g["dims"], seed=int(g["state_seed"]))
+    ts = evpp_b200.TSDF(device=0)
+    assert tuple(ts.index_bnd) == tuple(g["dims"]) and np.array_equal(ts.vol_origin, g["origin"]) and ts.N_samples == 56
+    ts.set_state(state, nray)
+    return ts
+
+
+def test_tsdf_render_rays_bit_exact():
+    """Voxel indices (after the reference's out-of-bounds cascade), unknown counts and first-hit samples are
+    bit-exact; the fp32 per-ray uncertainty and depth are bit-exact too (pure +,-,*,/ arithmetic)."""
+    g = load_golden("tsdf_small.npz")
+    ts = _tsdf_with_state(g)
+    _, depth, uncer, ex = ts.render(400, 400, g["K"], rays=(torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"])),
+                                    stages=True)
+    assert np.array_equal(ex["voxel_idx"].cpu().numpy(), g["voxel_idx"].astype(np.int32))
+    assert np.array_equal(ex["n_unknown"].cpu().numpy(), g["n_unknown"])
+    assert np.array_equal(ex["first_hit"].cpu().numpy(), g["first_hit"])
+    assert np.array_equal(depth.cpu().numpy(), g["depth"])
+    assert np.array_equal(uncer.cpu().numpy(), g["uncer"])
+    # axis-parallel rays: the slab test skips axes with |d| < 1e-6
+    _, d2, u2, _ = ts.render(400, 400, g["K"], rays=(torch.from_numpy(g["rays_o2"]), torch.from_numpy(g["rays_d2"])))
+    assert np.array_equal(d2.cpu().numpy(), g["depth2"]) and np.array_equal(u2.cpu().numpy(), g["uncer2"])
+    # empty ray list
+    _, d0, u0, _ = ts.render(400, 400, g["K"], rays=(torch.zeros(0, 3), torch.zeros(0, 3)))
+    assert d0.numel() == 0 and u0.numel() == 0
+
+
+def test_tsdf_view_scores_and_drop_in():
+    """get_uncertainty_tsdf: per-view mean uncertainty / mean valid depth from poses + pixel subsets, through
+    the host-buffer entry point; rays generated on the GPU must be the reference's rays bit for bit."""
+    g = load_golden("tsdf_small.npz")
+    ts = _tsdf_with_state(g)
+    v = g["views"]
+    u, d = ts.get_uncertainty_tsdf([list(x[0:3]) for x in v], list(v[:, 3]), list(v[:, 4]), pix_idx=g["pix"])
+    np.testing.assert_allclose(u, g["view_uncer"], rtol=1e-6)
+    np.testing.assert_allclose(d, g["view_depth"], rtol=1e-6)
+    # the live protocol draws 500 pixels per view from NumPy's global RNG (tsdf_gpu.py:497)
+    from oracle import tsdf_oracle as T
+    state, nray = T.synthetic_state_volume(g["dims"], seed=int(g["state_seed"]))
+    np.random.seed(7)
+    u1, d1 = ts.get_uncertainty_tsdf([list(x[0:3]) for x in v[:5]], list(v[:5, 3]), list(v[:5, 4]))
+    np.random.seed(7)
+    pix = np.stack([np.random.choice(400 * 400, size=[500], replace=False) for _ in range(5)])
+    ro, rd = O.build_view_rays(O.views_to_poses(v[:5]), 400, 400, g["K"], pix)
+    uo, do = T.render_rays(ro, rd, torch.from_numpy(state), torch.from_numpy(nray), g["origin"])
+    vu, vd = T.view_means(uo, do, 5, 500)
+    np.testing.assert_allclose(u1, vu, rtol=1e-6)
+    np.testing.assert_allclose(d1, vd, rtol=1e-6)
+    with pytest.raises(Exception):
+        evpp_b200_tsdf_without_state()
+
+
+def evpp_b200_tsdf_without_state():
+    import evpp_b200
+    ts = evpp_b200.TSDF(device=0)
+    ts.render(400, 400, None, rays=(torch.zeros(1, 3), torch.ones(1, 3)))   # no state volume -> EvppError
