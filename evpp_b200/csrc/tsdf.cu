@@ -4,7 +4,7 @@
 // The reference runs ~60 ATen launches and 6 host round-trips per 32768-ray chunk; here one thread
 // marches one ray through the 56 samples (the 0.5 MB uint8 state volume is L2/L1 resident) and one CTA
 // reduces one view.  Integer outputs (voxel index, unknown count, first-hit sample) are bit-exact with the
-// reference's fp32 arithmetic, quirks included (see oracle/tsdf_oracle.py for the list).
+// reference's fp32 arithmetic, quirks included (out-of-bounds cascade, first-hit rule, slab test).
 #include "common.cuh"
 #include "tsdf.cuh"
 
