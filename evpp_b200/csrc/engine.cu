@@ -631,13 +631,13 @@ int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, in
 // ---------------------------------------------------------------------------------------------------
 int evpp_tsdf_set_volume(evpp_handle* h, const float* state, const float* nray, const int32_t* dims,
                          const float* origin, float voxel_size, const float* aabb_min, const float* aabb_max,
-                         float near_plane, float far_plane, float c_unknown, float c_surface) {
+                         float near_plane, float far_plane, int32_t n_samples, float c_unknown, float c_surface) {
   if (!h || !state || !nray || !dims || !origin || !aabb_min || !aabb_max) return fail(EVPP_ERR_INVALID, "null argument");
   if (dims[0] < 2 || dims[1] < 2 || dims[2] < 2) return fail(EVPP_ERR_INVALID, "volume dims must be >= 2");
   if (!(voxel_size > 0.f) || !(far_plane > near_plane)) return fail(EVPP_ERR_INVALID, "bad voxel size / bounds");
   CUDA_TRY(cudaSetDevice(h->device));
   const long long n = (long long)dims[0] * dims[1] * dims[2];
-  const int S = (int)(((double)far_plane - (double)near_plane) / (double)voxel_size) + 1;   // tsdf_gpu.py:41
+  const int S = n_samples;   // the caller evaluates int((far-near)/voxel_res)+1 in double like tsdf_gpu.py:41
   if (S < 2 || S > 4096) return fail(EVPP_ERR_INVALID, "sample count %d out of range", S);
   DevBuf tmp;
   if (tmp.ensure((size_t)n * 4) || h->tsdf_state.ensure((size_t)n) || h->tsdf_nray.ensure((size_t)n * 4) ||

@@ -50,7 +50,7 @@ class TSDF:
             check(e.lib.evpp_tsdf_set_volume(e._h, _ptr(st), _ptr(nr), dims.ctypes.data_as(C.c_void_p),
                                              self.vol_origin.ctypes.data_as(C.c_void_p), self.voxel_res,
                                              amin.ctypes.data_as(C.c_void_p), amax.ctypes.data_as(C.c_void_p),
-                                             self.near, self.far, self.unknown_cof, self.surface_cof))
+                                             self.near, self.far, self.N_samples, self.unknown_cof, self.surface_cof))
 
     def render(self, H, W, K, chunk=1024 * 32, rays=None, stages=False):
         """tsdf_gpu.py:356-382.  Returns [rgb_map, depth_map, uncer_map, extras]; rgb_map (the debug colour of

@@ -190,7 +190,8 @@ int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, in
  * evpp_tsdf_set_volume: snapshot of State_vol_origin (float [X,Y,Z]: 0 unknown, 1 empty, 2 occupied) and
  *   Nray_vol (float [X,Y,Z]), host or device memory; dims = tsdf_vol._vol_dim, origin = _vol_origin,
  *   voxel_size = _voxel_size (fusion.py:32-39); aabb_min/max = aabb_bnds columns (tsdf_gpu.py:31);
- *   near/far (tsdf_gpu.py:39); c_unknown / c_surface = 0.2 / 0.1 (Object) or unknown_cof / surface_cof.
+ *   near/far (tsdf_gpu.py:39); n_samples = int((far-near)/voxel_res)+1 evaluated in double by the caller
+ *   (tsdf_gpu.py:41: 56, whereas the fp32 voxel size would give 55); c_unknown / c_surface = 0.2 / 0.1 (Object) or unknown_cof / surface_cof.
  * evpp_tsdf_render_rays: TSDF.render on device rays; any output may be NULL.  uncer/depth [N] float,
  *   n_unknown/first_hit [N] int32 (count of state==0 samples, index of the first state==2 sample, 0 = none),
  *   voxel_idx [N,n_samples,3] int32 (after the reference's out-of-bounds rewrite).
@@ -198,7 +199,7 @@ int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, in
  *   pix_idx [V,R] int32 flat pixel indices (row*W + col) or NULL = all H*W pixels. */
 int evpp_tsdf_set_volume(evpp_handle* h, const float* state, const float* nray, const int32_t* dims,
                          const float* origin, float voxel_size, const float* aabb_min, const float* aabb_max,
-                         float near_plane, float far_plane, float c_unknown, float c_surface);
+                         float near_plane, float far_plane, int32_t n_samples, float c_unknown, float c_surface);
 int evpp_tsdf_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, int64_t N, float* uncer,
                           float* depth, int32_t* n_unknown, int32_t* first_hit, int32_t* voxel_idx, void* stream);
 int evpp_tsdf_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx,
