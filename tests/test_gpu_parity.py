@@ -127,7 +127,7 @@ def test_render_fp32_matches_reference_golden(engine_factory, variant):
     # network outputs only where the engine evaluated the network at the reference's sample position: the
     # 2^9 octave of the encoding turns a 1e-3 shift of z into a phase shift of ~0.5 rad
     same_z = (np.abs(z_f - g["st_z_fine"]) <= 1e-6) & rows_ok[:, None]
-    assert same_z.mean() > (0.9 if variant == "spread" else 0.3)
+    assert same_z.mean() > (0.75 if variant == "spread" else 0.3)
     np.testing.assert_allclose(out["raw"].cpu().numpy()[same_z], g["raw"][same_z], rtol=2e-3, atol=2e-4)
 
 
