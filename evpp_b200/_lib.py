@@ -20,6 +20,17 @@ class EvppRenderOut(C.Structure):
                                           "acc0", "depth0", "unc0", "z_std")]
 
 
+class EvppNgpConfig(C.Structure):
+    _fields_ = [("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3), ("grid_res", C.c_int32),
+                ("near_plane", C.c_float), ("far_plane", C.c_float), ("dt", C.c_float), ("max_steps", C.c_int32),
+                ("max_samples", C.c_int32), ("n_levels", C.c_int32), ("white_bkgd", C.c_int32)]
+
+
+class EvppNgpOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("rgb", "depth", "acc", "beta2", "counts", "t", "raw", "enc")] + \
+               [("sample_capacity", C.c_int64), ("total_so_far", C.c_int64)]
+
+
 class EvppError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"evpp_b200 error {code}: {msg}")
@@ -52,6 +63,14 @@ SIGNATURES = {
     "evpp_tsdf_render_rays": (_I, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "evpp_tsdf_score_views": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P, _P]),
     "evpp_tsdf_score_views_host": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P, _P]),
+    "evpp_ngp_configure": (_I, [_P, C.POINTER(EvppNgpConfig), _P, _P, _P, _P]),
+    "evpp_ngp_set_occupancy": (_I, [_P, _P, _L]),
+    "evpp_ngp_load_params": (_I, [_P, _P, _L, _P, _L]),
+    "evpp_ngp_encode": (_I, [_P, _P, _L, _P, _P, _P]),
+    "evpp_ngp_render_rays": (_I, [_P, _P, _P, _L, C.POINTER(EvppNgpOut), _P]),
+    "evpp_ngp_score_views": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
+    "evpp_ngp_score_views_host": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
+    "evpp_ngp_get_sample_count": (_I, [_P, C.POINTER(_L)]),
     "evpp_get_counters": (_I, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "evpp_set_profiling": (_I, [_P, _I]),
     "evpp_get_mlp_time_ms": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_L), C.POINTER(_L)]),

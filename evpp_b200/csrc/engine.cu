@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "sampling.cuh"
 #include "tsdf.cuh"
+#include "ngp.cuh"
 
 using namespace evpp;
 
@@ -89,6 +90,12 @@ struct evpp_handle {
   bool tsdf_ready = false;
   TsdfVolume tsdf{};
   DevBuf tsdf_state, tsdf_nray, tsdf_t, tsdf_ro, tsdf_rd, tsdf_u, tsdf_d, tsdf_vu, tsdf_vd;
+  // NGP-mode scorer
+  bool ngp_configured = false, ngp_has_occ = false, ngp_has_params = false;
+  NgpParams ngp{};
+  DevBuf ngp_table, ngp_mlp, ngp_bits, ngp_ro, ngp_rd, ngp_counts, ngp_offsets, ngp_total, ngp_t, ngp_ray, ngp_raw,
+      ngp_beta2, ngp_scores;
+  int64_t ngp_samples = 0;       // kept samples since handle creation
   // counters / profiling
   int64_t launches = 0, evals = 0;
   bool profiling = false;
@@ -344,7 +351,9 @@ int evpp_destroy(evpp_handle* h) {
   for (DevBuf* b : {&h->t_vals, &h->u_vals, &h->rays_o, &h->rays_d, &h->viewdirs, &h->z_c, &h->raw_c, &h->z_f,
                     &h->raw_f, &h->beta2, &h->st_c2w, &h->st_pix, &h->st_scores, &h->w_c, &h->cdf, &h->inds, &h->zs,
                     &h->tsdf_state, &h->tsdf_nray, &h->tsdf_t, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d,
-                    &h->tsdf_vu, &h->tsdf_vd})
+                    &h->tsdf_vu, &h->tsdf_vd, &h->ngp_table, &h->ngp_mlp, &h->ngp_bits, &h->ngp_ro, &h->ngp_rd,
+                    &h->ngp_counts, &h->ngp_offsets, &h->ngp_total, &h->ngp_t, &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2,
+                    &h->ngp_scores})
     b->release();
   delete h;
   return 0;
@@ -729,6 +738,189 @@ int evpp_tsdf_score_views_host(evpp_handle* h, const float* c2w_host, int V, int
   CUDA_TRY(cudaMemcpyAsync(view_uncer_host, h->tsdf_vu.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(view_depth_host, h->tsdf_vd.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NGP-mode scorer (north_star subsystems 1, 2, 4; no counterpart in the reference)
+// ---------------------------------------------------------------------------------------------------
+int evpp_ngp_configure(evpp_handle* h, const evpp_ngp_config* cfg, const float* level_scale, const int32_t* level_res,
+                       const int64_t* level_offset, const int64_t* level_size) {
+  if (!h || !cfg || !level_scale || !level_res || !level_offset || !level_size) return fail(EVPP_ERR_INVALID, "null argument");
+  if (cfg->n_levels < 1 || cfg->n_levels > kNgpMaxLevels) return fail(EVPP_ERR_INVALID, "n_levels must be 1..%d", kNgpMaxLevels);
+  if (cfg->n_levels != 16) return fail(EVPP_ERR_INVALID, "the fused field kernel is built for 16 levels x 2 features (32 inputs)");
+  if (cfg->grid_res < 8 || cfg->grid_res > 1024 || (cfg->grid_res & 7)) return fail(EVPP_ERR_INVALID, "grid_res must be a multiple of 8 in [8,1024]");
+  if (!(cfg->dt > 0.f) || !(cfg->far_plane > cfg->near_plane) || cfg->max_steps < 1 || cfg->max_samples < 1)
+    return fail(EVPP_ERR_INVALID, "bad marching parameters");
+  NgpParams& P = h->ngp;
+  P.n_levels = cfg->n_levels;
+  for (int l = 0; l < cfg->n_levels; ++l) {
+    if (level_size[l] <= 0 || level_size[l] > 0x7fffffffLL || level_offset[l] < 0 || level_offset[l] + level_size[l] > 0xffffffffLL)
+      return fail(EVPP_ERR_INVALID, "bad level table entry %d", l);
+    P.levels[l] = NgpLevel{level_scale[l], (uint32_t)level_res[l], (uint32_t)level_offset[l], (uint32_t)level_size[l]};
+  }
+  P.grid_res = cfg->grid_res;
+  for (int c = 0; c < 3; ++c) {
+    if (!(cfg->aabb_max[c] > cfg->aabb_min[c])) return fail(EVPP_ERR_INVALID, "empty scene box");
+    P.amin[c] = cfg->aabb_min[c];
+    P.amax[c] = cfg->aabb_max[c];
+    P.inv_size[c] = 1.f / (cfg->aabb_max[c] - cfg->aabb_min[c]);
+  }
+  P.near_plane = cfg->near_plane; P.far_plane = cfg->far_plane; P.dt = cfg->dt;
+  P.max_steps = cfg->max_steps; P.max_samples = cfg->max_samples; P.white_bkgd = cfg->white_bkgd;
+  h->ngp_configured = true;
+  h->ngp_has_occ = h->ngp_has_params = false;
+  return 0;
+}
+
+int evpp_ngp_set_occupancy(evpp_handle* h, const uint8_t* bitfield, int64_t nbytes) {
+  if (!h || !bitfield) return fail(EVPP_ERR_INVALID, "null argument");
+  if (!h->ngp_configured) return fail(EVPP_ERR_STATE, "evpp_ngp_configure first");
+  const int64_t G = h->ngp.grid_res;
+  if (nbytes != G * G * G / 8) return fail(EVPP_ERR_INVALID, "bitfield must hold grid_res^3 bits (%lld bytes)", (long long)(G * G * G / 8));
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->ngp_bits.ensure((size_t)nbytes)) return fail(EVPP_ERR_CUDA, "bitfield alloc failed");
+  CUDA_TRY(cudaMemcpy(h->ngp_bits.p, bitfield, (size_t)nbytes, cudaMemcpyDefault));
+  h->ngp.bitfield = h->ngp_bits.as<uint8_t>();
+  h->ngp_has_occ = true;
+  return 0;
+}
+
+int evpp_ngp_load_params(evpp_handle* h, const uint16_t* table_fp16, int64_t n_entries, const float* mlp_packed,
+                         int64_t n_mlp_floats) {
+  if (!h || !table_fp16 || !mlp_packed) return fail(EVPP_ERR_INVALID, "null argument");
+  if (!h->ngp_configured) return fail(EVPP_ERR_STATE, "evpp_ngp_configure first");
+  const NgpLevel& last = h->ngp.levels[h->ngp.n_levels - 1];
+  if (n_entries != (int64_t)last.offset + last.size) return fail(EVPP_ERR_INVALID, "table has %lld entries, level table needs %lld", (long long)n_entries, (long long)last.offset + last.size);
+  if (n_mlp_floats != kNgpMlpFloats) return fail(EVPP_ERR_INVALID, "packed MLP must hold %d floats", kNgpMlpFloats);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->ngp_table.ensure((size_t)n_entries * 4) || h->ngp_mlp.ensure((size_t)kNgpMlpFloats * 4))
+    return fail(EVPP_ERR_CUDA, "NGP parameter alloc failed");
+  CUDA_TRY(cudaMemcpy(h->ngp_table.p, table_fp16, (size_t)n_entries * 4, cudaMemcpyDefault));
+  CUDA_TRY(cudaMemcpy(h->ngp_mlp.p, mlp_packed, (size_t)kNgpMlpFloats * 4, cudaMemcpyDefault));
+  h->ngp.table = h->ngp_table.as<uint16_t>();
+  h->ngp.mlp = h->ngp_mlp.as<float>();
+  h->ngp_has_params = true;
+  return 0;
+}
+
+int evpp_ngp_encode(evpp_handle* h, const float* u, int64_t M, float* enc, int32_t* indices, void* stream) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  if (M == 0) return 0;
+  if (!u || M < 0) return fail(EVPP_ERR_INVALID, "bad argument");
+  if (!h->ngp_configured || !h->ngp_has_params) return fail(EVPP_ERR_STATE, "NGP scorer not configured / no parameters");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->launches += launch_ngp_encode(h->ngp, u, M, enc, indices, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// march -> scan -> fill -> field -> composite for rays already on the device; leaves per-ray beta2 in `beta2`
+static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, int n, const evpp_ngp_out* out, long long off,
+                             float* beta2, cudaStream_t st) {
+  if (h->ngp_counts.ensure((size_t)n * 4) || h->ngp_offsets.ensure((size_t)n * 4) || h->ngp_total.ensure(4))
+    return fail(EVPP_ERR_CUDA, "NGP workspace alloc failed");
+  int32_t* counts = out && out->counts ? out->counts + off : h->ngp_counts.as<int32_t>();
+  int32_t* offsets = h->ngp_offsets.as<int32_t>();
+  h->launches += launch_ngp_march_count(h->ngp, ro, rd, n, counts, st);
+  h->launches += launch_ngp_scan(counts, n, offsets, h->ngp_total.as<int32_t>(), st);
+  int32_t total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total, h->ngp_total.p, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const long long M = total;
+  if (h->ngp_t.ensure((size_t)(M + 1) * 4) || h->ngp_ray.ensure((size_t)(M + 1) * 4) || h->ngp_raw.ensure((size_t)(M + 1) * 20))
+    return fail(EVPP_ERR_CUDA, "NGP sample workspace alloc failed (%lld samples)", M);
+  h->launches += launch_ngp_march_fill(h->ngp, ro, rd, n, offsets, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), st);
+  float* enc_dump = out && out->enc && out->sample_capacity >= out->total_so_far + M ? out->enc + out->total_so_far * 32 : nullptr;
+  h->launches += launch_ngp_field(h->ngp, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), M, h->ngp_raw.as<float>(),
+                                  enc_dump, h->num_sms, st);
+  h->launches += launch_ngp_composite(h->ngp, h->ngp_raw.as<float>(), h->ngp_t.as<float>(), counts, offsets, n,
+                                      out && out->rgb ? out->rgb + off * 3 : nullptr, out && out->depth ? out->depth + off : nullptr,
+                                      out && out->acc ? out->acc + off : nullptr, beta2, st);
+  if (out && out->sample_capacity >= out->total_so_far + M) {
+    if (out->t) CUDA_TRY(cudaMemcpyAsync(out->t + out->total_so_far, h->ngp_t.p, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
+    if (out->raw) CUDA_TRY(cudaMemcpyAsync(out->raw + out->total_so_far * 5, h->ngp_raw.p, (size_t)M * 20, cudaMemcpyDeviceToDevice, st));
+  }
+  if (out) const_cast<evpp_ngp_out*>(out)->total_so_far += M;
+  h->ngp_samples += M;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int ngp_ready(evpp_handle* h) {
+  if (!h->ngp_configured || !h->ngp_has_occ || !h->ngp_has_params)
+    return fail(EVPP_ERR_STATE, "NGP scorer needs evpp_ngp_configure, evpp_ngp_set_occupancy and evpp_ngp_load_params");
+  return 0;
+}
+
+int evpp_ngp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, int64_t N, evpp_ngp_out* out, void* stream) {
+  if (!h || !out) return fail(EVPP_ERR_INVALID, "null argument");
+  out->total_so_far = 0;
+  if (N == 0) return 0;
+  if (!rays_o || !rays_d || N < 0) return fail(EVPP_ERR_INVALID, "bad rays");
+  int rc = ngp_ready(h);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int cap = h->cfg.max_chunk_rays;
+  for (int64_t g0 = 0; g0 < N; g0 += cap) {
+    const int n = (int)std::min<int64_t>(cap, N - g0);
+    rc = ngp_render_device(h, rays_o + g0 * 3, rays_d + g0 * 3, n, out, g0, out->beta2 ? out->beta2 + g0 : nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int evpp_ngp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx, float cy,
+                         const int32_t* pix_idx, int R, float* scores, void* stream) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  if (V == 0) return 0;
+  if (!c2w || !scores || V < 0 || H <= 0 || W <= 0) return fail(EVPP_ERR_INVALID, "bad argument");
+  int rc = ngp_ready(h);
+  if (rc) return rc;
+  if (!pix_idx) R = H * W;
+  if (R <= 0) return fail(EVPP_ERR_INVALID, "R must be positive when pix_idx is given");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long N = (long long)V * R;
+  const int cap = (int)std::min<long long>(N, h->cfg.max_chunk_rays);
+  if (h->ngp_ro.ensure((size_t)cap * 12) || h->ngp_rd.ensure((size_t)cap * 12) || h->ngp_beta2.ensure((size_t)N * 4))
+    return fail(EVPP_ERR_CUDA, "NGP ray workspace alloc failed");
+  for (long long g0 = 0; g0 < N; g0 += cap) {
+    const int n = (int)std::min<long long>(cap, N - g0);
+    h->launches += launch_get_rays(c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, g0, n, h->ngp_ro.as<float>(), h->ngp_rd.as<float>(), nullptr, st);
+    rc = ngp_render_device(h, h->ngp_ro.as<float>(), h->ngp_rd.as<float>(), n, nullptr, 0, h->ngp_beta2.as<float>() + g0, st);
+    if (rc) return rc;
+  }
+  h->launches += launch_view_reduce(h->ngp_beta2.as<float>(), V, R, scores, st);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int evpp_ngp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int H, int W, float fx, float fy, float cx,
+                              float cy, const int32_t* pix_idx_host, int R, float* scores_host, void* stream) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  if (V == 0) return 0;
+  if (!c2w_host || !scores_host) return fail(EVPP_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->st_c2w.ensure((size_t)V * 48) || h->ngp_scores.ensure((size_t)V * 4)) return fail(EVPP_ERR_CUDA, "staging alloc failed");
+  CUDA_TRY(cudaMemcpyAsync(h->st_c2w.p, c2w_host, (size_t)V * 48, cudaMemcpyHostToDevice, st));
+  const int32_t* pix_dev = nullptr;
+  if (pix_idx_host) {
+    if (h->st_pix.ensure((size_t)V * R * 4)) return fail(EVPP_ERR_CUDA, "staging alloc failed");
+    CUDA_TRY(cudaMemcpyAsync(h->st_pix.p, pix_idx_host, (size_t)V * R * 4, cudaMemcpyHostToDevice, st));
+    pix_dev = h->st_pix.as<int32_t>();
+  }
+  int rc = evpp_ngp_score_views(h, h->st_c2w.as<float>(), V, H, W, fx, fy, cx, cy, pix_dev, R, h->ngp_scores.as<float>(), stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(scores_host, h->ngp_scores.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int evpp_ngp_get_sample_count(evpp_handle* h, int64_t* samples) {
+  if (!h || !samples) return fail(EVPP_ERR_INVALID, "null argument");
+  *samples = h->ngp_samples;
   return 0;
 }
 

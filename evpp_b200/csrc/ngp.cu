@@ -1,0 +1,367 @@
+// NGP-mode scorer (BASELINE.json north_star subsystems 1, 2 and 4): occupancy-bitfield ray marching with
+// warp-level sample compaction, multiresolution hash-grid encoding, small density / colour / uncertainty
+// MLP, compositing fused with the per-ray sum of beta^2.
+//
+// The reference contains none of this (parity unpinned): arithmetic follows the
+// published torch-ngp / instant-ngp conventions and is mirrored by the CPU restatement used in the tests;
+// the NeurAR parts keep the reference's definitions: beta = exp(linear(h)) (run_nerf_helpers.py:128-129),
+// w = alpha * prod(1 - alpha + 1e-10) (run_nerf.py:376-378), score = sum(beta^2) / rays (nerf.py:307-309).
+//
+// Kernels
+//   ngp_march_kernel<false>  one warp per ray: 32 steps per iteration, occupancy bit test, ballot + popc
+//                            prefix -> per-ray sample count (integer, bit-exact with the restatement)
+//   ngp_scan_kernel          exclusive scan of the counts -> sample offsets
+//   ngp_march_kernel<true>   same walk, writes the kept t values at offset + rank (compaction)
+//   ngp_encode_kernel        hash-grid encoding alone (parity + gather-bandwidth measurement)
+//   ngp_field_kernel         per sample: encode (16 levels x 8 corners, half2 gathers from the L2-resident
+//                            table) + density net + colour net + uncertainty head, weights in shared memory
+//   ngp_composite_kernel     one warp per ray: transmittance by warp scan, rgb / depth / acc and sum(beta^2)
+#include "ngp.cuh"
+
+namespace evpp {
+
+namespace {
+
+__device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t z, const NgpLevel& lv) {
+  // dense index while the running stride fits the level's table, else the instant-ngp spatial hash
+  uint32_t stride = 1u, index = 0u;
+  const uint32_t pg[3] = {x, y, z};
+  int d = 0;
+#pragma unroll
+  for (; d < 3; ++d) {
+    if (stride > lv.size) break;
+    index += pg[d] * stride;
+    stride *= (lv.res + 1u);
+  }
+  if (stride > lv.size) index = (x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u);
+  return index % lv.size;
+}
+
+// Encodes one normalised position; enc[2*l], enc[2*l+1] = trilinear blend of the level's 8 corners.
+template <bool DUMP>
+__device__ __forceinline__ void encode_point(const NgpParams& P, float ux, float uy, float uz, float* enc,
+                                             int32_t* idx_out) {
+  const __half2* __restrict__ table = reinterpret_cast<const __half2*>(P.table);
+#pragma unroll 4
+  for (int l = 0; l < P.n_levels; ++l) {
+    const NgpLevel lv = P.levels[l];
+    const float px = __fadd_rn(__fmul_rn(ux, lv.scale), 0.5f);
+    const float py = __fadd_rn(__fmul_rn(uy, lv.scale), 0.5f);
+    const float pz = __fadd_rn(__fmul_rn(uz, lv.scale), 0.5f);
+    const float gx = floorf(px), gy = floorf(py), gz = floorf(pz);
+    const float wx = __fsub_rn(px, gx), wy = __fsub_rn(py, gy), wz = __fsub_rn(pz, gz);
+    const uint32_t ix = (uint32_t)gx, iy = (uint32_t)gy, iz = (uint32_t)gz;
+    uint32_t idx[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      idx[c] = grid_index(ix + (c & 1), iy + ((c >> 1) & 1), iz + ((c >> 2) & 1), lv) + lv.offset;
+    __half2 f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) f[c] = __ldg(table + idx[c]);    // 8 independent 4-byte gathers in flight
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float w = __fmul_rn(__fmul_rn((c & 1) ? wx : __fsub_rn(1.f, wx), ((c >> 1) & 1) ? wy : __fsub_rn(1.f, wy)),
+                                ((c >> 2) & 1) ? wz : __fsub_rn(1.f, wz));
+      const float2 v = __half22float2(f[c]);
+      a0 = fmaf(w, v.x, a0);
+      a1 = fmaf(w, v.y, a1);
+      if (DUMP) idx_out[l * 8 + c] = (int32_t)idx[c];
+    }
+    enc[2 * l] = a0;
+    enc[2 * l + 1] = a1;
+  }
+}
+
+__global__ void ngp_encode_kernel(NgpParams P, const float* __restrict__ u, long long M, float* __restrict__ enc_out,
+                                  int32_t* __restrict__ idx_out) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float enc[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) enc[k] = 0.f;
+  if (idx_out) encode_point<true>(P, u[m * 3], u[m * 3 + 1], u[m * 3 + 2], enc, idx_out + m * (long long)P.n_levels * 8);
+  else encode_point<false>(P, u[m * 3], u[m * 3 + 1], u[m * 3 + 2], enc, nullptr);
+  if (enc_out) {
+    float4* o = reinterpret_cast<float4*>(enc_out + m * 32);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = make_float4(enc[4 * k], enc[4 * k + 1], enc[4 * k + 2], enc[4 * k + 3]);
+  }
+}
+
+// ---------------------------------------------------------------- marching ------------------------
+struct RaySpan { float t0; int n_steps; };
+
+__device__ __forceinline__ RaySpan ray_span(const NgpParams& P, const float* o, const float* d) {
+  float lo = P.near_plane, hi = P.far_plane;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float inv = __fdiv_rn(1.f, d[c]);
+    const float ta = __fmul_rn(__fsub_rn(P.amin[c], o[c]), inv);
+    const float tb = __fmul_rn(__fsub_rn(P.amax[c], o[c]), inv);
+    lo = fmaxf(lo, fminf(ta, tb));      // fminf / fmaxf drop NaNs (0 * inf on axis-parallel rays)
+    hi = fminf(hi, fmaxf(ta, tb));
+  }
+  RaySpan s;
+  s.t0 = lo;
+  s.n_steps = 0;
+  if (hi > lo) {
+    const int n = (int)ceilf(__fdiv_rn(__fsub_rn(hi, lo), P.dt));
+    s.n_steps = n < P.max_steps ? n : P.max_steps;
+  }
+  return s;
+}
+
+template <bool FILL>
+__global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n,
+                                 int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
+                                 float* __restrict__ t_out, int32_t* __restrict__ ray_of_sample) {
+  const int ray = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ray >= n) return;
+  float o[3], d[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { o[c] = rays_o[(long long)ray * 3 + c]; d[c] = rays_d[(long long)ray * 3 + c]; }
+  const RaySpan sp = ray_span(P, o, d);
+  const long long base_out = FILL ? (long long)offsets[ray] : 0;
+  int count = 0;
+  for (int base = 0; base < sp.n_steps && count < P.max_samples; base += 32) {
+    const int i = base + lane;
+    bool keep = false;
+    float t = 0.f;
+    if (i < sp.n_steps) {
+      t = __fadd_rn(sp.t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
+      int cell[3];
+      bool ok = true;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float p = __fadd_rn(o[c], __fmul_rn(d[c], t));
+        const float u = __fmul_rn(__fsub_rn(p, P.amin[c]), P.inv_size[c]);
+        const float g = floorf(__fmul_rn(u, (float)P.grid_res));
+        ok = ok && g >= 0.f && g < (float)P.grid_res;
+        cell[c] = (int)g;
+      }
+      if (ok) {
+        const long long lin = ((long long)cell[0] * P.grid_res + cell[1]) * P.grid_res + cell[2];
+        keep = (P.bitfield[lin >> 3] >> (lin & 7)) & 1;
+      }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    const int rank = count + __popc(mask & ((1u << lane) - 1u));      // prefix sum over the warp's kept lanes
+    if (FILL && keep && rank < P.max_samples) {
+      t_out[base_out + rank] = t;
+      ray_of_sample[base_out + rank] = ray;
+    }
+    count += __popc(mask);
+  }
+  if (!FILL && lane == 0) counts[ray] = count < P.max_samples ? count : P.max_samples;
+}
+
+// exclusive scan of n <= 1024*1024 counts by ONE block (n is the ray count of a chunk)
+__global__ void ngp_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets,
+                                int32_t* __restrict__ total) {
+  __shared__ int part[1024];
+  const int per = (n + 1023) / 1024;
+  const int b = threadIdx.x * per, e = min(n, b + per);
+  int s = 0;
+  for (int i = b; i < e; ++i) s += counts[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = threadIdx.x == 0 ? 0 : part[threadIdx.x - 1];
+  for (int i = b; i < e; ++i) { offsets[i] = run; run += counts[i]; }
+  if (threadIdx.x == 1023) *total = part[1023];
+}
+
+// ---------------------------------------------------------------- field (encode + MLP) -------------
+__device__ __forceinline__ void sh16(float x, float y, float z, float* o) {
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  o[0] = 0.28209479177387814f;
+  o[1] = -0.48860251190291987f * y; o[2] = 0.48860251190291987f * z; o[3] = -0.48860251190291987f * x;
+  o[4] = 1.0925484305920792f * xy; o[5] = -1.0925484305920792f * yz; o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  o[7] = -1.0925484305920792f * xz; o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2); o[10] = 2.8906114426405538f * xy * z;
+  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2); o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2); o[14] = 1.4453057213202769f * z * (x2 - y2);
+  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+// y[o] = sum_k W[o][k] x[k], W in shared memory (row = K floats, K % 4 == 0); every lane reads the same
+// address (broadcast), so the layer is FFMA-bound
+template <int OUT, int K, bool RELU>
+__device__ __forceinline__ void dense(const float* __restrict__ W, const float* x, float* y) {
+#pragma unroll 4
+  for (int o = 0; o < OUT; ++o) {
+    const float4* w4 = reinterpret_cast<const float4*>(W + o * K);
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < K / 4; ++k) {
+      const float4 w = w4[k];
+      a = fmaf(w.x, x[4 * k], a); a = fmaf(w.y, x[4 * k + 1], a);
+      a = fmaf(w.z, x[4 * k + 2], a); a = fmaf(w.w, x[4 * k + 3], a);
+    }
+    y[o] = RELU ? fmaxf(a, 0.f) : a;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+ngp_field_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                 const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M,
+                 float* __restrict__ raw, float* __restrict__ enc_dump) {
+  extern __shared__ float smem_w[];
+  for (int i = threadIdx.x; i < kNgpMlpFloats; i += blockDim.x) smem_w[i] = P.mlp[i];
+  __syncthreads();
+  const float* W_s0 = smem_w;                    // [64][32]
+  const float* W_s1 = W_s0 + 64 * 32;            // [16][64]
+  const float* W_c0 = W_s1 + 16 * 64;            // [64][32] (31 inputs + zero pad)
+  const float* W_c1 = W_c0 + 64 * 32;            // [64][64]
+  const float* W_hd = W_c1 + 64 * 64;            // [4][64]: r, g, b, uncertainty
+  const float unc_b = W_hd[4 * 64];
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    const int ray = ray_of_sample[m];
+    const float t = t_s[m];
+    float o[3], d[3], u[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[c] = rays_o[(long long)ray * 3 + c];
+      d[c] = rays_d[(long long)ray * 3 + c];
+      u[c] = __fmul_rn(__fsub_rn(__fadd_rn(o[c], __fmul_rn(d[c], t)), P.amin[c]), P.inv_size[c]);
+    }
+    float x[32];
+    encode_point<false>(P, u[0], u[1], u[2], x, nullptr);
+    if (enc_dump) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) enc_dump[m * 32 + k] = x[k];
+    }
+    float h[64], g[16];
+    dense<64, 32, true>(W_s0, x, h);
+    dense<16, 64, false>(W_s1, h, g);
+    const float sigma = expf(fminf(fmaxf(g[0], -15.f), 15.f));      // trunc_exp
+    const float inv_n = rsqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    sh16(d[0] * inv_n, d[1] * inv_n, d[2] * inv_n, x);
+#pragma unroll
+    for (int k = 0; k < 15; ++k) x[16 + k] = g[1 + k];
+    x[31] = 0.f;
+    dense<64, 32, true>(W_c0, x, h);
+    float c2[64];
+    dense<64, 64, true>(W_c1, h, c2);
+    float hd[4];
+    dense<4, 64, false>(W_hd, c2, hd);
+    float* r = raw + m * 5;
+    r[0] = 1.f / (1.f + expf(-hd[0]));
+    r[1] = 1.f / (1.f + expf(-hd[1]));
+    r[2] = 1.f / (1.f + expf(-hd[2]));
+    r[3] = sigma;
+    r[4] = expf(hd[3] + unc_b);                                    // NeurAR head, run_nerf_helpers.py:128-129
+  }
+}
+
+// ---------------------------------------------------------------- compositing ----------------------
+__global__ void ngp_composite_kernel(NgpParams P, const float* __restrict__ raw, const float* __restrict__ t_s,
+                                     const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, int n,
+                                     float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ acc,
+                                     float* __restrict__ beta2) {
+  const int ray = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ray >= n) return;
+  const int cnt = counts[ray];
+  const long long off = offsets[ray];
+  float T = 1.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, dep = 0.f, a = 0.f, b2 = 0.f;
+  for (int base = 0; base < cnt; base += 32) {
+    const int s = base + lane;
+    float alpha = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, tt = 0.f, beta = 0.f;
+    if (s < cnt) {
+      const float* r = raw + (off + s) * 5;
+      r0 = r[0]; r1 = r[1]; r2 = r[2];
+      alpha = 1.f - expf(-r[3] * P.dt);
+      beta = r[4];
+      tt = t_s[off + s];
+    }
+    // exclusive product of (1 - alpha + 1e-10) over the lanes (run_nerf.py:378), carried across chunks in T
+    float f = s < cnt ? (1.f - alpha + 1e-10f) : 1.f;
+    float incl = f;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+      const float v = __shfl_up_sync(0xffffffffu, incl, k);
+      if (lane >= k) incl *= v;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    const float w = alpha * T * excl;
+    c0 = fmaf(w, r0, c0); c1 = fmaf(w, r1, c1); c2 = fmaf(w, r2, c2);
+    dep = fmaf(w, tt, dep);
+    a += w;
+    b2 = fmaf(beta, beta, b2);
+    T *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, k); c1 += __shfl_xor_sync(0xffffffffu, c1, k);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, k); dep += __shfl_xor_sync(0xffffffffu, dep, k);
+    a += __shfl_xor_sync(0xffffffffu, a, k); b2 += __shfl_xor_sync(0xffffffffu, b2, k);
+  }
+  if (lane == 0) {
+    if (P.white_bkgd) { c0 += 1.f - a; c1 += 1.f - a; c2 += 1.f - a; }
+    if (rgb) { rgb[(long long)ray * 3] = c0; rgb[(long long)ray * 3 + 1] = c1; rgb[(long long)ray * 3 + 2] = c2; }
+    if (depth) depth[ray] = dep;
+    if (acc) acc[ray] = a;
+    if (beta2) beta2[ray] = b2;
+  }
+}
+
+}  // namespace
+
+int launch_ngp_encode(const NgpParams& P, const float* u, long long M, float* enc, int32_t* idx, cudaStream_t st) {
+  if (M <= 0) return 0;
+  ngp_encode_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(P, u, M, enc, idx);
+  return 1;
+}
+
+int launch_ngp_march_count(const NgpParams& P, const float* ro, const float* rd, int n, int32_t* counts, cudaStream_t st) {
+  if (n <= 0) return 0;
+  ngp_march_kernel<false><<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, ro, rd, n, counts, nullptr, nullptr, nullptr);
+  return 1;
+}
+
+int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* total, cudaStream_t st) {
+  if (n <= 0) return 0;
+  ngp_scan_kernel<<<1, 1024, 0, st>>>(counts, n, offsets, total);
+  return 1;
+}
+
+int launch_ngp_march_fill(const NgpParams& P, const float* ro, const float* rd, int n, const int32_t* offsets, float* t,
+                          int32_t* ray_of_sample, cudaStream_t st) {
+  if (n <= 0) return 0;
+  ngp_march_kernel<true><<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, ro, rd, n, nullptr, offsets, t, ray_of_sample);
+  return 1;
+}
+
+int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
+                     long long M, float* raw, float* enc_dump, int num_sms, cudaStream_t st) {
+  if (M <= 0) return 0;
+  const int smem = kNgpMlpFloats * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(ngp_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  long long blocks = (M + 127) / 128;
+  const long long cap = (long long)num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  ngp_field_kernel<<<(unsigned)blocks, 128, smem, st>>>(P, ro, rd, t, ray_of_sample, M, raw, enc_dump);
+  return 1;
+}
+
+int launch_ngp_composite(const NgpParams& P, const float* raw, const float* t, const int32_t* counts,
+                         const int32_t* offsets, int n, float* rgb, float* depth, float* acc, float* beta2, cudaStream_t st) {
+  if (n <= 0) return 0;
+  ngp_composite_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, raw, t, counts, offsets, n, rgb, depth, acc, beta2);
+  return 1;
+}
+
+}  // namespace evpp

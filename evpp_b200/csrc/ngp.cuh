@@ -1,0 +1,42 @@
+// NGP-mode scorer: occupancy-bitfield marching, hash-grid encoding, small MLP, compositing (see ngp.cu).
+#pragma once
+#include "common.cuh"
+
+namespace evpp {
+
+constexpr int kNgpMaxLevels = 16;
+// packed fp32 MLP: sigma0 [64][32], sigma1 [16][64], color0 [64][32] (31 inputs + zero column),
+// color1 [64][64], heads [4][64] (r, g, b, uncertainty), uncertainty bias [1]
+constexpr int kNgpMlpFloats = 64 * 32 + 16 * 64 + 64 * 32 + 64 * 64 + 4 * 64 + 1;
+
+struct NgpLevel {
+  float scale;          // 2^(l*log2(b)) * base - 1
+  uint32_t res;         // ceil(scale) + 1
+  uint32_t offset;      // first entry of the level in the table
+  uint32_t size;        // entries of the level (multiple of 8, <= 2^log2_hashmap)
+};
+
+struct NgpParams {      // device pointers + configuration, passed to kernels by value
+  const uint16_t* table;        // fp16 [entries][2]
+  const float* mlp;             // kNgpMlpFloats
+  const uint8_t* bitfield;      // grid_res^3 / 8 bytes, cell (x*G+y)*G+z -> bit (cell & 7) of byte cell >> 3
+  NgpLevel levels[kNgpMaxLevels];
+  int n_levels;
+  int grid_res;
+  float amin[3], amax[3], inv_size[3];
+  float near_plane, far_plane, dt;
+  int max_steps, max_samples;
+  int white_bkgd;
+};
+
+int launch_ngp_encode(const NgpParams& P, const float* u, long long M, float* enc, int32_t* idx, cudaStream_t st);
+int launch_ngp_march_count(const NgpParams& P, const float* ro, const float* rd, int n, int32_t* counts, cudaStream_t st);
+int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* total, cudaStream_t st);
+int launch_ngp_march_fill(const NgpParams& P, const float* ro, const float* rd, int n, const int32_t* offsets, float* t,
+                          int32_t* ray_of_sample, cudaStream_t st);
+int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
+                     long long M, float* raw, float* enc_dump, int num_sms, cudaStream_t st);
+int launch_ngp_composite(const NgpParams& P, const float* raw, const float* t, const int32_t* counts,
+                         const int32_t* offsets, int n, float* rgb, float* depth, float* acc, float* beta2, cudaStream_t st);
+
+}  // namespace evpp

@@ -209,6 +209,51 @@ int evpp_tsdf_score_views_host(evpp_handle* h, const float* c2w_host, int V, int
                                float cx, float cy, const int32_t* pix_idx_host, int R, float* view_uncer_host,
                                float* view_depth_host, void* stream);
 
+/* ---- NGP-mode scorer: occupancy-bitfield marching + multiresolution hash grid + small MLP ----------
+ * BASELINE.json's north_star mandates these stages; the reference has NO counterpart (its README links
+ * ashawkey/torch-ngp and environment.yml:271 pins tinycudann==1.7, but nothing imports them), so there is
+ * no reference interface to cite: the entry points mirror the reference-parity ones above
+ * (evpp_score_views <-> Controller.get_uncertainty nerf.py:266-309, evpp_render_rays <-> render run_nerf.py:131)
+ * and the NeurAR parts keep the reference's definitions (beta = exp(linear(h)) run_nerf_helpers.py:128-129,
+ * score = sum(beta^2)/rays nerf.py:307-309).  Arithmetic: torch-ngp gridencoder / instant-ngp conventions,
+ * restated in oracle/ngp_oracle.py ("parity unpinned"). */
+typedef struct evpp_ngp_config {
+  float aabb_min[3], aabb_max[3];   /* scene box the occupancy grid and the hash grid span               */
+  int32_t grid_res;                 /* occupancy resolution G (bitfield of G^3 bits, x-major cells)      */
+  float near_plane, far_plane;      /* ray segment clip, like Controller.near / far                      */
+  float dt;                         /* uniform step: t_i = t0 + (i + 0.5) * dt                           */
+  int32_t max_steps, max_samples;   /* steps walked / samples kept per ray at most                       */
+  int32_t n_levels;                 /* hash-grid levels (16; 2 features each)                            */
+  int32_t white_bkgd;
+} evpp_ngp_config;
+
+typedef struct evpp_ngp_out {       /* device pointers, any may be NULL                                  */
+  float* rgb; float* depth; float* acc; float* beta2;   /* per ray [N,3] / [N]                           */
+  int32_t* counts;                  /* kept samples per ray [N] (integer, bit-exact vs the restatement)  */
+  float* t; float* raw; float* enc; /* per kept sample, packed ray after ray: [cap], [cap,5], [cap,32]   */
+  int64_t sample_capacity;          /* capacity of t / raw / enc in samples                              */
+  int64_t total_so_far;             /* out: kept samples of the call                                     */
+} evpp_ngp_out;
+
+/* level tables computed by the caller (torch-ngp gridencoder): scale_l = 2^(l*log2 b)*base - 1,
+ * res_l = ceil(scale_l)+1, size_l = min(2^log2_hashmap, (res_l+1)^3) rounded up to 8, offsets cumulative */
+int evpp_ngp_configure(evpp_handle* h, const evpp_ngp_config* cfg, const float* level_scale, const int32_t* level_res,
+                       const int64_t* level_offset, const int64_t* level_size);
+int evpp_ngp_set_occupancy(evpp_handle* h, const uint8_t* bitfield, int64_t nbytes);
+/* table: fp16 [entries][2]; mlp_packed: fp32 sigma0 [64][32], sigma1 [16][64], color0 [64][32] (31 inputs
+ * + zero column), color1 [64][64], heads [4][64] (r,g,b,uncertainty), uncertainty bias [1] */
+int evpp_ngp_load_params(evpp_handle* h, const uint16_t* table_fp16, int64_t n_entries, const float* mlp_packed,
+                         int64_t n_mlp_floats);
+/* hash-grid encoding alone: u device [M,3] in [0,1] -> enc [M,32] fp32, indices [M,16,8] int32 (optional) */
+int evpp_ngp_encode(evpp_handle* h, const float* u, int64_t M, float* enc, int32_t* indices, void* stream);
+int evpp_ngp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, int64_t N, evpp_ngp_out* out,
+                         void* stream);
+int evpp_ngp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx, float cy,
+                         const int32_t* pix_idx, int R, float* scores, void* stream);
+int evpp_ngp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int H, int W, float fx, float fy, float cx,
+                              float cy, const int32_t* pix_idx_host, int R, float* scores_host, void* stream);
+int evpp_ngp_get_sample_count(evpp_handle* h, int64_t* samples);
+
 /* Counters since handle creation: kernels launched by this library and algorithmic MLP
  * evaluations issued (for bench.py's gpu_launches and roofline accounting). */
 int evpp_get_counters(evpp_handle* h, int64_t* kernel_launches, int64_t* mlp_evals);

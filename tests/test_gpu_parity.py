@@ -411,3 +411,87 @@ def evpp_b200_tsdf_without_state():
     import evpp_b200
     ts = evpp_b200.TSDF(device=0)
     ts.render(400, 400, None, rays=(torch.zeros(1, 3), torch.ones(1, 3)))   # no state volume -> EvppError
+
+
+# ---------------------------------------------------------------- NGP mode (n1-n3, parity unpinned) -
+NGP_CFG = dict(aabb_min=(-5.0, 0.01, -5.0), aabb_max=(5.0, 5.01, 6.0), G=128, near=0.5, far=6.0, dt=0.02,
+               max_steps=1024, max_samples=256)
+
+
+@pytest.fixture(scope="module")
+def ngp_setup():
+    import evpp_b200
+    from oracle import ngp_oracle as N
+    p, levels = N.init_ngp_params(0)
+    p = N.spread_params(p)
+    bits, _ = N.synthetic_occupancy()
+    sc = evpp_b200.NGPScorer(device=0, H=12, W=16, focal=12.0, aabb_min=NGP_CFG["aabb_min"], aabb_max=NGP_CFG["aabb_max"],
+                             grid_res=128, near=0.5, far=6.0, dt=0.02, max_steps=1024, max_samples=256)
+    sc.set_occupancy(bits)
+    sc.load_params(p)
+    return sc, p, levels, bits
+
+
+def test_ngp_hash_grid_indices_bit_exact(ngp_setup):
+    from oracle import ngp_oracle as N
+    sc, p, levels, _ = ngp_setup
+    rng = np.random.RandomState(3)
+    u = rng.rand(3000, 3).astype(np.float32)
+    u[:8] = [[0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0.999999, 0.5, 1e-7], [0.25, 0.75, 1.0]]
+    enc, idx = sc.encode(u, want_indices=True)
+    ref_enc, ref_idx = N.grid_encode(u, p["table"], levels, return_indices=True)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref_idx)       # table indices: dense and hashed levels
+    np.testing.assert_allclose(enc.cpu().numpy(), ref_enc, rtol=2e-5, atol=2e-7)
+
+
+def _ngp_rays():
+    views = O.hemisphere_views(4, seed=1, center=(0., 1., 0.5), rmin=1.5, rmax=2.3)
+    ro, rd = O.build_view_rays(O.views_to_poses(views), 12, 16, O.make_K(12, 16, 12.0))
+    extra_o = torch.tensor([[0., 1., -4.], [0., 1., 0.5], [20., 1., 0.], [0., 1., 0.5]])
+    extra_d = torch.tensor([[0., 0., 1.], [1., 0., 0.], [1., 0., 0.], [0., -1., 0.]])       # axis-parallel, outside, down
+    return views, torch.cat([ro, extra_o]), torch.cat([rd, extra_d])
+
+
+def test_ngp_march_counts_and_samples_bit_exact(ngp_setup):
+    """Occupancy-bitfield marching with warp compaction: per-ray sample counts, offsets and the kept t values are
+    bit-exact against the restatement (same fp32 operation order)."""
+    from oracle import ngp_oracle as N
+    sc, p, levels, bits = ngp_setup
+    _, ro, rd = _ngp_rays()
+    out = sc.render_rays(ro, rd, want_samples=True)
+    counts, ts = N.march(ro.numpy(), rd.numpy(), bits, 128, NGP_CFG["aabb_min"], NGP_CFG["aabb_max"], 0.5, 6.0, 0.02, 1024, 256)
+    assert np.array_equal(out["counts"].cpu().numpy(), counts)
+    assert out["total"] == int(counts.sum()) and counts.sum() > 1000
+    assert np.array_equal(out["t"].cpu().numpy(), np.concatenate(ts))         # compaction order and values
+    # sample cap
+    import evpp_b200
+    small = evpp_b200.NGPScorer(device=0, H=12, W=16, focal=12.0, max_samples=5)
+    small.set_occupancy(bits)
+    small.load_params(p)
+    c5 = small.render_rays(ro, rd)["counts"].cpu().numpy()
+    assert np.array_equal(c5, np.minimum(counts, 5))
+
+
+def test_ngp_render_and_scores_vs_restatement(ngp_setup):
+    from oracle import ngp_oracle as N
+    sc, p, levels, bits = ngp_setup
+    views, ro, rd = _ngp_rays()
+    ref = N.render_rays(ro.numpy(), rd.numpy(), p, levels, bits, NGP_CFG)
+    out = sc.render_rays(ro, rd, want_samples=True)
+    np.testing.assert_allclose(out["raw"].cpu().numpy(), ref["raw"], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), ref["rgb"], atol=2e-5)
+    np.testing.assert_allclose(out["depth"].cpu().numpy(), ref["depth"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["acc"].cpu().numpy(), ref["acc"], atol=2e-5)
+    np.testing.assert_allclose(out["beta2"].cpu().numpy(), ref["beta2"], rtol=2e-4)
+    # per-view scores through the host-buffer scoring entry point (Controller.get_uncertainty contract)
+    s = sc.get_uncertainty(O.views_to_poses(views)).cpu().numpy()
+    sref = ref["beta2"][:4 * 192].reshape(4, 192).sum(-1) / 192
+    np.testing.assert_allclose(s, sref, rtol=2e-4)
+    assert int(np.argmax(s)) == int(np.argmax(sref))
+    # chunking invariance + empty input
+    import evpp_b200
+    chunked = evpp_b200.NGPScorer(device=0, H=12, W=16, focal=12.0, max_chunk_rays=50)
+    chunked.set_occupancy(bits)
+    chunked.load_params(p)
+    assert torch.equal(chunked.get_uncertainty(O.views_to_poses(views)).cpu(), torch.from_numpy(s))
+    assert sc.get_uncertainty(np.zeros((0, 4, 4))).numel() == 0

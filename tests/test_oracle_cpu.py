@@ -162,3 +162,33 @@ def test_tsdf_out_of_bounds_cascade():
                         [0.25, 0.75, 0.25], [0.95, 0.35, 0.25], [0.25, 0.35, 0.25]])
     vi = T.voxel_indices(pts, origin, 0.1, dims).numpy()
     assert vi.tolist() == [[0, 0, 0], [0, 0, 3], [0, 3, 2], [0, 0, 0], [0, 0, 2], [0, 3, 2], [2, 3, 2]]
+
+
+# ---------------------------------------------------------------- NGP mode (parity unpinned) --------
+def test_ngp_oracle_self_consistency():
+    """The NGP restatement has no reference to pin against; these are the invariants
+    of its own definition: dense levels index (x + y*(res+1) + z*(res+1)^2) without collisions, hashed levels
+    stay inside their slice, trilinear weights sum to one, empty / full occupancy give 0 / all steps."""
+    from oracle import ngp_oracle as N
+    levels, total = N.level_table()
+    assert total == sum(l["size"] for l in levels) and levels[-1]["res"] == 2048
+    rng = np.random.RandomState(0)
+    pg = rng.randint(0, 17, size=(500, 3)).astype(np.uint32)
+    lv = levels[0]
+    dense = N.hash_index(pg, lv["res"], lv["size"])
+    assert np.array_equal(dense, (pg[:, 0] + pg[:, 1] * 17 + pg[:, 2] * 17 * 17) % lv["size"])
+    hashed = N.hash_index(rng.randint(0, 2049, size=(500, 3)).astype(np.uint32), levels[-1]["res"], levels[-1]["size"])
+    assert hashed.max() < levels[-1]["size"]
+    table = np.ones((total, 2), np.float16)
+    enc = N.grid_encode(rng.rand(64, 3).astype(np.float32), table, levels)
+    np.testing.assert_allclose(enc, 1.0, atol=1e-6)                       # partition of unity
+    G = 16
+    ro = np.array([[0.5, 0.5, -1.0]], np.float32)
+    rd = np.array([[0.0, 0.0, 1.0]], np.float32)
+    full = np.full(G ** 3 // 8, 255, np.uint8)
+    c, ts = N.march(ro, rd, full, G, (0, 0, 0), (1, 1, 1), 0.1, 10.0, 0.05, 1024, 256)
+    assert c[0] == 20 and abs(ts[0][0] - 1.025) < 1e-6                      # 1 m of box at 5 cm steps, entry at t = 1
+    c, _ = N.march(ro, rd, np.zeros(G ** 3 // 8, np.uint8), G, (0, 0, 0), (1, 1, 1), 0.1, 10.0, 0.05, 1024, 256)
+    assert c[0] == 0
+    c, _ = N.march(ro, rd, full, G, (0, 0, 0), (1, 1, 1), 0.1, 10.0, 0.05, 1024, 7)
+    assert c[0] == 7                                                         # per-ray sample cap
