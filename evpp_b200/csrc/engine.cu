@@ -757,7 +757,16 @@ int evpp_ngp_configure(evpp_handle* h, const evpp_ngp_config* cfg, const float* 
   for (int l = 0; l < cfg->n_levels; ++l) {
     if (level_size[l] <= 0 || level_size[l] > 0x7fffffffLL || level_offset[l] < 0 || level_offset[l] + level_size[l] > 0xffffffffLL)
       return fail(EVPP_ERR_INVALID, "bad level table entry %d", l);
-    P.levels[l] = NgpLevel{level_scale[l], (uint32_t)level_res[l], (uint32_t)level_offset[l], (uint32_t)level_size[l]};
+    // torch-ngp's index rule: add dimensions while the running stride fits the table, hash once it does not
+    const uint64_t r1 = (uint64_t)level_res[l] + 1, size = (uint64_t)level_size[l];
+    uint64_t stride = 1;
+    int d = 0;
+    for (; d < 3 && stride <= size; ++d) stride *= r1;
+    const bool hashed = stride > size;
+    if (hashed && (size & (size - 1))) return fail(EVPP_ERR_INVALID, "hashed level %d needs a power-of-two table size", l);
+    if (!hashed && d != 3) return fail(EVPP_ERR_INVALID, "internal: dense level %d", l);
+    P.levels[l] = NgpLevel{level_scale[l], (uint32_t)level_res[l], (uint32_t)level_offset[l], (uint32_t)level_size[l],
+                           hashed ? 1u : 0u, (uint32_t)r1, (uint32_t)(r1 * r1)};
   }
   P.grid_res = cfg->grid_res;
   for (int c = 0; c < 3; ++c) {

@@ -23,18 +23,11 @@ namespace evpp {
 namespace {
 
 __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t z, const NgpLevel& lv) {
-  // dense index while the running stride fits the level's table, else the instant-ngp spatial hash
-  uint32_t stride = 1u, index = 0u;
-  const uint32_t pg[3] = {x, y, z};
-  int d = 0;
-#pragma unroll
-  for (; d < 3; ++d) {
-    if (stride > lv.size) break;
-    index += pg[d] * stride;
-    stride *= (lv.res + 1u);
-  }
-  if (stride > lv.size) index = (x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u);
-  return index % lv.size;
+  // torch-ngp gridencoder rule: dense index x + y*(res+1) + z*(res+1)^2 while the table holds (res+1)^3 entries,
+  // else the instant-ngp spatial hash modulo the (power-of-two) table size.  Dense indices are < size by
+  // construction, so the reference formula's "% size" is the mask below / a no-op.
+  if (lv.hashed) return ((x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u)) & (lv.size - 1u);
+  return x + y * lv.stride_y + z * lv.stride_z;
 }
 
 // Encodes one normalised position; enc[2*l], enc[2*l+1] = trilinear blend of the level's 8 corners.
@@ -42,8 +35,8 @@ template <bool DUMP>
 __device__ __forceinline__ void encode_point(const NgpParams& P, float ux, float uy, float uz, float* enc,
                                              int32_t* idx_out) {
   const __half2* __restrict__ table = reinterpret_cast<const __half2*>(P.table);
-#pragma unroll 4
-  for (int l = 0; l < P.n_levels; ++l) {
+#pragma unroll
+  for (int l = 0; l < kNgpMaxLevels; ++l) {      // n_levels == 16 is enforced at configuration time
     const NgpLevel lv = P.levels[l];
     const float px = __fadd_rn(__fmul_rn(ux, lv.scale), 0.5f);
     const float py = __fadd_rn(__fmul_rn(uy, lv.scale), 0.5f);
@@ -157,25 +150,50 @@ __global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, 
   if (!FILL && lane == 0) counts[ray] = count < P.max_samples ? count : P.max_samples;
 }
 
-// exclusive scan of n <= 1024*1024 counts by ONE block (n is the ray count of a chunk)
+// exclusive scan of the per-ray counts by ONE block: tiles of 4096 counts (coalesced int4 loads), warp-shuffle
+// scans, running carry.  n is the ray count of a chunk (<= 2^20), so a single block is a few microseconds.
 __global__ void ngp_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets,
                                 int32_t* __restrict__ total) {
-  __shared__ int part[1024];
-  const int per = (n + 1023) / 1024;
-  const int b = threadIdx.x * per, e = min(n, b + per);
-  int s = 0;
-  for (int i = b; i < e; ++i) s += counts[i];
-  part[threadIdx.x] = s;
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+  for (int base = 0; base < n; base += 4096) {
+    const int i0 = base + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = i0 + j < n ? counts[i0 + j] : 0;
+    const int mine = v[0] + v[1] + v[2] + v[3];
+    int incl = mine;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, k);
+      if (lane >= k) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
     __syncthreads();
-    part[threadIdx.x] += v;
+    if (warp == 0) {
+      int w = warp_sum[lane];
+#pragma unroll
+      for (int k = 1; k < 32; k <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, k);
+        if (lane >= k) w += t;
+      }
+      warp_sum[lane] = w;     // inclusive over warps
+    }
+    __syncthreads();
+    int run = carry_s + (warp ? warp_sum[warp - 1] : 0) + incl - mine;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j < n) offsets[i0 + j] = run;
+      run += v[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = run;
     __syncthreads();
   }
-  int run = threadIdx.x == 0 ? 0 : part[threadIdx.x - 1];
-  for (int i = b; i < e; ++i) { offsets[i] = run; run += counts[i]; }
-  if (threadIdx.x == 1023) *total = part[1023];
+  if (threadIdx.x == 0) *total = carry_s;
 }
 
 // ---------------------------------------------------------------- field (encode + MLP) -------------
@@ -191,73 +209,138 @@ __device__ __forceinline__ void sh16(float x, float y, float z, float* o) {
   o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
 
-// y[o] = sum_k W[o][k] x[k], W in shared memory (row = K floats, K % 4 == 0); every lane reads the same
-// address (broadcast), so the layer is FFMA-bound
-template <int OUT, int K, bool RELU>
-__device__ __forceinline__ void dense(const float* __restrict__ W, const float* x, float* y) {
-#pragma unroll 4
-  for (int o = 0; o < OUT; ++o) {
-    const float4* w4 = reinterpret_cast<const float4*>(W + o * K);
-    float a = 0.f;
+// One dense layer for TWO samples of a thread: y[o] = sum_k WT[k][o] * x[k].  WT ([K][OUT], shared memory) is
+// read as broadcast float4s, the inputs come from the thread's own shared-memory column (stride kFieldThreads),
+// the 2 x OUT accumulators stay in registers: 2 * OUT FFMA per (OUT/4 + 2) shared loads.
+constexpr int kFieldThreads = 128;
+template <int K, int OUT>
+__device__ __forceinline__ void dense2(const float* __restrict__ WT, const float* x0, const float* x1, float (&y0)[OUT],
+                                       float (&y1)[OUT]) {
 #pragma unroll
-    for (int k = 0; k < K / 4; ++k) {
-      const float4 w = w4[k];
-      a = fmaf(w.x, x[4 * k], a); a = fmaf(w.y, x[4 * k + 1], a);
-      a = fmaf(w.z, x[4 * k + 2], a); a = fmaf(w.w, x[4 * k + 3], a);
+  for (int o = 0; o < OUT; ++o) { y0[o] = 0.f; y1[o] = 0.f; }
+#pragma unroll 2
+  for (int k = 0; k < K; ++k) {
+    const float a0 = x0[k * kFieldThreads], a1 = x1[k * kFieldThreads];
+    const float4* w4 = reinterpret_cast<const float4*>(WT + k * OUT);
+#pragma unroll
+    for (int o = 0; o < OUT / 4; ++o) {
+      const float4 w = w4[o];
+      y0[4 * o] = fmaf(a0, w.x, y0[4 * o]); y0[4 * o + 1] = fmaf(a0, w.y, y0[4 * o + 1]);
+      y0[4 * o + 2] = fmaf(a0, w.z, y0[4 * o + 2]); y0[4 * o + 3] = fmaf(a0, w.w, y0[4 * o + 3]);
+      y1[4 * o] = fmaf(a1, w.x, y1[4 * o]); y1[4 * o + 1] = fmaf(a1, w.y, y1[4 * o + 1]);
+      y1[4 * o + 2] = fmaf(a1, w.z, y1[4 * o + 2]); y1[4 * o + 3] = fmaf(a1, w.w, y1[4 * o + 3]);
     }
-    y[o] = RELU ? fmaxf(a, 0.f) : a;
   }
 }
 
-__global__ void __launch_bounds__(128)
+// shared memory: transposed weights (kNgpMlpFloats) + per-thread activation columns x[2][64][kFieldThreads]
+constexpr int kFieldSmemBytes = (kNgpMlpFloats + 3) / 4 * 16 + 2 * 64 * kFieldThreads * 4;
+
+__global__ void __launch_bounds__(kFieldThreads, 2)
 ngp_field_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                  const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M,
                  float* __restrict__ raw, float* __restrict__ enc_dump) {
-  extern __shared__ float smem_w[];
-  for (int i = threadIdx.x; i < kNgpMlpFloats; i += blockDim.x) smem_w[i] = P.mlp[i];
+  extern __shared__ __align__(16) float smem_w[];
+  float* WT_s0 = smem_w;                     // [32][64]
+  float* WT_s1 = WT_s0 + 32 * 64;            // [64][16]
+  float* WT_c0 = WT_s1 + 64 * 16;            // [32][64] (input 31 is the zero pad)
+  float* WT_c1 = WT_c0 + 32 * 64;            // [64][64]
+  float* WT_hd = WT_c1 + 64 * 64;            // [64][4]: r, g, b, uncertainty
+  float* xs = smem_w + (kNgpMlpFloats + 3) / 4 * 4;
+  {   // transpose the packed [OUT][K] matrices into [K][OUT]
+    const float* g = P.mlp;
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) WT_s0[(i % 32) * 64 + i / 32] = g[i];
+    g += 64 * 32;
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) WT_s1[(i % 64) * 16 + i / 64] = g[i];
+    g += 16 * 64;
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) WT_c0[(i % 32) * 64 + i / 32] = g[i];
+    g += 64 * 32;
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) WT_c1[(i % 64) * 64 + i / 64] = g[i];
+    g += 64 * 64;
+    for (int i = threadIdx.x; i < 4 * 64; i += blockDim.x) WT_hd[(i % 64) * 4 + i / 64] = g[i];
+  }
+  const float unc_b = P.mlp[kNgpMlpFloats - 1];
   __syncthreads();
-  const float* W_s0 = smem_w;                    // [64][32]
-  const float* W_s1 = W_s0 + 64 * 32;            // [16][64]
-  const float* W_c0 = W_s1 + 16 * 64;            // [64][32] (31 inputs + zero pad)
-  const float* W_c1 = W_c0 + 64 * 32;            // [64][64]
-  const float* W_hd = W_c1 + 64 * 64;            // [4][64]: r, g, b, uncertainty
-  const float unc_b = W_hd[4 * 64];
-  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
-    const int ray = ray_of_sample[m];
-    const float t = t_s[m];
-    float o[3], d[3], u[3];
+  float* x0 = xs + threadIdx.x;                               // sample slot 0: x0[k * kFieldThreads]
+  float* x1 = xs + 64 * kFieldThreads + threadIdx.x;          // sample slot 1
+  for (long long base = (long long)blockIdx.x * (2 * kFieldThreads); base < M; base += (long long)gridDim.x * (2 * kFieldThreads)) {
+    float sh[2][16];
+    long long ms[2];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      o[c] = rays_o[(long long)ray * 3 + c];
-      d[c] = rays_d[(long long)ray * 3 + c];
-      u[c] = __fmul_rn(__fsub_rn(__fadd_rn(o[c], __fmul_rn(d[c], t)), P.amin[c]), P.inv_size[c]);
+    for (int j = 0; j < 2; ++j) {
+      const long long m = base + j * kFieldThreads + threadIdx.x;
+      ms[j] = m;
+      float* x = j ? x1 : x0;
+      float enc[32];
+      if (m < M) {
+        const int ray = ray_of_sample[m];
+        const float t = t_s[m];
+        float d[3], u[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          d[c] = rays_d[(long long)ray * 3 + c];
+          u[c] = __fmul_rn(__fsub_rn(__fadd_rn(rays_o[(long long)ray * 3 + c], __fmul_rn(d[c], t)), P.amin[c]), P.inv_size[c]);
+        }
+        encode_point<false>(P, u[0], u[1], u[2], enc, nullptr);
+        const float inv_n = rsqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        sh16(d[0] * inv_n, d[1] * inv_n, d[2] * inv_n, sh[j]);
+        if (enc_dump) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) enc_dump[m * 32 + k] = enc[k];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) enc[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sh[j][k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) x[k * kFieldThreads] = enc[k];
     }
-    float x[32];
-    encode_point<false>(P, u[0], u[1], u[2], x, nullptr);
-    if (enc_dump) {
+    float sigma[2];
+    {
+      float h0[64], h1[64];
+      dense2<32, 64>(WT_s0, x0, x1, h0, h1);                  // density net, layer 0 (+ReLU)
 #pragma unroll
-      for (int k = 0; k < 32; ++k) enc_dump[m * 32 + k] = x[k];
+      for (int k = 0; k < 64; ++k) { x0[k * kFieldThreads] = fmaxf(h0[k], 0.f); x1[k * kFieldThreads] = fmaxf(h1[k], 0.f); }
     }
-    float h[64], g[16];
-    dense<64, 32, true>(W_s0, x, h);
-    dense<16, 64, false>(W_s1, h, g);
-    const float sigma = expf(fminf(fmaxf(g[0], -15.f), 15.f));      // trunc_exp
-    const float inv_n = rsqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    sh16(d[0] * inv_n, d[1] * inv_n, d[2] * inv_n, x);
+    {
+      float g0[16], g1[16];
+      dense2<64, 16>(WT_s1, x0, x1, g0, g1);                  // density net, layer 1: sigma + 15 geometric features
+      sigma[0] = expf(fminf(fmaxf(g0[0], -15.f), 15.f));      // trunc_exp
+      sigma[1] = expf(fminf(fmaxf(g1[0], -15.f), 15.f));
 #pragma unroll
-    for (int k = 0; k < 15; ++k) x[16 + k] = g[1 + k];
-    x[31] = 0.f;
-    dense<64, 32, true>(W_c0, x, h);
-    float c2[64];
-    dense<64, 64, true>(W_c1, h, c2);
-    float hd[4];
-    dense<4, 64, false>(W_hd, c2, hd);
-    float* r = raw + m * 5;
-    r[0] = 1.f / (1.f + expf(-hd[0]));
-    r[1] = 1.f / (1.f + expf(-hd[1]));
-    r[2] = 1.f / (1.f + expf(-hd[2]));
-    r[3] = sigma;
-    r[4] = expf(hd[3] + unc_b);                                    // NeurAR head, run_nerf_helpers.py:128-129
+      for (int k = 0; k < 16; ++k) { x0[k * kFieldThreads] = sh[0][k]; x1[k * kFieldThreads] = sh[1][k]; }
+#pragma unroll
+      for (int k = 0; k < 15; ++k) { x0[(16 + k) * kFieldThreads] = g0[1 + k]; x1[(16 + k) * kFieldThreads] = g1[1 + k]; }
+      x0[31 * kFieldThreads] = 0.f; x1[31 * kFieldThreads] = 0.f;
+    }
+    {
+      float h0[64], h1[64];
+      dense2<32, 64>(WT_c0, x0, x1, h0, h1);                  // colour net, layer 0 (+ReLU)
+#pragma unroll
+      for (int k = 0; k < 64; ++k) { x0[k * kFieldThreads] = fmaxf(h0[k], 0.f); x1[k * kFieldThreads] = fmaxf(h1[k], 0.f); }
+    }
+    {
+      float h0[64], h1[64];
+      dense2<64, 64>(WT_c1, x0, x1, h0, h1);                  // colour net, layer 1 (+ReLU)
+#pragma unroll
+      for (int k = 0; k < 64; ++k) { x0[k * kFieldThreads] = fmaxf(h0[k], 0.f); x1[k * kFieldThreads] = fmaxf(h1[k], 0.f); }
+    }
+    float hd0[4], hd1[4];
+    dense2<64, 4>(WT_hd, x0, x1, hd0, hd1);                   // rgb + uncertainty heads
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (ms[j] < M) {
+        const float* hd = j ? hd1 : hd0;
+        float* r = raw + ms[j] * 5;
+        r[0] = 1.f / (1.f + expf(-hd[0]));
+        r[1] = 1.f / (1.f + expf(-hd[1]));
+        r[2] = 1.f / (1.f + expf(-hd[2]));
+        r[3] = sigma[j];
+        r[4] = expf(hd[3] + unc_b);                            // NeurAR head, run_nerf_helpers.py:128-129
+      }
+    }
   }
 }
 
@@ -344,16 +427,11 @@ int launch_ngp_march_fill(const NgpParams& P, const float* ro, const float* rd, 
 int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
                      long long M, float* raw, float* enc_dump, int num_sms, cudaStream_t st) {
   if (M <= 0) return 0;
-  const int smem = kNgpMlpFloats * 4;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(ngp_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured = true;
-  }
-  long long blocks = (M + 127) / 128;
-  const long long cap = (long long)num_sms * 8;
+  cudaFuncSetAttribute(ngp_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFieldSmemBytes);
+  long long blocks = (M + 2 * kFieldThreads - 1) / (2 * kFieldThreads);
+  const long long cap = (long long)num_sms * 2;      // 2 resident CTAs per SM, grid-stride over the rest
   if (blocks > cap) blocks = cap;
-  ngp_field_kernel<<<(unsigned)blocks, 128, smem, st>>>(P, ro, rd, t, ray_of_sample, M, raw, enc_dump);
+  ngp_field_kernel<<<(unsigned)blocks, kFieldThreads, kFieldSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, raw, enc_dump);
   return 1;
 }
 

@@ -14,6 +14,8 @@ struct NgpLevel {
   uint32_t res;         // ceil(scale) + 1
   uint32_t offset;      // first entry of the level in the table
   uint32_t size;        // entries of the level (multiple of 8, <= 2^log2_hashmap)
+  uint32_t hashed;      // 1: (res+1)^3 exceeds the table -> spatial hash, size is a power of two; 0: dense, index < size
+  uint32_t stride_y, stride_z;   // dense strides (res+1), (res+1)^2
 };
 
 struct NgpParams {      // device pointers + configuration, passed to kernels by value
