@@ -83,3 +83,20 @@ def init_nerf_state_dict(seed=None, D=8, W=256, input_ch=63, input_ch_views=27, 
         sd[name + ".weight"] = l.weight.detach().clone()
         sd[name + ".bias"] = l.bias.detach().clone()
     return sd
+
+
+def room_occupancy_bitfield(G=128, aabb_min=(-5.0, 0.01, -5.0), aabb_max=(5.0, 5.01, 6.0)):
+    """Config 3 occupancy grid: a synthetic room shell (walls, floor and ceiling of a 5 x 2.5 x 5 m box, one voxel
+    thick) plus a 1 m cube, rasterised at G^3 over the scene box.  uint8 bitfield, cell (x*G+y)*G+z -> bit
+    (cell & 7) of byte cell >> 3."""
+    amin, amax = np.asarray(aabb_min, dtype=np.float64), np.asarray(aabb_max, dtype=np.float64)
+    c = (np.arange(G) + 0.5) / G
+    X, Y, Z = np.meshgrid(amin[0] + c * (amax[0] - amin[0]), amin[1] + c * (amax[1] - amin[1]),
+                          amin[2] + c * (amax[2] - amin[2]), indexing="ij")
+    vox = (amax - amin) / G
+    lo, hi = np.array([-2.5, 0.01, -2.0]), np.array([2.5, 2.51, 3.0])
+    inside = (X > lo[0]) & (X < hi[0]) & (Y > lo[1]) & (Y < hi[1]) & (Z > lo[2]) & (Z < hi[2])
+    core = (X > lo[0] + vox[0]) & (X < hi[0] - vox[0]) & (Y > lo[1] + vox[1]) & (Y < hi[1] - vox[1]) & \
+           (Z > lo[2] + vox[2]) & (Z < hi[2] - vox[2])
+    occ = (inside & ~core) | ((np.abs(X) < 0.5) & (Y < 1.0) & (np.abs(Z - 0.5) < 0.5))
+    return np.packbits(occ.reshape(-1), bitorder="little")
