@@ -44,3 +44,39 @@ def replicated_argmax(scores):
     """Highest index among exact ties, like the host tail (planner.select_nbv with 1 dir/location)."""
     s = scores.detach().cpu().numpy().astype(np.float64)
     return int(np.argsort(s, kind="stable")[-1])
+
+
+def render_sharded(render_fn, rays_o, rays_d, rank, world, group=None):
+    """Ray-sharded full-image render (render_path's caller shape, run_nerf.py:199-241): rank r renders the
+    contiguous block of rays ``shard_range(N, r, world)``; the per-ray maps are all-gathered so that every rank
+    holds the full image, and the per-image sum of beta^2 is the sum of the shards' partial sums.
+    render_fn(rays_o_block, rays_d_block) -> dict of per-ray tensors ([n] or [n,k]); returns the same dict for all
+    N rays."""
+    N = rays_o.shape[0]
+    b, e = shard_range(N, rank, world)
+    per = (N + world - 1) // world
+    local = render_fn(rays_o[b:e], rays_d[b:e]) if e > b else None
+    keys = sorted(local.keys()) if local is not None else None
+    if world > 1:
+        holder = [keys]
+        src = 0
+        dist.broadcast_object_list(holder, src=src, group=group)     # rank 0 always owns a non-empty block
+        keys = holder[0]
+    out = {}
+    for k in keys:
+        t = local[k] if local is not None else None
+        if world == 1:
+            out[k] = t
+            continue
+        shape_tail = list(t.shape[1:]) if t is not None else None
+        holder = [shape_tail, str(t.dtype) if t is not None else None]
+        dist.broadcast_object_list(holder, src=0, group=group)
+        shape_tail, dtype = holder[0], getattr(torch, holder[1].split(".")[-1])
+        dev = t.device if t is not None else rays_o.device
+        pad = torch.zeros([per] + shape_tail, dtype=dtype, device=dev)
+        if t is not None:
+            pad[:t.shape[0]] = t
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        out[k] = torch.cat(parts)[:N]
+    return out
