@@ -205,7 +205,7 @@ def run_ngp(args, rank, local_rank, world):
         line = {"metric": "candidate views scored/sec", "value": V_total / (ms_dev / 1e3), "unit": "views/s",
                 "rays_per_s": V_total * H * W / (ms_dev / 1e3), "samples_per_s": samples * world / (ms_dev / 1e3),
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f16 tables, f32 MLP", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16 tables and MLP operands, f32 accumulate", "data": "synthetic",
                 "config": {"workload": f"BASELINE configs[2] Room scene shape, NGP mode (no reference counterpart): {V} views x {W}x{H} rays per "
                                        "GPU, 128^3 occupancy bitfield (room shell + cube), 16-level 2^19 hash grid, dt 0.02 m",
                            "views_per_gpu": V, "rays_per_view": H * W, "samples_per_ray": samples / (V * H * W),
@@ -217,7 +217,7 @@ def run_ngp(args, rank, local_rank, world):
                              "frac": gather_gbs / d.get("hbm_gbs", 6650.0), "traffic": None,
                              "note": "algorithmic hash-grid gather bytes (512 B per kept sample) over the WHOLE step; the 24.5 MB table is "
                                      "L2-resident, so the relevant ceiling is the measured random-gather rate (profiles/r1_microbench.txt), "
-                                     "which the stand-alone encode kernel reaches to 87 %; the fused step is bound by the fp32 FFMA MLP"},
+                                     "which the stand-alone encode kernel reaches to 87 %; the fused step also runs the marching, the MLP (warp-level tensor-core MMA) and the compositing"},
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

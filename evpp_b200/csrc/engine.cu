@@ -842,7 +842,7 @@ static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, i
   h->launches += launch_ngp_march_fill(h->ngp, ro, rd, n, offsets, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), st);
   float* enc_dump = out && out->enc && out->sample_capacity >= out->total_so_far + M ? out->enc + out->total_so_far * 32 : nullptr;
   h->launches += launch_ngp_field(h->ngp, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), M, h->ngp_raw.as<float>(),
-                                  enc_dump, h->num_sms, st);
+                                  enc_dump, h->num_sms, h->cfg.precision != EVPP_PREC_FP32, st);
   h->launches += launch_ngp_composite(h->ngp, h->ngp_raw.as<float>(), h->ngp_t.as<float>(), counts, offsets, n,
                                       out && out->rgb ? out->rgb + off * 3 : nullptr, out && out->depth ? out->depth + off : nullptr,
                                       out && out->acc ? out->acc + off : nullptr, beta2, st);

@@ -14,7 +14,9 @@
 //   ngp_march_kernel<true>   same walk, writes the kept t values at offset + rank (compaction)
 //   ngp_encode_kernel        hash-grid encoding alone (parity + gather-bandwidth measurement)
 //   ngp_field_kernel         per sample: encode (16 levels x 8 corners, half2 gathers from the L2-resident
-//                            table) + density net + colour net + uncertainty head, weights in shared memory
+//                            table) + density net + colour net + uncertainty head, fp32 FFMA (exact mode)
+//   ngp_field_tc_kernel      same on the tensor cores (fp16 operands, fp32 accumulate): one warp per 32 samples,
+//                            the five layers chained through mma.m16n8k16 register fragments
 //   ngp_composite_kernel     one warp per ray: transmittance by warp scan, rgb / depth / acc and sum(beta^2)
 #include "ngp.cuh"
 
@@ -344,6 +346,223 @@ ngp_field_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __r
   }
 }
 
+// ---------------------------------------------------------------- field on the tensor cores ---------
+// Same network, fp16 operands / fp32 accumulation, one warp per 32 samples.  The five layers are chained in
+// REGISTERS: the fp32 accumulator fragments of mma.m16n8k16 (rows g / g+8, columns 2t, 2t+1 of an 8-wide tile)
+// of two neighbouring output tiles are exactly the A-operand fragment of the next layer's 16-wide K step, so
+// after ReLU + pack the activations never leave the register file.  Only the two network inputs (the 32 hash-grid
+// features and the 16 SH coefficients, which each lane computes for its own sample) are transposed into fragment
+// layout through a per-warp shared-memory staging tile.  Weights live in shared memory as fp16 [out][in] rows
+// padded by 8 halves (conflict-free 32-bit fragment loads).
+// (These small GEMMs -- N <= 64, K <= 64 -- cannot fill a 128-row tcgen05 tile without a second staging pass
+// through shared or tensor memory per layer; the warp-level MMA keeps the chain in registers instead.)
+constexpr int kTcWarps = 8;
+constexpr int kLd32 = 40, kLd64 = 72;            // padded row strides (halves) for K = 32 / K = 64 matrices
+constexpr int kTcW_s0 = 0;                       // [64][kLd32]
+constexpr int kTcW_s1 = kTcW_s0 + 64 * kLd32;    // [16][kLd64]
+constexpr int kTcW_c0 = kTcW_s1 + 16 * kLd64;    // [64][kLd32]: k 0..15 = SH, 16 = sigma column (zero), 17..31 = geo
+constexpr int kTcW_c1 = kTcW_c0 + 64 * kLd32;    // [64][kLd64]
+constexpr int kTcW_hd = kTcW_c1 + 64 * kLd64;    // [8][kLd64]: r, g, b, uncertainty, 4 zero rows
+constexpr int kTcW_end = kTcW_hd + 8 * kLd64;
+constexpr int kTcStageHalves = 32 * kLd32 + 32 * 24;                    // per warp: features [32][kLd32] + SH [32][24]
+constexpr int kFieldTcSmemBytes = (kTcW_end + kTcWarps * kTcStageHalves) * 2;
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// acc[mt][nt] (+)= A[mt][ks] * W^T for one layer; W: shared fp16 [N][LDW] (row = output unit)
+template <int KS, int NT, int LDW>
+__device__ __forceinline__ void layer_mma(const __half* __restrict__ W, const uint32_t (&a)[2][KS][4], float (&acc)[2][NT][4],
+                                          int g, int t, int k_off = 0) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const __half* w = W + (nt * 8 + g) * LDW + k_off + ks * 16 + 2 * t;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(w), b1 = *reinterpret_cast<const uint32_t*>(w + 8);
+      mma16816(acc[0][nt], a[0][ks], b0, b1);
+      mma16816(acc[1][nt], a[1][ks], b0, b1);
+    }
+  }
+}
+// accumulator tiles (2j, 2j+1) -> A fragment of K step j of the next layer (optionally through ReLU)
+template <int NT, bool RELU>
+__device__ __forceinline__ void to_operand(const float (&acc)[2][NT][4], uint32_t (&a)[2][NT / 2][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int j = 0; j < NT / 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float* c = acc[mt][2 * j + (q >> 1)];
+        float x = c[(q & 1) * 2], y = c[(q & 1) * 2 + 1];
+        if (RELU) { x = fmaxf(x, 0.f); y = fmaxf(y, 0.f); }
+        a[mt][j][q] = pack_h2(x, y);
+      }
+}
+template <int NT>
+__device__ __forceinline__ void zero_acc(float (&acc)[2][NT][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.f;
+}
+// fragment loads of a staged [32][LD] fp16 tile: rows = samples of the warp, K step ks
+template <int LD>
+__device__ __forceinline__ void load_a(const __half* st, int ks, int g, int t, uint32_t (&a0)[4], uint32_t (&a1)[4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    uint32_t* a = mt ? a1 : a0;
+    const __half* r0 = st + (mt * 16 + g) * LD + ks * 16 + 2 * t;
+    const __half* r1 = r0 + 8 * LD;
+    a[0] = *reinterpret_cast<const uint32_t*>(r0);
+    a[1] = *reinterpret_cast<const uint32_t*>(r1);
+    a[2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+    a[3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+  }
+}
+
+__global__ void __launch_bounds__(32 * kTcWarps, 2)
+ngp_field_tc_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                    const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M,
+                    float* __restrict__ raw, float* __restrict__ enc_dump) {
+  extern __shared__ __align__(16) __half smem_h[];
+  {   // fp32 packed weights -> padded fp16 [out][in]
+    const float* g = P.mlp;
+    for (int i = threadIdx.x; i < kTcW_end; i += blockDim.x) smem_h[i] = __float2half_rn(0.f);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) smem_h[kTcW_s0 + (i / 32) * kLd32 + i % 32] = __float2half_rn(g[i]);
+    g += 64 * 32;
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) smem_h[kTcW_s1 + (i / 64) * kLd64 + i % 64] = __float2half_rn(g[i]);
+    g += 16 * 64;
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+      // packed colour layer 0 columns: 0..15 SH, 16..30 geo, 31 zero  ->  k 0..15 SH, 16 zero (sigma), 17..31 geo
+      const int o = i / 32, k = i % 32;
+      if (k < 16) smem_h[kTcW_c0 + o * kLd32 + k] = __float2half_rn(g[i]);
+      else if (k < 31) smem_h[kTcW_c0 + o * kLd32 + k + 1] = __float2half_rn(g[i]);
+    }
+    g += 64 * 32;
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) smem_h[kTcW_c1 + (i / 64) * kLd64 + i % 64] = __float2half_rn(g[i]);
+    g += 64 * 64;
+    for (int i = threadIdx.x; i < 4 * 64; i += blockDim.x) smem_h[kTcW_hd + (i / 64) * kLd64 + i % 64] = __float2half_rn(g[i]);
+  }
+  const float unc_b = P.mlp[kNgpMlpFloats - 1];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  __half* st_enc = smem_h + kTcW_end + warp * kTcStageHalves;
+  __half* st_sh = st_enc + 32 * kLd32;
+  const long long n_groups = (M + 31) / 32;
+  for (long long grp = (long long)blockIdx.x * kTcWarps + warp; grp < n_groups; grp += (long long)gridDim.x * kTcWarps) {
+    const long long m = grp * 32 + lane;
+    {   // each lane: encoding + SH of its own sample -> staging rows
+      float enc[32], sh[16];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) enc[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) sh[k] = 0.f;
+      if (m < M) {
+        const int ray = ray_of_sample[m];
+        const float tt = t_s[m];
+        float d[3], u[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          d[c] = rays_d[(long long)ray * 3 + c];
+          u[c] = __fmul_rn(__fsub_rn(__fadd_rn(rays_o[(long long)ray * 3 + c], __fmul_rn(d[c], tt)), P.amin[c]), P.inv_size[c]);
+        }
+        encode_point<false>(P, u[0], u[1], u[2], enc, nullptr);
+        const float inv_n = rsqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        sh16(d[0] * inv_n, d[1] * inv_n, d[2] * inv_n, sh);
+        if (enc_dump) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) enc_dump[m * 32 + k] = enc[k];
+        }
+      }
+      __syncwarp();   // previous group's fragment loads are done
+      uint32_t* e32 = reinterpret_cast<uint32_t*>(st_enc + lane * kLd32);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) e32[k] = pack_h2(enc[2 * k], enc[2 * k + 1]);
+      uint32_t* s32 = reinterpret_cast<uint32_t*>(st_sh + lane * 24);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s32[k] = pack_h2(sh[2 * k], sh[2 * k + 1]);
+      __syncwarp();
+    }
+    // ---- density net ----
+    uint32_t aE[2][2][4];
+    load_a<kLd32>(st_enc, 0, g, t, aE[0][0], aE[1][0]);
+    load_a<kLd32>(st_enc, 1, g, t, aE[0][1], aE[1][1]);
+    uint32_t aH[2][4][4];
+    {
+      float acc[2][8][4];
+      zero_acc<8>(acc);
+      layer_mma<2, 8, kLd32>(smem_h + kTcW_s0, aE, acc, g, t);
+      to_operand<8, true>(acc, aH);
+    }
+    uint32_t aX[2][2][4];       // colour-net input: K step 0 = SH, K step 1 = [sigma_raw, geo15]
+    float sig[2][2];
+    {
+      float acc[2][2][4];
+      zero_acc<2>(acc);
+      layer_mma<4, 2, kLd64>(smem_h + kTcW_s1, aH, acc, g, t);
+      uint32_t aG[2][1][4];
+      to_operand<2, false>(acc, aG);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        sig[mt][0] = acc[mt][0][0];      // column 0 of rows g / g+8 lives on the lanes with t == 0
+        sig[mt][1] = acc[mt][0][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) aX[mt][1][q] = aG[mt][0][q];
+      }
+    }
+    load_a<24>(st_sh, 0, g, t, aX[0][0], aX[1][0]);
+    // ---- colour net ----
+    uint32_t aC[2][4][4];
+    {
+      float acc[2][8][4];
+      zero_acc<8>(acc);
+      layer_mma<2, 8, kLd32>(smem_h + kTcW_c0, aX, acc, g, t);
+      to_operand<8, true>(acc, aC);
+    }
+    uint32_t aD[2][4][4];
+    {
+      float acc[2][8][4];
+      zero_acc<8>(acc);
+      layer_mma<4, 8, kLd64>(smem_h + kTcW_c1, aC, acc, g, t);
+      to_operand<8, true>(acc, aD);
+    }
+    float hd[2][1][4];
+    zero_acc<1>(hd);
+    layer_mma<4, 1, kLd64>(smem_h + kTcW_hd, aD, hd, g, t);
+    // ---- outputs: lanes t == 0 hold (r, g) and sigma, lanes t == 1 hold (b, uncertainty) of rows g and g + 8
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const long long row = grp * 32 + mt * 16 + g + hrow * 8;
+        if (row < M) {
+          const float c0 = hd[mt][0][hrow * 2], c1 = hd[mt][0][hrow * 2 + 1];
+          float* r = raw + row * 5;
+          if (t == 0) {
+            r[0] = 1.f / (1.f + expf(-c0));
+            r[1] = 1.f / (1.f + expf(-c1));
+            r[3] = expf(fminf(fmaxf(sig[mt][hrow], -15.f), 15.f));      // trunc_exp
+          } else if (t == 1) {
+            r[2] = 1.f / (1.f + expf(-c0));
+            r[4] = expf(c1 + unc_b);                                     // NeurAR head, run_nerf_helpers.py:128-129
+          }
+        }
+      }
+  }
+}
+
 // ---------------------------------------------------------------- compositing ----------------------
 __global__ void ngp_composite_kernel(NgpParams P, const float* __restrict__ raw, const float* __restrict__ t_s,
                                      const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, int n,
@@ -425,8 +644,16 @@ int launch_ngp_march_fill(const NgpParams& P, const float* ro, const float* rd, 
 }
 
 int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
-                     long long M, float* raw, float* enc_dump, int num_sms, cudaStream_t st) {
+                     long long M, float* raw, float* enc_dump, int num_sms, bool tensor_cores, cudaStream_t st) {
   if (M <= 0) return 0;
+  if (tensor_cores) {
+    cudaFuncSetAttribute(ngp_field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFieldTcSmemBytes);
+    long long blocks = ((M + 31) / 32 + kTcWarps - 1) / kTcWarps;
+    const long long cap = (long long)num_sms * 2;
+    if (blocks > cap) blocks = cap;
+    ngp_field_tc_kernel<<<(unsigned)blocks, 32 * kTcWarps, kFieldTcSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, raw, enc_dump);
+    return 1;
+  }
   cudaFuncSetAttribute(ngp_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFieldSmemBytes);
   long long blocks = (M + 2 * kFieldThreads - 1) / (2 * kFieldThreads);
   const long long cap = (long long)num_sms * 2;      // 2 resident CTAs per SM, grid-stride over the rest

@@ -37,7 +37,7 @@ int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* tot
 int launch_ngp_march_fill(const NgpParams& P, const float* ro, const float* rd, int n, const int32_t* offsets, float* t,
                           int32_t* ray_of_sample, cudaStream_t st);
 int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
-                     long long M, float* raw, float* enc_dump, int num_sms, cudaStream_t st);
+                     long long M, float* raw, float* enc_dump, int num_sms, bool tensor_cores, cudaStream_t st);
 int launch_ngp_composite(const NgpParams& P, const float* raw, const float* t, const int32_t* counts,
                          const int32_t* offsets, int n, float* rgb, float* depth, float* acc, float* beta2, cudaStream_t st);
 

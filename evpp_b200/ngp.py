@@ -60,8 +60,10 @@ def pack_mlp(p):
 class NGPScorer:
     def __init__(self, engine=None, device=0, H=400, W=400, focal=300.0, aabb_min=(-5.0, 0.01, -5.0),
                  aabb_max=(5.0, 5.01, 6.0), grid_res=128, near=0.5, far=6.0, dt=0.02, max_steps=1024, max_samples=256,
-                 n_levels=16, base_res=16, log2_hashmap=19, desired_res=2048, white_bkgd=True, max_chunk_rays=0):
-        self.engine = engine if engine is not None else Engine(device=device, precision="fp32", near=near, far=far,
+                 n_levels=16, base_res=16, log2_hashmap=19, desired_res=2048, white_bkgd=True, max_chunk_rays=0,
+                 precision="fp16"):
+        """precision: "fp16" = small MLP on the tensor cores (fp16 operands, fp32 accumulate); "fp32" = exact FFMA."""
+        self.engine = engine if engine is not None else Engine(device=device, precision=precision, near=near, far=far,
                                                                max_chunk_rays=max_chunk_rays)
         self.H, self.W, self.focal = H, W, focal
         self.K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])

@@ -418,18 +418,28 @@ NGP_CFG = dict(aabb_min=(-5.0, 0.01, -5.0), aabb_max=(5.0, 5.01, 6.0), G=128, ne
                max_steps=1024, max_samples=256)
 
 
-@pytest.fixture(scope="module")
-def ngp_setup():
+_NGP_CACHE = {}
+
+
+def _ngp_make(precision):
     import evpp_b200
     from oracle import ngp_oracle as N
-    p, levels = N.init_ngp_params(0)
-    p = N.spread_params(p)
-    bits, _ = N.synthetic_occupancy()
-    sc = evpp_b200.NGPScorer(device=0, H=12, W=16, focal=12.0, aabb_min=NGP_CFG["aabb_min"], aabb_max=NGP_CFG["aabb_max"],
-                             grid_res=128, near=0.5, far=6.0, dt=0.02, max_steps=1024, max_samples=256)
-    sc.set_occupancy(bits)
-    sc.load_params(p)
-    return sc, p, levels, bits
+    if "params" not in _NGP_CACHE:
+        p, levels = N.init_ngp_params(0)
+        _NGP_CACHE["params"] = (N.spread_params(p), levels, N.synthetic_occupancy()[0])
+    p, levels, bits = _NGP_CACHE["params"]
+    if precision not in _NGP_CACHE:
+        sc = evpp_b200.NGPScorer(device=0, H=12, W=16, focal=12.0, aabb_min=NGP_CFG["aabb_min"], aabb_max=NGP_CFG["aabb_max"],
+                                 grid_res=128, near=0.5, far=6.0, dt=0.02, max_steps=1024, max_samples=256, precision=precision)
+        sc.set_occupancy(bits)
+        sc.load_params(p)
+        _NGP_CACHE[precision] = sc
+    return _NGP_CACHE[precision], p, levels, bits
+
+
+@pytest.fixture(scope="module")
+def ngp_setup():
+    return _ngp_make("fp32")
 
 
 def test_ngp_hash_grid_indices_bit_exact(ngp_setup):
@@ -472,25 +482,29 @@ def test_ngp_march_counts_and_samples_bit_exact(ngp_setup):
     assert np.array_equal(c5, np.minimum(counts, 5))
 
 
-def test_ngp_render_and_scores_vs_restatement(ngp_setup):
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("fp16", 4e-3)])
+def test_ngp_render_and_scores_vs_restatement(precision, tol):
+    """fp32 = FFMA field kernel; fp16 = tensor-core field kernel (fp16 operands, fp32 accumulate): the marching is
+    shared (integer-exact), network outputs within the 16-bit operand tolerance, per-view scores within 1e-3."""
     from oracle import ngp_oracle as N
-    sc, p, levels, bits = ngp_setup
+    sc, p, levels, bits = _ngp_make(precision)
     views, ro, rd = _ngp_rays()
     ref = N.render_rays(ro.numpy(), rd.numpy(), p, levels, bits, NGP_CFG)
     out = sc.render_rays(ro, rd, want_samples=True)
-    np.testing.assert_allclose(out["raw"].cpu().numpy(), ref["raw"], rtol=2e-4, atol=1e-6)
-    np.testing.assert_allclose(out["rgb"].cpu().numpy(), ref["rgb"], atol=2e-5)
-    np.testing.assert_allclose(out["depth"].cpu().numpy(), ref["depth"], rtol=1e-4, atol=1e-5)
-    np.testing.assert_allclose(out["acc"].cpu().numpy(), ref["acc"], atol=2e-5)
-    np.testing.assert_allclose(out["beta2"].cpu().numpy(), ref["beta2"], rtol=2e-4)
+    assert np.array_equal(out["counts"].cpu().numpy(), ref["counts"])
+    np.testing.assert_allclose(out["raw"].cpu().numpy(), ref["raw"], rtol=tol, atol=tol * 5e-3)
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), ref["rgb"], atol=tol * 0.1)
+    np.testing.assert_allclose(out["depth"].cpu().numpy(), ref["depth"], rtol=tol, atol=tol * 0.05)
+    np.testing.assert_allclose(out["acc"].cpu().numpy(), ref["acc"], atol=tol * 0.1)
+    np.testing.assert_allclose(out["beta2"].cpu().numpy(), ref["beta2"], rtol=tol, atol=tol * 1e-2)
     # per-view scores through the host-buffer scoring entry point (Controller.get_uncertainty contract)
     s = sc.get_uncertainty(O.views_to_poses(views)).cpu().numpy()
     sref = ref["beta2"][:4 * 192].reshape(4, 192).sum(-1) / 192
-    np.testing.assert_allclose(s, sref, rtol=2e-4)
+    np.testing.assert_allclose(s, sref, rtol=min(tol, 1e-3))
     assert int(np.argmax(s)) == int(np.argmax(sref))
     # chunking invariance + empty input
     import evpp_b200
-    chunked = evpp_b200.NGPScorer(device=0, H=12, W=16, focal=12.0, max_chunk_rays=50)
+    chunked = evpp_b200.NGPScorer(device=0, H=12, W=16, focal=12.0, max_chunk_rays=50, precision=precision)
     chunked.set_occupancy(bits)
     chunked.load_params(p)
     assert torch.equal(chunked.get_uncertainty(O.views_to_poses(views)).cpu(), torch.from_numpy(s))
