@@ -149,11 +149,18 @@ def run_ngp(args, rank, local_rank, world):
         dist.barrier()
     dev = torch.device("cuda", local_rank)
     H, W, focal, V = 96, 128, 96.0, 512
-    sc = evpp_b200.NGPScorer(device=local_rank, H=H, W=W, focal=focal)
-    sc.set_occupancy(S.room_occupancy_bitfield(128))
-    p = ngp.init_params(0)
-    p["table"] = (p["table"].astype(np.float32) * 2000).astype(np.float16)
-    sc.load_params(p)
+    tensorf = args.mode == "tensorf"
+    if tensorf:      # BASELINE configs[3]: VM-decomposed grids (res 300, 16 + 48 components) instead of the hash grid
+        sc = evpp_b200.TensoRFScorer(device=local_rank, H=H, W=W, focal=focal)
+        sc.set_occupancy(S.room_occupancy_bitfield(128))
+        sc.load_params(ngp.init_tensorf_params(0, R=300))
+    else:
+        sc = evpp_b200.NGPScorer(device=local_rank, H=H, W=W, focal=focal)
+        sc.set_occupancy(S.room_occupancy_bitfield(128))
+        p = ngp.init_params(0)
+        p["table"] = (p["table"].astype(np.float32) * 2000).astype(np.float16)
+        sc.load_params(p)
+    bytes_per_sample = 2304 if tensorf else 512      # 3 x (4 plane + 2 line corners) x 128 B  |  16 levels x 8 corners x 4 B
     views = S.room_views(V, seed=rank)
     poses_host = torch.Tensor(np.asarray(S.views_to_poses(views)))[:, :3, :4].contiguous()
     poses_dev, poses_pinned = poses_host.to(dev), poses_host.pin_memory()
@@ -201,13 +208,15 @@ def run_ngp(args, rank, local_rank, world):
     _, ms_e2e, _, _ = run(step_e2e, max(2, min(args.steps, 3)), 1)
     if rank == 0:
         d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        gather_gbs = samples * 512 / (ms_dev / 1e3) / 1e9
+        gather_gbs = samples * bytes_per_sample / (ms_dev / 1e3) / 1e9
         line = {"metric": "candidate views scored/sec", "value": V_total / (ms_dev / 1e3), "unit": "views/s",
                 "rays_per_s": V_total * H * W / (ms_dev / 1e3), "samples_per_s": samples * world / (ms_dev / 1e3),
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16 tables and MLP operands, f32 accumulate", "data": "synthetic",
-                "config": {"workload": f"BASELINE configs[2] Room scene shape, NGP mode (no reference counterpart): {V} views x {W}x{H} rays per "
-                                       "GPU, 128^3 occupancy bitfield (room shell + cube), 16-level 2^19 hash grid, dt 0.02 m",
+                "config": {"workload": (f"BASELINE configs[3] TensoRF variant of the Room sweep (no reference counterpart): {V} views x {W}x{H} rays "
+                                        "per GPU, 128^3 occupancy bitfield, VM grids res 300 with 16+48 components, dt 0.02 m") if tensorf else
+                                       (f"BASELINE configs[2] Room scene shape, NGP mode (no reference counterpart): {V} views x {W}x{H} rays per "
+                                        "GPU, 128^3 occupancy bitfield (room shell + cube), 16-level 2^19 hash grid, dt 0.02 m"),
                            "views_per_gpu": V, "rays_per_view": H * W, "samples_per_ray": samples / (V * H * W),
                            "l2": "256 MB L2 flush between timed steps"},
                 "e2e": {"value": V_total / (ms_e2e / 1e3), "unit": "views/s", "h2d_bytes_per_step": V * 48, "d2h_bytes_per_step": V * 4,
@@ -215,7 +224,7 @@ def run_ngp(args, rank, local_rank, world):
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": gather_gbs, "peak": d.get("hbm_gbs", 6650.0), "unit": "GB/s",
                              "frac": gather_gbs / d.get("hbm_gbs", 6650.0), "traffic": None,
-                             "note": "algorithmic hash-grid gather bytes (512 B per kept sample) over the WHOLE step; the 24.5 MB table is "
+                             "note": "algorithmic feature-gather bytes (hash grid: 512 B, VM grids: 2304 B per kept sample) over the WHOLE step; the 24.5 MB table is "
                                      "L2-resident, so the relevant ceiling is the measured random-gather rate (profiles/r1_microbench.txt), "
                                      "which the stand-alone encode kernel reaches to 87 %; the fused step also runs the marching, the MLP (warp-level tensor-core MMA) and the compositing"},
                 "clocks": clocks}
@@ -242,7 +251,7 @@ def main():
     ap.add_argument("--impl", default="evpp_b200")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="parity", choices=["parity", "ngp"],
+    ap.add_argument("--mode", default="parity", choices=["parity", "ngp", "tensorf"],
                     help="parity: the reference's scorer (headline, BASELINE configs[1]); ngp: occupancy grid + hash grid "
                          "scorer on the Room sweep shape (BASELINE configs[2]; no reference counterpart)")
     args = ap.parse_args()
@@ -253,7 +262,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if args.mode == "ngp":
+    if args.mode in ("ngp", "tensorf"):
         run_ngp(args, rank, local_rank, world)
         return
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "evpp_ngp_configure": (_I, [_P, C.POINTER(EvppNgpConfig), _P, _P, _P, _P]),
     "evpp_ngp_set_occupancy": (_I, [_P, _P, _L]),
     "evpp_ngp_load_params": (_I, [_P, _P, _L, _P, _L]),
+    "evpp_tensorf_load_params": (_I, [_P, _P, _P, _I, _P, _L]),
     "evpp_ngp_encode": (_I, [_P, _P, _L, _P, _P, _P]),
     "evpp_ngp_render_rays": (_I, [_P, _P, _P, _L, C.POINTER(EvppNgpOut), _P]),
     "evpp_ngp_score_views": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),

@@ -91,7 +91,8 @@ struct evpp_handle {
   TsdfVolume tsdf{};
   DevBuf tsdf_state, tsdf_nray, tsdf_t, tsdf_ro, tsdf_rd, tsdf_u, tsdf_d, tsdf_vu, tsdf_vd;
   // NGP-mode scorer
-  bool ngp_configured = false, ngp_has_occ = false, ngp_has_params = false;
+  bool ngp_configured = false, ngp_has_occ = false, ngp_has_params = false, ngp_tensorf = false;
+  DevBuf tf_planes, tf_lines, tf_mlp;
   NgpParams ngp{};
   DevBuf ngp_table, ngp_mlp, ngp_bits, ngp_ro, ngp_rd, ngp_counts, ngp_offsets, ngp_total, ngp_t, ngp_ray, ngp_raw,
       ngp_beta2, ngp_scores;
@@ -353,7 +354,7 @@ int evpp_destroy(evpp_handle* h) {
                     &h->tsdf_state, &h->tsdf_nray, &h->tsdf_t, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d,
                     &h->tsdf_vu, &h->tsdf_vd, &h->ngp_table, &h->ngp_mlp, &h->ngp_bits, &h->ngp_ro, &h->ngp_rd,
                     &h->ngp_counts, &h->ngp_offsets, &h->ngp_total, &h->ngp_t, &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2,
-                    &h->ngp_scores})
+                    &h->ngp_scores, &h->tf_planes, &h->tf_lines, &h->tf_mlp})
     b->release();
   delete h;
   return 0;
@@ -810,6 +811,29 @@ int evpp_ngp_load_params(evpp_handle* h, const uint16_t* table_fp16, int64_t n_e
   h->ngp.table = h->ngp_table.as<uint16_t>();
   h->ngp.mlp = h->ngp_mlp.as<float>();
   h->ngp_has_params = true;
+  h->ngp_tensorf = false;
+  return 0;
+}
+
+int evpp_tensorf_load_params(evpp_handle* h, const uint16_t* planes_fp16, const uint16_t* lines_fp16, int32_t res,
+                             const float* mlp_packed, int64_t n_mlp_floats) {
+  if (!h || !planes_fp16 || !lines_fp16 || !mlp_packed) return fail(EVPP_ERR_INVALID, "null argument");
+  if (!h->ngp_configured) return fail(EVPP_ERR_STATE, "evpp_ngp_configure first");
+  if (res < 2 || res > 2048) return fail(EVPP_ERR_INVALID, "grid resolution out of range");
+  if (n_mlp_floats != kTfMlpFloats) return fail(EVPP_ERR_INVALID, "packed TensoRF colour network must hold %d floats", kTfMlpFloats);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t pb = (size_t)3 * res * res * 64 * 2, lb = (size_t)3 * res * 64 * 2;
+  if (h->tf_planes.ensure(pb) || h->tf_lines.ensure(lb) || h->tf_mlp.ensure((size_t)kTfMlpFloats * 4))
+    return fail(EVPP_ERR_CUDA, "TensoRF parameter alloc failed");
+  CUDA_TRY(cudaMemcpy(h->tf_planes.p, planes_fp16, pb, cudaMemcpyDefault));
+  CUDA_TRY(cudaMemcpy(h->tf_lines.p, lines_fp16, lb, cudaMemcpyDefault));
+  CUDA_TRY(cudaMemcpy(h->tf_mlp.p, mlp_packed, (size_t)kTfMlpFloats * 4, cudaMemcpyDefault));
+  h->ngp.tf_planes = h->tf_planes.as<uint16_t>();
+  h->ngp.tf_lines = h->tf_lines.as<uint16_t>();
+  h->ngp.tf_mlp = h->tf_mlp.as<float>();
+  h->ngp.tf_res = res;
+  h->ngp_has_params = true;
+  h->ngp_tensorf = true;
   return 0;
 }
 
@@ -817,7 +841,8 @@ int evpp_ngp_encode(evpp_handle* h, const float* u, int64_t M, float* enc, int32
   if (!h) return fail(EVPP_ERR_INVALID, "null handle");
   if (M == 0) return 0;
   if (!u || M < 0) return fail(EVPP_ERR_INVALID, "bad argument");
-  if (!h->ngp_configured || !h->ngp_has_params) return fail(EVPP_ERR_STATE, "NGP scorer not configured / no parameters");
+  if (!h->ngp_configured || !h->ngp_has_params || h->ngp_tensorf)
+    return fail(EVPP_ERR_STATE, "hash-grid encoder not configured / no hash-grid parameters loaded");
   CUDA_TRY(cudaSetDevice(h->device));
   h->launches += launch_ngp_encode(h->ngp, u, M, enc, indices, (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
@@ -825,7 +850,7 @@ int evpp_ngp_encode(evpp_handle* h, const float* u, int64_t M, float* enc, int32
 }
 
 // march -> scan -> fill -> field -> composite for rays already on the device; leaves per-ray beta2 in `beta2`
-static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, int n, const evpp_ngp_out* out, long long off,
+static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, int n, evpp_ngp_out* out, long long off,
                              float* beta2, cudaStream_t st) {
   if (h->ngp_counts.ensure((size_t)n * 4) || h->ngp_offsets.ensure((size_t)n * 4) || h->ngp_total.ensure(4))
     return fail(EVPP_ERR_CUDA, "NGP workspace alloc failed");
@@ -841,8 +866,12 @@ static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, i
     return fail(EVPP_ERR_CUDA, "NGP sample workspace alloc failed (%lld samples)", M);
   h->launches += launch_ngp_march_fill(h->ngp, ro, rd, n, offsets, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), st);
   float* enc_dump = out && out->enc && out->sample_capacity >= out->total_so_far + M ? out->enc + out->total_so_far * 32 : nullptr;
-  h->launches += launch_ngp_field(h->ngp, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), M, h->ngp_raw.as<float>(),
-                                  enc_dump, h->num_sms, h->cfg.precision != EVPP_PREC_FP32, st);
+  if (h->ngp_tensorf)
+    h->launches += launch_tensorf_field(h->ngp, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), M, h->ngp_raw.as<float>(),
+                                        h->num_sms, st);
+  else
+    h->launches += launch_ngp_field(h->ngp, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), M, h->ngp_raw.as<float>(),
+                                    enc_dump, h->num_sms, h->cfg.precision != EVPP_PREC_FP32, st);
   h->launches += launch_ngp_composite(h->ngp, h->ngp_raw.as<float>(), h->ngp_t.as<float>(), counts, offsets, n,
                                       out && out->rgb ? out->rgb + off * 3 : nullptr, out && out->depth ? out->depth + off : nullptr,
                                       out && out->acc ? out->acc + off : nullptr, beta2, st);
@@ -850,7 +879,7 @@ static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, i
     if (out->t) CUDA_TRY(cudaMemcpyAsync(out->t + out->total_so_far, h->ngp_t.p, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
     if (out->raw) CUDA_TRY(cudaMemcpyAsync(out->raw + out->total_so_far * 5, h->ngp_raw.p, (size_t)M * 20, cudaMemcpyDeviceToDevice, st));
   }
-  if (out) const_cast<evpp_ngp_out*>(out)->total_so_far += M;
+  if (out) out->total_so_far += M;
   h->ngp_samples += M;
   CUDA_TRY(cudaGetLastError());
   return 0;

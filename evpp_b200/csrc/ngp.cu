@@ -563,6 +563,190 @@ ngp_field_tc_kernel(NgpParams P, const float* __restrict__ rays_o, const float* 
   }
 }
 
+// ---------------------------------------------------------------- TensoRF VM field ------------------
+// BASELINE configs[3]: the hash grid replaced by vector-matrix decomposed grids (three R x R planes and three
+// R-long lines, 16 density + 48 appearance components fused into 64-channel fp16 texels = one 128-byte line per
+// bilinear corner).  Eight lanes share a sample and read one 16-byte slice of each texel, so every corner is a
+// single coalesced 128-byte access; density = sum of plane x line products, the 144 appearance products go
+// through a per-warp staging tile into the same register-chained warp-MMA colour network as the hash-grid
+// backbone (basis 144 -> 27, [basis, SH16] -> 64 -> 64 -> rgb + NeurAR head).
+constexpr int kTfLdApp = 152;                                    // 144 appearance features + 8 pad (halves)
+constexpr int kTfLdC0 = 56;                                      // 48 inputs + 8 pad
+constexpr int kTfW_bs = 0;                                       // [32][kTfLdApp]  (27 rows used)
+constexpr int kTfW_c0 = kTfW_bs + 32 * kTfLdApp;                 // [64][kTfLdC0]: k 0..26 basis, 27..31 zero, 32..47 SH
+constexpr int kTfW_c1 = kTfW_c0 + 64 * kTfLdC0;                  // [64][kLd64]
+constexpr int kTfW_hd = kTfW_c1 + 64 * kLd64;                    // [8][kLd64]
+constexpr int kTfW_end = kTfW_hd + 8 * kLd64;
+constexpr int kTfStageHalves = 32 * kTfLdApp + 32 * 24 + 64;     // app [32][152] + SH [32][24] + sigma_feat [32] fp32
+constexpr int kTfWarps = 8;
+constexpr int kTensorfSmemBytes = (kTfW_end + kTfWarps * kTfStageHalves) * 2;
+
+__device__ __forceinline__ void tf_split(float u, int R, int& i0, float& f) {
+  const float pix = __fmul_rn(u, (float)(R - 1));              // align_corners = True
+  i0 = min(max((int)floorf(pix), 0), R - 2);
+  f = __fsub_rn(pix, (float)i0);
+}
+__device__ __forceinline__ void h8_to_f(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const float2 x = __half22float2(h[k]); f[2 * k] = x.x; f[2 * k + 1] = x.y; }
+}
+
+__global__ void __launch_bounds__(32 * kTfWarps, 1)
+tensorf_field_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                     const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M,
+                     float* __restrict__ raw) {
+  extern __shared__ __align__(16) __half smem_h[];
+  {
+    const float* g = P.tf_mlp;
+    for (int i = threadIdx.x; i < kTfW_end; i += blockDim.x) smem_h[i] = __float2half_rn(0.f);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 27 * 144; i += blockDim.x) smem_h[kTfW_bs + (i / 144) * kTfLdApp + i % 144] = __float2half_rn(g[i]);
+    g += 27 * 144;
+    for (int i = threadIdx.x; i < 64 * 43; i += blockDim.x) {
+      const int o = i / 43, k = i % 43;          // packed columns: 0..26 basis, 27..42 SH -> k 0..26, 32..47
+      smem_h[kTfW_c0 + o * kTfLdC0 + (k < 27 ? k : k + 5)] = __float2half_rn(g[i]);
+    }
+    g += 64 * 43;
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) smem_h[kTfW_c1 + (i / 64) * kLd64 + i % 64] = __float2half_rn(g[i]);
+    g += 64 * 64;
+    for (int i = threadIdx.x; i < 4 * 64; i += blockDim.x) smem_h[kTfW_hd + (i / 64) * kLd64 + i % 64] = __float2half_rn(g[i]);
+  }
+  const float unc_b = P.tf_mlp[kTfMlpFloats - 1];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  __half* st_app = smem_h + kTfW_end + warp * kTfStageHalves;
+  __half* st_sh = st_app + 32 * kTfLdApp;
+  float* st_sig = reinterpret_cast<float*>(st_sh + 32 * 24);
+  const int R = P.tf_res;
+  const uint4* planes = reinterpret_cast<const uint4*>(P.tf_planes);   // 8 uint4 per texel
+  const uint4* lines = reinterpret_cast<const uint4*>(P.tf_lines);
+  const long long n_groups = (M + 31) / 32;
+  for (long long grp = (long long)blockIdx.x * kTfWarps + warp; grp < n_groups; grp += (long long)gridDim.x * kTfWarps) {
+    __syncwarp();
+    // ---- SH of the lane's own sample ----
+    {
+      const long long m = grp * 32 + lane;
+      float sh[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) sh[k] = 0.f;
+      if (m < M) {
+        const int ray = ray_of_sample[m];
+        const float dx = rays_d[(long long)ray * 3], dy = rays_d[(long long)ray * 3 + 1], dz = rays_d[(long long)ray * 3 + 2];
+        const float inv_n = rsqrtf(dx * dx + dy * dy + dz * dz);
+        sh16(dx * inv_n, dy * inv_n, dz * inv_n, sh);
+      }
+      uint32_t* s32 = reinterpret_cast<uint32_t*>(st_sh + lane * 24);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s32[k] = pack_h2(sh[2 * k], sh[2 * k + 1]);
+    }
+    // ---- VM features: 8 lanes per sample (16-byte channel slices), 4 samples per pass ----
+    const int sub = lane & 7;
+#pragma unroll 1
+    for (int pass = 0; pass < 8; ++pass) {
+      const int srow = pass * 4 + (lane >> 3);
+      const long long m = grp * 32 + srow;
+      float u[3] = {0.f, 0.f, 0.f};
+      if (m < M) {
+        const int ray = ray_of_sample[m];
+        const float tt = t_s[m];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          u[c] = __fmul_rn(__fsub_rn(__fadd_rn(rays_o[(long long)ray * 3 + c], __fmul_rn(rays_d[(long long)ray * 3 + c], tt)), P.amin[c]), P.inv_size[c]);
+      }
+      float dsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int m0 = i == 2 ? 1 : 0, m1 = i == 0 ? 1 : 2, mv = 2 - i;     // matMode (0,1) (0,2) (1,2); vecMode 2,1,0
+        int x0, y0, z0;
+        float fx, fy, fz;
+        tf_split(u[m0], R, x0, fx);
+        tf_split(u[m1], R, y0, fy);
+        tf_split(u[mv], R, z0, fz);
+        const uint4* pl = planes + (((long long)i * R + y0) * R + x0) * 8 + sub;
+        const uint4 v00 = __ldg(pl), v01 = __ldg(pl + 8), v10 = __ldg(pl + (long long)R * 8), v11 = __ldg(pl + (long long)R * 8 + 8);
+        const uint4* ln = lines + ((long long)i * R + z0) * 8 + sub;
+        const uint4 l0 = __ldg(ln), l1 = __ldg(ln + 8);
+        float a[8], b[8], c[8], d[8], p0[8], p1[8];
+        h8_to_f(v00, a); h8_to_f(v01, b); h8_to_f(v10, c); h8_to_f(v11, d); h8_to_f(l0, p0); h8_to_f(l1, p1);
+        float prod[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float top = fmaf(fx, b[k] - a[k], a[k]), bot = fmaf(fx, d[k] - c[k], c[k]);
+          const float pv = fmaf(fy, bot - top, top);
+          const float lv = fmaf(fz, p1[k] - p0[k], p0[k]);
+          prod[k] = pv * lv;
+        }
+        if (sub < 2) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dsum += prod[k];
+        } else {
+          uint4 o;
+          o.x = pack_h2(prod[0], prod[1]); o.y = pack_h2(prod[2], prod[3]);
+          o.z = pack_h2(prod[4], prod[5]); o.w = pack_h2(prod[6], prod[7]);
+          *reinterpret_cast<uint4*>(st_app + srow * kTfLdApp + i * 48 + (sub - 2) * 8) = o;
+        }
+      }
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);      // lanes sub 0 and 1 hold the 16 density channels
+      if (sub == 0) st_sig[srow] = dsum;
+    }
+    __syncwarp();
+    // ---- colour network on the tensor cores ----
+    uint32_t aX[2][3][4];       // [basis32 (2 K steps) | SH16]
+    {
+      uint32_t aA[2][9][4];
+#pragma unroll
+      for (int ks = 0; ks < 9; ++ks) load_a<kTfLdApp>(st_app, ks, g, t, aA[0][ks], aA[1][ks]);
+      float acc[2][4][4];
+      zero_acc<4>(acc);
+      layer_mma<9, 4, kTfLdApp>(smem_h + kTfW_bs, aA, acc, g, t);
+      uint32_t aB[2][2][4];
+      to_operand<4, false>(acc, aB);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { aX[mt][0][q] = aB[mt][0][q]; aX[mt][1][q] = aB[mt][1][q]; }
+    }
+    load_a<24>(st_sh, 0, g, t, aX[0][2], aX[1][2]);
+    uint32_t aC[2][4][4];
+    {
+      float acc[2][8][4];
+      zero_acc<8>(acc);
+      layer_mma<3, 8, kTfLdC0>(smem_h + kTfW_c0, aX, acc, g, t);
+      to_operand<8, true>(acc, aC);
+    }
+    uint32_t aD[2][4][4];
+    {
+      float acc[2][8][4];
+      zero_acc<8>(acc);
+      layer_mma<4, 8, kLd64>(smem_h + kTfW_c1, aC, acc, g, t);
+      to_operand<8, true>(acc, aD);
+    }
+    float hd[2][1][4];
+    zero_acc<1>(hd);
+    layer_mma<4, 1, kLd64>(smem_h + kTfW_hd, aD, hd, g, t);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int srow = mt * 16 + g + hrow * 8;
+        const long long row = grp * 32 + srow;
+        if (row < M) {
+          const float c0 = hd[mt][0][hrow * 2], c1 = hd[mt][0][hrow * 2 + 1];
+          float* r = raw + row * 5;
+          if (t == 0) {
+            r[0] = 1.f / (1.f + expf(-c0));
+            r[1] = 1.f / (1.f + expf(-c1));
+            r[3] = expf(fminf(fmaxf(st_sig[srow], -15.f), 15.f));
+          } else if (t == 1) {
+            r[2] = 1.f / (1.f + expf(-c0));
+            r[4] = expf(c1 + unc_b);                                     // NeurAR head, run_nerf_helpers.py:128-129
+          }
+        }
+      }
+  }
+}
+
 // ---------------------------------------------------------------- compositing ----------------------
 __global__ void ngp_composite_kernel(NgpParams P, const float* __restrict__ raw, const float* __restrict__ t_s,
                                      const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, int n,
@@ -659,6 +843,16 @@ int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const
   const long long cap = (long long)num_sms * 2;      // 2 resident CTAs per SM, grid-stride over the rest
   if (blocks > cap) blocks = cap;
   ngp_field_kernel<<<(unsigned)blocks, kFieldThreads, kFieldSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, raw, enc_dump);
+  return 1;
+}
+
+int launch_tensorf_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
+                         long long M, float* raw, int num_sms, cudaStream_t st) {
+  if (M <= 0) return 0;
+  cudaFuncSetAttribute(tensorf_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTensorfSmemBytes);
+  long long blocks = ((M + 31) / 32 + kTfWarps - 1) / kTfWarps;
+  if (blocks > num_sms) blocks = num_sms;
+  tensorf_field_kernel<<<(unsigned)blocks, 32 * kTfWarps, kTensorfSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, raw);
   return 1;
 }
 

@@ -18,7 +18,15 @@ struct NgpLevel {
   uint32_t stride_y, stride_z;   // dense strides (res+1), (res+1)^2
 };
 
+// TensoRF VM backbone: packed fp32 colour network: basis [27][144], color0 [64][43] (27 basis + 16 SH inputs),
+// color1 [64][64], heads [4][64] (r, g, b, uncertainty), uncertainty bias [1]
+constexpr int kTfMlpFloats = 27 * 144 + 64 * 43 + 64 * 64 + 4 * 64 + 1;
+
 struct NgpParams {      // device pointers + configuration, passed to kernels by value
+  const uint16_t* tf_planes;    // TensoRF: fp16 [3][R][R][64] indexed [i][y][x][c] (16 density + 48 appearance channels)
+  const uint16_t* tf_lines;     // TensoRF: fp16 [3][R][64]
+  const float* tf_mlp;          // kTfMlpFloats
+  int tf_res;                   // R
   const uint16_t* table;        // fp16 [entries][2]
   const float* mlp;             // kNgpMlpFloats
   const uint8_t* bitfield;      // grid_res^3 / 8 bytes, cell (x*G+y)*G+z -> bit (cell & 7) of byte cell >> 3
@@ -38,6 +46,8 @@ int launch_ngp_march_fill(const NgpParams& P, const float* ro, const float* rd, 
                           int32_t* ray_of_sample, cudaStream_t st);
 int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
                      long long M, float* raw, float* enc_dump, int num_sms, bool tensor_cores, cudaStream_t st);
+int launch_tensorf_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
+                         long long M, float* raw, int num_sms, cudaStream_t st);
 int launch_ngp_composite(const NgpParams& P, const float* raw, const float* t, const int32_t* counts,
                          const int32_t* offsets, int n, float* rgb, float* depth, float* acc, float* beta2, cudaStream_t st);
 

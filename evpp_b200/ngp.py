@@ -157,3 +157,41 @@ class NGPScorer:
         n = C.c_int64(0)
         check(self.engine.lib.evpp_ngp_get_sample_count(self.engine._h, C.byref(n)))
         return n.value
+
+
+# ---------------------------------------------------------------------------------------------------------
+# TensoRF VM backbone (BASELINE configs[3]): same marching / compositing / scoring, other field
+# ---------------------------------------------------------------------------------------------------------
+TF_MLP_SHAPES = [("basis.w", (27, 144)), ("color0.w", (64, 43)), ("color1.w", (64, 64)), ("rgb.w", (3, 64)),
+                 ("unc.w", (1, 64)), ("unc.b", (1,))]
+
+
+def init_tensorf_params(seed=0, R=300):
+    """Random-init VM grids (fp16 [3][R][R][64] planes indexed [i][y][x][c], [3][R][64] lines; 16 density + 48
+    appearance channels per texel) and colour network (basis 144 -> 27, [basis, SH16] -> 64 -> 64 -> rgb + uncertainty)."""
+    rng = np.random.RandomState(seed)
+    p = {"planes": (rng.uniform(-1, 1, size=(3, R, R, 64)) * 0.35).astype(np.float16),
+         "lines": (rng.uniform(-1, 1, size=(3, R, 64)) * 0.35).astype(np.float16), "R": R}
+    for name, shape in TF_MLP_SHAPES:
+        if name == "unc.b":
+            continue
+        k = 1.0 / np.sqrt(shape[1])
+        p[name] = rng.uniform(-k, k, size=shape).astype(np.float32)
+    p["unc.b"] = rng.uniform(-0.125, 0.125, size=(1,)).astype(np.float32)
+    return p
+
+
+class TensoRFScorer(NGPScorer):
+    """NGPScorer with the hash grid replaced by vector-matrix decomposed grids."""
+
+    def load_params(self, p):
+        planes = np.ascontiguousarray(p["planes"], dtype=np.float16)
+        lines = np.ascontiguousarray(p["lines"], dtype=np.float16)
+        R = int(p["R"])
+        assert planes.shape == (3, R, R, 64) and lines.shape == (3, R, 64)
+        heads = np.concatenate([p["rgb.w"], p["unc.w"]], 0).astype(np.float32)
+        mlp = np.concatenate([p["basis.w"].reshape(-1), p["color0.w"].reshape(-1), p["color1.w"].reshape(-1),
+                              heads.reshape(-1), np.asarray(p["unc.b"], np.float32).reshape(-1)]).astype(np.float32)
+        check(self.engine.lib.evpp_tensorf_load_params(self.engine._h, planes.ctypes.data_as(C.c_void_p),
+                                                       lines.ctypes.data_as(C.c_void_p), R,
+                                                       mlp.ctypes.data_as(C.c_void_p), mlp.size))

@@ -244,6 +244,12 @@ int evpp_ngp_set_occupancy(evpp_handle* h, const uint8_t* bitfield, int64_t nbyt
  * + zero column), color1 [64][64], heads [4][64] (r,g,b,uncertainty), uncertainty bias [1] */
 int evpp_ngp_load_params(evpp_handle* h, const uint16_t* table_fp16, int64_t n_entries, const float* mlp_packed,
                          int64_t n_mlp_floats);
+/* TensoRF VM backbone instead of the hash grid (BASELINE configs[3]; same marching / compositing / scoring calls):
+ * planes fp16 [3][R][R][64] indexed [i][y][x][c], lines fp16 [3][R][64] (channels 0..15 density, 16..63 appearance;
+ * plane i spans axes (0,1) (0,2) (1,2), line i runs along axis 2, 1, 0), mlp_packed fp32: basis [27][144],
+ * color0 [64][43] (27 basis + 16 SH inputs), color1 [64][64], heads [4][64], uncertainty bias [1] */
+int evpp_tensorf_load_params(evpp_handle* h, const uint16_t* planes_fp16, const uint16_t* lines_fp16, int32_t res,
+                             const float* mlp_packed, int64_t n_mlp_floats);
 /* hash-grid encoding alone: u device [M,3] in [0,1] -> enc [M,32] fp32, indices [M,16,8] int32 (optional) */
 int evpp_ngp_encode(evpp_handle* h, const float* u, int64_t M, float* enc, int32_t* indices, void* stream);
 int evpp_ngp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, int64_t N, evpp_ngp_out* out,

@@ -232,6 +232,75 @@ def composite(raw, t, dt, white_bkgd=True):
     return rgb, float((w * t).sum()), float(acc), float((raw[:, 4] ** 2).sum())
 
 
+# ---------------------------------------------------------------------------------------------------
+# TensoRF VM backbone (BASELINE configs[3]; parity unpinned like the rest of this file)
+# ---------------------------------------------------------------------------------------------------
+TF_MAT = ((0, 1), (0, 2), (1, 2))     # plane i spans axes (x = u[m0], y = u[m1])   (torch-ngp tensoRF: matMode)
+TF_VEC = (2, 1, 0)                    # line i runs along this axis                  (vecMode)
+
+
+def init_tensorf_params(seed=0, R=300):
+    """VM-decomposed grids, 16 density + 48 appearance components fused into 64-channel texels (fp16):
+    planes [3][R][R][64] indexed [i][y][x][c], lines [3][R][64]; basis 144 -> 27 (no bias), colour net
+    [basis27, SH16] 43 -> 64 -> 64 -> 3, NeurAR head on the last hidden layer."""
+    rng = np.random.RandomState(seed)
+    p = {"planes": (rng.uniform(-1, 1, size=(3, R, R, 64)) * 0.35).astype(np.float16),
+         "lines": (rng.uniform(-1, 1, size=(3, R, 64)) * 0.35).astype(np.float16), "R": R}
+
+    def lin(o, i):
+        k = 1.0 / np.sqrt(i)
+        return rng.uniform(-k, k, size=(o, i)).astype(F)
+
+    p["basis.w"] = lin(27, 144) * F(4.0)
+    p["color0.w"] = lin(64, 43)
+    p["color1.w"] = lin(64, 64)
+    p["rgb.w"] = lin(3, 64)
+    p["unc.w"] = lin(1, 64) * F(4.0)
+    p["unc.b"] = rng.uniform(-0.125, 0.125, size=(1,)).astype(F)
+    return p
+
+
+def tensorf_features(u, p):
+    """u fp32 [M,3] in [0,1].  Returns (sigma_feat [M], app [M,144]); bilinear plane x linear line, align_corners=True:
+    pix = u*(R-1), i0 = clamp(floor(pix), 0, R-2), f = pix - i0 (fp32 like the kernel; blends in float64)."""
+    R = p["R"]
+    planes, lines = p["planes"].astype(np.float64), p["lines"].astype(np.float64)
+
+    def split(x):
+        pix = (x.astype(F) * F(R - 1)).astype(F)
+        i0 = np.clip(np.floor(pix).astype(np.int64), 0, R - 2)
+        return i0, (pix - i0.astype(F)).astype(F).astype(np.float64)
+
+    M = u.shape[0]
+    sig = np.zeros(M)
+    app = np.zeros((M, 144))
+    for i in range(3):
+        x0, fx = split(u[:, TF_MAT[i][0]])
+        y0, fy = split(u[:, TF_MAT[i][1]])
+        z0, fz = split(u[:, TF_VEC[i]])
+        P = planes[i]
+        top = (1 - fx)[:, None] * P[y0, x0] + fx[:, None] * P[y0, x0 + 1]
+        bot = (1 - fx)[:, None] * P[y0 + 1, x0] + fx[:, None] * P[y0 + 1, x0 + 1]
+        pv = (1 - fy)[:, None] * top + fy[:, None] * bot
+        lv = (1 - fz)[:, None] * lines[i][z0] + fz[:, None] * lines[i][z0 + 1]
+        prod = pv * lv
+        sig += prod[:, :16].sum(-1)
+        app[:, i * 48:(i + 1) * 48] = prod[:, 16:]
+    return sig, app
+
+
+def tensorf_forward(u, dirs, p):
+    """raw [M,5] = (r,g,b sigmoid, sigma = exp(clip(sigma_feat)), beta = exp(unc))."""
+    sig, app = tensorf_features(u, p)
+    b = app @ p["basis.w"].astype(np.float64).T
+    x = np.concatenate([b, sh16(dirs)], -1)
+    c = np.maximum(x @ p["color0.w"].astype(np.float64).T, 0.0)
+    c = np.maximum(c @ p["color1.w"].astype(np.float64).T, 0.0)
+    rgb = 1.0 / (1.0 + np.exp(-(c @ p["rgb.w"].astype(np.float64).T)))
+    beta = np.exp(c @ p["unc.w"].astype(np.float64).T + p["unc.b"].astype(np.float64))
+    return np.concatenate([rgb, np.exp(np.clip(sig, -15.0, 15.0))[:, None], beta], -1)
+
+
 def render_rays(rays_o, rays_d, p, levels, bitfield, cfg):
     """Full NGP-mode pipeline for a ray list.  Returns dict(counts, offsets, t, rgb, depth, acc, beta2)."""
     amin, amax = np.asarray(cfg["aabb_min"], dtype=F), np.asarray(cfg["aabb_max"], dtype=F)
@@ -249,8 +318,11 @@ def render_rays(rays_o, rays_d, p, levels, bitfield, cfg):
         if len(t):
             pts = (rays_o[r].astype(F)[None, :] + (rays_d[r].astype(F)[None, :] * t[:, None]).astype(F)).astype(F)
             u = ((pts - amin).astype(F) * inv_size).astype(F)
-            enc = grid_encode(u, p["table"], levels)
-            raw = mlp_forward(enc, np.repeat(vd[r][None, :], len(t), 0), p)
+            if "planes" in p:
+                raw = tensorf_forward(u, np.repeat(vd[r][None, :], len(t), 0), p)
+            else:
+                enc = grid_encode(u, p["table"], levels)
+                raw = mlp_forward(enc, np.repeat(vd[r][None, :], len(t), 0), p)
         else:
             raw = np.zeros((0, 5))
         raws.append(raw)

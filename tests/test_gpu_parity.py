@@ -509,3 +509,30 @@ def test_ngp_render_and_scores_vs_restatement(precision, tol):
     chunked.load_params(p)
     assert torch.equal(chunked.get_uncertainty(O.views_to_poses(views)).cpu(), torch.from_numpy(s))
     assert sc.get_uncertainty(np.zeros((0, 4, 4))).numel() == 0
+
+
+def test_tensorf_backbone_vs_restatement():
+    """TensoRF VM backbone (BASELINE configs[3], parity unpinned): same integer-exact marching, VM features + colour
+    network on the tensor cores within the 16-bit operand tolerance, per-view scores within 1e-3."""
+    import evpp_b200
+    from oracle import ngp_oracle as N
+    p = N.init_tensorf_params(0, R=96)
+    bits, _ = N.synthetic_occupancy()
+    sc = evpp_b200.TensoRFScorer(device=0, H=12, W=16, focal=12.0, aabb_min=NGP_CFG["aabb_min"], aabb_max=NGP_CFG["aabb_max"],
+                                 grid_res=128, near=0.5, far=6.0, dt=0.02, max_steps=1024, max_samples=256)
+    sc.set_occupancy(bits)
+    sc.load_params(p)
+    views, ro, rd = _ngp_rays()
+    ref = N.render_rays(ro.numpy(), rd.numpy(), p, None, bits, NGP_CFG)
+    out = sc.render_rays(ro, rd, want_samples=True)
+    assert np.array_equal(out["counts"].cpu().numpy(), ref["counts"])
+    assert np.array_equal(out["t"].cpu().numpy(), ref["t"])
+    np.testing.assert_allclose(out["raw"].cpu().numpy(), ref["raw"], rtol=6e-3, atol=3e-4)
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), ref["rgb"], atol=1e-3)
+    np.testing.assert_allclose(out["beta2"].cpu().numpy(), ref["beta2"], rtol=6e-3, atol=1e-4)
+    s = sc.get_uncertainty(O.views_to_poses(views)).cpu().numpy()
+    sref = ref["beta2"][:4 * 192].reshape(4, 192).sum(-1) / 192
+    np.testing.assert_allclose(s, sref, rtol=1e-3)
+    assert int(np.argmax(s)) == int(np.argmax(sref))
+    with pytest.raises(Exception):
+        sc.encode(torch.rand(4, 3))        # the hash-grid encoder is not available on a TensoRF scorer

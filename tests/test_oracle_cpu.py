@@ -192,3 +192,20 @@ def test_ngp_oracle_self_consistency():
     assert c[0] == 0
     c, _ = N.march(ro, rd, full, G, (0, 0, 0), (1, 1, 1), 0.1, 10.0, 0.05, 1024, 7)
     assert c[0] == 7                                                         # per-ray sample cap
+
+
+def test_tensorf_oracle_self_consistency():
+    """VM restatement invariants: constant grids give sigma_feat = 3 * 16 * p * l; corner coordinates are exact."""
+    from oracle import ngp_oracle as N
+    p = N.init_tensorf_params(0, R=8)
+    p["planes"][:] = np.float16(0.5)
+    p["lines"][:] = np.float16(0.25)
+    u = np.array([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [0.3, 0.6, 0.9]], np.float32)
+    sig, app = N.tensorf_features(u, p)
+    np.testing.assert_allclose(sig, 3 * 16 * 0.125, rtol=1e-12)
+    np.testing.assert_allclose(app, 0.125, rtol=1e-12)
+    q = N.init_tensorf_params(1, R=8)
+    sig, app = N.tensorf_features(np.array([[1.0, 0.0, 1.0]], np.float32), q)
+    P, L = q["planes"].astype(np.float64), q["lines"].astype(np.float64)
+    want = P[0, 0, 7, :16] @ L[0, 7, :16] + P[1, 7, 7, :16] @ L[1, 0, :16] + P[2, 7, 0, :16] @ L[2, 7, :16]
+    np.testing.assert_allclose(sig[0], want, rtol=1e-12)
