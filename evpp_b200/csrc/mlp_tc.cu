@@ -640,7 +640,7 @@ cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStrea
   return cudaLaunchKernelEx(&cfg, kern, cst, a);
 }
 
-int g_cluster = 1;   // CTAs sharing one weight stream (1 or 2); EVPP_TC_CLUSTER overrides
+int g_cluster = 2;   // CTAs sharing one weight stream by bulk-copy multicast (1 or 2); EVPP_TC_CLUSTER overrides
 
 template <bool RAYS>
 int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
