@@ -262,6 +262,9 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device visible -- the evpp_b200 engine has no CPU fallback "
+                 "(--impl reference times the reference algorithm on the host cores)")
     if args.mode in ("ngp", "tensorf"):
         run_ngp(args, rank, local_rank, world)
         return

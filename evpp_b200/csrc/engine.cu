@@ -97,6 +97,7 @@ struct evpp_handle {
   DevBuf ngp_table, ngp_mlp, ngp_bits, ngp_ro, ngp_rd, ngp_counts, ngp_offsets, ngp_total, ngp_t, ngp_ray, ngp_raw,
       ngp_beta2, ngp_scores;
   int64_t ngp_samples = 0;       // kept samples since handle creation
+  int ngp_chunk_rays = 1 << 20;  // rays per marching chunk (one count -> scan -> fill round trip each)
   // counters / profiling
   int64_t launches = 0, evals = 0;
   bool profiling = false;
@@ -317,6 +318,7 @@ int evpp_create(int device_ordinal, const evpp_config* cfg, evpp_handle** out) {
   evpp_handle* h = new evpp_handle();
   h->device = device_ordinal;
   h->cfg = *cfg;
+  h->ngp_chunk_rays = h->cfg.max_chunk_rays > 0 ? h->cfg.max_chunk_rays : (1 << 20);   // few samples per ray: larger chunks
   if (h->cfg.max_chunk_rays <= 0) h->cfg.max_chunk_rays = 131072;
   h->Sc = cfg->n_samples;
   h->Ni = cfg->n_importance;
@@ -899,7 +901,7 @@ int evpp_ngp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_
   int rc = ngp_ready(h);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
-  const int cap = h->cfg.max_chunk_rays;
+  const int cap = h->ngp_chunk_rays;
   for (int64_t g0 = 0; g0 < N; g0 += cap) {
     const int n = (int)std::min<int64_t>(cap, N - g0);
     rc = ngp_render_device(h, rays_o + g0 * 3, rays_d + g0 * 3, n, out, g0, out->beta2 ? out->beta2 + g0 : nullptr, (cudaStream_t)stream);
@@ -920,7 +922,7 @@ int evpp_ngp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, 
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const long long N = (long long)V * R;
-  const int cap = (int)std::min<long long>(N, h->cfg.max_chunk_rays);
+  const int cap = (int)std::min<long long>(N, h->ngp_chunk_rays);
   if (h->ngp_ro.ensure((size_t)cap * 12) || h->ngp_rd.ensure((size_t)cap * 12) || h->ngp_beta2.ensure((size_t)N * 4))
     return fail(EVPP_ERR_CUDA, "NGP ray workspace alloc failed");
   for (long long g0 = 0; g0 < N; g0 += cap) {

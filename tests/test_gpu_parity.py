@@ -536,3 +536,29 @@ def test_tensorf_backbone_vs_restatement():
     assert int(np.argmax(s)) == int(np.argmax(sref))
     with pytest.raises(Exception):
         sc.encode(torch.rand(4, 3))        # the hash-grid encoder is not available on a TensoRF scorer
+
+
+@pytest.mark.parametrize("lindisp,white,ns,ni", [(True, True, 64, 128), (False, False, 64, 128), (False, True, 32, 16)])
+def test_render_option_variants_vs_oracle(weights, lindisp, white, ns, ni):
+    """Renderer flags the reference exposes besides the live config (nerf_configs.py: lindisp, white_bkgd,
+    N_samples, N_importance): fp32 path against the oracle on the same rays."""
+    from evpp_b200 import Engine
+    c, f = weights["spread"]
+    eng = Engine(device=0, n_samples=ns, n_importance=ni, near=0.5, far=6.0, white_bkgd=white, lindisp=lindisp, precision="fp32")
+    eng.load_weights(0, c)
+    eng.load_weights(1, f)
+    H, W = 5, 7
+    K = O.make_K(H, W, 6.0)
+    rays = O.build_view_rays(O.views_to_poses(O.circle_views(3)), H, W, K)
+    with torch.no_grad():
+        ref = O.render(H, W, K, rays=rays, near=0.5, far=6.0, sd_coarse=c, sd_fine=f, N_samples=ns, N_importance=ni,
+                       white_bkgd=white, lindisp=lindisp)
+    out = eng.render_rays(rays[0], rays[1], 0.5, 6.0, want=("rgb", "disp", "acc", "depth", "unc"))
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), ref[0].numpy(), atol=3e-4)
+    np.testing.assert_allclose(out["acc"].cpu().numpy(), ref[2].numpy(), atol=3e-4)
+    np.testing.assert_allclose(out["depth"].cpu().numpy(), ref[4].numpy(), rtol=3e-4, atol=3e-4)
+    assert out["unc"].shape == (rays[0].shape[0], ns + ni)
+    u, ur = out["unc"].cpu().numpy(), ref[3].numpy()
+    close = np.isclose(u, ur, rtol=1e-3).mean()
+    assert close > 0.97, close          # samples whose position moved by a resampling knife-edge excepted
+    eng.close()
