@@ -336,11 +336,18 @@ __device__ __forceinline__ uint32_t relu2(uint32_t v) {   // max(x, 0) on a pack
 // flight while chunk k is converted and stored.
 template <bool BF16, int KIND, bool DBG>
 __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& args, const float* bias_l, int l,
-                                            uint32_t t_acc, int hf, int lane, uint32_t bar_a, const RowData& rd,
-                                            float& alpha, float (&hd)[4]) {
+                                            uint32_t t_acc, int hf, int lane, uint32_t bar_a, uint32_t bar_acc_l,
+                                            uint32_t acc_parity, const RowData& rd, float& alpha, float (&hd)[4]) {
   constexpr int NCH = KIND == 3 ? 2 : 4;
   constexpr int NC = kColsPerWarp;   // 16
   uint32_t r[2][NC];
+  // the first chunk is on the critical path (the next layer's MMAs wait for it): fetch its biases before the
+  // accumulator is ready
+  float4 bpre[NC / 4];
+#pragma unroll
+  for (int j = 0; j < NC / 4; ++j) bpre[j] = reinterpret_cast<const float4*>(bias_l + hf * NC)[j];
+  mbar_wait(bar_acc_l, acc_parity);
+  tc_fence_after();
   tmem_ld16(t_acc + (uint32_t)(hf * NC), r[0]);
 #pragma unroll
   for (int kb = 0; kb < NCH; ++kb) {
@@ -351,7 +358,7 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
     const float4* b4 = reinterpret_cast<const float4*>(bias_l + c0);   // shared memory, warp-uniform address
 #pragma unroll
     for (int j = 0; j < NC / 4; ++j) {
-      const float4 b = b4[j];
+      const float4 b = kb == 0 ? bpre[j] : b4[j];
       v[2 * j] = add2(make_float2(__uint_as_float(r[kb & 1][4 * j]), __uint_as_float(r[kb & 1][4 * j + 1])),
                       make_float2(b.x, b.y));
       v[2 * j + 1] = add2(make_float2(__uint_as_float(r[kb & 1][4 * j + 2]), __uint_as_float(r[kb & 1][4 * j + 3])),
@@ -509,16 +516,17 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
           for (int kb = 0; kb < layer_h_blocks(l); ++kb) {
-            mbar_wait(bar_a + 8 * kb, a_phase);
-            mbar_wait(bar_full + 8 * stage, phase);
+            mbar_wait(bar_full + 8 * stage, phase);     // weights first: prefetched long ago, off the critical path
+            const uint64_t b_desc0 = make_desc(sRing + stage * kStageBytes);
+            const uint32_t a_addr0 = a_tmem + (uint32_t)(kb * 64);
+            mbar_wait(bar_a + 8 * kb, a_phase);         // then the activations of this K-block
             tc_fence_after();
             if (kb == 0) EVPP_TRACE(l * 4 + 1);
             if (kb == 3) EVPP_TRACE(l * 4 + 2);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // A = the previous layer's activations, packed in place in the other accumulator region
-              umma_f16_ts(d_tmem, a_tmem + (uint32_t)(kb * 64 + k * 16),
-                          make_desc(sRing + stage * kStageBytes + k * 32), idesc, accumulate);
+              umma_f16_ts(d_tmem, a_addr0 + (uint32_t)(k * 16), b_desc0 + (uint64_t)(k * 2), idesc, accumulate);   // +32 B per K step
               accumulate = 1;
             }
             if (C == 1) umma_commit(bar_empty + 8 * stage); else umma_commit_mcast(bar_empty + 8 * stage, mc_mask);
@@ -552,15 +560,14 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
 #pragma unroll 1
       for (int l = 0; l < kLayers; ++l) {
         const int ab = l & 1;
-        mbar_wait(bar_acc + 8 * ab, acc_phase[ab]);
+        const uint32_t bar_l = bar_acc + 8 * ab, par_l = acc_phase[ab];
         acc_phase[ab] ^= 1u;
-        tc_fence_after();
-        if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 0);
+        if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 0);   // (before the accumulator wait)
         const uint32_t t_acc = t_lane + (uint32_t)(ab * 256);
-        if (l == 9)      drain_layer<BF16, 3, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, cur, alpha, hd);
-        else if (l == 8) drain_layer<BF16, 2, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, cur, alpha, hd);
-        else if (l == 7) drain_layer<BF16, 1, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, cur, alpha, hd);
-        else             drain_layer<BF16, 0, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, cur, alpha, hd);
+        if (l == 9)      drain_layer<BF16, 3, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd);
+        else if (l == 8) drain_layer<BF16, 2, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd);
+        else if (l == 7) drain_layer<BF16, 1, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd);
+        else             drain_layer<BF16, 0, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd);
         if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 1);
         // The epilogue warps now idle until the next layer's MMAs finish: use the window to stage operands.
         if (l == 0) {
