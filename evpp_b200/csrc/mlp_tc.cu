@@ -334,10 +334,13 @@ __device__ __forceinline__ uint32_t relu2(uint32_t v) {   // max(x, 0) on a pack
 // 2: feature_linear (no ReLU); 3: view layer (ReLU + rgb / uncertainty heads, nothing stored).
 // A warp owns kColsPerWarp columns of each 64-column chunk of its 32 rows; the TMEM load of chunk k+1 is in
 // flight while chunk k is converted and stored.
-template <bool BF16, int KIND, bool DBG>
+// HFC >= 0 makes the warp's column slice a compile-time constant, so that the head weights of layers 7 and 9 become
+// immediate constant-bank operands of the FFMAs instead of indexed constant loads.
+template <bool BF16, int KIND, bool DBG, int HFC = -1>
 __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& args, const float* bias_l, int l,
                                             uint32_t t_acc, int hf, int lane, uint32_t bar_a, uint32_t bar_acc_l,
                                             uint32_t acc_parity, const RowData& rd, float& alpha, float (&hd)[4]) {
+  if (HFC >= 0) hf = HFC;
   constexpr int NCH = KIND == 3 ? 2 : 4;
   constexpr int NC = kColsPerWarp;   // 16
   uint32_t r[2][NC];
@@ -564,10 +567,18 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
         acc_phase[ab] ^= 1u;
         if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 0);   // (before the accumulator wait)
         const uint32_t t_acc = t_lane + (uint32_t)(ab * 256);
-        if (l == 9)      drain_layer<BF16, 3, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd);
-        else if (l == 8) drain_layer<BF16, 2, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd);
-        else if (l == 7) drain_layer<BF16, 1, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd);
-        else             drain_layer<BF16, 0, DBG>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd);
+#define EVPP_DRAIN(KIND_, HFC_) \
+  drain_layer<BF16, KIND_, DBG, HFC_>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd)
+        if (l == 9) {
+          if (hf == 0) EVPP_DRAIN(3, 0); else if (hf == 1) EVPP_DRAIN(3, 1); else if (hf == 2) EVPP_DRAIN(3, 2); else EVPP_DRAIN(3, 3);
+        } else if (l == 8) {
+          EVPP_DRAIN(2, -1);
+        } else if (l == 7) {
+          if (hf == 0) EVPP_DRAIN(1, 0); else if (hf == 1) EVPP_DRAIN(1, 1); else if (hf == 2) EVPP_DRAIN(1, 2); else EVPP_DRAIN(1, 3);
+        } else {
+          EVPP_DRAIN(0, -1);
+        }
+#undef EVPP_DRAIN
         if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 1);
         // The epilogue warps now idle until the next layer's MMAs finish: use the window to stage operands.
         if (l == 0) {
