@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_EVAL = 1187072.0
 V_PER_RANK, IMG_H, IMG_W, FOCAL = 512, 60, 80, 60.0
+WORKLOAD = "object"
 NEAR, FAR = 0.5, 6.0
 S_C, S_I = 64, 128
 EVALS_PER_RAY = S_C + (S_C + S_I)
@@ -80,7 +81,7 @@ def make_workload(rank):
     torch.manual_seed(0)
     c = S.init_nerf_state_dict()
     f = S.init_nerf_state_dict()
-    views = S.hemisphere_views(V_PER_RANK, seed=rank)
+    views = S.room_views(V_PER_RANK, seed=rank) if WORKLOAD == "room" else S.hemisphere_views(V_PER_RANK, seed=rank)
     poses = torch.Tensor(np.asarray(S.views_to_poses(views)))[:, :3, :4].contiguous()
     return c, f, views, poses
 
@@ -235,7 +236,9 @@ def run_ngp(args, rank, local_rank, world):
 
 
 def workload_config(world, engine_desc):
-    return {"workload": f"BASELINE configs[1] Object scene: {V_PER_RANK} hemisphere candidate views x {IMG_W}x{IMG_H} rays per GPU, "
+    name = ("BASELINE configs[2] Room scene sweep (4096 poses at 8 GPUs), reference-parity scorer" if WORKLOAD == "room"
+            else "BASELINE configs[1] Object scene")
+    return {"workload": f"{name}: {V_PER_RANK} candidate views x {IMG_W}x{IMG_H} rays per GPU, "
                         f"{S_C}+{S_I} samples/ray ({EVALS_PER_RAY} MLP evals/ray), reference-parity scorer "
                         "(freq. encoding + 8x256 NeRF + NeurAR uncertainty head, random-init seed 0)",
             "views_per_gpu": V_PER_RANK, "rays_per_view": IMG_H * IMG_W, "near": NEAR, "far": FAR,
@@ -251,10 +254,16 @@ def main():
     ap.add_argument("--impl", default="evpp_b200")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="object", choices=["object", "room"],
+                    help="object: BASELINE configs[1] (512 hemisphere views x 80x60 rays per GPU, the headline); room: the "
+                         "4096-view Room sweep of configs[2] in reference-parity mode (512 views x 128x96 rays per GPU)")
     ap.add_argument("--mode", default="parity", choices=["parity", "ngp", "tensorf"],
                     help="parity: the reference's scorer (headline, BASELINE configs[1]); ngp: occupancy grid + hash grid "
                          "scorer on the Room sweep shape (BASELINE configs[2]; no reference counterpart)")
     args = ap.parse_args()
+    if args.workload == "room":
+        global IMG_H, IMG_W, FOCAL, WORKLOAD
+        IMG_H, IMG_W, FOCAL, WORKLOAD = 96, 128, 96.0, "room"
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
