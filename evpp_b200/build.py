@@ -9,7 +9,7 @@ LIBDIR = os.path.join(ROOT, "lib")
 LIB = os.path.join(LIBDIR, "libevpp_b200.so")
 SOURCES = ["engine.cu", "sampling.cu", "mlp_simt.cu", "mlp_tc.cu", "tsdf.cu", "ngp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "--split-compile", "0"]
 
 
 def _stale():

@@ -3,26 +3,28 @@
 // NeRF.forward (run_nerf_helpers.py:108-134) of the reference for the bulk (fp16 / bf16 operand,
 // fp32 accumulate) pass.  The fp32 twin is mlp_simt.cu.
 //
-// One persistent CTA per SM (optionally clusters of C CTAs sharing the weight stream by bulk-copy
-// multicast).  A CTA owns one 128-row tile at a time:
+// One persistent CTA per SM, in clusters of 2 CTAs sharing the weight stream by bulk-copy multicast.  A CTA owns one
+// 128-row tile at a time and runs all ten GEMM layers on it without the activations ever leaving tensor memory:
 //
-//   shared memory   A[4]   4 x 16 KB   current activations h (128 rows x 256 ch), as four K-blocks of
-//                                      64 channels, K-major, 128-byte swizzle (UMMA canonical layout)
-//                   X      16 KB       the 63-ch position embedding (layers 0 and 5), later the 27-ch
-//                                      direction embedding (view layer), same layout
-//                   ring   4 x 32 KB   weight K-blocks W[:, 64k..64k+63] ([N rows x 128 B], pre-swizzled
-//                                      on the host) streamed from L2 with cp.async.bulk + mbarrier
-//   tensor memory   acc[2] 2 x 256 col fp32 accumulators (128 lanes x 256 columns), layer l -> acc[l&1]
+//   shared memory   X      16 KB       the 63-ch position embedding (layers 0 and 5), K-major, 128-byte swizzle
+//                   XD      8 KB       the 27-ch direction embedding (view layer), 64-byte swizzle
+//                   ring   6 x 32 KB   weight K-blocks W[:, 64k..64k+63] ([N rows x 128 B], pre-swizzled on the host)
+//                                      streamed from L2 with cp.async.bulk(.multicast) + mbarrier transaction counts
+//                   bias   10 KB       fp32 biases of the ten layers
+//   tensor memory   2 x 256 columns    layer l accumulates (fp32) into region l & 1; the epilogue packs the 16-bit
+//                                      activations IN PLACE (16 fp32 columns -> 8 packed columns at the same offset),
+//                                      which is the A-operand layout of layer l+1's TS-mode MMAs (D = other region)
 //
-//   warp 0  (1 lane)  weight producer: 39 bulk copies per tile through the 4-stage ring
-//   warp 1  (1 lane)  tcgen05.mma issuer: D[128 x N] += A[128 x 16] * W[N x 16]^T, 4 per K-block
-//   warps 4-11        encode the tile, then per layer drain the accumulator with tcgen05.ld, add bias,
-//                     ReLU, convert and store the next layer's A operand K-block by K-block; the MMA
-//                     warp starts layer l+1 on K-block k as soon as that block is written, i.e. the
-//                     epilogue of layer l overlaps the MMAs of layer l+1 (which go to the other
-//                     accumulator).  alpha / rgb / uncertainty heads are fp32 FFMA in the epilogue.
+//   warps 0-15        encode the tile, then per layer drain the accumulator 64 columns at a time (tcgen05.ld, bias,
+//                     ReLU + pack in one F2FP.RELU, tcgen05.st); layer l+1's K-block k is issued as soon as chunk k
+//                     is stored.  alpha / rgb / uncertainty heads are fp32 FFMA on the un-rounded activations.
+//   warp 16 (1 lane)  weight producer: 39 bulk copies per tile through the 6-stage ring
+//   warp 17 (1 lane)  tcgen05.mma issuer (elect.sync, so each MMA is a single uniform-datapath instruction):
+//                     D[128 x N] += A[128 x 16] * W[N x 16]^T, 4 per K-block.  The last K-blocks of a 256-wide layer
+//                     run as two N = 128 halves (columns 0..127 first), so the drain of the first half overlaps
+//                     the second half's MMAs (SPLIT template parameter).
 //
-// Activations never leave the SM; per row the kernel reads 4 B (z) and writes 20 B.
+// Per row the kernel reads 4 B (z) and writes 20 B.
 #include "common.cuh"
 
 namespace evpp {
@@ -52,7 +54,7 @@ constexpr int kOffMisc = kOffBias + kLayers * 256 * 4;
 struct Misc {
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  uint64_t acc_full[2];
+  uint64_t acc_full[4];   // [accumulator region][column half]
   uint64_t a_ready[4];
   uint64_t x_ready;
   uint64_t xd_ready;
@@ -91,6 +93,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
       "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -201,6 +213,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// One lane of a converged warp.  Unlike `lane == 0`, elect.sync lets the compiler prove that a single thread runs
+// the region, so each tcgen05.mma / tcgen05.commit becomes ONE uniform-datapath instruction instead of an
+// ELECT / branch loop over the "possibly divergent" active lanes (5 instructions and a branch per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -214,6 +234,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
+}
+
+// pack2 of max(x, 0): one F2FP.RELU instead of a conversion and a packed max
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
+  uint32_t r;
+  if (BF16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 
 // byte offset of 16-byte chunk `ch` (8 channels) of row `row` inside a swizzled 16 KB K-block
@@ -317,19 +346,6 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return c;
 }
-template <bool BF16>
-__device__ __forceinline__ uint32_t relu2(uint32_t v) {   // max(x, 0) on a packed pair; commutes with the rounding
-  if (BF16) {
-    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&v);
-    x = __hmax2(x, __floats2bfloat162_rn(0.f, 0.f));
-    return *reinterpret_cast<uint32_t*>(&x);
-  } else {
-    __half2 x = *reinterpret_cast<__half2*>(&v);
-    x = __hmax2(x, __floats2half2_rn(0.f, 0.f));
-    return *reinterpret_cast<uint32_t*>(&x);
-  }
-}
-
 // Drains one layer's accumulator.  KIND 0: ReLU layer -> next A operand; 1: layer 7 (ReLU + alpha head);
 // 2: feature_linear (no ReLU); 3: view layer (ReLU + rgb / uncertainty heads, nothing stored).
 // A warp owns kColsPerWarp columns of each 64-column chunk of its 32 rows; the TMEM load of chunk k+1 is in
@@ -339,7 +355,8 @@ __device__ __forceinline__ uint32_t relu2(uint32_t v) {   // max(x, 0) on a pack
 template <bool BF16, int KIND, bool DBG, int HFC = -1>
 __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& args, const float* bias_l, int l,
                                             uint32_t t_acc, int hf, int lane, uint32_t bar_a, uint32_t bar_acc_l,
-                                            uint32_t acc_parity, const RowData& rd, float& alpha, float (&hd)[4]) {
+                                            uint32_t acc_parity, const RowData& rd, float& alpha, float (&hd)[4],
+                                            long long* tr = nullptr, long long* tr0 = nullptr) {
   if (HFC >= 0) hf = HFC;
   constexpr int NCH = KIND == 3 ? 2 : 4;
   constexpr int NC = kColsPerWarp;   // 16
@@ -349,13 +366,28 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
   float4 bpre[NC / 4];
 #pragma unroll
   for (int j = 0; j < NC / 4; ++j) bpre[j] = reinterpret_cast<const float4*>(bias_l + hf * NC)[j];
+  // columns 0..127 and 128..255 of the accumulator become final separately (bar_acc_l, bar_acc_l + 8): the MMA
+  // issuer runs the last K-blocks of a layer as two N = 128 halves so that this drain starts while the second
+  // half is still on the tensor pipe
   mbar_wait(bar_acc_l, acc_parity);
   tc_fence_after();
+  if (DBG && tr && lane == 0) tr[0] = clk();
   tmem_ld16(t_acc + (uint32_t)(hf * NC), r[0]);
+  bool half1_early = false;
 #pragma unroll
   for (int kb = 0; kb < NCH; ++kb) {
     tmem_ld_wait();
-    if (kb + 1 < NCH) tmem_ld16(t_acc + (uint32_t)((kb + 1) * 64 + hf * NC), r[(kb + 1) & 1]);
+    if (kb + 1 < NCH) {
+      if (kb + 1 == 2) {
+        half1_early = __all_sync(0xffffffffu, mbar_test(bar_acc_l + 8, acc_parity));
+        if (half1_early) {
+          tc_fence_after();
+          tmem_ld16(t_acc + (uint32_t)((kb + 1) * 64 + hf * NC), r[(kb + 1) & 1]);
+        }
+      } else {
+        tmem_ld16(t_acc + (uint32_t)((kb + 1) * 64 + hf * NC), r[(kb + 1) & 1]);
+      }
+    }
     const int c0 = kb * 64 + hf * NC;
     float2 v[NC / 2];
     const float4* b4 = reinterpret_cast<const float4*>(bias_l + c0);   // shared memory, warp-uniform address
@@ -406,19 +438,27 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
       uint32_t pk[NC / 2];
 #pragma unroll
       for (int j = 0; j < NC / 2; ++j) {
-        pk[j] = pack2<BF16>(v[j].x, v[j].y);
-        if (KIND == 0 && !DBG) pk[j] = relu2<BF16>(pk[j]);
+        pk[j] = (KIND == 0 && !DBG) ? pack2_relu<BF16>(v[j].x, v[j].y) : pack2<BF16>(v[j].x, v[j].y);
       }
       tmem_st8(t_acc + (uint32_t)c0, pk);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a + 8 * kb);
+      if (DBG && tr && lane == 0) tr[1 + kb] = clk();
+      if (DBG && tr0 && lane == 0 && kb == 0) tr0[0] = clk();
+    }
+    if (kb == 1 && NCH > 2 && !half1_early) {
+      mbar_wait(bar_acc_l + 8, acc_parity);
+      tc_fence_after();
+      tmem_ld16(t_acc + (uint32_t)(2 * 64 + hf * NC), r[0]);
     }
   }
+  if (NCH == 2) mbar_wait(bar_acc_l + 8, acc_parity);   // keeps the phase of the (unused) second-half barrier in step
 }
 
-template <bool BF16, bool RAYS, int C, bool DBG>
+// SPLIT: hidden K-blocks kb >= SPLIT of a 256-wide layer are issued as two N = 128 halves (4 = none)
+template <bool BF16, bool RAYS, int C, bool DBG, int SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -444,8 +484,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, C);
     }
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_acc + 8, 1);
+    for (int k = 0; k < 4; ++k) mbar_init(bar_acc + 8 * k, 1);
     for (int k = 0; k < 4; ++k) mbar_init(bar_a + 8 * k, kEpiWarps);
     mbar_init(bar_x, kEpiWarps);
     mbar_init(bar_xd, kEpiWarps);
@@ -468,7 +507,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
 
   if (warp == kProducerWarp) {
     // ================= weight producer =================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < ntile_iters; ++it) {
         const uint8_t* src = args.image;
@@ -476,7 +515,9 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
           const int nblk = layer_has_x(l) + layer_h_blocks(l);
           const uint32_t bytes = (uint32_t)layer_n(l) * 128u;
           for (int b = 0; b < nblk; ++b) {
+            if (l == 4 && b == 0) EVPP_TRACE(117);
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            if (l == 4 && b == 0) EVPP_TRACE(118);
             mbar_expect_tx(bar_full + 8 * stage, bytes);
             if (C == 1) {
               bulk_g2s(sRing + stage * kStageBytes, src, bytes, bar_full + 8 * stage);
@@ -491,10 +532,23 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
         }
       }
     }
+    if (DBG && lane == 31 && args.trace && blockIdx.x == 0) {
+      // diagnostics: when each accumulator half of each layer really becomes final (tile 2 of CTA 0)
+      uint32_t ph[2] = {0u, 0u};
+      for (int it = 0; it < ntile_iters; ++it)
+        for (int l = 0; l < kLayers; ++l) {
+          mbar_wait(bar_acc + 16 * (l & 1), ph[l & 1]);
+          EVPP_TRACE(70 + 2 * l);
+          mbar_wait(bar_acc + 16 * (l & 1) + 8, ph[l & 1]);
+          EVPP_TRACE(71 + 2 * l);
+          ph[l & 1] ^= 1u;
+        }
+    }
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0, a_phase = 0, x_phase = 0, xd_phase = 0;
+      bool pre_full = false;   // the next weight stage's arrival was already awaited (static after unrolling)
       for (int it = 0; it < ntile_iters; ++it) {
         for (int l = 0; l < kLayers; ++l) {
           const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 256u;
@@ -506,7 +560,8 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
             // layers 0 and 5 read the position embedding (X), the view layer the direction embedding (XD)
             if (l == 0) { mbar_wait(bar_x, x_phase); x_phase ^= 1u; }
             if (l == 9) { mbar_wait(bar_xd, xd_phase); xd_phase ^= 1u; }
-            mbar_wait(bar_full + 8 * stage, phase);
+            if (!pre_full) mbar_wait(bar_full + 8 * stage, phase);
+            pre_full = false;
             tc_fence_after();
             const int ksteps = l == 9 ? 2 : 4;
             const uint32_t xa = l == 9 ? sXD : sX;
@@ -518,8 +573,11 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
             if (C == 1) umma_commit(bar_empty + 8 * stage); else umma_commit_mcast(bar_empty + 8 * stage, mc_mask);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          for (int kb = 0; kb < layer_h_blocks(l); ++kb) {
-            mbar_wait(bar_full + 8 * stage, phase);     // weights first: prefetched long ago, off the critical path
+          const int nfull = (layer_n(l) == 256 && layer_h_blocks(l) == 4) ? SPLIT : layer_h_blocks(l);
+          for (int kb = 0; kb < nfull; ++kb) {
+            if (!pre_full) mbar_wait(bar_full + 8 * stage, phase);   // weights first: prefetched long ago, off the critical path
+            pre_full = false;
+            if (kb == 0 && l == 4) EVPP_TRACE(116);
             const uint64_t b_desc0 = make_desc(sRing + stage * kStageBytes);
             const uint32_t a_addr0 = a_tmem + (uint32_t)(kb * 64);
             mbar_wait(bar_a + 8 * kb, a_phase);         // then the activations of this K-block
@@ -535,8 +593,43 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
             if (C == 1) umma_commit(bar_empty + 8 * stage); else umma_commit_mcast(bar_empty + 8 * stage, mc_mask);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
+          if (nfull < layer_h_blocks(l)) {
+            // The remaining K-blocks as two N = 128 halves (weight rows 0..127 -> accumulator columns 0..127 first):
+            // the first half's columns are final, and its drain starts, while the second half is still computing.
+            const uint32_t idesc_h = make_idesc(BF16, 128);
+            uint32_t s2 = stage, p2 = phase;
+            for (int kb = nfull; kb < 4; ++kb) {
+              mbar_wait(bar_full + 8 * s2, p2);
+              const uint64_t b_desc0 = make_desc(sRing + s2 * kStageBytes);
+              const uint32_t a_addr0 = a_tmem + (uint32_t)(kb * 64);
+              mbar_wait(bar_a + 8 * kb, a_phase);
+              tc_fence_after();
+              if (kb == 3) EVPP_TRACE(l * 4 + 2);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ts(d_tmem, a_addr0 + (uint32_t)(k * 16), b_desc0 + (uint64_t)(k * 2), idesc_h, 1u);
+              if (++s2 == kStages) { s2 = 0; p2 ^= 1u; }
+            }
+            umma_commit(bar_acc + 16 * (l & 1));
+            // The issuer crawls while the epilogue warps are busy (it loses most issue slots to them), and after
+            // the second half it is on the critical path to the next layer: look at the next layer's first
+            // weight stage now, while the tensor pipe still has queued work.
+            mbar_wait(bar_full + 8 * s2, p2);
+            pre_full = true;
+            for (int kb = nfull; kb < 4; ++kb) {
+              const uint64_t b_desc0 = make_desc(sRing + stage * kStageBytes + 16384);
+              const uint32_t a_addr0 = a_tmem + (uint32_t)(kb * 64);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ts(d_tmem + 128u, a_addr0 + (uint32_t)(k * 16), b_desc0 + (uint64_t)(k * 2), idesc_h, 1u);
+              if (C == 1) umma_commit(bar_empty + 8 * stage); else umma_commit_mcast(bar_empty + 8 * stage, mc_mask);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          } else {
+            umma_commit(bar_acc + 16 * (l & 1));
+          }
           if (l >= 1) a_phase ^= 1u;
-          umma_commit(bar_acc + 8 * (l & 1));
+          umma_commit(bar_acc + 16 * (l & 1) + 8);
           EVPP_TRACE(l * 4 + 3);
         }
       }
@@ -563,12 +656,16 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
 #pragma unroll 1
       for (int l = 0; l < kLayers; ++l) {
         const int ab = l & 1;
-        const uint32_t bar_l = bar_acc + 8 * ab, par_l = acc_phase[ab];
+        const uint32_t bar_l = bar_acc + 16 * ab, par_l = acc_phase[ab];
         acc_phase[ab] ^= 1u;
         if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 0);   // (before the accumulator wait)
         const uint32_t t_acc = t_lane + (uint32_t)(ab * 256);
+        long long* tr = nullptr;
+        if (DBG && args.trace && blockIdx.x == 0 && it == 2 && l == 3 && (warp == 0 || warp == kEpiWarps - 1))
+          tr = args.trace + (warp == 0 ? 90 : 95);
+        long long* tr0 = (DBG && args.trace && blockIdx.x == 0 && it == 2 && l == 3) ? args.trace + 100 + warp : nullptr;
 #define EVPP_DRAIN(KIND_, HFC_) \
-  drain_layer<BF16, KIND_, DBG, HFC_>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd)
+  drain_layer<BF16, KIND_, DBG, HFC_>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd, tr, tr0)
         if (l == 9) {
           if (hf == 0) EVPP_DRAIN(3, 0); else if (hf == 1) EVPP_DRAIN(3, 1); else if (hf == 2) EVPP_DRAIN(3, 2); else EVPP_DRAIN(3, 3);
         } else if (l == 8) {
@@ -638,9 +735,9 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   }
 }
 
-template <bool BF16, bool RAYS, int C, bool DBG>
+template <bool BF16, bool RAYS, int C, bool DBG, int SPLIT>
 cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStream_t st) {
-  auto kern = mlp_tc_kernel<BF16, RAYS, C, DBG>;
+  auto kern = mlp_tc_kernel<BF16, RAYS, C, DBG, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -659,6 +756,22 @@ cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStrea
 }
 
 int g_cluster = 2;   // CTAs sharing one weight stream by bulk-copy multicast (1 or 2); EVPP_TC_CLUSTER overrides
+int g_split = 2;     // hidden K-blocks >= g_split run as two N = 128 halves (1..4, 4 = off); EVPP_TC_SPLIT overrides
+
+template <bool RAYS, int SPLIT>
+cudaError_t launch_split(const TcWeights& w, const TcArgs& a, int C, long long grid, cudaStream_t st) {
+  const bool bf = w.dtype == EVPP_PREC_BF16;
+  cudaError_t e;
+#define EVPP_TC_DISPATCH(CC, DD)                                                              \
+  e = bf ? launch_one<true, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st)                 \
+         : launch_one<false, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st)
+  if (a.dbg || a.trace) {
+    EVPP_TC_DISPATCH(1, !RAYS);
+  } else if (C == 2) { EVPP_TC_DISPATCH(2, false); }
+  else { EVPP_TC_DISPATCH(1, false); }
+#undef EVPP_TC_DISPATCH
+  return e;
+}
 
 template <bool RAYS>
 int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
@@ -668,6 +781,10 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
     if (const char* e = getenv("EVPP_TC_CLUSTER")) {
       const int c = atoi(e);
       if (c == 1 || c == 2) g_cluster = c;
+    }
+    if (const char* e = getenv("EVPP_TC_SPLIT")) {
+      const int c = atoi(e);
+      if (c >= 1 && c <= 4) g_split = c;
     }
     env_read = true;
   }
@@ -681,17 +798,14 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   a.dbg = w.dbg;
   a.dbg_layer = w.dbg_layer;
   a.trace = w.trace;
-  const bool bf = w.dtype == EVPP_PREC_BF16;
+  if ((a.dbg || a.trace) && RAYS) return -1;
   cudaError_t e;
-#define EVPP_TC_DISPATCH(CC, DD)                                                       \
-  e = bf ? launch_one<true, RAYS, CC, DD>(*w.consts, a, (int)grid, st)                 \
-         : launch_one<false, RAYS, CC, DD>(*w.consts, a, (int)grid, st)
-  if (a.dbg || a.trace) {
-    if (RAYS) return -1;
-    EVPP_TC_DISPATCH(1, !RAYS);
-  } else if (C == 2) { EVPP_TC_DISPATCH(2, false); }
-  else { EVPP_TC_DISPATCH(1, false); }
-#undef EVPP_TC_DISPATCH
+  switch (g_split) {
+    case 1: e = launch_split<RAYS, 1>(w, a, C, grid, st); break;
+    case 2: e = launch_split<RAYS, 2>(w, a, C, grid, st); break;
+    case 3: e = launch_split<RAYS, 3>(w, a, C, grid, st); break;
+    default: e = launch_split<RAYS, 4>(w, a, C, grid, st); break;
+  }
   return e == cudaSuccess ? 1 : -1;
 }
 

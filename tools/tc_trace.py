@@ -26,3 +26,11 @@ for l in range(10):
     e = t[40 + 3 * l:40 + 3 * l + 3] - t0
     print(f"{l:5d} | {m[0]:8d} {m[1]:8d} {m[2]:8d} {m[3]:8d} | {e[0]:8d} {e[1]:8d} {e[2]:8d}")
 print("tile total (layer-0 start -> layer-9 stored):", t[40 + 28] - t0)
+print("accumulator halves final (monitor thread):")
+for l in range(10):
+    print(f"{l:5d} | half0 {t[70 + 2 * l] - t0:8d}  half1 {t[71 + 2 * l] - t0:8d}")
+for name, b in (("warp 0", 90), ("warp 15", 95)):
+    print(f"layer-3 drain, {name}: acc wait done {t[b] - t0}, chunk arrivals {[int(x - t0) for x in t[b + 1:b + 5]]}")
+print("layer-3 chunk-0 arrival per epilogue warp:", [int(x - t0) for x in t[100:116]])
+print("layer-4 issuer: weights of K-block 0 present at", int(t[116] - t0))
+print("layer-4 K-block 0 weights: producer reached the stage at", int(t[117] - t0), "stage free at", int(t[118] - t0))

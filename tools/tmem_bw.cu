@@ -49,7 +49,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 
 // PIPE: 0 = loads only, 1 = loads + a concurrent stream of 128x256x16 MMAs into columns 0..255 (loads read 256..511)
 template <int SHAPE, int PIPE>
-__global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long long* cycles, uint32_t* sink, int n_mma, int mma_mode, int with_st) {
+__global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long long* cycles, uint32_t* sink, int n_mma, int mma_mode, int with_st, int d_col = 0, int d_alt = 128, int ld_base = -1) {
   __shared__ uint32_t tmem_base_s;
   __shared__ uint64_t mma_bar;
   extern __shared__ __align__(1024) uint8_t ops[];   // 16 KB A + 32 KB B (contents irrelevant, zeroed)
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long 
         for (int i = 0; i < n_mma; ++i) {
           const uint64_t bd = make_desc(smem_u32(ops) + 16384 + (i & 3) * 32);
           const uint32_t a = tmem + 256 + (i & 7) * 16;
-          const uint32_t d = tmem + (mma_mode == 1 ? ((i >> 3) & 1) * 128 : 0);
+          const uint32_t d = tmem + (uint32_t)d_col + (mma_mode == 1 ? ((i >> 3) & 1) * (uint32_t)d_alt : 0);
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                        ::"r"(d), "r"(a), "l"(bd), "r"(idesc), "r"(1));
         }
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long 
       cycles[148 + blockIdx.x] = t_mma;
     }
   }
-  const uint32_t col_base = PIPE == 1 ? (mma_mode ? 384u : 256u) : 0u;
+  const uint32_t col_base = ld_base >= 0 ? (uint32_t)ld_base : (PIPE == 1 ? (mma_mode ? 384u : 256u) : 0u);
   const uint32_t col_mask = PIPE == 1 ? (mma_mode ? 127u : 255u) : 511u;
   if (warp < nwarps) {
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(544, 1) bw_kernel(int iters, int nwarps, long 
 }
 
 template <int SHAPE, int PIPE>
-void run(int nwarps, const char* name, int mma_mode = 0, int with_st = 0, int iters = 4096) {
+void run(int nwarps, const char* name, int mma_mode = 0, int with_st = 0, int iters = 4096, int d_col = 0, int d_alt = 128, int ld_base = -1) {
   long long* cyc; uint32_t* sink;
   cudaMalloc(&cyc, 296 * 8); cudaMalloc(&sink, 4);
   cudaMemset(cyc, 0, 296 * 8);
@@ -137,12 +137,12 @@ void run(int nwarps, const char* name, int mma_mode = 0, int with_st = 0, int it
   const double bytes = (double)iters * nwarps * 32 * (SHAPE == 16 ? 16 : 32) * 4;
   // size the MMA stream to last about as long as the loads would at ~60 B/cycle (128 cycles per MMA)
   const int n_mma = PIPE ? (int)(bytes / 200.0 / (mma_mode == 1 ? 64.0 : 128.0)) : 0;
-  k<<<148, 544, 49152>>>(iters, nwarps, cyc, sink, n_mma, mma_mode, with_st);
-  k<<<148, 544, 49152>>>(iters, nwarps, cyc, sink, n_mma, mma_mode, with_st);
+  k<<<148, 544, 49152>>>(iters, nwarps, cyc, sink, n_mma, mma_mode, with_st, d_col, d_alt, ld_base);
+  k<<<148, 544, 49152>>>(iters, nwarps, cyc, sink, n_mma, mma_mode, with_st, d_col, d_alt, ld_base);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[296];
   cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
-  printf("%-12s %s mode=%d st=%d warps=%2d  %s  ld cycles=%lld -> %.1f B/cycle/SM", name, PIPE ? "+MMA" : "    ", mma_mode, with_st, nwarps, cudaGetErrorString(e), h[0],
+  printf("%-12s %s mode=%d st=%d warps=%2d D=%d/alt%d ld@%d  %s  ld cycles=%lld -> %.1f B/cycle/SM", name, PIPE ? "+MMA" : "    ", mma_mode, with_st, nwarps, d_col, d_alt, ld_base, cudaGetErrorString(e), h[0],
          bytes / (double)h[0]);
   if (PIPE) printf("   | %d MMAs in %lld cycles = %.1f cycles/MMA", n_mma, h[148], (double)h[148] / n_mma);
   printf("\n");
@@ -157,5 +157,12 @@ int main() {
   run<16, 1>(16, "32x32b.x16", 1, 1);   // TS N=128 + loads + stores
   run<16, 1>(4, "32x32b.x16", 1, 1);
   run<16, 1>(1, "32x32b.x16", 1, 1);
+  // where the concurrent ld/st stream sits relative to the MMAs' accumulator columns (A is always read from 256..383)
+  run<16, 1>(16, "32x32b.x16", 1, 1, 4096, 128, 0, 0);     // N=128 D=128..255, ld/st 0..127   (same 256-column region)
+  run<16, 1>(16, "32x32b.x16", 1, 1, 4096, 128, 0, 384);   // N=128 D=128..255, ld/st 384..511
+  run<16, 1>(16, "32x32b.x16", 1, 1, 4096, 0, 0, 384);     // N=128 D=0..127,   ld/st 384..511
+  run<16, 1>(16, "32x32b.x16", 1, 1, 4096, 0, 0, 128);     // N=128 D=0..127,   ld/st 128..255
+  run<16, 1>(16, "32x32b.x16", 2, 1, 4096, 0, 0, 0);       // N=256 D=0..255,   ld/st 0..127 (same columns)
+  run<16, 1>(16, "32x32b.x16", 1, 0, 4096, 128, 0, 0);     // N=128 D=128..255, ld only 0..127
   return 0;
 }
