@@ -767,7 +767,8 @@ cudaError_t launch_split(const TcWeights& w, const TcArgs& a, int C, long long g
          : launch_one<false, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st)
   if (a.dbg || a.trace) {
     EVPP_TC_DISPATCH(1, !RAYS);
-  } else if (C == 2) { EVPP_TC_DISPATCH(2, false); }
+  } else if (C == 4) { EVPP_TC_DISPATCH(4, false); }
+  else if (C == 2) { EVPP_TC_DISPATCH(2, false); }
   else { EVPP_TC_DISPATCH(1, false); }
 #undef EVPP_TC_DISPATCH
   return e;
@@ -780,11 +781,11 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   if (!env_read) {
     if (const char* e = getenv("EVPP_TC_CLUSTER")) {
       const int c = atoi(e);
-      if (c == 1 || c == 2) g_cluster = c;
+      if (c == 1 || c == 2 || c == 4) g_cluster = c;
     }
     if (const char* e = getenv("EVPP_TC_SPLIT")) {
       const int c = atoi(e);
-      if (c >= 1 && c <= 4) g_split = c;
+      if (c == 2 || c == 4) g_split = c;
     }
     env_read = true;
   }
@@ -793,6 +794,23 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   long long grid = ntiles < num_sms ? ntiles : num_sms;
   grid = (grid + C - 1) / C * C;
   if (grid > num_sms) grid = num_sms / C * C;
+  if (C == 4) {
+    // 4-CTA clusters do not tile every GPC: keep the persistent grid to what is co-resident
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(148); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      auto kern = mlp_tc_kernel<false, true, 4, false, 2>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) max_clusters = num_sms / 4;
+      if (getenv("EVPP_TC_VERBOSE")) fprintf(stderr, "evpp: %d co-resident 4-CTA clusters\n", max_clusters);
+    }
+    if (grid > (long long)max_clusters * 4) grid = (long long)max_clusters * 4;
+  }
   a.tiles_per_cta = (int)((ntiles + grid - 1) / grid);
   a.image = reinterpret_cast<const uint8_t*>(w.image);
   a.dbg = w.dbg;
@@ -801,9 +819,7 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   if ((a.dbg || a.trace) && RAYS) return -1;
   cudaError_t e;
   switch (g_split) {
-    case 1: e = launch_split<RAYS, 1>(w, a, C, grid, st); break;
     case 2: e = launch_split<RAYS, 2>(w, a, C, grid, st); break;
-    case 3: e = launch_split<RAYS, 3>(w, a, C, grid, st); break;
     default: e = launch_split<RAYS, 4>(w, a, C, grid, st); break;
   }
   return e == cudaSuccess ? 1 : -1;

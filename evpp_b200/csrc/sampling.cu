@@ -1,7 +1,7 @@
 // Ray generation, sampling, compositing and score reduction kernels.
-// All are tiny next to the MLP (a ray costs 304 MFLOP of MLP and ~6 KB of traffic here), so they
-// are written for reference-identical arithmetic first: one thread walks one ray sequentially,
-// exactly like the serial cumprod / cumsum / searchsorted of the reference's ATen CPU ops.
+// All are small next to the MLP (a ray costs 304 MFLOP of MLP and ~6 KB of traffic here); they are written for
+// reference-identical arithmetic first (the serial cumprod / cumsum / searchsorted semantics of the reference's
+// ATen CPU ops) and for coalesced HBM traffic second (one warp per ray, rows staged in shared memory).
 #include "sampling.cuh"
 
 namespace evpp {
@@ -76,93 +76,226 @@ __device__ __forceinline__ float ray_norm(const float* d) {
   return __fsqrt_rn(__fmaf_rn(d[2], d[2], __fmaf_rn(d[1], d[1], __fmul_rn(d[0], d[0]))));
 }
 
-// raw2outputs (run_nerf.py:344-388) for one ray, sequentially.  w_out (local or global) receives
-// the weights if non-null.
-template <typename WOut>
-__device__ __forceinline__ void composite_ray(const float* __restrict__ raw, const float* __restrict__ z,
-                                              float dnorm, int S, int white_bkgd, int t,
-                                              const CompositeOut& co, WOut w_store) {
-  // torch.cumprod / cumsum on CPU accumulate fp32 inputs in double and round each output to
-  // fp32 (at::acc_type<float,false>); T is carried the same way.
-  double T = 1.0;
-  float acc = 0.f, depth = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, b2 = 0.f;
-  float zi = z[0];
-  for (int i = 0; i < S; ++i) {
-    const float* rw = raw + (long long)i * 5;
-    const float zn = (i + 1 < S) ? z[i + 1] : 0.f;
-    float dist = (i + 1 < S) ? __fsub_rn(zn, zi) : 1e10f;
+// ---------------------------------------------------------------------------------------------------------
+// Per-ray kernels: ONE WARP PER RAY.  Global traffic is coalesced (a ray's raw / z rows are contiguous and are
+// staged in the warp's shared-memory scratch); everything that is elementwise in the reference (alpha, sigmoid,
+// pdf, inverse-cdf lookups, merge ranks) runs across the 32 lanes; everything the reference computes as a serial
+// recurrence keeps its exact serial order so that results are bit-identical to a sequential walk:
+//   - transmittance: torch.cumprod on CPU carries the product in double and rounds each output to fp32
+//     (at::acc_type<float,false>) -> one lane runs the S-step double chain;
+//   - the six per-ray sums (acc, depth, rgb, sum beta^2) are fp32 fused-multiply-add chains in sample order ->
+//     six lanes run one chain each, in lockstep (the same FFMA instruction with per-lane operands).
+constexpr int kRayWarps = 8;   // warps (= rays in flight) per CTA
+
+// Per-warp scratch, planar so that the serial stages read four consecutive samples with one 16-byte load.
+// Sp = S rounded up to a multiple of 4.
+struct RayScratch {
+  float* pl;    // [5][Sp]  planes 0..2 = sigmoid(rgb), 3 = alpha, then weight, 4 = beta
+  float* sz;    // [Sp]     z
+  double* dT;   // [Sp]     (double)((1 - alpha) + 1e-10), then the transmittance before each sample
+  float* ones;  // [4]      1.0f
+  int Sp;
+};
+__host__ __device__ constexpr int ray_sp(int S) { return (S + 3) & ~3; }
+__host__ __device__ constexpr int ray_scratch_floats(int S) { return 8 * ray_sp(S) + 4; }
+__host__ __device__ constexpr int resample_scratch_floats(int Sc, int Ni) {
+  return ray_scratch_floats(Sc) + ((2 * Sc + 2 * Ni + 3) & ~3);   // + cdf[Sc], z_samples[Ni], merged[Sc+Ni]
+}
+__device__ __forceinline__ RayScratch ray_scratch(float* base, int S) {
+  const int Sp = ray_sp(S);
+  return RayScratch{base + 2 * Sp, base + 7 * Sp, reinterpret_cast<double*>(base), base + 8 * Sp, Sp};
+}
+
+// raw2outputs (run_nerf.py:344-388) for one ray by one warp.  On return plane 3 holds weights[i].
+__device__ __forceinline__ void composite_ray_warp(const float* __restrict__ raw, const float* __restrict__ z, float dnorm,
+                                                   int S, int white_bkgd, long long t, const CompositeOut& co,
+                                                   const RayScratch& sc, int lane) {
+  const int Sp = sc.Sp;
+  float* pl = sc.pl;
+  float* sz = sc.sz;
+  double* dT = sc.dT;
+  for (int k = lane; k < S; k += 32) sz[k] = z[k];
+  if (lane < 4) sc.ones[lane] = 1.f;
+  __syncwarp();
+  // stage 1, elementwise over the samples.  The fp32 -> fp64 conversion of the transmittance factor happens here,
+  // in parallel: conversions run on the 16-lane XU pipe and cost a full warp slot each, so they must not sit in
+  // the single-lane recurrence below.
+#pragma unroll 2
+  for (int i = lane; i < S; i += 32) {
+    const float* rw = raw + i * 5;
+    const float x0 = rw[0], x1 = rw[1], x2 = rw[2], x3 = rw[3], x4 = rw[4];
+    const float zi = sz[i];
+    float dist = (i + 1 < S) ? __fsub_rn(sz[i + 1], zi) : 1e10f;
     dist = __fmul_rn(dist, dnorm);
-    const float sigma = fmaxf(rw[3], 0.f);
+    const float sigma = fmaxf(x3, 0.f);
     const float alpha = __fsub_rn(1.f, expf(__fmul_rn(-sigma, dist)));
-    const float w = __fmul_rn(alpha, (float)T);
-    T = T * (double)__fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
-    w_store(i, w);
-    c0 = __fmaf_rn(w, 1.f / (1.f + expf(-rw[0])), c0);
-    c1 = __fmaf_rn(w, 1.f / (1.f + expf(-rw[1])), c1);
-    c2 = __fmaf_rn(w, 1.f / (1.f + expf(-rw[2])), c2);
-    depth = __fmaf_rn(w, zi, depth);
-    acc += w;
-    const float beta = rw[4];
-    b2 = __fmaf_rn(beta, beta, b2);
-    if (co.unc) co.unc[(long long)t * S + i] = beta;
-    zi = zn;
+    dT[i] = (double)__fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+    pl[0 * Sp + i] = 1.f / (1.f + expf(-x0));
+    pl[1 * Sp + i] = 1.f / (1.f + expf(-x1));
+    pl[2 * Sp + i] = 1.f / (1.f + expf(-x2));
+    pl[3 * Sp + i] = alpha;
+    pl[4 * Sp + i] = x4;
+    if (co.unc) co.unc[t * S + i] = x4;
   }
-  if (white_bkgd) { c0 += 1.f - acc; c1 += 1.f - acc; c2 += 1.f - acc; }
-  if (co.rgb) { co.rgb[(long long)t * 3 + 0] = c0; co.rgb[(long long)t * 3 + 1] = c1; co.rgb[(long long)t * 3 + 2] = c2; }
-  if (co.depth) co.depth[t] = depth;
-  if (co.acc) co.acc[t] = acc;
-  if (co.disp) {
-    const float q = depth / acc;   // 0/0 -> NaN propagates like torch.max(1e-10, nan)
-    co.disp[t] = 1.f / (isnan(q) ? q : fmaxf(1e-10f, q));
+  __syncwarp();
+  // stage 2, the transmittance recurrence in double (torch.cumprod's accumulation type on CPU), one lane:
+  // dT[i] <- product of the factors before sample i
+  if (lane == 0) {
+    double T = 1.0;
+    int i = 0;
+    for (; i + 4 <= S; i += 4) {
+      const double2 f01 = *reinterpret_cast<const double2*>(dT + i);
+      const double2 f23 = *reinterpret_cast<const double2*>(dT + i + 2);
+      double2 o01, o23;
+      o01.x = T; T = T * f01.x;
+      o01.y = T; T = T * f01.y;
+      o23.x = T; T = T * f23.x;
+      o23.y = T; T = T * f23.y;
+      *reinterpret_cast<double2*>(dT + i) = o01;
+      *reinterpret_cast<double2*>(dT + i + 2) = o23;
+    }
+    for (; i < S; ++i) { const double f = dT[i]; dT[i] = T; T = T * f; }
   }
-  if (co.beta2) co.beta2[t] = b2;
+  __syncwarp();
+  // weights = alpha * (float)T, elementwise again (the fp64 -> fp32 rounding of every output, like cumprod's)
+  for (int i = lane; i < S; i += 32) {
+    const float w = __fmul_rn(pl[3 * Sp + i], (float)dT[i]);
+    pl[3 * Sp + i] = w;
+    if (co.weights) co.weights[t * S + i] = w;
+  }
+  __syncwarp();
+  // stage 3, six fp32 FMA chains in sample order: lane 0 acc (x = 1: fma(w, 1, acc) rounds exactly like acc + w),
+  // 1 depth (x = z), 2..4 rgb (x = sigmoid), 5 sum of beta^2 (a = x = beta)
+  float accum = 0.f;
+  if (lane < 6) {
+    const float* ap = pl + (lane == 5 ? 4 : 3) * Sp;
+    const float* xp = lane == 0 ? sc.ones : lane == 1 ? sz : lane == 5 ? pl + 4 * Sp : pl + (lane - 2) * Sp;
+    const int xs = lane == 0 ? 0 : 1;
+    int i = 0;
+    for (; i + 8 <= S; i += 8) {
+      const float4 a0 = *reinterpret_cast<const float4*>(ap + i), a1 = *reinterpret_cast<const float4*>(ap + i + 4);
+      const float4 x0 = *reinterpret_cast<const float4*>(xp + i * xs), x1 = *reinterpret_cast<const float4*>(xp + (i + 4) * xs);
+      accum = __fmaf_rn(a0.x, x0.x, accum); accum = __fmaf_rn(a0.y, x0.y, accum);
+      accum = __fmaf_rn(a0.z, x0.z, accum); accum = __fmaf_rn(a0.w, x0.w, accum);
+      accum = __fmaf_rn(a1.x, x1.x, accum); accum = __fmaf_rn(a1.y, x1.y, accum);
+      accum = __fmaf_rn(a1.z, x1.z, accum); accum = __fmaf_rn(a1.w, x1.w, accum);
+    }
+    for (; i < S; ++i) accum = __fmaf_rn(ap[i], xp[i * xs], accum);
+  }
+  const float acc = __shfl_sync(0xffffffffu, accum, 0);
+  const float depth = __shfl_sync(0xffffffffu, accum, 1);
+  if (lane >= 2 && lane <= 4 && co.rgb) {
+    float c = accum;
+    if (white_bkgd) c += 1.f - acc;
+    co.rgb[t * 3 + (lane - 2)] = c;
+  }
+  if (lane == 0) {
+    if (co.depth) co.depth[t] = depth;
+    if (co.acc) co.acc[t] = acc;
+    if (co.disp) {
+      const float q = depth / acc;   // 0/0 -> NaN propagates like torch.max(1e-10, nan)
+      co.disp[t] = 1.f / (isnan(q) ? q : fmaxf(1e-10f, q));
+    }
+  }
+  if (lane == 5 && co.beta2) co.beta2[t] = accum;
 }
 
-__global__ void composite_kernel(const float* __restrict__ raw, const float* __restrict__ z,
-                                 const float* __restrict__ rays_d, int n, int S, int white_bkgd,
-                                 CompositeOut co) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * kRayWarps)
+composite_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int n,
+                 int S, int white_bkgd, CompositeOut co) {
+  extern __shared__ __align__(16) float ray_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * kRayWarps + warp;
   if (t >= n) return;
-  const float dn = ray_norm(rays_d + (long long)t * 3);
-  float* wg = co.weights ? co.weights + (long long)t * S : nullptr;
-  composite_ray(raw + (long long)t * S * 5, z + (long long)t * S, dn, S, white_bkgd, t, co,
-                [wg](int i, float w) { if (wg) wg[i] = w; });
+  const RayScratch sc = ray_scratch(ray_smem + (size_t)warp * ray_scratch_floats(S), S);
+  const float dn = ray_norm(rays_d + t * 3);
+  composite_ray_warp(raw + t * S * 5, z + t * S, dn, S, white_bkgd, t, co, sc, lane);
 }
 
-// Coarse compositing + sample_pdf(det) (run_nerf_helpers.py:216-259) + sort(cat) (run_nerf.py:483).
-__global__ void coarse_resample_kernel(const float* __restrict__ raw, const float* __restrict__ z,
-                                       const float* __restrict__ rays_d, const float* __restrict__ u_vals,
-                                       int n, int Sc, int Ni, int white_bkgd, CompositeOut co,
-                                       float* __restrict__ z_fine, float* __restrict__ cdf_dump,
-                                       int32_t* __restrict__ inds_dump, float* __restrict__ zs_dump) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// Coarse compositing + sample_pdf(det) (run_nerf_helpers.py:216-259) + sort(cat) (run_nerf.py:483), one warp per ray.
+//
+// sample_pdf's two double-precision accumulations (sum of the weights, cumsum of the pdf; torch accumulates fp32
+// sums in double on CPU) are EXACT for these inputs, whatever the order: every addend is an fp32 number in
+// [1e-5 / 2, 2) (the weights are >= 0 and get + 1e-5, the pdf entries are >= 1e-5 / (1 + 126e-5)), so all partial
+// sums are multiples of 2^-41 below 2^7 -> at most 48 significant bits < 53.  A parallel reduction / scan in double
+// therefore returns the very same values as the reference's serial loops.  The inverse-cdf lookup is
+// searchsorted(right=True) = upper_bound on the non-decreasing cdf; the final sort(cat[...]) is the stable merge
+// of two sorted runs (coarse entries first on ties), whose output positions are ranks found by binary search.
+__global__ void __launch_bounds__(32 * kRayWarps)
+coarse_resample_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                       const float* __restrict__ u_vals, int n, int Sc, int Ni, int white_bkgd, CompositeOut co,
+                       float* __restrict__ z_fine, float* __restrict__ cdf_dump, int32_t* __restrict__ inds_dump,
+                       float* __restrict__ zs_dump) {
+  extern __shared__ __align__(16) float ray_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * kRayWarps + warp;
   if (t >= n) return;
-  float w[kMaxSc];
-  float cdf[kMaxSc];
-  float zs[kMaxSf];
-  const float* zc = z + (long long)t * Sc;
-  const float dn = ray_norm(rays_d + (long long)t * 3);
-  float* wg = co.weights ? co.weights + (long long)t * Sc : nullptr;
-  composite_ray(raw + (long long)t * Sc * 5, zc, dn, Sc, white_bkgd, t, co,
-                [&w, wg](int i, float v) { w[i] = v; if (wg) wg[i] = v; });
+  const int per_warp = resample_scratch_floats(Sc, Ni);
+  float* base = ray_smem + (size_t)warp * per_warp;
+  const RayScratch sc = ray_scratch(base, Sc);
+  float* cdf = base + ray_scratch_floats(Sc);   // [Sc]
+  float* zs = cdf + Sc;                          // [Ni]
+  float* zf = zs + Ni;                           // [Sc + Ni]
+  const float* wts = sc.pl + 3 * sc.Sp;          // coarse weights after composite_ray_warp
+  const float* zc = sc.sz;
+  const float dn = ray_norm(rays_d + t * 3);
+  composite_ray_warp(raw + t * Sc * 5, z + t * Sc, dn, Sc, white_bkgd, t, co, sc, lane);
+  __syncwarp();
 
-  // pdf over weights[1:-1] + 1e-5, cdf = [0, cumsum(pdf)]  -> nb = Sc-1 entries
+  // pdf over weights[1:-1] + 1e-5, cdf = [0, cumsum(pdf)]  -> nb = Sc-1 entries; lane L owns entries
+  // k = 1 + L*B .. 1 + L*B + B-1 of the cumsum
   const int nb = Sc - 1;
-  double sumd = 0.0;
-  for (int k = 1; k < Sc - 1; ++k) { w[k] = __fadd_rn(w[k], 1e-5f); sumd += (double)w[k]; }
+  const int npdf = Sc - 2;
+  const int B = (npdf + 31) / 32;      // <= 4 (Sc <= 128)
+  float wk[4];
+  double part = 0.0;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int k = 1 + lane * B + m;
+    wk[m] = 0.f;
+    if (m < B && k <= npdf) {
+      wk[m] = __fadd_rn(wts[k], 1e-5f);
+      part += (double)wk[m];
+    }
+  }
+  double sumd = part;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sumd += __shfl_xor_sync(0xffffffffu, sumd, o);
   const float sum = (float)sumd;
-  cdf[0] = 0.f;
+  double loc[4];
   double run = 0.0;
-  for (int k = 1; k < nb; ++k) { run += (double)__fdiv_rn(w[k], sum); cdf[k] = (float)run; }
-  if (cdf_dump) for (int k = 0; k < nb; ++k) cdf_dump[(long long)t * nb + k] = cdf[k];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int k = 1 + lane * B + m;
+    if (m < B && k <= npdf) run += (double)__fdiv_rn(wk[m], sum);
+    loc[m] = run;
+  }
+  double incl = run;   // inclusive scan of the per-lane totals
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  const double excl = incl - run;   // exact: all of these are multiples of 2^-41 below 2^7
+  if (lane == 0) cdf[0] = 0.f;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int k = 1 + lane * B + m;
+    if (m < B && k <= npdf) cdf[k] = (float)(excl + loc[m]);
+  }
+  __syncwarp();
+  if (cdf_dump) for (int k = lane; k < nb; k += 32) cdf_dump[t * nb + k] = cdf[k];
 
-  // inverse-cdf lookups; u ascending -> searchsorted(right=True) advances monotonically
-  int idx = 0;
-  float mean = 0.f;
-  for (int j = 0; j < Ni; ++j) {
+  // inverse-cdf lookups
+  for (int j = lane; j < Ni; j += 32) {
     const float u = u_vals[j];
-    while (idx < nb && cdf[idx] <= u) ++idx;
-    if (inds_dump) inds_dump[(long long)t * Ni + j] = idx;
+    int lo = 0, hi = nb;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+    }
+    const int idx = lo;
+    if (inds_dump) inds_dump[t * Ni + j] = idx;
     const int below = idx - 1 > 0 ? idx - 1 : 0;
     const int above = idx < nb - 1 ? idx : nb - 1;
     float denom = __fsub_rn(cdf[above], cdf[below]);
@@ -172,30 +305,53 @@ __global__ void coarse_resample_kernel(const float* __restrict__ raw, const floa
     const float ba = __fmul_rn(0.5f, __fadd_rn(zc[above + 1], zc[above]));
     const float s = __fadd_rn(bb, __fmul_rn(tt, __fsub_rn(ba, bb)));
     zs[j] = s;
-    mean += s;
-    if (zs_dump) zs_dump[(long long)t * Ni + j] = s;
+    if (zs_dump) zs_dump[t * Ni + j] = s;
   }
-  if (co.z_std) {   // torch.std(z_samples, unbiased=False) (run_nerf.py:501)
+  __syncwarp();
+  if (co.z_std && lane == 0) {   // torch.std(z_samples, unbiased=False) (run_nerf.py:501)
+    float mean = 0.f;
+    for (int j = 0; j < Ni; ++j) mean += zs[j];
     mean /= (float)Ni;
     float var = 0.f;
     for (int j = 0; j < Ni; ++j) { const float dlt = zs[j] - mean; var = fmaf(dlt, dlt, var); }
     co.z_std[t] = sqrtf(var / (float)Ni);
   }
-  // torch.sort(cat[z_vals, z_samples]): both runs are ascending up to rounding; make the
-  // sample run exactly sorted (no-op walk when it already is), then merge.
-  for (int j = 1; j < Ni; ++j) {
-    const float v = zs[j];
-    int k = j - 1;
-    while (k >= 0 && zs[k] > v) { zs[k + 1] = zs[k]; --k; }
-    zs[k + 1] = v;
+  // torch.sort(cat[z_vals, z_samples]): both runs are ascending up to rounding; make the sample run exactly
+  // sorted (almost never needed), then merge by rank.
+  bool unsorted = false;
+  for (int j = lane + 1; j < Ni; j += 32) unsorted |= zs[j - 1] > zs[j];
+  if (__any_sync(0xffffffffu, unsorted)) {
+    if (lane == 0) {
+      for (int j = 1; j < Ni; ++j) {
+        const float v = zs[j];
+        int k = j - 1;
+        while (k >= 0 && zs[k] > v) { zs[k + 1] = zs[k]; --k; }
+        zs[k + 1] = v;
+      }
+    }
+    __syncwarp();
   }
-  float* zf = z_fine + (long long)t * (Sc + Ni);
-  int a = 0, b = 0;
-  for (int o = 0; o < Sc + Ni; ++o) {
-    const bool take_c = (b >= Ni) || (a < Sc && zc[a] <= zs[b]);
-    zf[o] = take_c ? zc[a] : zs[b];
-    if (take_c) ++a; else ++b;
+  for (int a = lane; a < Sc; a += 32) {   // coarse entry a goes after the samples strictly below it
+    const float v = zc[a];
+    int lo = 0, hi = Ni;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (zs[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    zf[a + lo] = v;
   }
+  for (int b = lane; b < Ni; b += 32) {   // sample b goes after the coarse entries <= it
+    const float v = zs[b];
+    int lo = 0, hi = Sc;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (zc[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    zf[b + lo] = v;
+  }
+  __syncwarp();
+  float* zg = z_fine + t * (Sc + Ni);
+  for (int o = lane; o < Sc + Ni; o += 32) zg[o] = zf[o];
 }
 
 // score[v] = sum_rays beta2 / R   (nerf.py:307-309); fp64 tree, deterministic.
@@ -291,19 +447,29 @@ int launch_coarse_z(const float* t_vals, int n, int S, float near_plane, float f
   return 1;
 }
 
+template <typename K>
+static bool ray_kernel_smem(K kern, size_t bytes) {
+  if (bytes <= 48 * 1024) return true;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+}
+
 int launch_coarse_resample(const float* raw, const float* z, const float* rays_d, const float* u_vals, int n,
                            int Sc, int Ni, int white_bkgd, CompositeOut co, float* z_fine, float* cdf_dump,
                            int32_t* inds_dump, float* zs_dump, cudaStream_t st) {
   if (n <= 0) return 0;
-  coarse_resample_kernel<<<(n + 127) / 128, 128, 0, st>>>(raw, z, rays_d, u_vals, n, Sc, Ni, white_bkgd, co,
-                                                          z_fine, cdf_dump, inds_dump, zs_dump);
+  const size_t smem = (size_t)kRayWarps * resample_scratch_floats(Sc, Ni) * sizeof(float);
+  if (!ray_kernel_smem(coarse_resample_kernel, smem)) return -1;
+  coarse_resample_kernel<<<(n + kRayWarps - 1) / kRayWarps, 32 * kRayWarps, smem, st>>>(
+      raw, z, rays_d, u_vals, n, Sc, Ni, white_bkgd, co, z_fine, cdf_dump, inds_dump, zs_dump);
   return 1;
 }
 
 int launch_composite(const float* raw, const float* z, const float* rays_d, int n, int S, int white_bkgd,
                      CompositeOut co, cudaStream_t st) {
   if (n <= 0) return 0;
-  composite_kernel<<<(n + 127) / 128, 128, 0, st>>>(raw, z, rays_d, n, S, white_bkgd, co);
+  const size_t smem = (size_t)kRayWarps * ray_scratch_floats(S) * sizeof(float);
+  if (!ray_kernel_smem(composite_kernel, smem)) return -1;
+  composite_kernel<<<(n + kRayWarps - 1) / kRayWarps, 32 * kRayWarps, smem, st>>>(raw, z, rays_d, n, S, white_bkgd, co);
   return 1;
 }
 
