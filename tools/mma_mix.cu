@@ -80,6 +80,5 @@ int main() {
   { Pattern p{}; for (int i = 0; i < 2; ++i) { add(p, 4, 128, 0); add(p, 4, 128, 128); } add(p, 8, 128, 0); add(p, 8, 128, 128);
     run("2 x (4 h0, 4 h1), 8 h0, 8 h1, all N128", p); }
   { Pattern p{}; add(p, 8, 256, 0); add(p, 8, 192, 0); add(p, 8, 64, 192); run("8 x N256, 8 x N192, 8 x N64 @192", p); }
-  { Pattern p{}; add(p, 8, 256, 0); add(p, 8, 64, 0); add(p, 8, 192, 64); run("8 x N256, 8 x N64, 8 x N192 @64", p); }
   return 0;
 }
