@@ -376,10 +376,10 @@ def main():
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                              "frac": achieved / sustained,
-                             # DRAM bytes per launch: 11.8 B per MLP evaluation measured by ncu --set full
-                             # (profiles/r1_mlp_tc_ncu_metrics.txt: 51.2 MB for a 4.33 M-evaluation launch) x the
+                             # DRAM bytes per launch: 11.97 B per MLP evaluation measured by ncu --set full
+                             # (profiles/r1_mlp_tc_ncu_metrics.txt: 51.8 MB for a 4.33 M-evaluation launch) x the
                              # evaluations of an average launch of this run; algorithmic = 24 B/evaluation + 36 B/ray
-                             "traffic": (11.8 * mlp_evals / max(1, mlp_launches)) if tensor else None,
+                             "traffic": (11.97 * mlp_evals / max(1, mlp_launches)) if tensor else None,
                              "traffic_unit": "bytes/launch (ncu dram__bytes_read+write per evaluation x evaluations per launch)",
                              "peak_source": f"{src} bf16_tflops_sustained (cuBLAS bf16 under the power cap; the kernel is timed inside a long step)",
                              "kernel": "mlp_tc_kernel (fused encode + 10-layer NeRF/NeurAR MLP, tcgen05 TS-mode, activations in tensor memory)" if tensor else "mlp_simt_kernel (fp32 FFMA; tensor peak shown for scale only)",
