@@ -107,10 +107,11 @@ __device__ __forceinline__ RaySpan ray_span(const NgpParams& P, const float* o, 
   return s;
 }
 
-template <bool FILL>
+// Count pass.  One warp per ray walks 32 steps per iteration, tests the occupancy bit of each step's cell and
+// ballots the kept lanes.  The ballots are stored (masks[ray][word]) so that the fill pass replays them instead of
+// recomputing cells and bitfield lookups.
 __global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n,
-                                 int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
-                                 float* __restrict__ t_out, int32_t* __restrict__ ray_of_sample) {
+                                 int32_t* __restrict__ counts, uint32_t* __restrict__ masks, int words_per_ray) {
   const int ray = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (ray >= n) return;
@@ -118,14 +119,13 @@ __global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, 
 #pragma unroll
   for (int c = 0; c < 3; ++c) { o[c] = rays_o[(long long)ray * 3 + c]; d[c] = rays_d[(long long)ray * 3 + c]; }
   const RaySpan sp = ray_span(P, o, d);
-  const long long base_out = FILL ? (long long)offsets[ray] : 0;
+  uint32_t* mrow = masks + (long long)ray * words_per_ray;
   int count = 0;
   for (int base = 0; base < sp.n_steps && count < P.max_samples; base += 32) {
     const int i = base + lane;
     bool keep = false;
-    float t = 0.f;
     if (i < sp.n_steps) {
-      t = __fadd_rn(sp.t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
+      const float t = __fadd_rn(sp.t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
       int cell[3];
       bool ok = true;
 #pragma unroll
@@ -142,18 +142,108 @@ __global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, 
       }
     }
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    const int rank = count + __popc(mask & ((1u << lane) - 1u));      // prefix sum over the warp's kept lanes
-    if (FILL && keep && rank < P.max_samples) {
-      t_out[base_out + rank] = t;
-      ray_of_sample[base_out + rank] = ray;
-    }
+    if (lane == 0 && (base >> 5) < words_per_ray) mrow[base >> 5] = mask;
     count += __popc(mask);
   }
-  if (!FILL && lane == 0) counts[ray] = count < P.max_samples ? count : P.max_samples;
+  if (lane == 0) counts[ray] = count < P.max_samples ? count : P.max_samples;
 }
 
-// exclusive scan of the per-ray counts by ONE block: tiles of 4096 counts (coalesced int4 loads), warp-shuffle
-// scans, running carry.  n is the ray count of a chunk (<= 2^20), so a single block is a few microseconds.
+// Fill pass: kept step i of a ray (bit i & 31 of ballot word i >> 5) gets slot offsets[ray] + (number of kept steps
+// before it) -- the warp-level compaction of the count pass, replayed across the words: lane w owns word w, a
+// shuffle scan of the popcounts gives its first slot.  Words after the one where the count pass stopped (sample
+// budget reached) were never written; every rank they produce is >= counts[ray] and is dropped.
+__global__ void ngp_fill_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n,
+                                const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
+                                const uint32_t* __restrict__ masks, int words_per_ray, float* __restrict__ t_out,
+                                int32_t* __restrict__ ray_of_sample) {
+  const int ray = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ray >= n) return;
+  const int cnt = counts[ray];
+  if (cnt == 0) return;
+  float o[3], d[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { o[c] = rays_o[(long long)ray * 3 + c]; d[c] = rays_d[(long long)ray * 3 + c]; }
+  const RaySpan sp = ray_span(P, o, d);
+  const long long base_out = offsets[ray];
+  const uint32_t* mrow = masks + (long long)ray * words_per_ray;
+  int n_words = (sp.n_steps + 31) >> 5;
+  if (n_words > words_per_ray) n_words = words_per_ray;
+  int carry = 0;
+  for (int w0 = 0; w0 < n_words && carry < cnt; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t m = w < n_words ? mrow[w] : 0u;
+    const int pc = __popc(m);
+    int incl = pc;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, k);
+      if (lane >= k) incl += v;
+    }
+    int rank = carry + incl - pc;
+    while (m && rank < cnt) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int i = w * 32 + b;
+      t_out[base_out + rank] = __fadd_rn(sp.t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
+      ray_of_sample[base_out + rank] = ray;
+      ++rank;
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// Exclusive scan of the per-ray counts in three small launches: per-tile sums (4096 counts per block), a single
+// block scanning the (<= a few hundred) tile sums with the kernel below, and per-tile local scans.
+constexpr int kScanTile = 4096;   // 256 threads x 16 counts
+
+__global__ void __launch_bounds__(256) ngp_tile_sum_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ tile_sums) {
+  __shared__ int warp_sum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * kScanTile + threadIdx.x * 16;
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += i0 + j < n ? counts[i0 + j] : 0;
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  if (lane == 0) warp_sum[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += warp_sum[k];
+    tile_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) ngp_tile_scan_kernel(const int32_t* __restrict__ counts, int n,
+                                                            const int32_t* __restrict__ tile_offsets,
+                                                            int32_t* __restrict__ offsets) {
+  __shared__ int warp_sum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * kScanTile + threadIdx.x * 16;
+  int v[16];
+  int mine = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { v[j] = i0 + j < n ? counts[i0 + j] : 0; mine += v[j]; }
+  int incl = mine;
+#pragma unroll
+  for (int k = 1; k < 32; k <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, k);
+    if (lane >= k) incl += t;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  int run = tile_offsets[blockIdx.x] + incl - mine;
+  for (int k = 0; k < warp; ++k) run += warp_sum[k];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (i0 + j < n) offsets[i0 + j] = run;
+    run += v[j];
+  }
+}
+
+// exclusive scan by ONE block: tiles of 4096 entries, warp-shuffle scans, running carry (used on the tile sums)
 __global__ void ngp_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets,
                                 int32_t* __restrict__ total) {
   __shared__ int warp_sum[32];
@@ -748,18 +838,25 @@ tensorf_field_kernel(NgpParams P, const float* __restrict__ rays_o, const float*
 }
 
 // ---------------------------------------------------------------- compositing ----------------------
+// Eight lanes per ray (four rays per warp): kept samples per ray average below ten, so a full warp per ray would
+// idle most lanes.  Transmittance = exclusive product of (1 - alpha + 1e-10) by an 8-wide shuffle scan, carried
+// across groups of eight samples in T.
 __global__ void ngp_composite_kernel(NgpParams P, const float* __restrict__ raw, const float* __restrict__ t_s,
                                      const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, int n,
                                      float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ acc,
                                      float* __restrict__ beta2) {
-  const int ray = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (ray >= n) return;
-  const int cnt = counts[ray];
-  const long long off = offsets[ray];
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool live = gid < n;
+  const int ray = live ? (int)gid : 0;
+  const int cnt = live ? counts[ray] : 0;
+  const long long off = live ? offsets[ray] : 0;
+  int maxcnt = cnt;
+#pragma unroll
+  for (int k = 16; k >= 8; k >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, k));
   float T = 1.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, dep = 0.f, a = 0.f, b2 = 0.f;
-  for (int base = 0; base < cnt; base += 32) {
-    const int s = base + lane;
+  for (int base = 0; base < maxcnt; base += 8) {
+    const int s = base + sub;
     float alpha = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, tt = 0.f, beta = 0.f;
     if (s < cnt) {
       const float* r = raw + (off + s) * 5;
@@ -768,30 +865,29 @@ __global__ void ngp_composite_kernel(NgpParams P, const float* __restrict__ raw,
       beta = r[4];
       tt = t_s[off + s];
     }
-    // exclusive product of (1 - alpha + 1e-10) over the lanes (run_nerf.py:378), carried across chunks in T
-    float f = s < cnt ? (1.f - alpha + 1e-10f) : 1.f;
+    const float f = s < cnt ? (1.f - alpha + 1e-10f) : 1.f;   // run_nerf.py:378
     float incl = f;
 #pragma unroll
-    for (int k = 1; k < 32; k <<= 1) {
-      const float v = __shfl_up_sync(0xffffffffu, incl, k);
-      if (lane >= k) incl *= v;
+    for (int k = 1; k < 8; k <<= 1) {
+      const float v = __shfl_up_sync(0xffffffffu, incl, k, 8);
+      if (sub >= k) incl *= v;
     }
-    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = 1.f;
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1, 8);
+    if (sub == 0) excl = 1.f;
     const float w = alpha * T * excl;
     c0 = fmaf(w, r0, c0); c1 = fmaf(w, r1, c1); c2 = fmaf(w, r2, c2);
     dep = fmaf(w, tt, dep);
     a += w;
     b2 = fmaf(beta, beta, b2);
-    T *= __shfl_sync(0xffffffffu, incl, 31);
+    T *= __shfl_sync(0xffffffffu, incl, 7, 8);
   }
 #pragma unroll
-  for (int k = 16; k > 0; k >>= 1) {
+  for (int k = 4; k > 0; k >>= 1) {
     c0 += __shfl_xor_sync(0xffffffffu, c0, k); c1 += __shfl_xor_sync(0xffffffffu, c1, k);
     c2 += __shfl_xor_sync(0xffffffffu, c2, k); dep += __shfl_xor_sync(0xffffffffu, dep, k);
     a += __shfl_xor_sync(0xffffffffu, a, k); b2 += __shfl_xor_sync(0xffffffffu, b2, k);
   }
-  if (lane == 0) {
+  if (live && sub == 0) {
     if (P.white_bkgd) { c0 += 1.f - a; c1 += 1.f - a; c2 += 1.f - a; }
     if (rgb) { rgb[(long long)ray * 3] = c0; rgb[(long long)ray * 3 + 1] = c1; rgb[(long long)ray * 3 + 2] = c2; }
     if (depth) depth[ray] = dep;
@@ -808,22 +904,39 @@ int launch_ngp_encode(const NgpParams& P, const float* u, long long M, float* en
   return 1;
 }
 
-int launch_ngp_march_count(const NgpParams& P, const float* ro, const float* rd, int n, int32_t* counts, cudaStream_t st) {
+int ngp_mask_words(const NgpParams& P) {
+  // n_steps <= min(max_steps, ceil((far - near) / dt)) up to rounding of the fp32 span: + 2 steps of margin
+  const double span = ((double)P.far_plane - (double)P.near_plane) / (double)P.dt;
+  long long bound = (long long)std::ceil(span) + 2;
+  if (bound > P.max_steps) bound = P.max_steps;
+  if (bound < 1) bound = 1;
+  return (int)((bound + 31) / 32);
+}
+
+int ngp_scan_tiles(int n) { return (n + kScanTile - 1) / kScanTile; }
+
+int launch_ngp_march_count(const NgpParams& P, const float* ro, const float* rd, int n, int32_t* counts, uint32_t* masks,
+                           cudaStream_t st) {
   if (n <= 0) return 0;
-  ngp_march_kernel<false><<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, ro, rd, n, counts, nullptr, nullptr, nullptr);
+  ngp_march_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, ro, rd, n, counts, masks, ngp_mask_words(P));
   return 1;
 }
 
-int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* total, cudaStream_t st) {
+// tile_ws: 2 * ngp_scan_tiles(n) ints
+int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* total, int32_t* tile_ws, cudaStream_t st) {
   if (n <= 0) return 0;
-  ngp_scan_kernel<<<1, 1024, 0, st>>>(counts, n, offsets, total);
-  return 1;
+  const int tiles = ngp_scan_tiles(n);
+  ngp_tile_sum_kernel<<<tiles, 256, 0, st>>>(counts, n, tile_ws);
+  ngp_scan_kernel<<<1, 1024, 0, st>>>(tile_ws, tiles, tile_ws + tiles, total);
+  ngp_tile_scan_kernel<<<tiles, 256, 0, st>>>(counts, n, tile_ws + tiles, offsets);
+  return 3;
 }
 
-int launch_ngp_march_fill(const NgpParams& P, const float* ro, const float* rd, int n, const int32_t* offsets, float* t,
-                          int32_t* ray_of_sample, cudaStream_t st) {
+int launch_ngp_march_fill(const NgpParams& P, const float* ro, const float* rd, int n, const int32_t* counts,
+                          const int32_t* offsets, const uint32_t* masks, float* t, int32_t* ray_of_sample, cudaStream_t st) {
   if (n <= 0) return 0;
-  ngp_march_kernel<true><<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, ro, rd, n, nullptr, offsets, t, ray_of_sample);
+  ngp_fill_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, ro, rd, n, counts, offsets, masks,
+                                                                               ngp_mask_words(P), t, ray_of_sample);
   return 1;
 }
 
@@ -859,7 +972,7 @@ int launch_tensorf_field(const NgpParams& P, const float* ro, const float* rd, c
 int launch_ngp_composite(const NgpParams& P, const float* raw, const float* t, const int32_t* counts,
                          const int32_t* offsets, int n, float* rgb, float* depth, float* acc, float* beta2, cudaStream_t st) {
   if (n <= 0) return 0;
-  ngp_composite_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, raw, t, counts, offsets, n, rgb, depth, acc, beta2);
+  ngp_composite_kernel<<<(unsigned)(((long long)n * 8 + 255) / 256), 256, 0, st>>>(P, raw, t, counts, offsets, n, rgb, depth, acc, beta2);
   return 1;
 }
 
