@@ -94,7 +94,7 @@ struct evpp_handle {
   bool ngp_configured = false, ngp_has_occ = false, ngp_has_params = false, ngp_tensorf = false;
   DevBuf tf_planes, tf_lines, tf_mlp;
   NgpParams ngp{};
-  DevBuf ngp_table, ngp_mlp, ngp_bits, ngp_ro, ngp_rd, ngp_counts, ngp_offsets, ngp_total, ngp_masks, ngp_tiles, ngp_t, ngp_ray, ngp_raw,
+  DevBuf ngp_table, ngp_mlp, ngp_bits, ngp_ro, ngp_rd, ngp_counts, ngp_offsets, ngp_total, ngp_masks, ngp_tiles, ngp_t0, ngp_t, ngp_ray, ngp_raw,
       ngp_beta2, ngp_scores;
   int64_t ngp_samples = 0;       // kept samples since handle creation
   int ngp_chunk_rays = 1 << 20;  // rays per marching chunk (one count -> scan -> fill round trip each)
@@ -355,7 +355,7 @@ int evpp_destroy(evpp_handle* h) {
                     &h->raw_f, &h->beta2, &h->st_c2w, &h->st_pix, &h->st_scores, &h->w_c, &h->cdf, &h->inds, &h->zs,
                     &h->tsdf_state, &h->tsdf_nray, &h->tsdf_t, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d,
                     &h->tsdf_vu, &h->tsdf_vd, &h->ngp_table, &h->ngp_mlp, &h->ngp_bits, &h->ngp_ro, &h->ngp_rd,
-                    &h->ngp_counts, &h->ngp_offsets, &h->ngp_total, &h->ngp_masks, &h->ngp_tiles, &h->ngp_t, &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2,
+                    &h->ngp_counts, &h->ngp_offsets, &h->ngp_total, &h->ngp_masks, &h->ngp_tiles, &h->ngp_t0, &h->ngp_t, &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2,
                     &h->ngp_scores, &h->tf_planes, &h->tf_lines, &h->tf_mlp})
     b->release();
   delete h;
@@ -855,11 +855,11 @@ int evpp_ngp_encode(evpp_handle* h, const float* u, int64_t M, float* enc, int32
 static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, int n, evpp_ngp_out* out, long long off,
                              float* beta2, cudaStream_t st) {
   if (h->ngp_counts.ensure((size_t)n * 4) || h->ngp_offsets.ensure((size_t)n * 4) || h->ngp_total.ensure(4) ||
-      h->ngp_masks.ensure((size_t)n * ngp_mask_words(h->ngp) * 4) || h->ngp_tiles.ensure((size_t)2 * ngp_scan_tiles(n) * 4))
+      h->ngp_masks.ensure((size_t)n * ngp_mask_words(h->ngp) * 4) || h->ngp_tiles.ensure((size_t)2 * ngp_scan_tiles(n) * 4) || h->ngp_t0.ensure((size_t)n * 4))
     return fail(EVPP_ERR_CUDA, "NGP workspace alloc failed");
   int32_t* counts = out && out->counts ? out->counts + off : h->ngp_counts.as<int32_t>();
   int32_t* offsets = h->ngp_offsets.as<int32_t>();
-  h->launches += launch_ngp_march_count(h->ngp, ro, rd, n, counts, h->ngp_masks.as<uint32_t>(), st);
+  h->launches += launch_ngp_march_count(h->ngp, ro, rd, n, counts, h->ngp_masks.as<uint32_t>(), h->ngp_t0.as<float>(), st);
   h->launches += launch_ngp_scan(counts, n, offsets, h->ngp_total.as<int32_t>(), h->ngp_tiles.as<int32_t>(), st);
   int32_t total = 0;
   CUDA_TRY(cudaMemcpyAsync(&total, h->ngp_total.p, 4, cudaMemcpyDeviceToHost, st));
@@ -867,8 +867,8 @@ static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, i
   const long long M = total;
   if (h->ngp_t.ensure((size_t)(M + 1) * 4) || h->ngp_ray.ensure((size_t)(M + 1) * 4) || h->ngp_raw.ensure((size_t)(M + 1) * 20))
     return fail(EVPP_ERR_CUDA, "NGP sample workspace alloc failed (%lld samples)", M);
-  h->launches += launch_ngp_march_fill(h->ngp, ro, rd, n, counts, offsets, h->ngp_masks.as<uint32_t>(), h->ngp_t.as<float>(),
-                                        h->ngp_ray.as<int32_t>(), st);
+  h->launches += launch_ngp_march_fill(h->ngp, n, counts, offsets, h->ngp_masks.as<uint32_t>(), h->ngp_t0.as<float>(),
+                                        h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), st);
   float* enc_dump = out && out->enc && out->sample_capacity >= out->total_so_far + M ? out->enc + out->total_so_far * 32 : nullptr;
   if (h->ngp_tensorf)
     h->launches += launch_tensorf_field(h->ngp, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), M, h->ngp_raw.as<float>(),

@@ -111,7 +111,8 @@ __device__ __forceinline__ RaySpan ray_span(const NgpParams& P, const float* o, 
 // ballots the kept lanes.  The ballots are stored (masks[ray][word]) so that the fill pass replays them instead of
 // recomputing cells and bitfield lookups.
 __global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n,
-                                 int32_t* __restrict__ counts, uint32_t* __restrict__ masks, int words_per_ray) {
+                                 int32_t* __restrict__ counts, uint32_t* __restrict__ masks, int words_per_ray,
+                                 float* __restrict__ t0_out) {
   const int ray = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (ray >= n) return;
@@ -121,75 +122,93 @@ __global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, 
   const RaySpan sp = ray_span(P, o, d);
   uint32_t* mrow = masks + (long long)ray * words_per_ray;
   int count = 0;
-  for (int base = 0; base < sp.n_steps && count < P.max_samples; base += 32) {
-    const int i = base + lane;
-    bool keep = false;
-    if (i < sp.n_steps) {
-      const float t = __fadd_rn(sp.t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
-      int cell[3];
-      bool ok = true;
+  // Four 32-step batches per iteration: their cell computations and bitfield loads are independent, so they are
+  // issued together; the sequential rule "stop once the sample budget is reached" is applied afterwards, batch by
+  // batch, exactly as a one-batch-at-a-time walk would.
+  for (int base0 = 0; base0 < sp.n_steps && count < P.max_samples; base0 += 128) {
+    unsigned bal[4];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float p = __fadd_rn(o[c], __fmul_rn(d[c], t));
-        const float u = __fmul_rn(__fsub_rn(p, P.amin[c]), P.inv_size[c]);
-        const float g = floorf(__fmul_rn(u, (float)P.grid_res));
-        ok = ok && g >= 0.f && g < (float)P.grid_res;
-        cell[c] = (int)g;
+    for (int j = 0; j < 4; ++j) {
+      const int i = base0 + j * 32 + lane;
+      bool keep = false;
+      if (i < sp.n_steps) {
+        const float t = __fadd_rn(sp.t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
+        int cell[3];
+        bool ok = true;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float p = __fadd_rn(o[c], __fmul_rn(d[c], t));
+          const float u = __fmul_rn(__fsub_rn(p, P.amin[c]), P.inv_size[c]);
+          const float g = floorf(__fmul_rn(u, (float)P.grid_res));
+          ok = ok && g >= 0.f && g < (float)P.grid_res;
+          cell[c] = (int)g;
+        }
+        if (ok) {
+          const long long lin = ((long long)cell[0] * P.grid_res + cell[1]) * P.grid_res + cell[2];
+          keep = (P.bitfield[lin >> 3] >> (lin & 7)) & 1;
+        }
       }
-      if (ok) {
-        const long long lin = ((long long)cell[0] * P.grid_res + cell[1]) * P.grid_res + cell[2];
-        keep = (P.bitfield[lin >> 3] >> (lin & 7)) & 1;
+      bal[j] = __ballot_sync(0xffffffffu, keep);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int base = base0 + j * 32;
+      if (base < sp.n_steps && count < P.max_samples) {
+        if (lane == 0 && (base >> 5) < words_per_ray) mrow[base >> 5] = bal[j];
+        count += __popc(bal[j]);
       }
     }
-    const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0 && (base >> 5) < words_per_ray) mrow[base >> 5] = mask;
-    count += __popc(mask);
   }
-  if (lane == 0) counts[ray] = count < P.max_samples ? count : P.max_samples;
+  if (lane == 0) {
+    counts[ray] = count < P.max_samples ? count : P.max_samples;
+    t0_out[ray] = sp.t0;
+  }
 }
 
 // Fill pass: kept step i of a ray (bit i & 31 of ballot word i >> 5) gets slot offsets[ray] + (number of kept steps
-// before it) -- the warp-level compaction of the count pass, replayed across the words: lane w owns word w, a
-// shuffle scan of the popcounts gives its first slot.  Words after the one where the count pass stopped (sample
-// budget reached) were never written; every rank they produce is >= counts[ray] and is dropped.
-__global__ void ngp_fill_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n,
-                                const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
-                                const uint32_t* __restrict__ masks, int words_per_ray, float* __restrict__ t_out,
-                                int32_t* __restrict__ ray_of_sample) {
-  const int ray = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (ray >= n) return;
-  const int cnt = counts[ray];
-  if (cnt == 0) return;
-  float o[3], d[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { o[c] = rays_o[(long long)ray * 3 + c]; d[c] = rays_d[(long long)ray * 3 + c]; }
-  const RaySpan sp = ray_span(P, o, d);
-  const long long base_out = offsets[ray];
+// before it) -- the warp-level compaction of the count pass, replayed across the words.  Eight lanes per ray, lane
+// w owns word w of a group of eight words, a shuffle scan of the popcounts gives its first slot.  Words the count
+// pass never wrote (after the ray's last step, or after the sample budget was reached) only produce ranks
+// >= counts[ray], which are dropped, so neither the step count nor the span has to be recomputed: the ray's first
+// sample position t0 is all that is carried over.
+__global__ void ngp_fill_kernel(NgpParams P, int n, const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
+                                const uint32_t* __restrict__ masks, int words_per_ray, const float* __restrict__ t0_in,
+                                float* __restrict__ t_out, int32_t* __restrict__ ray_of_sample) {
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool live = gid < n;
+  const int ray = live ? (int)gid : 0;
   const uint32_t* mrow = masks + (long long)ray * words_per_ray;
-  int n_words = (sp.n_steps + 31) >> 5;
-  if (n_words > words_per_ray) n_words = words_per_ray;
+  const int cnt = live ? counts[ray] : 0;
+  const long long base_out = offsets[ray];
+  const float t0 = t0_in[ray];
+  uint32_t m_next = (live && sub < words_per_ray) ? mrow[sub] : 0u;
+  // groups of a warp run the same number of rounds (the shuffles need all 32 lanes)
+  int rounds = cnt > 0 ? (words_per_ray + 7) >> 3 : 0;
+#pragma unroll
+  for (int k = 16; k >= 8; k >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, k));
   int carry = 0;
-  for (int w0 = 0; w0 < n_words && carry < cnt; w0 += 32) {
-    const int w = w0 + lane;
-    uint32_t m = w < n_words ? mrow[w] : 0u;
+  for (int r = 0; r < rounds; ++r) {
+    const int w = r * 8 + sub;
+    uint32_t m = carry < cnt ? m_next : 0u;
+    if (r + 1 < rounds) m_next = (live && w + 8 < words_per_ray) ? mrow[w + 8] : 0u;
     const int pc = __popc(m);
     int incl = pc;
 #pragma unroll
-    for (int k = 1; k < 32; k <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, k);
-      if (lane >= k) incl += v;
+    for (int k = 1; k < 8; k <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, k, 8);
+      if (sub >= k) incl += v;
     }
     int rank = carry + incl - pc;
     while (m && rank < cnt) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
       const int i = w * 32 + b;
-      t_out[base_out + rank] = __fadd_rn(sp.t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
+      t_out[base_out + rank] = __fadd_rn(t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
       ray_of_sample[base_out + rank] = ray;
       ++rank;
     }
-    carry += __shfl_sync(0xffffffffu, incl, 31);
+    carry += __shfl_sync(0xffffffffu, incl, 7, 8);
   }
 }
 
@@ -916,9 +935,9 @@ int ngp_mask_words(const NgpParams& P) {
 int ngp_scan_tiles(int n) { return (n + kScanTile - 1) / kScanTile; }
 
 int launch_ngp_march_count(const NgpParams& P, const float* ro, const float* rd, int n, int32_t* counts, uint32_t* masks,
-                           cudaStream_t st) {
+                           float* t0, cudaStream_t st) {
   if (n <= 0) return 0;
-  ngp_march_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, ro, rd, n, counts, masks, ngp_mask_words(P));
+  ngp_march_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, ro, rd, n, counts, masks, ngp_mask_words(P), t0);
   return 1;
 }
 
@@ -932,11 +951,11 @@ int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* tot
   return 3;
 }
 
-int launch_ngp_march_fill(const NgpParams& P, const float* ro, const float* rd, int n, const int32_t* counts,
-                          const int32_t* offsets, const uint32_t* masks, float* t, int32_t* ray_of_sample, cudaStream_t st) {
+int launch_ngp_march_fill(const NgpParams& P, int n, const int32_t* counts, const int32_t* offsets, const uint32_t* masks,
+                          const float* t0, float* t, int32_t* ray_of_sample, cudaStream_t st) {
   if (n <= 0) return 0;
-  ngp_fill_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, ro, rd, n, counts, offsets, masks,
-                                                                               ngp_mask_words(P), t, ray_of_sample);
+  ngp_fill_kernel<<<(unsigned)(((long long)n * 8 + 255) / 256), 256, 0, st>>>(P, n, counts, offsets, masks, ngp_mask_words(P), t0,
+                                                                              t, ray_of_sample);
   return 1;
 }
 

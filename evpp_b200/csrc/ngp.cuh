@@ -43,10 +43,10 @@ int launch_ngp_encode(const NgpParams& P, const float* u, long long M, float* en
 int ngp_mask_words(const NgpParams& P);   // ballot words per ray kept between the count and the fill pass
 int ngp_scan_tiles(int n);                // the scan needs a workspace of 2 * ngp_scan_tiles(n) ints
 int launch_ngp_march_count(const NgpParams& P, const float* ro, const float* rd, int n, int32_t* counts, uint32_t* masks,
-                           cudaStream_t st);
+                           float* t0, cudaStream_t st);
 int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* total, int32_t* tile_ws, cudaStream_t st);
-int launch_ngp_march_fill(const NgpParams& P, const float* ro, const float* rd, int n, const int32_t* counts,
-                          const int32_t* offsets, const uint32_t* masks, float* t, int32_t* ray_of_sample, cudaStream_t st);
+int launch_ngp_march_fill(const NgpParams& P, int n, const int32_t* counts, const int32_t* offsets, const uint32_t* masks,
+                          const float* t0, float* t, int32_t* ray_of_sample, cudaStream_t st);
 int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
                      long long M, float* raw, float* enc_dump, int num_sms, bool tensor_cores, cudaStream_t st);
 int launch_tensorf_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
