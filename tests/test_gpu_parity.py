@@ -478,8 +478,31 @@ def test_ngp_march_counts_and_samples_bit_exact(ngp_setup):
     small = evpp_b200.NGPScorer(device=0, H=12, W=16, focal=12.0, max_samples=5)
     small.set_occupancy(bits)
     small.load_params(p)
-    c5 = small.render_rays(ro, rd)["counts"].cpu().numpy()
-    assert np.array_equal(c5, np.minimum(counts, 5))
+    o5 = small.render_rays(ro, rd, want_samples=True)
+    assert np.array_equal(o5["counts"].cpu().numpy(), np.minimum(counts, 5))
+    assert np.array_equal(o5["t"].cpu().numpy(), np.concatenate([t[:5] for t in ts]))   # budget reached mid-ray
+
+
+@pytest.mark.parametrize("dt,max_steps,max_samples", [(0.004, 1024, 256), (0.003, 2000, 64), (0.05, 1024, 256)])
+def test_ngp_march_step_and_budget_variants(ngp_setup, dt, max_steps, max_samples):
+    """The fill pass replays the count pass's ballot words (8 words per round): more than 32 words per ray, the step
+    cap, the sample budget and a multi-tile scan (14 404 rays > one 4096-count tile), all bit-exact."""
+    import evpp_b200
+    from oracle import ngp_oracle as N
+    _, p, levels, bits = ngp_setup
+    views = O.hemisphere_views(3, seed=2, center=(0., 1., 0.5), rmin=1.5, rmax=2.3)
+    ro, rd = O.build_view_rays(O.views_to_poses(views), 60, 80, O.make_K(60, 80, 60.0))
+    _, eo, ed = _ngp_rays()
+    ro, rd = torch.cat([ro, eo[-4:]]), torch.cat([rd, ed[-4:]])
+    sc = evpp_b200.NGPScorer(device=0, H=60, W=80, focal=60.0, dt=dt, max_steps=max_steps, max_samples=max_samples)
+    sc.set_occupancy(bits)
+    sc.load_params(p)
+    out = sc.render_rays(ro, rd, want_samples=True)
+    counts, ts = N.march(ro.numpy(), rd.numpy(), bits, 128, NGP_CFG["aabb_min"], NGP_CFG["aabb_max"], 0.5, 6.0, dt, max_steps,
+                         max_samples)
+    assert np.array_equal(out["counts"].cpu().numpy(), counts)
+    assert out["total"] == int(counts.sum())
+    assert np.array_equal(out["t"].cpu().numpy(), np.concatenate(ts))
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("fp16", 4e-3)])
