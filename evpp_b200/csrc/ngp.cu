@@ -133,19 +133,20 @@ __global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, 
       bool keep = false;
       if (i < sp.n_steps) {
         const float t = __fadd_rn(sp.t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
-        int cell[3];
+        // cell = floor(u * G) per axis, inside the grid iff 0 <= cell < G: one round-down conversion and one
+        // unsigned compare per axis (grid_res <= 1024, so the linear index fits 32 bits)
+        uint32_t cell[3];
         bool ok = true;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float p = __fadd_rn(o[c], __fmul_rn(d[c], t));
           const float u = __fmul_rn(__fsub_rn(p, P.amin[c]), P.inv_size[c]);
-          const float g = floorf(__fmul_rn(u, (float)P.grid_res));
-          ok = ok && g >= 0.f && g < (float)P.grid_res;
-          cell[c] = (int)g;
+          cell[c] = (uint32_t)__float2int_rd(__fmul_rn(u, (float)P.grid_res));
+          ok = ok && cell[c] < (uint32_t)P.grid_res;
         }
         if (ok) {
-          const long long lin = ((long long)cell[0] * P.grid_res + cell[1]) * P.grid_res + cell[2];
-          keep = (P.bitfield[lin >> 3] >> (lin & 7)) & 1;
+          const uint32_t lin = (cell[0] * (uint32_t)P.grid_res + cell[1]) * (uint32_t)P.grid_res + cell[2];
+          keep = (P.bitfield[lin >> 3] >> (lin & 7u)) & 1;
         }
       }
       bal[j] = __ballot_sync(0xffffffffu, keep);
