@@ -115,12 +115,25 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     poses = O.views_to_poses(views)
-    per_step = 1                                             # bounded sample: 1 view (4800 rays) per step
+    on_gpu = args.ref_device == "cuda"
+    if on_gpu:
+        # informational: the reference's torch path (same ops, same order) with its tensors on cuda:0
+        import warnings
+        warnings.simplefilter("ignore")
+        torch.set_default_device("cuda")
+        torch.set_default_tensor_type(torch.cuda.FloatTensor)      # the legacy torch.Tensor(...) constructors too
+        c = {k: v.cuda() for k, v in c.items()}
+        f = {k: v.cuda() for k, v in f.items()}
+    per_step = 8 if on_gpu else 1                            # bounded sample: 1 view (4800 rays) per step on the host
     times = []
     with torch.no_grad():
         for s in range(args.warmup + args.steps):
+            if on_gpu:
+                torch.cuda.synchronize()
             t0 = time.time()
-            O.score_views(poses[s % 8:s % 8 + per_step], IMG_H, IMG_W, K, NEAR, FAR, c, f)
+            sc = O.score_views(poses[(s % 8) * per_step:(s % 8) * per_step + per_step], IMG_H, IMG_W, K, NEAR, FAR, c, f)
+            if on_gpu:
+                sc = sc.cpu()
             if s >= args.warmup:
                 times.append(time.time() - t0)
     ms = 1e3 * float(np.mean(times))
@@ -129,9 +142,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "candidate views scored/sec", "value": val, "unit": "views/s",
             "rays_per_s": val * IMG_H * IMG_W, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(world, "host CPU, torch fp32"),
+            "data": "synthetic", "config": workload_config(world, "reference torch path on cuda:0 (informational)" if on_gpu else "host CPU, torch fp32"),
             "cpu_baseline": {"value": val, "unit": "views/s", "cores": threads, "kind": kind,
-                             "sample": f"{per_step} view(s) x {IMG_W}x{IMG_H} rays per step of the {V_PER_RANK}-view workload; oracle port, bit-identical to the reference's render() on CPU (oracle/make_golden.py)"},
+                             "sample": f"{per_step} view(s) x {IMG_W}x{IMG_H} rays per step of the {V_PER_RANK}-view workload; oracle port, bit-identical to the reference's render() on CPU (oracle/make_golden.py)"
+                                       + ("; THIS RUN: the same torch ops on cuda:0, not the host" if on_gpu else "")},
             "e2e": {"value": val, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -254,6 +268,9 @@ def main():
     ap.add_argument("--impl", default="evpp_b200")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: 'cuda' runs the same reference torch path on cuda:0 (informational row; "
+                         "the reference arm the driver compares against is the CPU one)")
     ap.add_argument("--workload", default="object", choices=["object", "room"],
                     help="object: BASELINE configs[1] (512 hemisphere views x 80x60 rays per GPU, the headline); room: the "
                          "4096-view Room sweep of configs[2] in reference-parity mode (512 views x 128x96 rays per GPU)")

@@ -1,5 +1,5 @@
 """GPU-box diagnostic: per-layer activations of the tcgen05 MLP against a torch fp32 restatement
-(computed on the GPU with the same weights).  Usage: python tools/tc_debug.py [fp16|bf16]"""
+(computed on the GPU with the same weights).  Usage: python tests/diag_tc_layers.py [fp16|bf16]"""
 import os
 import sys
 import numpy as np
