@@ -59,6 +59,9 @@ SIGNATURES = {
     "evpp_composite": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "evpp_resample": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "evpp_select_nbv": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "evpp_surrogate_param_count": (_I, []),
+    "evpp_surrogate_fit": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P]),
+    "evpp_surrogate_query": (_I, [_P, _P, _P, _L, _P, _P]),
     "evpp_tsdf_set_volume": (_I, [_P, _P, _P, _P, _P, _F, _P, _P, _F, _F, _I, _F, _F]),
     "evpp_tsdf_render_rays": (_I, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "evpp_tsdf_score_views": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P, _P]),

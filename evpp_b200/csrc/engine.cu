@@ -14,6 +14,7 @@
 #include "sampling.cuh"
 #include "tsdf.cuh"
 #include "ngp.cuh"
+#include "surrogate.cuh"
 
 using namespace evpp;
 
@@ -94,7 +95,7 @@ struct evpp_handle {
   bool ngp_configured = false, ngp_has_occ = false, ngp_has_params = false, ngp_tensorf = false;
   DevBuf tf_planes, tf_lines, tf_mlp;
   NgpParams ngp{};
-  DevBuf ngp_table, ngp_mlp, ngp_bits, ngp_ro, ngp_rd, ngp_counts, ngp_offsets, ngp_total, ngp_masks, ngp_tiles, ngp_t0, ngp_t, ngp_ray, ngp_raw,
+  DevBuf ngp_table, ngp_mlp, ngp_bits, ngp_ro, ngp_rd, ngp_counts, ngp_offsets, ngp_total, sg_ws, ngp_masks, ngp_tiles, ngp_t0, ngp_t, ngp_ray, ngp_raw,
       ngp_beta2, ngp_scores;
   int64_t ngp_samples = 0;       // kept samples since handle creation
   int ngp_chunk_rays = 1 << 20;  // rays per marching chunk (one count -> scan -> fill round trip each)
@@ -356,7 +357,7 @@ int evpp_destroy(evpp_handle* h) {
                     &h->tsdf_state, &h->tsdf_nray, &h->tsdf_t, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d,
                     &h->tsdf_vu, &h->tsdf_vd, &h->ngp_table, &h->ngp_mlp, &h->ngp_bits, &h->ngp_ro, &h->ngp_rd,
                     &h->ngp_counts, &h->ngp_offsets, &h->ngp_total, &h->ngp_masks, &h->ngp_tiles, &h->ngp_t0, &h->ngp_t, &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2,
-                    &h->ngp_scores, &h->tf_planes, &h->tf_lines, &h->tf_mlp})
+                    &h->ngp_scores, &h->tf_planes, &h->tf_lines, &h->tf_mlp, &h->sg_ws})
     b->release();
   delete h;
   return 0;
@@ -634,6 +635,43 @@ int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, in
   CUDA_TRY(cudaSetDevice(h->device));
   h->launches += launch_select_nbv(scores, weight, V, dirs_per_location, norm_scores, best_dir, winner_view,
                                    (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// planner surrogate g_phi (plannerServer_*/core/vpp.py:26-67, 619-654)
+// ---------------------------------------------------------------------------------------------------
+int evpp_surrogate_param_count(void) { return kSurrogateParams; }
+
+int evpp_surrogate_fit(evpp_handle* h, float* params, const float* xyz, const float* gain, int N, int epochs, float lr,
+                       float* loss_curve, void* stream) {
+  if (!h || !params || !xyz || !gain) return fail(EVPP_ERR_INVALID, "null argument");
+  if (N < 1 || N > kSurrogateMaxN) return fail(EVPP_ERR_INVALID, "N (%d) must be in [1,%d]", N, kSurrogateMaxN);
+  if (epochs < 0 || !(lr > 0.f)) return fail(EVPP_ERR_INVALID, "bad epochs / lr");
+  if (epochs == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t moments = 2 * (size_t)kSurrogateParams;
+  if (h->sg_ws.ensure((moments + surrogate_workspace_floats(N)) * 4)) return fail(EVPP_ERR_CUDA, "surrogate workspace alloc failed");
+  float* m = h->sg_ws.as<float>();
+  CUDA_TRY(cudaMemsetAsync(m, 0, moments * 4, st));     // a fresh optimizer per fit, like train_only
+  const int nl = launch_surrogate_fit(params, m, m + kSurrogateParams, xyz, gain, N, epochs, lr, m + moments, loss_curve, st);
+  if (nl < 0) return fail(EVPP_ERR_CUDA, "surrogate kernel configuration failed");
+  h->launches += nl;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int evpp_surrogate_query(evpp_handle* h, const float* params, const float* xyz, int64_t M, float* out, void* stream) {
+  if (!h || !params) return fail(EVPP_ERR_INVALID, "null argument");
+  if (M < 0 || M > (1ll << 30)) return fail(EVPP_ERR_INVALID, "bad M");
+  if (M == 0) return 0;
+  if (!xyz || !out) return fail(EVPP_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int nl = launch_surrogate_query(params, xyz, (int)M, out, (cudaStream_t)stream);
+  if (nl < 0) return fail(EVPP_ERR_CUDA, "surrogate kernel configuration failed");
+  h->launches += nl;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -57,3 +57,82 @@ def score_and_select(engine, views, H, W, K, dirs_per_location=1, depth_clip=Non
     ws = np.sort(scores * w)
     margin = float((ws[-1] - ws[-2]) / ws[-1]) if len(ws) > 1 else float("inf")
     return {"scores": scores, "data": data, "nbv": nbv, "winner": win, "margin": margin}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# surrogate g_phi: class MLP (plannerServer_*/core/vpp.py:26-67) and
+# Viewpath_planner.train_only (vpp.py:619-654), fitted and queried on the GPU (evpp_b200/csrc/surrogate.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+_SG_LAYERS = ["layer1"] + [f"layer2_{i}" for i in range(1, 9)] + ["layer3"]
+
+
+class MLP:
+    """Drop-in for the planners' ``MLP`` module: same parameter names (``state_dict()`` / ``load_state_dict()``),
+    same default initialisation (torch.nn.Linear's, drawn in the reference's construction order, so an identical
+    ``torch.manual_seed`` gives identical initial weights), ``mlp(x)`` for ``x`` of shape [3] or [M, 3].
+    The parameters live on the engine's device as one packed vector; queries and the fit are CUDA kernels."""
+
+    def __init__(self, engine, state_dict=None):
+        self.engine = engine
+        if state_dict is None:
+            mods = [torch.nn.Linear(3, 64)] + [torch.nn.Linear(64, 64) for _ in range(8)] + [torch.nn.Linear(64, 1)]
+            state_dict = {f"{n}.{p}": getattr(m, p).detach() for n, m in zip(_SG_LAYERS, mods) for p in ("weight", "bias")}
+        self.params = torch.empty(engine.lib.evpp_surrogate_param_count(), device=engine.device, dtype=torch.float32)
+        self.loss_curve = None
+        self.load_state_dict(state_dict)
+
+    def load_state_dict(self, sd):
+        flat = torch.cat([torch.as_tensor(sd[f"{n}.{p}"]).detach().to(torch.float32).reshape(-1).cpu()
+                          for n in _SG_LAYERS for p in ("weight", "bias")])
+        if flat.numel() != self.params.numel():
+            raise ValueError(f"state_dict holds {flat.numel()} values, the surrogate has {self.params.numel()}")
+        self.params.copy_(flat)
+
+    def state_dict(self):
+        from collections import OrderedDict
+        flat, sd, o = self.params.detach().cpu(), OrderedDict(), 0
+        for n in _SG_LAYERS:
+            fin, fout = (3, 64) if n == "layer1" else ((64, 1) if n == "layer3" else (64, 64))
+            sd[f"{n}.weight"] = flat[o:o + fin * fout].reshape(fout, fin).clone(); o += fin * fout
+            sd[f"{n}.bias"] = flat[o:o + fout].clone(); o += fout
+        return sd
+
+    def __call__(self, x):
+        from .engine import _ptr, _stream_ptr
+        x = torch.as_tensor(x, dtype=torch.float32)
+        single = x.dim() == 1
+        pts = x.reshape(-1, 3).to(self.engine.device).contiguous()
+        out = torch.empty(pts.shape[0], device=self.engine.device, dtype=torch.float32)
+        with torch.cuda.device(self.engine.device):
+            _lib_check(self.engine.lib.evpp_surrogate_query(self.engine._h, _ptr(self.params), _ptr(pts), pts.shape[0],
+                                                            _ptr(out), _stream_ptr(self.engine.device)))
+        return out.reshape(1) if single else out.reshape(-1, 1)
+
+    # the reference moves the module around with .to(device) / .cpu(); placement is the engine's here
+    def to(self, *_a, **_k):
+        return self
+
+    def cpu(self):
+        return self
+
+
+def _lib_check(rc):
+    from ._lib import check
+    check(rc)
+
+
+def train_only(mlp, data, N=100, epochs=300, lr=0.001):
+    """``Viewpath_planner.train_only(mlp, data, N)`` (vpp.py:619-654): 300 full-batch Adam steps (lr 1e-3) on the MSE
+    between ``mlp(data[:N, 0:3])`` and ``data[:N, 5]``; one kernel launch.  Returns ``mlp`` (trained in place);
+    ``mlp.loss_curve`` holds the loss before each step (the reference's ``mlp_loss`` list)."""
+    from .engine import _ptr, _stream_ptr
+    data = np.asarray(data, dtype=np.float64)
+    e = mlp.engine
+    xyz = torch.tensor(np.ascontiguousarray(data[0:N, 0:3])).to(torch.float32).to(e.device).contiguous()
+    gain = torch.tensor(np.ascontiguousarray(data[0:N, 5])).to(torch.float32).to(e.device).contiguous()
+    loss = torch.empty(int(epochs), device=e.device, dtype=torch.float32)
+    with torch.cuda.device(e.device):
+        _lib_check(e.lib.evpp_surrogate_fit(e._h, _ptr(mlp.params), _ptr(xyz), _ptr(gain), int(N), int(epochs), float(lr),
+                                            _ptr(loss), _stream_ptr(e.device)))
+    mlp.loss_curve = loss
+    return mlp

@@ -182,6 +182,23 @@ int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, in
                     int dirs_per_location, float* norm_scores, int32_t* best_dir,
                     int32_t* winner_view, void* stream);
 
+/* ---- Planner surrogate g_phi ----
+ * The small MLP the planners fit to the (location -> normalised gain) rows of one planning step and then query
+ * inside weighted A* (class MLP, plannerServer_Object/core/vpp.py:26-67; identical in plannerServer_Room).
+ * params: device float[evpp_surrogate_param_count()] = the module's state_dict flattened in its own order
+ * (layer1.weight [64,3], layer1.bias, layer2_1 .. layer2_8 (weight [64,64], bias), layer3.weight [1,64],
+ * layer3.bias); layer2_2 is declared by the reference but never used by forward(): it is carried through untouched.
+ *
+ * evpp_surrogate_fit: Viewpath_planner.train_only (vpp.py:619-654): `epochs` full-batch steps of torch.optim.Adam
+ * (lr, betas (0.9, 0.999), eps 1e-8, fresh moments) on F.mse_loss over N <= 128 points; xyz device [N,3], gain device
+ * [N]; params is updated in place; loss_curve (device float[epochs], may be NULL) receives the loss BEFORE each
+ * step, like the reference's mlp_loss list.  One kernel launch.
+ * evpp_surrogate_query: mlp(x) for M points (vpp.py:233,242,487; localPlanner.py:126 via env.get_gain). */
+int evpp_surrogate_param_count(void);
+int evpp_surrogate_fit(evpp_handle* h, float* params, const float* xyz, const float* gain, int N, int epochs, float lr,
+                       float* loss_curve, void* stream);
+int evpp_surrogate_query(evpp_handle* h, const float* params, const float* xyz, int64_t M, float* out, void* stream);
+
 /* ---- Stage-1 candidate scorer: occupancy-state ray cast through the planner's TSDF state volume ----
  * Replaces TSDF.render_rays + isectSegAABB_gpu + get_uncertainty_tsdf
  * (plannerServer_Object/core/tsdf_gpu.py:198-354, :67-114, :473-530; the Room copy differs only in the

@@ -585,3 +585,61 @@ def test_render_option_variants_vs_oracle(weights, lindisp, white, ns, ni):
     close = np.isclose(u, ur, rtol=1e-3).mean()
     assert close > 0.97, close          # samples whose position moved by a resampling knife-edge excepted
     eng.close()
+
+
+# ---------------------------------------------------------------- planner surrogate g_phi (row f3) ----
+def test_surrogate_fit_and_queries(engine_factory):
+    """class MLP + Viewpath_planner.train_only (vpp.py:26-67, 619-654) on the GPU against the run of the reference
+    code stored in tests/golden/surrogate.npz.  Forward values and the first optimizer steps are compared tightly;
+    a 300-step Adam trajectory is chaotic in the last bits (the reference's own fp32 and fp64 runs end 0.06 apart in
+    predictions), so the end state is bounded by that reference-intrinsic spread."""
+    import evpp_b200
+    from conftest import load_golden
+    from oracle import surrogate_oracle as SO
+    g = load_golden("surrogate.npz")
+    eng = engine_factory("plain", "fp32")
+    data, init = g["data"], SO.unpack_state_dict(g["init_params"])
+    mlp = evpp_b200.MLP(eng, init)
+    x = data[:, 0:3]
+    # queries: batch, single point, more points than one 128-point tile, and the state_dict round trip
+    np.testing.assert_allclose(mlp(x).cpu().numpy().reshape(-1), g["pred_init"], rtol=0, atol=2e-7)
+    assert mlp(x[0]).shape == (1,) and abs(float(mlp(x[0])[0]) - g["pred_init"][0]) < 2e-7
+    xs = torch.rand(1000, 3) * 8 - 4
+    ref = SO.MLP()
+    ref.load_state_dict(mlp.state_dict())
+    np.testing.assert_allclose(mlp(xs).cpu().numpy(), ref(xs).detach().numpy(), rtol=0, atol=2e-6)
+    assert np.array_equal(SO.pack_state_dict(mlp.state_dict()), g["init_params"])
+    # one Adam step: the update is lr * g / (|g| + 1e-8), i.e. +-lr for every gradient above rounding noise.  Compare
+    # every parameter whose reference gradient is not noise; the remaining ones may step with the other sign.
+    ref0 = SO.MLP()
+    ref0.load_state_dict(init)
+    loss = torch.nn.functional.mse_loss(ref0(torch.tensor(x).to(torch.float32)),
+                                        torch.tensor(data[:, 5].reshape(-1, 1)).to(torch.float32))
+    loss.backward()
+    grad = np.concatenate([(getattr(getattr(ref0, l), p).grad if getattr(getattr(ref0, l), p).grad is not None
+                            else torch.zeros_like(getattr(getattr(ref0, l), p))).numpy().reshape(-1)
+                           for l in SO.LAYERS for p in ("weight", "bias")])
+    evpp_b200.train_only(mlp, data, N=100, epochs=1)
+    p1 = mlp.params.cpu().numpy()
+    solid = np.abs(grad) > 1e-5
+    assert solid.mean() > 0.3                                            # layer2_2 (12 % of the parameters) has no gradient at all
+    np.testing.assert_allclose(p1[solid], g["params_after_1"][solid], rtol=0, atol=2e-6)
+    assert np.abs(p1 - g["params_after_1"]).max() <= 2.001e-3            # noise-level gradients: at most a sign flip of lr
+    assert np.array_equal(p1[~(np.abs(grad) > 0)], g["init_params"][~(np.abs(grad) > 0)])   # layer2_2 and dead units: untouched
+    assert abs(float(mlp.loss_curve[0]) / g["loss_curve"][0] - 1) < 1e-6
+    # ten steps: the loss curve follows the reference's to 1e-4
+    mlp.load_state_dict(init)
+    evpp_b200.train_only(mlp, data, N=100, epochs=10)
+    np.testing.assert_allclose(mlp.loss_curve.cpu().numpy(), g["loss_curve"][:10], rtol=1e-4)
+    # the full fit
+    mlp.load_state_dict(init)
+    evpp_b200.train_only(mlp, data, N=100)
+    lc = mlp.loss_curve.cpu().numpy()
+    assert lc.shape == (300,) and lc[-1] < 0.01 * lc[0]
+    assert 0.5 < lc[-1] / g["loss_curve"][-1] < 2.0
+    pred = mlp(x).cpu().numpy().reshape(-1)
+    assert np.abs(pred - g["pred_trained"]).max() < 0.06
+    assert np.sqrt(np.mean((pred - data[:, 5]) ** 2)) < 0.06               # it fits the gains it was given
+    # argument checks
+    with pytest.raises(Exception):
+        evpp_b200.train_only(mlp, np.zeros((200, 6)), N=200)

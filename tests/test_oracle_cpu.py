@@ -1,6 +1,8 @@
 """CPU tests (-m "not gpu"): the oracle restatement against the committed golden fixtures (which
 were produced by the UNMODIFIED reference, oracle/make_golden.py) and, when /root/reference is
 present, against the reference itself."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -209,3 +211,43 @@ def test_tensorf_oracle_self_consistency():
     P, L = q["planes"].astype(np.float64), q["lines"].astype(np.float64)
     want = P[0, 0, 7, :16] @ L[0, 7, :16] + P[1, 7, 7, :16] @ L[1, 0, :16] + P[2, 7, 0, :16] @ L[2, 7, :16]
     np.testing.assert_allclose(sig[0], want, rtol=1e-12)
+
+
+# ---------------------------------------------------------------- planner surrogate g_phi (row f3) ----
+def test_surrogate_oracle_matches_golden():
+    """The restatement of class MLP / train_only reproduces the reference code's run stored in the fixture: initial
+    weights (same seed, same construction order), initial predictions, every Adam step."""
+    import torch
+    from oracle import surrogate_oracle as SO
+    g = load_golden("surrogate.npz")
+    torch.manual_seed(0)
+    mlp = SO.MLP()
+    assert np.array_equal(SO.pack_state_dict(mlp.state_dict()), g["init_params"])
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)      # the fixture was written single-threaded: sgemm's summation order is part of the result
+    try:
+        x = torch.tensor(g["data"][:, 0:3]).to(torch.float32)
+        assert np.array_equal(mlp(x).detach().numpy().reshape(-1), g["pred_init"])
+        mlp, losses = SO.train_only(mlp, g["data"], N=100, epochs=10)
+        assert np.array_equal(SO.pack_state_dict(mlp.state_dict()), g["params_after_10"])
+        assert np.array_equal(np.asarray(losses), g["loss_curve"][:10])
+    finally:
+        torch.set_num_threads(threads)
+    sd = SO.unpack_state_dict(g["init_params"])
+    assert np.array_equal(SO.pack_state_dict(sd), g["init_params"]) and len(sd) == 20
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference"), reason="reference tree not present")
+def test_surrogate_oracle_bit_exact_vs_reference_source():
+    import torch
+    from oracle import surrogate_oracle as SO
+    RefMLP, ref_train = SO.reference_symbols()
+    data = SO.synthetic_gain_samples(3)
+    torch.manual_seed(5)
+    ref = RefMLP()
+    torch.manual_seed(5)
+    mine = SO.MLP()
+    ref = ref_train(None, ref, data, N=100)
+    mine, losses = SO.train_only(mine, data, N=100)
+    assert np.array_equal(SO.pack_state_dict(ref.state_dict()), SO.pack_state_dict(mine.state_dict()))
+    assert losses[-1] < 0.1 * losses[0]
