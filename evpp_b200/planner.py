@@ -136,3 +136,71 @@ def train_only(mlp, data, N=100, epochs=300, lr=0.001):
                                             _ptr(loss), _stream_ptr(e.device)))
     mlp.loss_curve = loss
     return mlp
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Viewpath_planner.sample_direction (plannerServer_Object/core/vpp.py:144-210, plannerServer_Room/core/vpp.py:141-200):
+# the two-stage candidate scoring of one planning step, with both stages on the GPU scorers
+# ---------------------------------------------------------------------------------------------------------------------
+def direction_fan(locations, object_center, scene="object"):
+    """The candidate directions of every location: Object 3 pitches x 5 yaws around the look-at direction
+    (vpp.py:150-161), Room 5 pitches (around atan2(-dy, 0.6)) x 12 yaws over the full circle (Room vpp.py:147-159).
+    Returns views [L * fan, 5] = (x, y, z, u, v) and the fan size."""
+    locations = np.asarray(locations, dtype=np.float64)
+    views = []
+    for i in range(locations.shape[0]):
+        x, y, z = locations[i, 0], locations[i, 1], locations[i, 2]
+        dx, dy, dz = object_center[0] - x, object_center[1] - y, object_center[2] - z
+        if scene == "object":
+            u_center = np.arctan2(-dy, np.sqrt(dx ** 2 + dz ** 2))
+            v_center = np.arctan2(dx, dz)
+            us = np.linspace(u_center - 5 / 180 * np.pi, u_center + 5 / 180 * np.pi, 3)
+            vs = np.linspace(v_center - 10 / 180 * np.pi, v_center + 10 / 180 * np.pi, 5)
+        else:
+            u_center = np.arctan2(-dy, 0.6)
+            us = np.linspace(u_center - 30 / 180 * np.pi, u_center + 30 / 180 * np.pi, 5)
+            vs = np.linspace((0) / 180 * np.pi, (360) / 180 * np.pi, 12)
+        for u in us:
+            for v in vs:
+                if u < -np.pi / 2.0:
+                    u = -np.pi / 2.0
+                if u > np.pi / 2.0:
+                    u = np.pi / 2.0
+                views.append([x, y, z, u, v])
+    fan = 15 if scene == "object" else 60
+    return np.array(views), fan
+
+
+def sample_direction(locations, tsdf, get_uncertainty, object_center, scene="object"):
+    """Drop-in for ``Viewpath_planner.sample_direction(locations)``: stage 1 scores the whole direction fan with the
+    TSDF occupancy ray cast (``tsdf.get_uncertainty_tsdf``, evpp_b200.TSDF), keeps the 3 best directions per location,
+    stage 2 scores those with the NeRF uncertainty (``get_uncertainty(locations, us, vs) -> (uncers, _, _)``, the
+    reference's interface2 signature; pass ``evpp_b200.views.get_uncertainty`` or an Engine-backed callable), the
+    Object scene weights by the depth clip, the best direction per location is kept and the gains are normalised by
+    their maximum.  Returns data [L, 6] = (x, y, z, u, v, gain) like the reference."""
+    locations = np.asarray(locations, dtype=np.float64)
+    sample_num = locations.shape[0]
+    views, fan = direction_fan(locations, object_center, scene)
+    uncer, depth = tsdf.get_uncertainty_tsdf(views[:, 0:3].tolist(), views[:, 3].tolist(), views[:, 4].tolist())
+    depth = np.array(depth)
+    data_buff = np.concatenate((views, np.array(uncer).reshape(sample_num * fan, 1)), axis=1)
+    select_views, select_depth = [], []
+    for i in range(sample_num):
+        dir_buff = data_buff[i * fan:(i + 1) * fan]
+        depth_buff = depth[i * fan:(i + 1) * fan]
+        index = (np.argsort(dir_buff[:, 5]))[::-1]
+        for j in range(3):
+            select_views.append(dir_buff[index[j]].tolist())
+            select_depth.append(depth_buff[index[j]])
+    select_views = np.array(select_views)
+    select_depth = np.array(select_depth)
+    uncer, _, _ = get_uncertainty(select_views[:, 0:3].tolist(), select_views[:, 3].tolist(), select_views[:, 4].tolist())
+    uncer = np.array(uncer)
+    if scene == "object":
+        uncer = uncer * depth_clip_object(select_depth)      # the Room planner computes a clip and does not apply it
+    uncer = np.array(uncer).reshape((sample_num * 3, 1))
+    data_buff = np.concatenate((select_views[:, 0:5], uncer), axis=1)
+    data = np.array([list(data_buff[i * 3:(i + 1) * 3][np.argmax(data_buff[i * 3:(i + 1) * 3][:, 5])])
+                     for i in range(int(data_buff.shape[0] / 3))])           # get_maxdirdata, vpp.py:214-220
+    data[:, 5] = data[:, 5] / np.max(data[:, 5])
+    return data

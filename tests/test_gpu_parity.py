@@ -643,3 +643,43 @@ def test_surrogate_fit_and_queries(engine_factory):
     # argument checks
     with pytest.raises(Exception):
         evpp_b200.train_only(mlp, np.zeros((200, 6)), N=200)
+
+
+def test_planning_step_end_to_end(weights):
+    """One planning step with every stage on the GPU, through the reference's call shapes: direction fan -> stage-1 TSDF
+    scores -> top 3 per location -> stage-2 NeRF uncertainty (Controller.get_uncertainty) -> depth clip / per-location
+    maximum / normalisation (sample_direction) -> surrogate fit (train_only) -> batched and single g_phi queries.
+    With the explicit pixel subsets fixed by the NumPy seed the step is deterministic."""
+    import evpp_b200
+    g = load_golden("tsdf_small.npz")
+    ts = _tsdf_with_state(g)
+    c, f = weights["spread"]
+    ctl = evpp_b200.Controller(H=30, W=40, focal=30.0, near=0.5, far=6.0, precision="fp16", sample_num=None)
+    ctl.copy_model(c, f)
+
+    def get_uncertainty(locations, us, vs):           # interface2.get_uncertainty's return shape: (uncers, [], [])
+        poses = [evpp_b200.get_pose(locations[i], us[i], vs[i]) for i in range(len(locations))]
+        return ctl.get_uncertainty(poses).cpu().numpy().tolist(), [], []
+
+    views = O.hemisphere_views(100, seed=4)
+    locations = np.asarray(views)[:, 0:3]
+    out = []
+    for _ in range(2):
+        np.random.seed(11)
+        data = evpp_b200.sample_direction(locations, ts, get_uncertainty, [0.0, 1.0, 0.0], scene="object")
+        out.append(data)
+    assert np.array_equal(out[0], out[1])
+    data = out[0]
+    assert data.shape == (100, 6) and np.array_equal(data[:, 0:3], locations)
+    assert data[:, 5].max() == 1.0 and (data[:, 5] > 0).all() and np.isfinite(data).all()
+    fan, _ = evpp_b200.direction_fan(locations, [0.0, 1.0, 0.0], "object")
+    for i in range(100):                               # the kept direction is one of the location's 15 candidates
+        assert (np.abs(fan[i * 15:(i + 1) * 15, 3:5] - data[i, 3:5]).sum(axis=1) == 0).any()
+    mlp = evpp_b200.MLP(ctl.engine)
+    mlp = evpp_b200.train_only(mlp, data[0:100], N=100).to("cuda")
+    lc = mlp.loss_curve.cpu().numpy()
+    assert lc[-1] < 0.5 * lc[0]
+    gains = mlp(torch.tensor(locations).to(torch.float32)).detach().cpu().numpy()
+    assert gains.shape == (100, 1) and np.isfinite(gains).all()
+    assert np.sqrt(np.mean((gains[:, 0] - data[:, 5]) ** 2)) < 0.25
+    assert np.isfinite(mlp(torch.tensor(list(locations[0])).to(torch.float32)).detach().cpu().numpy()[0])   # vpp.py:487
