@@ -249,6 +249,150 @@ def run_ngp(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_planner(args, rank, local_rank, world):
+    """One planning step of the Object planner in the reference's live protocol (SURVEY.md section 8, rows a11-a13 + f3):
+    100 locations x 15 directions = 1500 stage-1 views x 500 random pixels through the TSDF state volume, the 3 best
+    directions per location = 300 stage-2 views x 1000 random pixels of the 400x400 image through the NeRF
+    (Controller.get_uncertainty), depth clip / per-location maximum / normalisation, the surrogate fit (300 Adam epochs
+    on the 100 gains) and 1000 surrogate queries.  A step is host-driven by nature (the top-3 selection sits between the
+    stages), so the timed region is wall clock around the whole step with a device synchronise on both sides: `value`
+    and `e2e` are the same measurement.  N > 1 runs independent replicas (a planning step does not shard)."""
+    import evpp_b200
+    from evpp_b200 import synthetic as S
+    torch.cuda.set_device(local_rank)
+    H = W = 400
+    focal = 300.0
+    c, f = S.init_nerf_state_dict(0), S.init_nerf_state_dict(1)
+    ctl = evpp_b200.Controller(H=H, W=W, focal=focal, near=0.5, far=6.0, precision=args.precision, sample_num=1000, device=local_rank,
+                               pixel_sampler=args.pixel_sampler)
+    ctl.copy_model(c, f)
+    ts = evpp_b200.TSDF(engine=ctl.engine, pixel_sampler=args.pixel_sampler)
+    state, nray = S.state_volume(ts.index_bnd, seed=0)
+    ts.set_state(state, nray)
+    locations = np.asarray(S.hemisphere_views(100, seed=rank))[:, 0:3]
+    center = [0.0, 1.0, 0.0]
+    mlp = evpp_b200.MLP(ctl.engine)
+    t_stage = {"stage1_tsdf": 0.0, "stage2_nerf": 0.0, "fit": 0.0, "queries": 0.0}
+
+    def timed(key, fn):
+        def wrapper(*a, **k):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn(*a, **k)
+            torch.cuda.synchronize()
+            t_stage[key] += time.perf_counter() - t0
+            return r
+        return wrapper
+
+    class TsdfTimed:
+        get_uncertainty_tsdf = staticmethod(timed("stage1_tsdf", ts.get_uncertainty_tsdf))
+
+    def get_uncertainty(locs, us, vs):
+        poses = [evpp_b200.get_pose(locs[i], us[i], vs[i]) for i in range(len(locs))]
+        return ctl.get_uncertainty(poses).cpu().numpy().tolist(), [], []
+
+    get_uncertainty = timed("stage2_nerf", get_uncertainty)
+    test_pts = torch.tensor(np.random.RandomState(1).uniform(-3, 3, size=(1000, 3))).to(torch.float32)
+
+    def step():
+        data = evpp_b200.sample_direction(locations, TsdfTimed, get_uncertainty, center, scene="object")
+        timed("fit", evpp_b200.train_only)(mlp, data[0:100], N=100)
+        g = timed("queries", lambda: mlp(test_pts).detach().cpu())()
+        return data, g
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local_rank))
+    for _ in range(args.warmup):
+        step()
+    for k in t_stage:
+        t_stage[k] = 0.0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctl.engine.counters()[0]
+    ctl.engine.set_profiling(True)
+    wall = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step()
+        torch.cuda.synchronize()
+        wall += time.perf_counter() - t0
+    mlp_ms, mlp_launches, mlp_evals = ctl.engine.mlp_time()
+    ctl.engine.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctl.engine.counters()[0] - l0
+    if rank != 0:
+        return
+    sec = wall / args.steps
+    views = 1500 + 300
+    tensor = args.precision != "fp32"
+    d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = d.get("bf16_tflops_sustained", 1399.2)
+    achieved = FLOP_PER_EVAL * mlp_evals / (mlp_ms / 1e3) / 1e12 if mlp_ms > 0 else 0.0
+    cpu = None if args.no_cpu_baseline else planner_cpu_baseline(c, f, locations, center, state, nray, ts)
+    line = {"metric": "candidate views scored/sec", "value": views * world / sec, "unit": "views/s",
+            "planning_steps_per_s": world / sec, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
+            "higher_is_better": True, "scaling": "weak (independent replicas: a planning step does not shard)", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate (stage 2); u8 / f32 (stage 1); f32 (surrogate)" if tensor else "f32", "data": "synthetic",
+            "config": {"workload": "one planning step of the Object planner, live protocol: 100 locations x 15 directions = 1500 stage-1 "
+                                   "views x 500 px (TSDF state volume 100x50x110), top 3 per location = 300 stage-2 views x 1000 px of "
+                                   "400x400 (64+128 samples/ray), selection, surrogate fit (300 Adam epochs, 100 points), 1000 queries",
+                       "stage_ms": {k: 1e3 * v / args.steps for k, v in t_stage.items()},
+                       "host_logic_ms": 1e3 * (sec - sum(t_stage.values()) / args.steps),
+                       "pixel_sampler": args.pixel_sampler + (" (pixel subsets drawn on the device, evpp_sample_pixels)" if args.pixel_sampler == "device" else
+                                                             " (the reference's np.random.choice(160000, R, replace=False) per pose on the host: ~2 ms per view)"),
+                       "l2": "256 MB L2 flush between timed steps"},
+            "e2e": {"value": views * world / sec, "unit": "views/s", "h2d_bytes_per_step": 1500 * (48 + 2000) + 300 * (48 + 4000) + 100 * 16,
+                    "d2h_bytes_per_step": 1500 * 8 + 300 * 4 + 1000 * 4,
+                    "api": "evpp_b200.sample_direction / train_only / MLP.__call__ over evpp_tsdf_score_views_host, evpp_score_views, evpp_surrogate_fit, evpp_surrogate_query"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "mlp_tc_kernel inside stage 2 (300 views x 1000 rays = 2 launches of 19.2 M and 57.6 M evaluations)",
+                         "mlp_share_of_step": mlp_ms / 1e3 / (sec * args.steps) if sec > 0 else None},
+            "clocks": clocks}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def planner_cpu_baseline(c, f, locations, center, state, nray, ts):
+    """The same planning step with the oracle ports on the host (all threads), stages timed on bounded samples and scaled:
+    stage 1 on 30 of the 1500 views, stage 2 on 2 of the 300 views, the surrogate fit and the queries in full."""
+    import evpp_b200
+    from oracle import evpp_oracle as O, tsdf_oracle as T, surrogate_oracle as SO
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    K = O.make_K(400, 400, 300.0)
+    views, _ = evpp_b200.direction_fan(locations, center, "object")
+    rs = np.random.RandomState(0)
+    with torch.no_grad():
+        v1 = views[:30]
+        pix = np.stack([rs.choice(400 * 400, size=[500], replace=False) for _ in range(len(v1))])
+        t0 = time.time()
+        ro, rd = O.build_view_rays(O.views_to_poses(v1), 400, 400, K, pix)
+        T.render_rays(ro, rd, torch.from_numpy(state), torch.from_numpy(nray), ts.vol_origin)
+        t1 = (time.time() - t0) / len(v1)
+        v2 = views[:2]
+        pix = np.stack([rs.choice(400 * 400, size=[1000], replace=False) for _ in range(len(v2))])
+        O.score_views(O.views_to_poses(v2[:1]), 400, 400, K, 0.5, 6.0, c, f, pix_idx=pix[:1])
+        t0 = time.time()
+        O.score_views(O.views_to_poses(v2), 400, 400, K, 0.5, 6.0, c, f, pix_idx=pix)
+        t2 = (time.time() - t0) / len(v2)
+    data = SO.synthetic_gain_samples(0)
+    t0 = time.time()
+    m, _ = SO.train_only(SO.MLP(), data, N=100)
+    t3 = time.time() - t0
+    t0 = time.time()
+    with torch.no_grad():
+        m(torch.rand(1000, 3))
+    t4 = time.time() - t0
+    sec = 1500 * t1 + 300 * t2 + t3 + t4
+    return {"value": 1800 / sec, "unit": "views/s", "cores": threads, "kind": "port",
+            "sample": f"stage 1: 30 of 1500 views ({1e3 * t1:.1f} ms/view), stage 2: 2 of 300 views ({1e3 * t2:.0f} ms/view), surrogate fit in full "
+                      f"({t3:.2f} s), 1000 queries ({1e3 * t4:.1f} ms); scaled step {sec:.1f} s"}
+
+
 def workload_config(world, engine_desc):
     name = ("BASELINE configs[2] Room scene sweep (4096 poses at 8 GPUs), reference-parity scorer" if WORKLOAD == "room"
             else "BASELINE configs[1] Object scene")
@@ -268,13 +412,15 @@ def main():
     ap.add_argument("--impl", default="evpp_b200")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pixel-sampler", default="device", choices=["device", "numpy"],
+                    help="--mode planner only: where the random pixel subsets of the live protocol are drawn")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' runs the same reference torch path on cuda:0 (informational row; "
                          "the reference arm the driver compares against is the CPU one)")
     ap.add_argument("--workload", default="object", choices=["object", "room"],
                     help="object: BASELINE configs[1] (512 hemisphere views x 80x60 rays per GPU, the headline); room: the "
                          "4096-view Room sweep of configs[2] in reference-parity mode (512 views x 128x96 rays per GPU)")
-    ap.add_argument("--mode", default="parity", choices=["parity", "ngp", "tensorf"],
+    ap.add_argument("--mode", default="parity", choices=["parity", "ngp", "tensorf", "planner"],
                     help="parity: the reference's scorer (headline, BASELINE configs[1]); ngp: occupancy grid + hash grid "
                          "scorer on the Room sweep shape (BASELINE configs[2]; no reference counterpart)")
     args = ap.parse_args()
@@ -293,6 +439,9 @@ def main():
                  "(--impl reference times the reference algorithm on the host cores)")
     if args.mode in ("ngp", "tensorf"):
         run_ngp(args, rank, local_rank, world)
+        return
+    if args.mode == "planner":
+        run_planner(args, rank, local_rank, world)
         return
 
     import torch.distributed as dist

@@ -59,6 +59,7 @@ SIGNATURES = {
     "evpp_composite": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "evpp_resample": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "evpp_select_nbv": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "evpp_sample_pixels": (_I, [_P, C.c_uint64, _I, _I, _I, _P, _P]),
     "evpp_surrogate_param_count": (_I, []),
     "evpp_surrogate_fit": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P]),
     "evpp_surrogate_query": (_I, [_P, _P, _P, _L, _P, _P]),

@@ -642,6 +642,17 @@ int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, in
 // ---------------------------------------------------------------------------------------------------
 // planner surrogate g_phi (plannerServer_*/core/vpp.py:26-67, 619-654)
 // ---------------------------------------------------------------------------------------------------
+int evpp_sample_pixels(evpp_handle* h, uint64_t seed, int V, int R, int n_pixels, int32_t* pix_idx, void* stream) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  if (V < 0 || R < 0 || n_pixels <= 0 || R > n_pixels) return fail(EVPP_ERR_INVALID, "need 0 <= R <= n_pixels");
+  if (V == 0 || R == 0) return 0;
+  if (!pix_idx) return fail(EVPP_ERR_INVALID, "null pix_idx");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->launches += launch_pixel_subset(seed, V, R, n_pixels, pix_idx, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int evpp_surrogate_param_count(void) { return kSurrogateParams; }
 
 int evpp_surrogate_fit(evpp_handle* h, float* params, const float* xyz, const float* gain, int N, int epochs, float lr,

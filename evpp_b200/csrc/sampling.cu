@@ -354,6 +354,38 @@ coarse_resample_kernel(const float* __restrict__ raw, const float* __restrict__ 
   for (int o = lane; o < Sc + Ni; o += 32) zg[o] = zf[o];
 }
 
+// Random pixel subsets drawn on the device: R DISTINCT pixels of each view's n-pixel image.  The reference draws
+// them on the host with np.random.choice(n, R, replace=False) per pose (nerf.py:287, tsdf_gpu.py:497), which shuffles
+// all n = 160 000 pixel ids for every pose (2 ms per view, seconds per planning step).  Here pixel k of view v is
+// perm_v(k), k < R, where perm_v is a keyed pseudo-random permutation of [0, n): a 4-round Feistel network on the
+// next even power of two with cycle walking back into the domain -- O(1) per pixel, distinct by construction.
+// Not the reference's RNG stream (callers that need that pass pix_idx explicitly); same sampling model.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__global__ void pixel_subset_kernel(uint64_t seed, int V, int R, uint32_t n, int half_bits, int32_t* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)V * R) return;
+  const uint32_t v = (uint32_t)(t / R), k = (uint32_t)(t % R);
+  const uint32_t mask = (1u << half_bits) - 1u;
+  uint32_t key[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) key[r] = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x9e3779b9u * (v * 4u + r + 1u)));
+  uint32_t x = k;
+  do {
+    uint32_t l = x >> half_bits, rr = x & mask;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t nl = rr;
+      rr = l ^ (mix32(rr ^ key[r]) & mask);
+      l = nl;
+    }
+    x = (l << half_bits) | rr;
+  } while (x >= n);
+  out[t] = (int32_t)x;
+}
+
 // score[v] = sum_rays beta2 / R   (nerf.py:307-309); fp64 tree, deterministic.
 __global__ void view_reduce_kernel(const float* __restrict__ beta2, int R, float* __restrict__ scores) {
   __shared__ double sh[256];
@@ -470,6 +502,15 @@ int launch_composite(const float* raw, const float* z, const float* rays_d, int 
   const size_t smem = (size_t)kRayWarps * ray_scratch_floats(S) * sizeof(float);
   if (!ray_kernel_smem(composite_kernel, smem)) return -1;
   composite_kernel<<<(n + kRayWarps - 1) / kRayWarps, 32 * kRayWarps, smem, st>>>(raw, z, rays_d, n, S, white_bkgd, co);
+  return 1;
+}
+
+int launch_pixel_subset(uint64_t seed, int V, int R, int n_pixels, int32_t* out, cudaStream_t st) {
+  const long long total = (long long)V * R;
+  if (total <= 0) return 0;
+  int half_bits = 1;
+  while ((1ll << (2 * half_bits)) < n_pixels) ++half_bits;
+  pixel_subset_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(seed, V, R, (uint32_t)n_pixels, half_bits, out);
   return 1;
 }
 

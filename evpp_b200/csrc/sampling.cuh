@@ -26,6 +26,8 @@ int launch_coarse_resample(const float* raw, const float* z, const float* rays_d
 // raw2outputs on the final pass, fused with the per-ray sum of beta^2
 int launch_composite(const float* raw, const float* z, const float* rays_d, int n, int S, int white_bkgd,
                      CompositeOut co, cudaStream_t st);
+// R distinct pseudo-random pixel ids in [0, n_pixels) per view (keyed Feistel permutation), out [V,R]
+int launch_pixel_subset(uint64_t seed, int V, int R, int n_pixels, int32_t* out, cudaStream_t st);
 int launch_view_reduce(const float* beta2, int V, int R, float* scores, cudaStream_t st);
 int launch_select_nbv(const float* scores, const float* weight, int V, int dirs, float* norm_scores,
                       int32_t* best_dir, int32_t* winner, cudaStream_t st);

@@ -242,6 +242,14 @@ class Engine:
                                            _ptr(best), _ptr(win), _stream_ptr(self.device)))
         return norm, best, win
 
+    def sample_pixels(self, V, R, n_pixels, seed):
+        """R distinct pseudo-random pixel ids per view on the device (evpp_sample_pixels), int32 [V, R]."""
+        out = torch.empty(V, R, device=self.device, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_sample_pixels(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)), V, R, n_pixels, _ptr(out),
+                                              _stream_ptr(self.device)))
+        return out
+
     # ---- counters -----------------------------------------------------------------------------------
     def counters(self):
         a, b = C.c_int64(0), C.c_int64(0)

@@ -11,13 +11,18 @@ from .run_nerf import _intrinsics
 
 class Controller:
     def __init__(self, H=400, W=400, focal=300.0, near=0.5, far=80.0, N_samples=64, N_importance=128,
-                 white_bkgd=True, device=0, precision="fp16", sample_num=1000, max_chunk_rays=0):
+                 white_bkgd=True, device=0, precision="fp16", sample_num=1000, max_chunk_rays=0,
+                 pixel_sampler="numpy", seed=0):
         """Defaults are the live constants: views.py:21-23 (H, W, focal), nerf.py:100-101 (near, far),
         config.txt:10-13, nerf.py:276 (sample_num)."""
         self.H, self.W, self.focal = H, W, focal
         self.K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])   # nerf.py:112-116
         self.near, self.far = near, far
         self.sample_num = sample_num
+        # "numpy": the reference's protocol, one np.random.choice(H*W, sample_num, replace=False) per pose from NumPy's
+        # global RNG (nerf.py:287) -- same pixels as the reference for the same RNG state, 2 ms of host time per pose.
+        # "device": distinct pseudo-random pixels drawn by a kernel (evpp_sample_pixels), no host work per pose.
+        self.pixel_sampler, self._seed = pixel_sampler, int(seed)
         self.engine = Engine(device=device, n_samples=N_samples, n_importance=N_importance, near=near, far=far,
                              white_bkgd=white_bkgd, precision=precision, max_chunk_rays=max_chunk_rays)
         self.uncertainty_kargs = None
@@ -42,9 +47,13 @@ class Controller:
             raise TypeError("'NoneType' object is not subscriptable (weights not handed off: call copy_model)")
         poses = torch.Tensor(np.asarray(poses, dtype=np.float64))[:, :3, :4].contiguous()   # fp64 -> fp32, nerf.py:278
         V = poses.shape[0]
+        fx, fy, cx, cy = _intrinsics(self.K)
+        if pix_idx is None and self.sample_num is not None and self.pixel_sampler == "device":
+            self._seed += 1
+            pix_dev = self.engine.sample_pixels(V, self.sample_num, self.H * self.W, self._seed)
+            return self.engine.score_views(poses, self.H, self.W, fx, fy, cx, cy, pix_dev)
         if pix_idx is None:
             pix_idx = self._pixel_subset(V)
-        fx, fy, cx, cy = _intrinsics(self.K)
         pix_t = None if pix_idx is None else torch.as_tensor(np.ascontiguousarray(pix_idx, dtype=np.int32))
         scores = self.engine.score_views_host(poses, self.H, self.W, fx, fy, cx, cy, pix_t)
         return scores.to(self.engine.device)

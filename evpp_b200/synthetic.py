@@ -100,3 +100,24 @@ def room_occupancy_bitfield(G=128, aabb_min=(-5.0, 0.01, -5.0), aabb_max=(5.0, 5
            (Z > lo[2] + vox[2]) & (Z < hi[2] - vox[2])
     occ = (inside & ~core) | ((np.abs(X) < 0.5) & (Y < 1.0) & (np.abs(Z - 0.5) < 0.5))
     return np.packbits(occ.reshape(-1), bitorder="little")
+
+
+def state_volume(dims, seed=0):
+    """Synthetic planner state map for benchmarks: State_vol_origin (0 unknown, 1 empty, 2 occupied) and Nray_vol in the
+    layout evpp_b200.TSDF.set_state takes.  An observed ball around the scene centre, an occupied box shell, a floor and
+    sparse specks; voxel [0,0,0] is empty as in the reference (tsdf_gpu.py:779)."""
+    rng = np.random.RandomState(seed)
+    X, Y, Z = [int(v) for v in dims]
+    gx, gy, gz = np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij")
+    state = np.zeros((X, Y, Z), dtype=np.float32)
+    c = np.array([X / 2, Y / 3, Z / 2])
+    state[np.sqrt((gx - c[0]) ** 2 + (gy - c[1]) ** 2 + (gz - c[2]) ** 2) < 0.38 * min(X, Z)] = 1
+    box = (np.abs(gx - c[0]) < 10) & (gy < 25) & (np.abs(gz - c[2]) < 15)
+    inner = (np.abs(gx - c[0]) < 9) & (gy < 24) & (np.abs(gz - c[2]) < 14)
+    state[box & ~inner] = 2
+    state[(gy <= 1) & (state == 1)] = 2
+    state[rng.rand(X, Y, Z) < 0.002] = 2
+    state[0, 0, 0] = 1
+    nray = np.zeros_like(state)
+    nray[state == 2] = rng.randint(0, 40, size=int((state == 2).sum())).astype(np.float32)
+    return state, nray

@@ -19,7 +19,8 @@ NEAR, FAR, VOXEL_RES = 0.5, 6.0, 0.1
 
 class TSDF:
     def __init__(self, engine=None, device=0, H=400, W=400, K=None, vol_bnds=VOL_BNDS, aabb_bnds=AABB_BNDS,
-                 voxel_res=VOXEL_RES, near=NEAR, far=FAR, unknown_cof=0.2, surface_cof=0.1, sample_num=500):
+                 voxel_res=VOXEL_RES, near=NEAR, far=FAR, unknown_cof=0.2, surface_cof=0.1, sample_num=500,
+                 pixel_sampler="numpy", seed=0):
         self.engine = engine if engine is not None else Engine(device=device, precision="fp32", near=near, far=far)
         self.H, self.W = H, W
         self.K = np.array([[300, 0, 200], [0, 300, 200], [0, 0, 1]], dtype=np.float64) if K is None else np.asarray(K)
@@ -28,6 +29,7 @@ class TSDF:
         self.voxel_res, self.near, self.far = float(voxel_res), float(near), float(far)
         self.unknown_cof, self.surface_cof = float(unknown_cof), float(surface_cof)
         self.sample_num = sample_num
+        self.pixel_sampler, self._seed = pixel_sampler, int(seed)   # "numpy": tsdf_gpu.py:497's protocol; "device": evpp_sample_pixels
         # fusion.py:37-39
         self.index_bnd = np.ceil((self.vol_bnds[:, 1] - self.vol_bnds[:, 0]) / self.voxel_res).astype(int)
         self.vol_origin = self.vol_bnds[:, 0].astype(np.float32)
@@ -83,6 +85,18 @@ class TSDF:
         if V == 0:
             return [], []
         poses = torch.Tensor(np.asarray(poses, dtype=np.float64))[:, :3, :4].contiguous()
+        if pix_idx is None and self.sample_num is not None and self.pixel_sampler == "device":
+            e = self.engine
+            self._seed += 1
+            pix_dev = e.sample_pixels(V, self.sample_num, self.H * self.W, self._seed)
+            fx, fy, cx, cy = _intrinsics(self.K)
+            c2w = poses.to(e.device)
+            u = torch.empty(V, device=e.device, dtype=torch.float32)
+            d = torch.empty(V, device=e.device, dtype=torch.float32)
+            with torch.cuda.device(e.device):
+                check(e.lib.evpp_tsdf_score_views(e._h, _ptr(c2w), V, self.H, self.W, fx, fy, cx, cy, _ptr(pix_dev),
+                                                  self.sample_num, _ptr(u), _ptr(d), _stream_ptr(e.device)))
+            return u.tolist(), d.tolist()
         if pix_idx is None and self.sample_num is not None:
             pix_idx = np.stack([np.random.choice(self.H * self.W, size=[self.sample_num], replace=False) for _ in range(V)])
         pix_t = None if pix_idx is None else torch.as_tensor(np.ascontiguousarray(pix_idx, dtype=np.int32))

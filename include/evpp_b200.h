@@ -182,6 +182,14 @@ int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, in
                     int dirs_per_location, float* norm_scores, int32_t* best_dir,
                     int32_t* winner_view, void* stream);
 
+/* Random pixel subsets on the device: pix_idx (device int32 [V,R]) receives R DISTINCT pixel ids in [0, H*W) per
+ * view, the input evpp_score_views / evpp_tsdf_score_views take.  Replaces the per-pose
+ * np.random.choice(H*W, R, replace=False) of Controller.get_uncertainty (nerf.py:284-290) and
+ * get_uncertainty_tsdf (tsdf_gpu.py:497), which shuffles all H*W ids on the host for every pose.  Same sampling
+ * model, a different random stream (keyed by `seed`); callers that need the reference's NumPy stream pass their own
+ * pix_idx instead. */
+int evpp_sample_pixels(evpp_handle* h, uint64_t seed, int V, int R, int n_pixels, int32_t* pix_idx, void* stream);
+
 /* ---- Planner surrogate g_phi ----
  * The small MLP the planners fit to the (location -> normalised gain) rows of one planning step and then query
  * inside weighted A* (class MLP, plannerServer_Object/core/vpp.py:26-67; identical in plannerServer_Room).

@@ -683,3 +683,34 @@ def test_planning_step_end_to_end(weights):
     assert gains.shape == (100, 1) and np.isfinite(gains).all()
     assert np.sqrt(np.mean((gains[:, 0] - data[:, 5]) ** 2)) < 0.25
     assert np.isfinite(mlp(torch.tensor(list(locations[0])).to(torch.float32)).detach().cpu().numpy()[0])   # vpp.py:487
+
+
+def test_device_pixel_sampler(engine_factory, weights):
+    """evpp_sample_pixels: R distinct pixels per view in range, deterministic per seed, different per view and per
+    seed, close to uniform; scores with device-drawn subsets equal the scores of the same subsets passed explicitly,
+    and their mean over views agrees with NumPy-drawn subsets (same sampling model, different stream)."""
+    import evpp_b200
+    eng = engine_factory("spread", "fp32")
+    n = 400 * 400
+    p = eng.sample_pixels(64, 1000, n, seed=5).cpu().numpy()
+    assert p.shape == (64, 1000) and p.min() >= 0 and p.max() < n
+    assert all(len(np.unique(row)) == 1000 for row in p)
+    assert np.array_equal(p, eng.sample_pixels(64, 1000, n, seed=5).cpu().numpy())
+    assert not np.array_equal(p[0], p[1]) and not np.array_equal(p, eng.sample_pixels(64, 1000, n, seed=6).cpu().numpy())
+    hist = np.bincount(p.reshape(-1) * 16 // n, minlength=16)
+    assert hist.min() > 0.9 * 4000 and hist.max() < 1.1 * 4000                     # 64000 draws over 16 bins
+    for nn, rr in ((7, 7), (1200, 1200), (4097, 100), (1, 1)):                     # whole-domain permutations, odd sizes
+        q = eng.sample_pixels(3, rr, nn, seed=1).cpu().numpy()
+        assert q.min() >= 0 and q.max() < nn and all(len(np.unique(row)) == rr for row in q)
+    c, f = weights["spread"]
+    ctl = evpp_b200.Controller(H=60, W=80, focal=60.0, near=0.5, far=6.0, precision="fp32", sample_num=400,
+                               pixel_sampler="device", seed=3)
+    ctl.copy_model(c, f)
+    poses = O.views_to_poses(O.hemisphere_views(24, seed=2))
+    s_dev = ctl.get_uncertainty(poses).cpu().numpy()
+    pix = ctl.engine.sample_pixels(24, 400, 60 * 80, seed=4).cpu().numpy()        # the Controller advanced its seed 3 -> 4
+    np.testing.assert_allclose(s_dev, ctl.get_uncertainty(poses, pix_idx=pix).cpu().numpy(), rtol=1e-6)
+    ctl.pixel_sampler = "numpy"
+    np.random.seed(0)
+    s_np = ctl.get_uncertainty(poses).cpu().numpy()
+    assert abs(s_dev.mean() / s_np.mean() - 1) < 0.05
