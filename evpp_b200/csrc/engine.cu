@@ -663,7 +663,7 @@ int evpp_surrogate_fit(evpp_handle* h, float* params, const float* xyz, const fl
   if (epochs == 0) return 0;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t moments = 2 * (size_t)kSurrogateParams;
+  const size_t moments = (2 * (size_t)kSurrogateParams + 3) & ~(size_t)3;   // keeps the activation workspace 16-byte aligned
   if (h->sg_ws.ensure((moments + surrogate_workspace_floats(N)) * 4)) return fail(EVPP_ERR_CUDA, "surrogate workspace alloc failed");
   float* m = h->sg_ws.as<float>();
   CUDA_TRY(cudaMemsetAsync(m, 0, moments * 4, st));     // a fresh optimizer per fit, like train_only
