@@ -714,3 +714,37 @@ def test_device_pixel_sampler(engine_factory, weights):
     np.random.seed(0)
     s_np = ctl.get_uncertainty(poses).cpu().numpy()
     assert abs(s_dev.mean() / s_np.mean() - 1) < 0.05
+
+
+def test_concurrent_handles_from_two_threads(weights):
+    """The reference's servers are thread-per-request (nerfServer/core/views.py:79): two request threads, each with its
+    own engine handle and CUDA stream, score different view sets at the same time (ctypes releases the GIL during the
+    calls) and must reproduce the single-threaded scores bit for bit."""
+    import threading
+    import evpp_b200
+    c, f = weights["spread"]
+    views = [O.hemisphere_views(24, seed=s) for s in (11, 12)]
+    poses = [torch.Tensor(np.asarray(O.views_to_poses(v)))[:, :3, :4].contiguous() for v in views]
+    engines = []
+    for _ in range(2):
+        e = evpp_b200.Engine(device=0, precision="fp16", near=0.5, far=6.0)
+        e.load_weights(0, c)
+        e.load_weights(1, f)
+        engines.append(e)
+    ref = [engines[i].score_views_host(poses[i], 30, 40, 30.0, 30.0, 20.0, 15.0).clone() for i in range(2)]
+    out, errs = [None, None], []
+
+    def work(i):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(5):
+                    out[i] = engines[i].score_views_host(poses[i], 30, 40, 30.0, 30.0, 20.0, 15.0).clone()
+        except Exception as ex:          # noqa: BLE001
+            errs.append(ex)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for i in range(2):
+        assert torch.equal(out[i], ref[i])
