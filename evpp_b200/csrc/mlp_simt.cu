@@ -246,12 +246,8 @@ int grid_for(long long M) {
 int launch_mlp_simt(const SimtWeights& w, const RayBatch& rb, float* raw, cudaStream_t st) {
   const long long M = (long long)rb.n * rb.S;
   if (M <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(mlp_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    cudaFuncSetAttribute(mlp_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    configured = true;
-  }
+  // per launch, not once per process: the attribute is per device, and one process may drive several (nerf.py:269-273)
+  cudaFuncSetAttribute(mlp_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   mlp_simt_kernel<true><<<grid_for(M), NT, sizeof(Smem), st>>>(w, rb, nullptr, nullptr, M, raw);
   return 1;
 }
@@ -259,12 +255,7 @@ int launch_mlp_simt(const SimtWeights& w, const RayBatch& rb, float* raw, cudaSt
 int launch_mlp_simt_points(const SimtWeights& w, const float* pts, const float* dirs, int64_t M, float* out,
                            cudaStream_t st) {
   if (M <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(mlp_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    cudaFuncSetAttribute(mlp_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    configured = true;
-  }
+  cudaFuncSetAttribute(mlp_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   RayBatch rb{};
   mlp_simt_kernel<false><<<grid_for(M), NT, sizeof(Smem), st>>>(w, rb, pts, dirs, (long long)M, out);
   return 1;

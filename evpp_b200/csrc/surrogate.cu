@@ -532,25 +532,20 @@ size_t surrogate_workspace_floats(int n) { return (size_t)(kHid + 1) * n * kH + 
 int launch_surrogate_fit(float* params, float* m, float* v, const float* x, const float* target, int n, int epochs, float lr,
                          float* workspace, float* loss_out, cudaStream_t st) {
   if (n <= 0 || epochs <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(surrogate_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess ||
-        cudaFuncSetAttribute(surrogate_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess)
-      return -1;
-    configured = true;
-  }
+  // kernel attributes are per device and one process may drive several: set them per launch
+  if (cudaFuncSetAttribute(surrogate_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) return -1;
   float* act = workspace;
   float* yws = workspace + (size_t)(kHid + 1) * n * kH;
   float* dbuf = yws + kSurrogateMaxN;
-  static int use_cluster = -1;
+  static int use_cluster = -1;       // process-wide preference; the attribute itself is set per launch
   if (use_cluster < 0) {
     const char* e = getenv("EVPP_SG_CLUSTER");
     use_cluster = (e && atoi(e) == 0) ? 0 : 1;
-    if (use_cluster && cudaFuncSetAttribute(surrogate_fit_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)sizeof(CluSmem)) != cudaSuccess) {
-      cudaGetLastError();
-      use_cluster = 0;
-    }
+  }
+  if (use_cluster && cudaFuncSetAttribute(surrogate_fit_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(CluSmem)) != cudaSuccess) {
+    cudaGetLastError();
+    use_cluster = 0;
   }
   if (use_cluster) {
     surrogate_fit_cluster_kernel<<<kClu, kCluThreads, sizeof(CluSmem), st>>>(params, m, v, x, target, n, epochs, lr, act, dbuf, loss_out);
@@ -564,12 +559,7 @@ int launch_surrogate_fit(float* params, float* m, float* v, const float* x, cons
 
 int launch_surrogate_query(const float* params, const float* x, int M, float* out, cudaStream_t st) {
   if (M <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(surrogate_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess)
-      return -1;
-    configured = true;
-  }
+  if (cudaFuncSetAttribute(surrogate_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) return -1;
   surrogate_query_kernel<<<(M + kSurrogateMaxN - 1) / kSurrogateMaxN, kSgThreads, sizeof(Smem), st>>>(params, x, M, out);
   return 1;
 }

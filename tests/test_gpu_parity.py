@@ -748,3 +748,28 @@ def test_concurrent_handles_from_two_threads(weights):
     assert not errs
     for i in range(2):
         assert torch.equal(out[i], ref[i])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(weights):
+    """The reference keeps model replicas on several GPUs of ONE process (Controller.get_uncertainty picks one,
+    nerf.py:269-273).  Engines on cuda:0 and cuda:1 in the same process give identical scores, for the NeRF scorer, the
+    surrogate and the device pixel sampler (kernel attributes and workspaces are per device)."""
+    import evpp_b200
+    c, f = weights["spread"]
+    poses = torch.Tensor(np.asarray(O.views_to_poses(O.hemisphere_views(12, seed=3))))[:, :3, :4].contiguous()
+    res = []
+    for dev in (0, 1):
+        e = evpp_b200.Engine(device=dev, precision="fp16", near=0.5, far=6.0)
+        e.load_weights(0, c)
+        e.load_weights(1, f)
+        s = e.score_views_host(poses, 30, 40, 30.0, 30.0, 20.0, 15.0).clone()
+        s32 = e.rescore_views_fp32(poses, np.arange(4, dtype=np.int32), 30, 40, 30.0, 30.0, 20.0, 15.0).clone()
+        pix = e.sample_pixels(4, 100, 1200, seed=1).cpu()
+        torch.manual_seed(0)
+        mlp = evpp_b200.MLP(e)
+        data = np.concatenate([np.random.RandomState(0).rand(100, 5), np.random.RandomState(1).rand(100, 1)], axis=1)
+        evpp_b200.train_only(mlp, data, N=100, epochs=20)
+        res.append((s, s32, pix, mlp.params.cpu(), mlp(torch.rand(7, 3, generator=torch.Generator().manual_seed(1))).cpu()))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
