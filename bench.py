@@ -288,8 +288,7 @@ def run_planner(args, rank, local_rank, world):
         get_uncertainty_tsdf = staticmethod(timed("stage1_tsdf", ts.get_uncertainty_tsdf))
 
     def get_uncertainty(locs, us, vs):
-        poses = [evpp_b200.get_pose(locs[i], us[i], vs[i]) for i in range(len(locs))]
-        return ctl.get_uncertainty(poses).cpu().numpy().tolist(), [], []
+        return ctl.get_uncertainty(evpp_b200.get_poses(locs, us, vs)).cpu().numpy().tolist(), [], []
 
     get_uncertainty = timed("stage2_nerf", get_uncertainty)
     test_pts = torch.tensor(np.random.RandomState(1).uniform(-3, 3, size=(1000, 3))).to(torch.float32)

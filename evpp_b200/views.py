@@ -5,7 +5,7 @@ engine through any HTTP front end.  The reference returns ``None`` (HTTP 500) fo
 here a wrong method raises ``ValueError``."""
 import json
 
-from .run_nerf import get_pose
+from .run_nerf import get_pose, get_poses  # noqa: F401
 
 
 def get_uncertainty(controller, body, method="POST"):
@@ -15,7 +15,7 @@ def get_uncertainty(controller, body, method="POST"):
         raise ValueError("get_uncertainty expects POST")
     data = json.loads(body) if isinstance(body, (bytes, str)) else body
     locations, us, vs = data["locations"], data["us"], data["vs"]
-    poses = [get_pose(locations[i], us[i], vs[i]) for i in range(len(locations))]
+    poses = get_poses(locations, us, vs)          # == [get_pose(locations[i], us[i], vs[i]) for i in ...] (views.py:104-107)
     uncers = controller.get_uncertainty(poses)
     return {"uncers": uncers.cpu().numpy().tolist()}
 

@@ -296,3 +296,15 @@ def test_sample_direction_matches_reference_source(scene):
     mine = evpp_b200.sample_direction(locations, Stub.tsdf, fake_nerf, Stub.object_center, scene=scene)
     assert mine.shape == ref.shape == (17, 6)
     assert np.array_equal(mine, ref)
+
+
+def test_get_poses_equals_get_pose():
+    """The vectorised pose builder returns, element for element, what the per-view get_pose (views.py:141-150) returns."""
+    import evpp_b200
+    rng = np.random.RandomState(0)
+    n = 5000
+    loc, u, v = rng.uniform(-5, 5, (n, 3)), rng.uniform(-1.6, 1.6, n), rng.uniform(-7, 7, n)
+    ref = np.array([evpp_b200.get_pose(list(loc[i]), u[i], v[i]) for i in range(n)], dtype=np.float64)
+    assert np.array_equal(ref, evpp_b200.get_poses(loc, u, v))
+    assert np.array_equal(ref[:50], evpp_b200.get_poses(loc[:50].tolist(), u[:50].tolist(), v[:50].tolist()))
+    assert np.array_equal(ref, np.array([O.get_pose(list(loc[i]), u[i], v[i]) for i in range(n)], dtype=np.float64))
