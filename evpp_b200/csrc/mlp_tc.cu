@@ -294,7 +294,7 @@ struct TcArgs {
   float* dbg;        // optional [M,256] dump of the activations written by layer dbg_layer
   int dbg_layer;
   int tiles_per_cta;
-  long long* trace;  // optional [128] clock64 stamps of CTA 0's third tile (DBG kernels only)
+  long long* trace;  // optional [128] clock64 stamps of CTA 0's third tile (kernels built with DM != 0 only)
 };
 
 __device__ __forceinline__ long long clk() {
@@ -304,7 +304,7 @@ __device__ __forceinline__ long long clk() {
 }
 #define EVPP_TRACE(idx)                                                              \
   do {                                                                               \
-    if (DBG && args.trace && blockIdx.x == 0 && it == 2) args.trace[(idx)] = clk();  \
+    if (TR && args.trace && blockIdx.x == 0 && it == 2) args.trace[(idx)] = clk();   \
   } while (0)
 
 struct RowData {     // what one epilogue thread knows about its row of the current tile
@@ -352,7 +352,7 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 // flight while chunk k is converted and stored.
 // HFC >= 0 makes the warp's column slice a compile-time constant, so that the head weights of layers 7 and 9 become
 // immediate constant-bank operands of the FFMAs instead of indexed constant loads.
-template <bool BF16, int KIND, bool DBG, int HFC = -1>
+template <bool BF16, int KIND, bool DBG, bool TR, int HFC = -1>
 __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& args, const float* bias_l, int l,
                                             uint32_t t_acc, int hf, int lane, uint32_t bar_a, uint32_t bar_acc_l,
                                             uint32_t acc_parity, const RowData& rd, float& alpha, float (&hd)[4],
@@ -371,7 +371,7 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
   // half is still on the tensor pipe
   mbar_wait(bar_acc_l, acc_parity);
   tc_fence_after();
-  if (DBG && tr && lane == 0) tr[0] = clk();
+  if (TR && tr && lane == 0) tr[0] = clk();
   tmem_ld16(t_acc + (uint32_t)(hf * NC), r[0]);
   bool half1_early = false;
 #pragma unroll
@@ -445,8 +445,8 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a + 8 * kb);
-      if (DBG && tr && lane == 0) tr[1 + kb] = clk();
-      if (DBG && tr0 && lane == 0 && kb == 0) tr0[0] = clk();
+      if (TR && tr && lane == 0) tr[1 + kb] = clk();
+      if (TR && tr0 && lane == 0 && kb == 0) tr0[0] = clk();
     }
     if (kb == 1 && NCH > 2 && !half1_early) {
       mbar_wait(bar_acc_l + 8, acc_parity);
@@ -458,9 +458,13 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
 }
 
 // SPLIT: hidden K-blocks kb >= SPLIT of a 256-wide layer are issued as two N = 128 halves (4 = none)
-template <bool BF16, bool RAYS, int C, bool DBG, int SPLIT>
+// DM: 0 = production, 1 = per-layer activation dumps + pipeline trace (fp32 ReLU path), 2 = pipeline trace only
+// (production arithmetic and timing)
+template <bool BF16, bool RAYS, int C, int DM, int SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcArgs args) {
+  constexpr bool DBG = DM == 1;
+  constexpr bool TR = DM != 0;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   const uint32_t smem_base = smem_u32(smem_dyn);
   if (smem_base & 1023u) __trap();   // the 128-byte swizzle atoms need 1024-byte aligned blocks
@@ -532,7 +536,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
         }
       }
     }
-    if (DBG && lane == 31 && args.trace && blockIdx.x == 0) {
+    if (TR && lane == 31 && args.trace && blockIdx.x == 0) {
       // diagnostics: when each accumulator half of each layer really becomes final (tile 2 of CTA 0)
       uint32_t ph[2] = {0u, 0u};
       for (int it = 0; it < ntile_iters; ++it)
@@ -661,11 +665,11 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
         if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 0);   // (before the accumulator wait)
         const uint32_t t_acc = t_lane + (uint32_t)(ab * 256);
         long long* tr = nullptr;
-        if (DBG && args.trace && blockIdx.x == 0 && it == 2 && l == 3 && (warp == 0 || warp == kEpiWarps - 1))
+        if (TR && args.trace && blockIdx.x == 0 && it == 2 && l == 3 && (warp == 0 || warp == kEpiWarps - 1))
           tr = args.trace + (warp == 0 ? 90 : 95);
-        long long* tr0 = (DBG && args.trace && blockIdx.x == 0 && it == 2 && l == 3) ? args.trace + 100 + warp : nullptr;
+        long long* tr0 = (TR && args.trace && blockIdx.x == 0 && it == 2 && l == 3) ? args.trace + 100 + warp : nullptr;
 #define EVPP_DRAIN(KIND_, HFC_) \
-  drain_layer<BF16, KIND_, DBG, HFC_>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd, tr, tr0)
+  drain_layer<BF16, KIND_, DBG, TR, HFC_>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd, tr, tr0)
         if (l == 9) {
           if (hf == 0) EVPP_DRAIN(3, 0); else if (hf == 1) EVPP_DRAIN(3, 1); else if (hf == 2) EVPP_DRAIN(3, 2); else EVPP_DRAIN(3, 3);
         } else if (l == 8) {
@@ -735,9 +739,9 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   }
 }
 
-template <bool BF16, bool RAYS, int C, bool DBG, int SPLIT>
+template <bool BF16, bool RAYS, int C, int DM, int SPLIT>
 cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStream_t st) {
-  auto kern = mlp_tc_kernel<BF16, RAYS, C, DBG, SPLIT>;
+  auto kern = mlp_tc_kernel<BF16, RAYS, C, DM, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -765,11 +769,13 @@ cudaError_t launch_split(const TcWeights& w, const TcArgs& a, int C, long long g
 #define EVPP_TC_DISPATCH(CC, DD)                                                              \
   e = bf ? launch_one<true, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st)                 \
          : launch_one<false, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st)
-  if (a.dbg || a.trace) {
-    EVPP_TC_DISPATCH(1, !RAYS);
-  } else if (C == 4) { EVPP_TC_DISPATCH(4, false); }
-  else if (C == 2) { EVPP_TC_DISPATCH(2, false); }
-  else { EVPP_TC_DISPATCH(1, false); }
+  if (a.dbg) {
+    EVPP_TC_DISPATCH(1, RAYS ? 0 : 1);
+  } else if (a.trace) {          // production kernel (cluster, packed epilogue) with the clock stamps compiled in
+    if (C == 2) { EVPP_TC_DISPATCH(2, RAYS ? 0 : 2); } else { EVPP_TC_DISPATCH(1, RAYS ? 0 : 2); }
+  } else if (C == 4) { EVPP_TC_DISPATCH(4, 0); }
+  else if (C == 2) { EVPP_TC_DISPATCH(2, 0); }
+  else { EVPP_TC_DISPATCH(1, 0); }
 #undef EVPP_TC_DISPATCH
   return e;
 }
