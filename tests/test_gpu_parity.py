@@ -561,7 +561,11 @@ def test_tensorf_backbone_vs_restatement():
         sc.encode(torch.rand(4, 3))        # the hash-grid encoder is not available on a TensoRF scorer
 
 
-@pytest.mark.parametrize("lindisp,white,ns,ni", [(True, True, 64, 128), (False, False, 64, 128), (False, True, 32, 16)])
+@pytest.mark.parametrize("lindisp,white,ns,ni", [(True, True, 64, 128), (False, False, 64, 128), (False, True, 32, 16),
+                                                 # sample counts that are not multiples of 4 / 32 (scalar tails and padded
+                                                 # planes of the warp-per-ray kernels), the minimum and the maximum
+                                                 (False, True, 7, 5), (False, False, 33, 31), (True, True, 4, 1),
+                                                 (False, True, 128, 256), (False, True, 65, 130)])
 def test_render_option_variants_vs_oracle(weights, lindisp, white, ns, ni):
     """Renderer flags the reference exposes besides the live config (nerf_configs.py: lindisp, white_bkgd,
     N_samples, N_importance): fp32 path against the oracle on the same rays."""
