@@ -294,6 +294,8 @@ struct TcArgs {
   float* dbg;        // optional [M,256] dump of the activations written by layer dbg_layer
   int dbg_layer;
   int tiles_per_cta;
+  long long tile0;     // this launch owns tiles [tile0, tile_end): CTA b takes tile0 + b + it * gridDim.x
+  long long tile_end;
   long long* trace;  // optional [128] clock64 stamps of CTA 0's third tile (kernels built with DM != 0 only)
 };
 
@@ -306,6 +308,10 @@ __device__ __forceinline__ long long clk() {
   do {                                                                               \
     if (TR && args.trace && blockIdx.x == 0 && it == 2) args.trace[(idx)] = clk();   \
   } while (0)
+
+#ifdef EVPP_TC_DIAG
+__device__ unsigned long long g_diag[2][160][3];   // [4-cluster | 2-cluster launch][CTA][start ns, end ns, smid]
+#endif
 
 struct RowData {     // what one epilogue thread knows about its row of the current tile
   float p[3];
@@ -507,7 +513,19 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   const uint32_t tmem = misc.tmem_base;
 
   const int ntile_iters = args.tiles_per_cta;
-  const long long ntiles = (args.M + kTileM - 1) / kTileM;
+  const long long ntiles = args.tile_end;
+  // Hybrid launch (launch_any): a dependent launch that fills the SMs this grid's clusters cannot tile may start as
+  // soon as every CTA of this grid is resident.  Without a dependent launch this is a no-op.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#ifdef EVPP_TC_DIAG
+  if (threadIdx.x == 0) {
+    unsigned long long t; unsigned sm;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    g_diag[C == 4 ? 0 : 1][blockIdx.x][0] = t;
+    g_diag[C == 4 ? 0 : 1][blockIdx.x][2] = sm;
+  }
+#endif
 
   if (warp == kProducerWarp) {
     // ================= weight producer =================
@@ -647,7 +665,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t acc_phase[2] = {0u, 0u};
     RowData cur, nxt;
-    load_row<RAYS>(args, (long long)blockIdx.x, ntiles, row, cur);
+    load_row<RAYS>(args, args.tile0 + (long long)blockIdx.x, ntiles, row, cur);
     if (hf == 0) {
       encode_store<BF16, kLpos, false>(cur.p, sX + row_off, row, 8);
       fence_proxy_async();
@@ -693,7 +711,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
           if (lane == 0) mbar_arrive(bar_xd);
         } else if (l == 5) {
           // X <- position embedding of the NEXT tile (layer 5's MMAs were the last readers of this tile's)
-          load_row<RAYS>(args, (long long)blockIdx.x + (long long)(it + 1) * gridDim.x,
+          load_row<RAYS>(args, args.tile0 + (long long)blockIdx.x + (long long)(it + 1) * gridDim.x,
                          it + 1 < ntile_iters ? ntiles : 0, row, nxt);
           if (hf == 0) {
             encode_store<BF16, kLpos, false>(nxt.p, sX + row_off, row, 8);
@@ -737,10 +755,20 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
+#ifdef EVPP_TC_DIAG
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_diag[C == 4 ? 0 : 1][blockIdx.x][1] = t;
+  }
+#endif
+  // A dependent (filler) launch must not complete before the grid it was launched behind: the next kernel in the
+  // stream reads the rows of both.  No-op for an ordinary launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 template <bool BF16, bool RAYS, int C, int DM, int SPLIT>
-cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStream_t st) {
+cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStream_t st, bool dependent = false) {
   auto kern = mlp_tc_kernel<BF16, RAYS, C, DM, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;
@@ -749,13 +777,15 @@ cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStrea
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = dependent ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, cst, a);
 }
 
@@ -763,12 +793,13 @@ int g_cluster = 2;   // CTAs sharing one weight stream by bulk-copy multicast (1
 int g_split = 2;     // hidden K-blocks >= g_split run as two N = 128 halves (1..4, 4 = off); EVPP_TC_SPLIT overrides
 
 template <bool RAYS, int SPLIT>
-cudaError_t launch_split(const TcWeights& w, const TcArgs& a, int C, long long grid, cudaStream_t st) {
+cudaError_t launch_split(const TcWeights& w, const TcArgs& a, int C, long long grid, cudaStream_t st,
+                         bool dependent = false) {
   const bool bf = w.dtype == EVPP_PREC_BF16;
   cudaError_t e;
 #define EVPP_TC_DISPATCH(CC, DD)                                                              \
-  e = bf ? launch_one<true, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st)                 \
-         : launch_one<false, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st)
+  e = bf ? launch_one<true, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st, dependent)      \
+         : launch_one<false, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st, dependent)
   if (a.dbg) {
     EVPP_TC_DISPATCH(1, RAYS ? 0 : 1);
   } else if (a.trace) {          // production kernel (cluster, packed epilogue) with the clock stamps compiled in
@@ -780,6 +811,28 @@ cudaError_t launch_split(const TcWeights& w, const TcArgs& a, int C, long long g
   return e;
 }
 
+// How many 4-CTA clusters of this kernel are co-resident (they do not tile every GPC: 33 on a 148-SM B200).
+int max_clusters_of_4(int num_sms) {
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    auto kern = mlp_tc_kernel<false, true, 4, false, 2>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    int mc = 0;
+    if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc <= 0) mc = num_sms / 4;
+    if (getenv("EVPP_TC_VERBOSE")) fprintf(stderr, "evpp: %d co-resident 4-CTA clusters\n", mc);
+    max_clusters = mc;
+  }
+  return max_clusters;
+}
+
+float g_hybrid_ratio = 1.066f;   // per-SM speed of a 4-CTA cluster relative to a 2-CTA cluster (measured)
+
 template <bool RAYS>
 int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   if (a.M <= 0) return 0;
@@ -787,47 +840,108 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   if (!env_read) {
     if (const char* e = getenv("EVPP_TC_CLUSTER")) {
       const int c = atoi(e);
-      if (c == 1 || c == 2 || c == 4) g_cluster = c;
+      if (c == 1 || c == 2 || c == 4 || c == 42) g_cluster = c;
     }
     if (const char* e = getenv("EVPP_TC_SPLIT")) {
       const int c = atoi(e);
       if (c == 2 || c == 4) g_split = c;
     }
+    if (const char* e = getenv("EVPP_TC_HYBRID_R")) {
+      const float r = (float)atof(e);
+      if (r > 0.5f && r < 2.f) g_hybrid_ratio = r;
+    }
     env_read = true;
   }
-  const int C = g_cluster;
   const long long ntiles = (a.M + kTileM - 1) / kTileM;
+  a.image = reinterpret_cast<const uint8_t*>(w.image);
+  a.dbg = w.dbg;
+  a.dbg_layer = w.dbg_layer;
+  a.trace = w.trace;
+  a.tile0 = 0;
+  a.tile_end = ntiles;
+  if ((a.dbg || a.trace) && RAYS) return -1;
+
+  // Hybrid 4 + 2: 4-CTA clusters share one weight stream four ways (L2 reads quartered) but leave 16 of the 148 SMs
+  // idle; a second launch of 2-CTA clusters, released by griddepcontrol.launch_dependents as soon as every 4-CTA
+  // cluster is resident, takes those SMs and a proportional slice of the tiles.
+  if (g_cluster == 42 && !a.dbg && !a.trace && ntiles >= 32LL * num_sms) {
+    const long long grid_a = (long long)max_clusters_of_4(num_sms) * 4;
+    const long long grid_b = (num_sms - grid_a) / 2 * 2;
+    if (grid_a > 0 && grid_b > 0) {
+      const double share_a = grid_a * (double)g_hybrid_ratio / (grid_a * (double)g_hybrid_ratio + grid_b);
+      long long tiles_a = (long long)(ntiles * share_a) / grid_a * grid_a;
+      TcArgs aa = a, ab = a;
+      aa.tile_end = tiles_a;
+      aa.tiles_per_cta = (int)(tiles_a / grid_a);
+      ab.tile0 = tiles_a;
+      ab.tiles_per_cta = (int)((ntiles - tiles_a + grid_b - 1) / grid_b);
+      cudaError_t e = g_split == 2 ? launch_split<RAYS, 2>(w, aa, 4, grid_a, st) : launch_split<RAYS, 4>(w, aa, 4, grid_a, st);
+      if (e != cudaSuccess) return -1;
+      e = g_split == 2 ? launch_split<RAYS, 2>(w, ab, 2, grid_b, st, true) : launch_split<RAYS, 4>(w, ab, 2, grid_b, st, true);
+#ifdef EVPP_TC_DIAG
+      {
+        static int shown = 0;
+        if (shown < 4 && ntiles > 100000) {
+          ++shown;
+          cudaStreamSynchronize(st);
+          static unsigned long long hd[2][160][3];
+          cudaMemcpyFromSymbol(hd, g_diag, sizeof(hd));
+          unsigned long long t0 = ~0ull;
+          for (int k = 0; k < 2; ++k)
+            for (int b = 0; b < (k ? grid_b : grid_a); ++b) t0 = hd[k][b][0] < t0 ? hd[k][b][0] : t0;
+          for (int k = 0; k < 2; ++k) {
+            unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0;
+            for (int b = 0; b < (k ? grid_b : grid_a); ++b) {
+              s0 = hd[k][b][0] < s0 ? hd[k][b][0] : s0; s1 = hd[k][b][0] > s1 ? hd[k][b][0] : s1;
+              e0 = hd[k][b][1] < e0 ? hd[k][b][1] : e0; e1 = hd[k][b][1] > e1 ? hd[k][b][1] : e1;
+            }
+            fprintf(stderr, "diag %s: start %.3f..%.3f ms, end %.3f..%.3f ms, tiles/cta %d; smids:", k ? "B(2)" : "A(4)",
+                    (s0 - t0) * 1e-6, (s1 - t0) * 1e-6, (e0 - t0) * 1e-6, (e1 - t0) * 1e-6, k ? ab.tiles_per_cta : aa.tiles_per_cta);
+            if (k) for (int b = 0; b < grid_b; ++b) fprintf(stderr, " %llu", hd[k][b][2]);
+            fprintf(stderr, "\n");
+          }
+        }
+      }
+#endif
+      return e == cudaSuccess ? 2 : -1;
+    }
+  }
+
+  const int C = g_cluster == 42 ? 2 : g_cluster;
   long long grid = ntiles < num_sms ? ntiles : num_sms;
   grid = (grid + C - 1) / C * C;
   if (grid > num_sms) grid = num_sms / C * C;
   if (C == 4) {
     // 4-CTA clusters do not tile every GPC: keep the persistent grid to what is co-resident
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(148); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
-      auto kern = mlp_tc_kernel<false, true, 4, false, 2>;
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-      if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) max_clusters = num_sms / 4;
-      if (getenv("EVPP_TC_VERBOSE")) fprintf(stderr, "evpp: %d co-resident 4-CTA clusters\n", max_clusters);
-    }
-    if (grid > (long long)max_clusters * 4) grid = (long long)max_clusters * 4;
+    const long long cap = (long long)max_clusters_of_4(num_sms) * 4;
+    if (grid > cap) grid = cap;
   }
   a.tiles_per_cta = (int)((ntiles + grid - 1) / grid);
-  a.image = reinterpret_cast<const uint8_t*>(w.image);
-  a.dbg = w.dbg;
-  a.dbg_layer = w.dbg_layer;
-  a.trace = w.trace;
-  if ((a.dbg || a.trace) && RAYS) return -1;
   cudaError_t e;
   switch (g_split) {
     case 2: e = launch_split<RAYS, 2>(w, a, C, grid, st); break;
     default: e = launch_split<RAYS, 4>(w, a, C, grid, st); break;
   }
+#ifdef EVPP_TC_DIAG
+  {
+    static int shown = 0;
+    if (shown < 6 && ntiles > 50000 && e == cudaSuccess) {
+      ++shown;
+      cudaStreamSynchronize(st);
+      static unsigned long long hd[2][160][3];
+      cudaMemcpyFromSymbol(hd, g_diag, sizeof(hd));
+      const int k = C == 4 ? 0 : 1;
+      unsigned long long s0 = ~0ull, e0 = ~0ull, e1 = 0;
+      for (int b = 0; b < grid; ++b) {
+        s0 = hd[k][b][0] < s0 ? hd[k][b][0] : s0;
+        e0 = hd[k][b][1] < e0 ? hd[k][b][1] : e0; e1 = hd[k][b][1] > e1 ? hd[k][b][1] : e1;
+      }
+      fprintf(stderr, "diag C=%d: end %.3f..%.3f ms, tiles/cta %d; (smid:end)", C, (e0 - s0) * 1e-6, (e1 - s0) * 1e-6, a.tiles_per_cta);
+      for (int b = 0; b < grid; b += C) fprintf(stderr, " %llu:%.2f", hd[k][b][2], (hd[k][b][1] - s0) * 1e-6);
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
   return e == cudaSuccess ? 1 : -1;
 }
 
