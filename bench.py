@@ -249,6 +249,125 @@ def run_ngp(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_fullres(args, rank, local_rank, world):
+    """BASELINE configs[4]: full-resolution uncertainty render sweep (640x480 rays per view, 64+128 samples), the rays
+    of every image sharded over the ranks (strong scaling: a step renders the same 8 views of the 256-view sweep at
+    any N).  Per-ray rgb / depth / acc / sum(beta^2) maps are all-gathered, per-view scores all-reduced."""
+    import torch.distributed as dist
+    import evpp_b200
+    from evpp_b200 import dist as edist, synthetic as S
+    from __graft_entry__ import build
+    if local_rank == 0:
+        build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    dev = torch.device("cuda", local_rank)
+    H, W, focal, V = 480, 640, 480.0, 8
+    n_pix = H * W
+    torch.manual_seed(0)
+    c, f = S.init_nerf_state_dict(), S.init_nerf_state_dict()
+    views = S.hemisphere_views(256, seed=0)[:V]
+    poses_host = torch.Tensor(np.asarray(S.views_to_poses(views)))[:, :3, :4].contiguous()
+    eng = evpp_b200.Engine(device=local_rank, n_samples=S_C, n_importance=S_I, near=NEAR, far=FAR, white_bkgd=True,
+                           precision=args.precision)
+    eng.load_weights(0, c)
+    eng.load_weights(1, f)
+    poses_dev, poses_pinned = poses_host.to(dev), poses_host.pin_memory()
+    maps_pinned = torch.empty(V, n_pix, 6, dtype=torch.float32).pin_memory()
+    scores_pinned = torch.empty(V, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sweep(poses):
+        def block(b, e):
+            pix = torch.arange(b, e, dtype=torch.int32, device=dev)[None, :].expand(V, e - b).contiguous()
+            ro, rd, _ = eng.get_rays(poses, H, W, focal, focal, 0.5 * W, 0.5 * H, pix)
+            o = eng.render_rays(ro, rd, NEAR, FAR, want=("rgb", "depth", "acc", "unc"))
+            beta2 = o["unc"].square().sum(-1, keepdim=True)          # per-ray sum over the 192 samples
+            return torch.cat([o["rgb"], o["depth"][:, None], o["acc"][:, None], beta2], -1).view(V, e - b, 6)
+        return edist.render_views_ray_sharded(block, V, n_pix, rank, world, device=dev)
+
+    def step_device():
+        return sweep(poses_dev)
+
+    def step_e2e():
+        maps, scores = sweep(poses_pinned.to(dev, non_blocking=True))
+        maps_pinned.copy_(maps, non_blocking=True)
+        scores_pinned.copy_(scores, non_blocking=True)
+        torch.cuda.synchronize()
+        return scores_pinned
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if profile:
+            eng.set_profiling(True)
+        l0, _ = eng.counters()
+        total_ms, wall = 0.0, 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev0.record()
+            fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            wall += time.perf_counter() - t0
+            total_ms += ev0.elapsed_time(ev1)
+        l1, _ = eng.counters()
+        t = torch.tensor([total_ms, wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item() / steps, t[1].item() / steps, l1 - l0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, _, launches = timed(step_device, args.steps, args.warmup, profile=True)
+    mlp_ms, mlp_launches, mlp_evals = eng.mlp_time()
+    eng.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    _, ms_e2e, _ = timed(step_e2e, max(2, min(args.steps, 3)), 1)
+    if rank == 0:
+        sustained, _, src = peaks()
+        # the same numbers must come out at every N (rays are independent): fp64 sums of the gathered maps and scores
+        check = {"scores": [float(x) for x in scores_pinned[:4]], "maps_sum": float(maps_pinned.sum(dtype=torch.float64)),
+                 "depth_sum": float(maps_pinned[..., 3].sum(dtype=torch.float64))}
+        flops_per_launch = FLOP_PER_EVAL * mlp_evals / max(1, mlp_launches)
+        avg_launch_ms = mlp_ms / max(1, mlp_launches)
+        achieved = flops_per_launch / (avg_launch_ms / 1e3) / 1e12 if avg_launch_ms > 0 else 0.0
+        line = {"metric": "candidate views scored/sec", "value": V / (ms_dev / 1e3), "unit": "views/s",
+                "rays_per_s": V * n_pix / (ms_dev / 1e3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16 operands, f32 accumulate (tcgen05)" if args.precision == "fp16" else args.precision, "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[4] full-resolution uncertainty render sweep: {V} of the 256 views per step x {W}x{H} rays, "
+                                       f"{S_C}+{S_I} samples/ray, reference-parity renderer; per-ray rgb/depth/acc/sum(beta^2) maps + per-view scores",
+                           "views_per_step": V, "rays_per_view": n_pix,
+                           "parallelism": f"rays of every image sharded over {world} GPU(s): all_gather of the maps "
+                                          f"({V * n_pix * 24 / 1e6:.0f} MB), all_reduce of the per-view partial sums",
+                           "l2": "per-step working set exceeds L2; 256 MB L2 flush between timed steps"},
+                "e2e": {"value": V / (ms_e2e / 1e3), "unit": "views/s", "h2d_bytes_per_step": V * 48,
+                        "d2h_bytes_per_step": V * n_pix * 24 + V * 4,
+                        "api": "Engine.get_rays + Engine.render_rays (== render()) + dist.render_views_ray_sharded; maps and scores to pinned host memory"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                             "traffic": 11.97 * mlp_evals / max(1, mlp_launches),
+                             "peak_source": f"{src} bf16_tflops_sustained", "kernel": "mlp_tc_kernel",
+                             "flop_per_launch": flops_per_launch, "avg_launch_ms": avg_launch_ms,
+                             "mlp_share_of_step": mlp_ms / (ms_dev * args.steps) if ms_dev > 0 else None},
+                "check": check, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_planner(args, rank, local_rank, world):
     """One planning step of the Object planner in the reference's live protocol (SURVEY.md section 8, rows a11-a13 + f3):
     100 locations x 15 directions = 1500 stage-1 views x 500 random pixels through the TSDF state volume, the 3 best
@@ -419,9 +538,10 @@ def main():
     ap.add_argument("--workload", default="object", choices=["object", "room"],
                     help="object: BASELINE configs[1] (512 hemisphere views x 80x60 rays per GPU, the headline); room: the "
                          "4096-view Room sweep of configs[2] in reference-parity mode (512 views x 128x96 rays per GPU)")
-    ap.add_argument("--mode", default="parity", choices=["parity", "ngp", "tensorf", "planner"],
+    ap.add_argument("--mode", default="parity", choices=["parity", "ngp", "tensorf", "planner", "fullres"],
                     help="parity: the reference's scorer (headline, BASELINE configs[1]); ngp: occupancy grid + hash grid "
-                         "scorer on the Room sweep shape (BASELINE configs[2]; no reference counterpart)")
+                         "scorer on the Room sweep shape (BASELINE configs[2]; no reference counterpart); fullres: BASELINE configs[4], "
+                         "640x480 renders with the rays of every image sharded over the ranks (strong scaling)")
     args = ap.parse_args()
     if args.workload == "room":
         global IMG_H, IMG_W, FOCAL, WORKLOAD
@@ -441,6 +561,9 @@ def main():
         return
     if args.mode == "planner":
         run_planner(args, rank, local_rank, world)
+        return
+    if args.mode == "fullres":
+        run_fullres(args, rank, local_rank, world)
         return
 
     import torch.distributed as dist

@@ -789,8 +789,30 @@ cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStrea
   return cudaLaunchKernelEx(&cfg, kern, cst, a);
 }
 
-int g_cluster = 2;   // CTAs sharing one weight stream by bulk-copy multicast (1 or 2); EVPP_TC_CLUSTER overrides
-int g_split = 2;     // hidden K-blocks >= g_split run as two N = 128 halves (1..4, 4 = off); EVPP_TC_SPLIT overrides
+// Launch options, read from the environment once (thread-safe: initialised as a function-local static).
+struct TcEnv {
+  int cluster = 2;             // CTAs sharing one weight stream by bulk-copy multicast (1, 2, 4, or 42 = hybrid 4 + 2); EVPP_TC_CLUSTER
+  int split = 2;               // hidden K-blocks >= split run as two N = 128 halves (2, or 4 = off); EVPP_TC_SPLIT
+  float hybrid_ratio = 1.066f; // per-SM speed of a 4-CTA cluster relative to a 2-CTA cluster; EVPP_TC_HYBRID_R
+  TcEnv() {
+    if (const char* e = getenv("EVPP_TC_CLUSTER")) {
+      const int c = atoi(e);
+      if (c == 1 || c == 2 || c == 4 || c == 42) cluster = c;
+    }
+    if (const char* e = getenv("EVPP_TC_SPLIT")) {
+      const int c = atoi(e);
+      if (c == 2 || c == 4) split = c;
+    }
+    if (const char* e = getenv("EVPP_TC_HYBRID_R")) {
+      const float r = (float)atof(e);
+      if (r > 0.5f && r < 2.f) hybrid_ratio = r;
+    }
+  }
+};
+const TcEnv& tc_env() {
+  static const TcEnv env;
+  return env;
+}
 
 template <bool RAYS, int SPLIT>
 cudaError_t launch_split(const TcWeights& w, const TcArgs& a, int C, long long grid, cudaStream_t st,
@@ -813,8 +835,7 @@ cudaError_t launch_split(const TcWeights& w, const TcArgs& a, int C, long long g
 
 // How many 4-CTA clusters of this kernel are co-resident (they do not tile every GPC: 33 on a 148-SM B200).
 int max_clusters_of_4(int num_sms) {
-  static int max_clusters = -1;
-  if (max_clusters < 0) {
+  static const int max_clusters = [num_sms] {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(148); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
     cudaLaunchAttribute attr[1];
@@ -826,32 +847,17 @@ int max_clusters_of_4(int num_sms) {
     int mc = 0;
     if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc <= 0) mc = num_sms / 4;
     if (getenv("EVPP_TC_VERBOSE")) fprintf(stderr, "evpp: %d co-resident 4-CTA clusters\n", mc);
-    max_clusters = mc;
-  }
+    return mc;
+  }();
   return max_clusters;
 }
-
-float g_hybrid_ratio = 1.066f;   // per-SM speed of a 4-CTA cluster relative to a 2-CTA cluster (measured)
 
 template <bool RAYS>
 int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   if (a.M <= 0) return 0;
-  static bool env_read = false;
-  if (!env_read) {
-    if (const char* e = getenv("EVPP_TC_CLUSTER")) {
-      const int c = atoi(e);
-      if (c == 1 || c == 2 || c == 4 || c == 42) g_cluster = c;
-    }
-    if (const char* e = getenv("EVPP_TC_SPLIT")) {
-      const int c = atoi(e);
-      if (c == 2 || c == 4) g_split = c;
-    }
-    if (const char* e = getenv("EVPP_TC_HYBRID_R")) {
-      const float r = (float)atof(e);
-      if (r > 0.5f && r < 2.f) g_hybrid_ratio = r;
-    }
-    env_read = true;
-  }
+  const TcEnv& env = tc_env();
+  const int g_cluster = env.cluster, g_split = env.split;
+  const float g_hybrid_ratio = env.hybrid_ratio;
   const long long ntiles = (a.M + kTileM - 1) / kTileM;
   a.image = reinterpret_cast<const uint8_t*>(w.image);
   a.dbg = w.dbg;

@@ -1,7 +1,8 @@
 """Multi-GPU layer: one process per GPU, candidate views sharded in contiguous blocks, one small
 all_gather of per-view scores (NCCL over NVLink on the GPU box, gloo in CPU tests), arg-max
 replicated on every rank.  Views are independent, so there is no data-path collective besides
-the score gather."""
+the score gather.  The full-resolution render sweep (BASELINE configs[4]) shards the RAYS of
+every image instead: one all_gather of the per-ray maps and one all_reduce of the per-view partial sums of beta^2."""
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -80,3 +81,35 @@ def render_sharded(render_fn, rays_o, rays_d, rank, world, group=None):
         dist.all_gather(parts, pad, group=group)
         out[k] = torch.cat(parts)[:N]
     return out
+
+
+def render_views_ray_sharded(render_block, V, n_pixels, rank, world, device="cpu", group=None):
+    """Full-resolution sweep, ray-sharded: rank r renders pixels
+    ``shard_range(n_pixels, r, world)`` of EVERY one of the V views.
+
+    render_block(b, e) -> float32 [V, e-b, C] per-ray maps of pixel block [b, e); the LAST channel is the ray's
+    sum over samples of beta^2.  Returns (maps [V, n_pixels, C] on every rank, scores [V] float32) with
+    scores = sum over all rays and samples of beta^2 / n_pixels (Controller.get_uncertainty, nerf.py:307-309):
+    one all_gather of the padded blocks and one all_reduce(sum) of the fp64 per-view partial sums."""
+    b, e = shard_range(n_pixels, rank, world)
+    per = (n_pixels + world - 1) // world
+    local = render_block(b, e) if e > b else None
+    if world == 1:
+        return local, (local[..., -1].sum(1, dtype=torch.float64) / n_pixels).to(torch.float32)
+    C = torch.tensor([local.shape[-1] if local is not None else 0], device=device)
+    dist.all_reduce(C, op=dist.ReduceOp.MAX, group=group)
+    C = int(C.item())
+    pad = torch.zeros(V, per, C, dtype=torch.float32, device=device)
+    if local is not None:
+        pad[:, :e - b] = local
+    if pad.device.type == "cuda":
+        out = torch.empty(world, V, per, C, dtype=torch.float32, device=device)
+        dist.all_gather_into_tensor(out, pad, group=group)
+    else:
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        out = torch.stack(parts)
+    maps = out.permute(1, 0, 2, 3).reshape(V, world * per, C)[:, :n_pixels]
+    partial = pad[..., -1].sum(1, dtype=torch.float64)        # the padding rows are zero
+    dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+    return maps, (partial / n_pixels).to(torch.float32)

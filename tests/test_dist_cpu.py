@@ -4,6 +4,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -119,3 +120,45 @@ def test_wire_shim_round_trip():
     import pytest
     with pytest.raises(ValueError):
         views.get_uncertainty(FakeController(), body, method="GET")
+
+
+def _sweep_block(V, b, e):
+    """Stand-in per-ray maps of pixels [b, e) of V views: [V, e-b, 3] = (depth-like, acc-like, beta^2 sum)."""
+    pix = torch.arange(b, e, dtype=torch.float32)[None, :]
+    v = torch.arange(V, dtype=torch.float32)[:, None]
+    return torch.stack([pix * 0.5 + v, (pix + 1) / (v + 2), (0.01 * pix + 0.1 * v) ** 2], -1)
+
+
+def _sweep_worker(rank, world, port, V, n_pixels, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    maps, scores = edist.render_views_ray_sharded(lambda b, e: _sweep_block(V, b, e), V, n_pixels, rank, world)
+    q.put((rank, maps.numpy(), scores.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_pixels", [37, 2])
+def test_two_rank_ray_sharded_view_sweep(n_pixels):
+    """BASELINE configs[4]: every rank renders a pixel block of every view; maps are all-gathered, the per-view
+    score is the all-reduced sum of beta^2 / rays (odd pixel count: the last block is short)."""
+    V = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, V, n_pixels, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = _sweep_block(V, 0, n_pixels)
+    ref_scores = (full[..., -1].sum(1, dtype=torch.float64) / n_pixels).to(torch.float32).numpy()
+    one_maps, one_scores = edist.render_views_ray_sharded(lambda b, e: _sweep_block(V, b, e), V, n_pixels, 0, 1)
+    np.testing.assert_array_equal(one_maps.numpy(), full.numpy())
+    for rank, maps, scores in res:
+        np.testing.assert_array_equal(maps, full.numpy())
+        np.testing.assert_allclose(scores, ref_scores, rtol=1e-6)
+        np.testing.assert_allclose(scores, one_scores.numpy(), rtol=1e-6)
