@@ -296,6 +296,7 @@ struct TcArgs {
   int tiles_per_cta;
   long long tile0;     // this launch owns tiles [tile0, tile_end): CTA b takes tile0 + b + it * gridDim.x
   long long tile_end;
+  int pdl;             // 1: main grid of a hybrid launch (releases its dependent), 2: the dependent filler grid, 0: neither
   long long* trace;  // optional [128] clock64 stamps of CTA 0's third tile (kernels built with DM != 0 only)
 };
 
@@ -515,8 +516,8 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   const int ntile_iters = args.tiles_per_cta;
   const long long ntiles = args.tile_end;
   // Hybrid launch (launch_any): a dependent launch that fills the SMs this grid's clusters cannot tile may start as
-  // soon as every CTA of this grid is resident.  Without a dependent launch this is a no-op.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // soon as every CTA of this grid is resident.
+  if (args.pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef EVPP_TC_DIAG
   if (threadIdx.x == 0) {
     unsigned long long t; unsigned sm;
@@ -763,8 +764,8 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   }
 #endif
   // A dependent (filler) launch must not complete before the grid it was launched behind: the next kernel in the
-  // stream reads the rows of both.  No-op for an ordinary launch.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // stream reads the rows of both.
+  if (args.pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 template <bool BF16, bool RAYS, int C, int DM, int SPLIT>
@@ -865,6 +866,7 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   a.trace = w.trace;
   a.tile0 = 0;
   a.tile_end = ntiles;
+  a.pdl = 0;
   if ((a.dbg || a.trace) && RAYS) return -1;
 
   // Hybrid 4 + 2: 4-CTA clusters share one weight stream four ways (L2 reads quartered) but leave 16 of the 148 SMs
@@ -880,6 +882,8 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
       aa.tile_end = tiles_a;
       aa.tiles_per_cta = (int)(tiles_a / grid_a);
       ab.tile0 = tiles_a;
+      aa.pdl = 1;
+      ab.pdl = 2;
       ab.tiles_per_cta = (int)((ntiles - tiles_a + grid_b - 1) / grid_b);
       cudaError_t e = g_split == 2 ? launch_split<RAYS, 2>(w, aa, 4, grid_a, st) : launch_split<RAYS, 4>(w, aa, 4, grid_a, st);
       if (e != cudaSuccess) return -1;
