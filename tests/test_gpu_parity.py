@@ -351,6 +351,32 @@ def test_full_size_properties(engine_factory, weights):
     np.testing.assert_allclose(s[:3].cpu().numpy(), ref, rtol=1e-3)
 
 
+def test_full_resolution_view_spans_chunks(engine_factory, weights):
+    """BASELINE configs[4] shape: one 640x480 view = 307,200 rays = three workspace chunks.  The fused score must equal
+    the sum of the per-ray beta^2 that render_rays (== render()) returns for the same rays in ray-sharded blocks, and a
+    pixel subset of the same view must match the oracle."""
+    eng = engine_factory("spread", precision="fp16")
+    H, W = 480, 640
+    K = O.make_K(H, W, 480.0)
+    views = O.hemisphere_views(2, seed=3)[:1]
+    poses = torch.Tensor(np.asarray(O.views_to_poses(views)))[:, :3, :4].contiguous().cuda()
+    s = eng.score_views(poses, H, W, *_intr(K))
+    ro, rd, _ = eng.get_rays(poses, H, W, *_intr(K))
+    assert ro.shape[0] == H * W
+    total = 0.0
+    for b in range(0, H * W, 100_000):                      # ragged blocks, as two or more ranks would render them
+        o = eng.render_rays(ro[b:b + 100_000], rd[b:b + 100_000], 0.5, 6.0, want=("unc", "depth"))
+        total += float(o["unc"].double().square().sum())
+        assert torch.isfinite(o["depth"]).all()
+    np.testing.assert_allclose(float(s[0]), total / (H * W), rtol=2e-6)
+    pix = torch.randperm(H * W, generator=torch.Generator().manual_seed(1))[:96].to(torch.int32)[None, :].contiguous()
+    s_sub = eng.score_views(poses, H, W, *_intr(K), pix_idx=pix.cuda())
+    c, f = weights["spread"]
+    with torch.no_grad():
+        ref = O.score_views(O.views_to_poses(views), H, W, K, 0.5, 6.0, c, f, pix_idx=pix.numpy().astype(np.int64))
+    np.testing.assert_allclose(s_sub.cpu().numpy(), np.asarray(ref, dtype=np.float32), rtol=1e-3)
+
+
 # ---------------------------------------------------------------- stage-1 TSDF scorer (a13 / f1) ---
 def _tsdf_with_state(g):
     import evpp_b200
