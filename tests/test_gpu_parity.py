@@ -328,6 +328,48 @@ def test_zero_density_resample_branch(engine_factory, weights):
     eng.close()
 
 
+def test_c_abi_error_codes(weights):
+    """Error behaviour at the C ABI (include/evpp_b200.h): int return codes, message in evpp_last_error(), no
+    exceptions or aborts across the boundary; a failed call leaves the handle usable."""
+    import ctypes as C
+    from evpp_b200 import Engine, EvppError
+    from evpp_b200 import _lib
+    lib = _lib.load()
+    K = O.make_K(3, 5, 4.0)
+    poses = torch.Tensor(np.asarray(O.views_to_poses(O.circle_views(2))))[:, :3, :4].contiguous().cuda()
+    eng = Engine(device=0, near=0.5, far=6.0, precision="fp32")
+    with pytest.raises(EvppError) as ei:                      # weights not loaded
+        eng.score_views(poses, 3, 5, *_intr(K))
+    assert ei.value.code == -3 and "weights" in str(ei.value)
+    c, f = weights["plain"]
+    eng.load_weights(0, c)
+    with pytest.raises(EvppError) as ei:                      # fine net still missing
+        eng.score_views(poses, 3, 5, *_intr(K))
+    assert ei.value.code == -3
+    eng.load_weights(1, f)
+    s = eng.score_views(poses, 3, 5, *_intr(K))               # the handle survived the failed calls
+    assert torch.isfinite(s).all()
+    with pytest.raises(EvppError) as ei:                      # bad image size
+        eng.score_views(poses, 0, 5, *_intr(K))
+    assert ei.value.code == -1
+    for bad in (dict(n_samples=64, n_importance=100000), dict(precision=7), dict(device=99)):
+        with pytest.raises(EvppError) as ei:
+            Engine(**{"device": 0, "near": 0.5, "far": 6.0, **bad})
+        assert ei.value.code in (-1, -4)
+    h = C.c_void_p()
+    assert lib.evpp_create(0, None, C.byref(h)) == -1 and not h.value       # null config
+    assert lib.evpp_destroy(None) == 0                                        # destroying nothing is not an error
+    from evpp_b200 import NGPScorer
+    sc = NGPScorer(engine=eng, H=3, W=5, focal=4.0)
+    with pytest.raises(EvppError) as ei:                      # NGP scorer without occupancy grid / parameters
+        sc.score_views(poses)
+    assert ei.value.code == -3
+    with pytest.raises(EvppError) as ei:                      # bitfield of the wrong size
+        sc.set_occupancy(np.zeros(5, np.uint8))
+    assert ei.value.code == -1
+    eng.close()
+
+
 # ---------------------------------------------------------------- size-independent properties ---
 def test_full_size_properties(engine_factory, weights):
     """Object-scene shape (80x60 rays/view): sharding invariance, permutation equivariance and
