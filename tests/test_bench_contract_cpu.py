@@ -31,3 +31,33 @@ def test_product_arm_has_no_cpu_fallback():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode != 0                      # fails loudly: no CUDA device, no CPU fallback
     assert "no CPU fallback" in (res.stderr + res.stdout)
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ (measured on the B200 boxes) carry every key of the contract, a roofline
+    whose fraction is achieved / peak, an e2e block with the host<->device bytes and clocks without thermal or
+    hardware slowdown."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*.jsonl")))
+    assert files
+    n = 0
+    for f in files:
+        for raw in open(f):
+            line = json.loads(raw)
+            n += 1
+            for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                      "vs_baseline", "dtype", "data", "config", "e2e"):
+                assert k in line, (f, k)
+            assert line["value"] > 0 and "workload" in line["config"] and line["vs_baseline"] is None
+            if line.get("impl") == "reference":
+                assert line["gpu_launches"] == 0 and line["cpu_baseline"]["kind"] == "port"
+                continue
+            assert line["gpu_launches"] > 0
+            assert line["steps"] >= 1 and line["warmup"] >= 3
+            r = line["roofline"]
+            assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+            e = line["e2e"]
+            assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+            bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
+            assert not bad, (f, bad)
+    assert n >= 8
