@@ -4,6 +4,8 @@ same seeded inputs and against the committed reference-generated golden fixtures
 Tolerances (SURVEY.md appendix B / BASELINE.json north_star): integer and index work bit-exact;
 fp32 path 1e-5-class; tensor-core (fp16/bf16 operand, fp32 accumulate) path: per-view score within
 1e-3 relative, next-best view identical."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -12,6 +14,7 @@ from conftest import load_golden
 from oracle import evpp_oracle as O
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TC_PRECISIONS = ["fp16", "bf16"]
 
 
@@ -368,6 +371,45 @@ def test_c_abi_error_codes(weights):
         sc.set_occupancy(np.zeros(5, np.uint8))
     assert ei.value.code == -1
     eng.close()
+
+
+def test_hybrid_cluster_launch_is_bit_identical(engine_factory):
+    """EVPP_TC_CLUSTER=42 (4-CTA clusters + a programmatic dependent launch of 2-CTA clusters on the SMs they cannot
+    tile) only changes which CTA owns which 128-row tile: scores must be bit-identical
+    to the default 2-CTA launch.  The option is read once per process, so the hybrid run is a subprocess."""
+    import subprocess
+    import sys
+    g = load_golden("config1_spread.npz")
+    H, W = int(g["H"]), int(g["W"])
+    K = O.make_K(H, W, float(g["focal"]))
+    poses = torch.Tensor(np.asarray(O.views_to_poses(g["views"])))[:, :3, :4].contiguous()
+    eng = engine_factory("spread", precision="fp16")
+    l0 = eng.counters()[0]
+    ref = eng.score_views(poses.cuda(), H, W, *_intr(K)).cpu().numpy()
+    launches_default = eng.counters()[0] - l0
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from evpp_b200 import Engine\n"
+        "from oracle import evpp_oracle as O\n"
+        "torch.manual_seed(0)\n"
+        "c = O.init_nerf_state_dict(); f = O.init_nerf_state_dict()\n"
+        "c, f = O.spread_variant(c), O.spread_variant(f)\n"
+        f"g = np.load({os.path.join(ROOT, 'tests', 'golden', 'config1_spread.npz')!r})\n"
+        "H, W = int(g['H']), int(g['W']); K = O.make_K(H, W, float(g['focal']))\n"
+        "poses = torch.Tensor(np.asarray(O.views_to_poses(g['views'])))[:, :3, :4].contiguous().cuda()\n"
+        "e = Engine(device=0, near=0.5, far=6.0, precision='fp16'); e.load_weights(0, c); e.load_weights(1, f)\n"
+        "s = e.score_views(poses, H, W, K[0][0], K[1][1], K[0][2], K[1][2]).cpu().numpy()\n"
+        "print('SCORES', ' '.join(repr(float(x)) for x in s))\n"
+        "print('LAUNCHES', e.counters()[0])\n")
+    env = dict(os.environ, EVPP_TC_CLUSTER="42")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("SCORES")][-1]
+    hyb = np.array([float(x) for x in line.split()[1:]], dtype=np.float32)
+    assert np.array_equal(hyb, ref)
+    launches_hybrid = int([l for l in res.stdout.splitlines() if l.startswith("LAUNCHES")][-1].split()[1])
+    assert launches_hybrid == launches_default + 2        # the coarse and the fine MLP pass are two launches each
 
 
 # ---------------------------------------------------------------- size-independent properties ---
