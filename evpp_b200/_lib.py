@@ -5,8 +5,9 @@ import os
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libevpp_b200.so")
 
-EVPP_PREC_FP32, EVPP_PREC_FP16, EVPP_PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": 0, "fp16": 1, "bf16": 2}
+EVPP_PREC_FP32, EVPP_PREC_FP16, EVPP_PREC_BF16, EVPP_PREC_FP16X2, EVPP_PREC_FP16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": 0, "fp16": 1, "bf16": 2, "fp16x2": 3, "fp16x3": 4}
+EVPP_ERR_NONFINITE = -5
 
 
 class EvppConfig(C.Structure):
@@ -49,6 +50,8 @@ SIGNATURES = {
     "evpp_score_views": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
     "evpp_score_views_host": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
     "evpp_rescore_views_fp32": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
+    "evpp_rescore_views": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _I, _P, _P]),
+    "evpp_set_score_mode": (_I, [_P, _I]),
     "evpp_render_rays": (_I, [_P, _P, _P, _L, _F, _F, _I, C.POINTER(EvppRenderOut), _P]),
     "evpp_get_rays": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P, _P, _P]),
     "evpp_mlp_forward": (_I, [_P, _I, _I, _P, _P, _L, _P, _P]),
@@ -79,6 +82,7 @@ SIGNATURES = {
     "evpp_get_counters": (_I, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "evpp_set_profiling": (_I, [_P, _I]),
     "evpp_get_mlp_time_ms": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_L), C.POINTER(_L)]),
+    "evpp_get_mlp_profile": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_L), C.POINTER(_L), C.POINTER(C.c_double)]),
 }
 
 

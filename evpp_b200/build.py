@@ -1,37 +1,63 @@
-"""Build the CUDA shared library in-tree (evpp_b200/lib/libevpp_b200.so) with nvcc for sm_100a."""
+"""Build the CUDA shared library in-tree (evpp_b200/lib/libevpp_b200.so) with nvcc for sm_100a.
+
+Every source is compiled to its own object (in parallel, re-compiled only when it or a header changed) and the
+objects are linked into one shared library; the objects live next to the library and are git-ignored."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
 LIBDIR = os.path.join(ROOT, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libevpp_b200.so")
 SOURCES = ["engine.cu", "sampling.cu", "mlp_simt.cu", "mlp_tc.cu", "tsdf.cu", "ngp.cu", "surrogate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--split-compile", "0"]
+              "-Xcompiler", "-fPIC", "--split-compile", "0"]
 
 
-def _stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "..", "include", "evpp_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+def _headers():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
+        [os.path.join(ROOT, "..", "include", "evpp_b200.h"), os.path.abspath(__file__)]
+
+
+def _obj(src):
+    return os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+
+
+def _stale_sources(force):
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    out = []
+    for s in SOURCES:
+        o = _obj(s)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(os.path.join(CSRC, s)), hdr_t):
+            out.append(s)
+    return out
 
 
 def build(force=False, verbose=False):
-    if not force and not _stale():
+    stale = _stale_sources(force)
+    if not stale and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(_obj(s)) for s in SOURCES):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+
+    def compile_one(src):
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", os.path.join(CSRC, src), "-o", _obj(src)]
+        return src, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(stale), os.cpu_count() or 1))) as ex:
+        for src, res in ex.map(compile_one, stale):
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr)
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] +
+                         [_obj(s) for s in SOURCES], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -45,11 +45,12 @@ struct TcConsts {             // fp32 epilogue constants, passed to the kernel b
   float w_rgb[3][128];
   float w_unc[128];
   float head_b[8];            // alpha, r, g, b, uncertainty
+  float inv_wscale[12];       // split-precision passes: 1 / (power-of-two scale of layer l's weight image)
 };
 struct TcWeights {
   const void* image;          // device: pre-tiled, pre-swizzled B-operand K-blocks, streamed with cp.async.bulk
   const TcConsts* consts;     // host
-  int dtype;                  // EVPP_PREC_FP16 / EVPP_PREC_BF16
+  int dtype;                  // EVPP_PREC_FP16 / EVPP_PREC_BF16 / EVPP_PREC_FP16X2 / EVPP_PREC_FP16X3
   float* dbg;                 // optional device [M,256] dump of one layer's activations (parity tests)
   int dbg_layer;
   long long* trace;           // optional device [128] clock64 stamps of one tile's pipeline (diagnostics)
@@ -68,13 +69,13 @@ struct RayBatch {             // device pointers of one chunk
 int launch_mlp_simt(const SimtWeights& w, const RayBatch& rb, float* raw, cudaStream_t st);
 int launch_mlp_simt_points(const SimtWeights& w, const float* pts, const float* dirs, int64_t M, float* out,
                            cudaStream_t st);
-int launch_mlp_tc(const TcWeights& w, const RayBatch& rb, float* raw, int num_sms, cudaStream_t st);
+// heads: 0 = raw [n,S,5]; 1 = sigma only -> raw [n,S] (pass stops after layer 7); 2 = beta only -> raw [n,S]
+int launch_mlp_tc(const TcWeights& w, const RayBatch& rb, float* raw, int num_sms, cudaStream_t st, int heads = 0);
 int launch_mlp_tc_points(const TcWeights& w, const float* pts, const float* dirs, int64_t M, float* out,
                          int num_sms, cudaStream_t st);
 size_t tc_weight_image_bytes();
 // host-side repack of one network: fills `image` (tc_weight_image_bytes()) from fp32 state_dict tensors
 void tc_pack_weights(const std::vector<std::vector<float>>& tensors, int dtype, std::vector<uint8_t>& image,
                      TcConsts& consts);
-int tc_configure();   // sets kernel attributes; returns cudaError_t as int
 
 }  // namespace evpp

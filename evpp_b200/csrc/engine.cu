@@ -62,10 +62,36 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+constexpr int kNumPrec = 5;   // evpp_precision values
+
+// FLOPs the MLP kernel really executes per evaluation: the full network, the sigma-only
+// coarse pass (layers 0..7 + alpha head) and the beta-only fine pass (no alpha / rgb heads)
+constexpr double kFlopFull = kFlopPerEval;
+constexpr double kFlopSigmaOnly = 2.0 * (63 * 256 + 4 * 256 * 256 + 319 * 256 + 2 * 256 * 256 + 256);
+constexpr double kFlopBetaOnly = kFlopPerEval - 2.0 * (256 + 3 * 128);
+
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it
+// (one process may drive several GPUs, nerf.py:269-273).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+#define EVPP_ON_DEVICE(dev)      \
+  DeviceGuard _guard(dev);       \
+  CUDA_TRY(_guard.err)
+
 struct NetWeights {
   bool loaded = false;
-  DevBuf simt_stream, bias, head_w, head_b, tc_image[3];   // tc_image indexed by precision (1,2)
-  bool tc_ready[3] = {false, false, false};
+  DevBuf simt_stream, bias, head_w, head_b, tc_image[kNumPrec];   // tc_image indexed by precision (1..4)
+  bool tc_ready[kNumPrec] = {false, false, false, false, false};
   TcConsts tc_consts{};
   std::vector<std::vector<float>> host;                   // fp32 state_dict tensors (for lazy tc repack)
 };
@@ -82,7 +108,8 @@ struct evpp_handle {
   // chunk workspace
   int chunk_cap = 0;
   DevBuf rays_o, rays_d, viewdirs, z_c, raw_c, z_f, raw_f;
-  DevBuf beta2, st_c2w, st_pix, st_scores;
+  DevBuf beta2, st_c2w, st_pix, st_scores, nonfinite;
+  bool score_full_outputs = false;   // evpp_set_score_mode: scoring calls run the full network like render()
   // stage capture
   bool capture = false;
   DevBuf w_c, cdf, inds, zs;
@@ -104,7 +131,8 @@ struct evpp_handle {
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   std::vector<int64_t> prof_evals;
-  double prof_ms = 0.0;
+  std::vector<double> prof_flops;
+  double prof_ms = 0.0, prof_total_flops = 0.0;
   int64_t prof_launches = 0, prof_total_evals = 0;
 };
 
@@ -158,8 +186,6 @@ int ensure_tc(evpp_handle* h, int which, int prec) {
   tc_pack_weights(nw.host, prec, image, nw.tc_consts);
   if (nw.tc_image[prec].ensure(image.size())) return fail(EVPP_ERR_CUDA, "tc weight image alloc failed");
   CUDA_TRY(cudaMemcpy(nw.tc_image[prec].p, image.data(), image.size(), cudaMemcpyHostToDevice));
-  int e = tc_configure();
-  if (e) return fail(EVPP_ERR_CUDA, "tcgen05 kernel configuration failed: %s", cudaGetErrorString((cudaError_t)e));
   nw.tc_ready[prec] = true;
   return 0;
 }
@@ -171,7 +197,8 @@ TcWeights tc_of(const NetWeights& nw, int prec, float* dbg = nullptr, int dbg_la
   return TcWeights{nw.tc_image[prec].p, &nw.tc_consts, prec, dbg, dbg_layer, trace};
 }
 
-int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw, cudaStream_t st) {
+// heads: 0 = raw [n,S,5]; 1 = sigma only, 2 = beta only -> raw [n,S] (tensor-core precisions only)
+int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw, cudaStream_t st, int heads = 0) {
   NetWeights& nw = h->net[which];
   if (!nw.loaded) return fail(EVPP_ERR_STATE, "weights of net %d not loaded (evpp_load_nerf_weights)", which);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -182,17 +209,19 @@ int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw,
   }
   int nl = 0;
   if (prec == EVPP_PREC_FP32) {
+    if (heads != 0) return fail(EVPP_ERR_INVALID, "internal: the fp32 FFMA kernel has no score-only variant");
     nl = launch_mlp_simt(simt_of(nw), rb, raw, st);
   } else {
     int rc = ensure_tc(h, which, prec);
     if (rc) return rc;
-    nl = launch_mlp_tc(tc_of(nw, prec), rb, raw, h->num_sms, st);
+    nl = launch_mlp_tc(tc_of(nw, prec), rb, raw, h->num_sms, st, heads);
     if (nl < 0) return fail(EVPP_ERR_CUDA, "tcgen05 MLP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (h->profiling) {
     cudaEventRecord(e1, st);
     h->prof_events.emplace_back(e0, e1);
     h->prof_evals.push_back((int64_t)rb.n * rb.S);
+    h->prof_flops.push_back((double)rb.n * rb.S * (heads == 1 ? kFlopSigmaOnly : heads == 2 ? kFlopBetaOnly : kFlopFull));
   }
   h->launches += nl;
   h->evals += (int64_t)rb.n * rb.S;
@@ -201,14 +230,21 @@ int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw,
 }
 
 // One chunk of rays already in h->rays_*: coarse pass, resample, fine pass, composite.
+// Score-only calls (out == nullptr: only the per-ray sum of beta^2 leaves the chunk) skip what the score does not
+// depend on -- Controller.get_uncertainty reads raw[..., 4] of the final pass and nothing else (nerf.py:307-309):
+// the coarse pass stops at its sigma (all sample_pdf needs), the final pass skips the alpha / rgb heads, and the
+// two compositing kernels shrink to the weights and to the beta^2 chain.  Every value that reaches the score is
+// computed by the same instructions in the same order as in the full path: the scores are bit-identical.
 int render_chunk(evpp_handle* h, int n, float near_plane, float far_plane, int prec, const evpp_render_out* out,
                  long long off, float* beta2, cudaStream_t st) {
   const int Sc = h->Sc, Ni = h->Ni, Sf = h->Sf;
+  const bool score_only = !out && beta2 && !h->capture && !h->score_full_outputs && prec != EVPP_PREC_FP32;
   h->launches += launch_coarse_z(h->t_vals.as<float>(), n, Sc, near_plane, far_plane, h->cfg.lindisp,
                                  h->z_c.as<float>(), st);
   RayBatch rb{h->rays_o.as<float>(), h->rays_d.as<float>(), h->viewdirs.as<float>(), h->z_c.as<float>(), n, Sc};
-  int rc = run_mlp(h, EVPP_NET_COARSE, prec, rb, h->raw_c.as<float>(), st);
+  int rc = run_mlp(h, EVPP_NET_COARSE, prec, rb, h->raw_c.as<float>(), st, score_only ? (Ni > 0 ? 1 : 2) : 0);
   if (rc) return rc;
+  int nl;
   CompositeOut co{};
   if (Ni > 0) {
     if (out) {
@@ -220,17 +256,25 @@ int render_chunk(evpp_handle* h, int n, float near_plane, float far_plane, int p
       co.z_std = out->z_std ? out->z_std + off : nullptr;
     }
     co.weights = h->capture ? h->w_c.as<float>() : nullptr;
-    h->launches += launch_coarse_resample(
+    nl = launch_coarse_resample(
         h->raw_c.as<float>(), h->z_c.as<float>(), h->rays_d.as<float>(), h->u_vals.as<float>(), n, Sc, Ni,
         h->cfg.white_bkgd, co, h->z_f.as<float>(), h->capture ? h->cdf.as<float>() : nullptr,
-        h->capture ? h->inds.as<int32_t>() : nullptr, h->capture ? h->zs.as<float>() : nullptr, st);
+        h->capture ? h->inds.as<int32_t>() : nullptr, h->capture ? h->zs.as<float>() : nullptr, st, score_only);
+    if (nl < 0) return fail(EVPP_ERR_CUDA, "resampling kernel configuration failed (shared memory for %d + %d samples)", Sc, Ni);
+    h->launches += nl;
     RayBatch rf{h->rays_o.as<float>(), h->rays_d.as<float>(), h->viewdirs.as<float>(), h->z_f.as<float>(), n, Sf};
-    rc = run_mlp(h, EVPP_NET_FINE, prec, rf, h->raw_f.as<float>(), st);
+    rc = run_mlp(h, EVPP_NET_FINE, prec, rf, h->raw_f.as<float>(), st, score_only ? 2 : 0);
     if (rc) return rc;
   }
   const float* raw = Ni > 0 ? h->raw_f.as<float>() : h->raw_c.as<float>();
   const float* z = Ni > 0 ? h->z_f.as<float>() : h->z_c.as<float>();
   const int S = Ni > 0 ? Sf : Sc;
+  if (score_only) {
+    h->launches += launch_beta2(raw, n, S, beta2, st);
+    h->last_n = n;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   CompositeOut cf{};
   if (out) {
     cf.rgb = out->rgb ? out->rgb + off * 3 : nullptr;
@@ -243,7 +287,9 @@ int render_chunk(evpp_handle* h, int n, float near_plane, float far_plane, int p
   }
   if (Ni == 0 && h->capture) cf.weights = h->w_c.as<float>();
   cf.beta2 = beta2;
-  h->launches += launch_composite(raw, z, h->rays_d.as<float>(), n, S, h->cfg.white_bkgd, cf, st);
+  nl = launch_composite(raw, z, h->rays_d.as<float>(), n, S, h->cfg.white_bkgd, cf, st);
+  if (nl < 0) return fail(EVPP_ERR_CUDA, "compositing kernel configuration failed (shared memory for %d samples)", S);
+  h->launches += nl;
   h->last_n = n;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -273,7 +319,8 @@ int score_views_device(evpp_handle* h, const float* c2w, int V, int H, int W, fl
   const int cap = (int)std::min<long long>(N, h->cfg.max_chunk_rays);
   int rc = ensure_workspace(h, cap);
   if (rc) return rc;
-  if (h->beta2.ensure((size_t)N * 4)) return fail(EVPP_ERR_CUDA, "beta2 buffer alloc failed");
+  if (h->beta2.ensure((size_t)N * 4) || h->nonfinite.ensure(4)) return fail(EVPP_ERR_CUDA, "beta2 buffer alloc failed");
+  CUDA_TRY(cudaMemsetAsync(h->nonfinite.p, 0, 4, st));
   for (long long g0 = 0; g0 < N; g0 += cap) {
     const int n = (int)std::min<long long>(cap, N - g0);
     h->launches += launch_get_rays(c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, g0, n, h->rays_o.as<float>(),
@@ -281,7 +328,7 @@ int score_views_device(evpp_handle* h, const float* c2w, int V, int H, int W, fl
     rc = render_chunk(h, n, h->cfg.near_plane, h->cfg.far_plane, prec, nullptr, 0, h->beta2.as<float>() + g0, st);
     if (rc) return rc;
   }
-  h->launches += launch_view_reduce(h->beta2.as<float>(), V, R, scores, st);
+  h->launches += launch_view_reduce(h->beta2.as<float>(), V, R, scores, h->nonfinite.as<int>(), st);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -314,8 +361,8 @@ int evpp_create(int device_ordinal, const evpp_config* cfg, evpp_handle** out) {
     return fail(EVPP_ERR_INVALID, "n_samples %d out of range [4,%d]", cfg->n_samples, kMaxSc);
   if (cfg->n_importance < 0 || cfg->n_importance + cfg->n_samples > kMaxSf)
     return fail(EVPP_ERR_INVALID, "n_samples+n_importance %d exceeds %d", cfg->n_importance + cfg->n_samples, kMaxSf);
-  if (cfg->precision < 0 || cfg->precision > 2) return fail(EVPP_ERR_INVALID, "bad precision %d", cfg->precision);
-  CUDA_TRY(cudaSetDevice(device_ordinal));
+  if (cfg->precision < 0 || cfg->precision >= kNumPrec) return fail(EVPP_ERR_INVALID, "bad precision %d", cfg->precision);
+  EVPP_ON_DEVICE(device_ordinal);
   evpp_handle* h = new evpp_handle();
   h->device = device_ordinal;
   h->cfg = *cfg;
@@ -344,7 +391,7 @@ int evpp_create(int device_ordinal, const evpp_config* cfg, evpp_handle** out) {
 
 int evpp_destroy(evpp_handle* h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   for (auto& pr : h->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (int i = 0; i < 2; ++i) {
@@ -353,7 +400,7 @@ int evpp_destroy(evpp_handle* h) {
     for (auto& b : nw.tc_image) b.release();
   }
   for (DevBuf* b : {&h->t_vals, &h->u_vals, &h->rays_o, &h->rays_d, &h->viewdirs, &h->z_c, &h->raw_c, &h->z_f,
-                    &h->raw_f, &h->beta2, &h->st_c2w, &h->st_pix, &h->st_scores, &h->w_c, &h->cdf, &h->inds, &h->zs,
+                    &h->raw_f, &h->beta2, &h->nonfinite, &h->st_c2w, &h->st_pix, &h->st_scores, &h->w_c, &h->cdf, &h->inds, &h->zs,
                     &h->tsdf_state, &h->tsdf_nray, &h->tsdf_t, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d,
                     &h->tsdf_vu, &h->tsdf_vd, &h->ngp_table, &h->ngp_mlp, &h->ngp_bits, &h->ngp_ro, &h->ngp_rd,
                     &h->ngp_counts, &h->ngp_offsets, &h->ngp_total, &h->ngp_masks, &h->ngp_tiles, &h->ngp_t0, &h->ngp_t, &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2,
@@ -367,7 +414,7 @@ int evpp_load_nerf_weights(evpp_handle* h, int which, const float* packed, const
   if (!h || !packed || !offsets) return fail(EVPP_ERR_INVALID, "null argument");
   if (which != 0 && which != 1) return fail(EVPP_ERR_INVALID, "which_net must be 0 (coarse) or 1 (fine)");
   if (n != 26) return fail(EVPP_ERR_INVALID, "expected 26 state_dict tensors (NeRF D=8,W=256,use_viewdirs), got %d", n);
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   NetWeights& nw = h->net[which];
   nw.host.assign(26, {});
   for (int i = 0; i < 26; ++i) {
@@ -430,7 +477,7 @@ int evpp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, floa
   if (!h) return fail(EVPP_ERR_INVALID, "null handle");
   if (V == 0) return 0;   // empty candidate list: nothing to score (empty tensors carry null pointers)
   if (!c2w || !scores) return fail(EVPP_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   return score_views_device(h, c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, scores, h->cfg.precision,
                             (cudaStream_t)stream);
 }
@@ -452,7 +499,12 @@ static int score_host_impl(evpp_handle* h, const float* c2w_host, int V, int H, 
                               h->st_scores.as<float>(), prec, st);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(scores_host, h->st_scores.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
+  int32_t bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bad, h->nonfinite.p, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  if (bad)
+    return fail(EVPP_ERR_NONFINITE, "%d of %d view scores are not finite (precision %d: 16-bit activations overflowed; retry with "
+                "EVPP_PREC_BF16 or EVPP_PREC_FP32)", (int)bad, V, prec);
   return 0;
 }
 
@@ -462,17 +514,18 @@ int evpp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int H, i
   if (!h) return fail(EVPP_ERR_INVALID, "null handle");
   if (V == 0) return 0;
   if (!c2w_host || !scores_host) return fail(EVPP_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   return score_host_impl(h, c2w_host, V, H, W, fx, fy, cx, cy, pix_idx_host, R, scores_host, h->cfg.precision,
                          (cudaStream_t)stream);
 }
 
-int evpp_rescore_views_fp32(evpp_handle* h, const float* c2w_host, const int32_t* view_ids, int K, int H, int W,
-                            float fx, float fy, float cx, float cy, const int32_t* pix_idx_host, int R,
-                            float* scores_host, void* stream) {
+int evpp_rescore_views(evpp_handle* h, const float* c2w_host, const int32_t* view_ids, int K, int H, int W,
+                       float fx, float fy, float cx, float cy, const int32_t* pix_idx_host, int R, int precision,
+                       float* scores_host, void* stream) {
   if (!h || !c2w_host || !view_ids || !scores_host) return fail(EVPP_ERR_INVALID, "null argument");
+  if (precision < 0 || precision >= kNumPrec) return fail(EVPP_ERR_INVALID, "bad precision %d", precision);
   if (K <= 0) return 0;
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   std::vector<float> poses((size_t)K * 12);
   std::vector<int32_t> pix;
   if (pix_idx_host) pix.resize((size_t)K * R);
@@ -482,7 +535,20 @@ int evpp_rescore_views_fp32(evpp_handle* h, const float* c2w_host, const int32_t
     if (pix_idx_host) memcpy(&pix[(size_t)k * R], pix_idx_host + (size_t)view_ids[k] * R, (size_t)R * 4);
   }
   return score_host_impl(h, poses.data(), K, H, W, fx, fy, cx, cy, pix_idx_host ? pix.data() : nullptr, R,
-                         scores_host, EVPP_PREC_FP32, (cudaStream_t)stream);
+                         scores_host, precision, (cudaStream_t)stream);
+}
+
+int evpp_rescore_views_fp32(evpp_handle* h, const float* c2w_host, const int32_t* view_ids, int K, int H, int W,
+                            float fx, float fy, float cx, float cy, const int32_t* pix_idx_host, int R,
+                            float* scores_host, void* stream) {
+  return evpp_rescore_views(h, c2w_host, view_ids, K, H, W, fx, fy, cx, cy, pix_idx_host, R, EVPP_PREC_FP32,
+                            scores_host, stream);
+}
+
+int evpp_set_score_mode(evpp_handle* h, int full_outputs) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  h->score_full_outputs = full_outputs != 0;
+  return 0;
 }
 
 int evpp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, int64_t N, float near_plane,
@@ -492,8 +558,8 @@ int evpp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, i
   if (N == 0) return 0;
   if (!rays_o || !rays_d) return fail(EVPP_ERR_INVALID, "null rays");
   if (precision < 0) precision = h->cfg.precision;
-  if (precision > 2) return fail(EVPP_ERR_INVALID, "bad precision");
-  CUDA_TRY(cudaSetDevice(h->device));
+  if (precision >= kNumPrec) return fail(EVPP_ERR_INVALID, "bad precision");
+  EVPP_ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int cap = (int)std::min<int64_t>(N, h->cfg.max_chunk_rays);
   int rc = ensure_workspace(h, cap);
@@ -517,7 +583,7 @@ int evpp_get_rays(evpp_handle* h, const float* c2w, int V, int H, int W, float f
   const long long N = (long long)V * R;
   if (N <= 0) return 0;
   if (N > 0x7fffffffLL) return fail(EVPP_ERR_INVALID, "too many rays for one call");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   h->launches += launch_get_rays(c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, 0, (int)N, rays_o, rays_d, viewdirs,
                                  (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
@@ -530,7 +596,7 @@ static int mlp_forward_impl(evpp_handle* h, int which, int precision, const floa
   if (!h || !pts || !dirs || !out) return fail(EVPP_ERR_INVALID, "null argument");
   if (which != 0 && which != 1) return fail(EVPP_ERR_INVALID, "bad net");
   if (M <= 0) return 0;
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   NetWeights& nw = h->net[which];
   if (!nw.loaded) return fail(EVPP_ERR_STATE, "weights of net %d not loaded", which);
   if (precision < 0) precision = h->cfg.precision;
@@ -538,7 +604,7 @@ static int mlp_forward_impl(evpp_handle* h, int which, int precision, const floa
   if (precision == EVPP_PREC_FP32) {
     if (dbg) return fail(EVPP_ERR_INVALID, "layer dumps exist for the tensor-core path only");
     h->launches += launch_mlp_simt_points(simt_of(nw), pts, dirs, M, out, st);
-  } else if (precision <= 2) {
+  } else if (precision < kNumPrec) {
     int rc = ensure_tc(h, which, precision);
     if (rc) return rc;
     int nl = launch_mlp_tc_points(tc_of(nw, precision, dbg, dbg_layer, trace), pts, dirs, M, out, h->num_sms, st);
@@ -596,7 +662,7 @@ int evpp_stage_dump(evpp_handle* h, int stage, void* out, int64_t* count, void* 
   *count = cnt;
   if (!out) return 0;
   if (!src) return fail(EVPP_ERR_STATE, "stage %d not captured (evpp_set_stage_capture before rendering)", stage);
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   CUDA_TRY(cudaMemcpyAsync(out, src, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
@@ -605,11 +671,13 @@ int evpp_composite(evpp_handle* h, const float* raw, const float* z, const float
                    float* rgb, float* disp, float* acc, float* depth, float* weights, float* beta2, void* stream) {
   if (!h || !raw || !z || !rays_d) return fail(EVPP_ERR_INVALID, "null argument");
   if (n <= 0) return 0;
-  if (S < 1) return fail(EVPP_ERR_INVALID, "bad S");
-  CUDA_TRY(cudaSetDevice(h->device));
+  if (S < 1 || S > kMaxSf) return fail(EVPP_ERR_INVALID, "S (%d) must be in [1,%d]", S, kMaxSf);
+  EVPP_ON_DEVICE(h->device);
   CompositeOut co{};
   co.rgb = rgb; co.disp = disp; co.acc = acc; co.depth = depth; co.weights = weights; co.beta2 = beta2;
-  h->launches += launch_composite(raw, z, rays_d, n, S, h->cfg.white_bkgd, co, (cudaStream_t)stream);
+  const int nl = launch_composite(raw, z, rays_d, n, S, h->cfg.white_bkgd, co, (cudaStream_t)stream);
+  if (nl < 0) return fail(EVPP_ERR_CUDA, "compositing kernel configuration failed (shared memory for %d samples)", S);
+  h->launches += nl;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -619,10 +687,12 @@ int evpp_resample(evpp_handle* h, const float* raw_coarse, const float* z_coarse
   if (!h || !raw_coarse || !z_coarse || !rays_d || !z_fine) return fail(EVPP_ERR_INVALID, "null argument");
   if (h->Ni <= 0) return fail(EVPP_ERR_STATE, "engine configured with n_importance == 0");
   if (n <= 0) return 0;
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   CompositeOut co{};
-  h->launches += launch_coarse_resample(raw_coarse, z_coarse, rays_d, h->u_vals.as<float>(), n, h->Sc, h->Ni,
+  const int nl = launch_coarse_resample(raw_coarse, z_coarse, rays_d, h->u_vals.as<float>(), n, h->Sc, h->Ni,
                                         h->cfg.white_bkgd, co, z_fine, cdf, inds, z_samples, (cudaStream_t)stream);
+  if (nl < 0) return fail(EVPP_ERR_CUDA, "resampling kernel configuration failed");
+  h->launches += nl;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -632,7 +702,7 @@ int evpp_select_nbv(evpp_handle* h, const float* scores, const float* weight, in
   if (!h || !scores) return fail(EVPP_ERR_INVALID, "null argument");
   if (dirs_per_location <= 0 || V <= 0 || V % dirs_per_location)
     return fail(EVPP_ERR_INVALID, "V (%d) must be a positive multiple of dirs_per_location (%d)", V, dirs_per_location);
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   h->launches += launch_select_nbv(scores, weight, V, dirs_per_location, norm_scores, best_dir, winner_view,
                                    (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
@@ -647,7 +717,7 @@ int evpp_sample_pixels(evpp_handle* h, uint64_t seed, int V, int R, int n_pixels
   if (V < 0 || R < 0 || n_pixels <= 0 || R > n_pixels) return fail(EVPP_ERR_INVALID, "need 0 <= R <= n_pixels");
   if (V == 0 || R == 0) return 0;
   if (!pix_idx) return fail(EVPP_ERR_INVALID, "null pix_idx");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   h->launches += launch_pixel_subset(seed, V, R, n_pixels, pix_idx, (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -661,7 +731,7 @@ int evpp_surrogate_fit(evpp_handle* h, float* params, const float* xyz, const fl
   if (N < 1 || N > kSurrogateMaxN) return fail(EVPP_ERR_INVALID, "N (%d) must be in [1,%d]", N, kSurrogateMaxN);
   if (epochs < 0 || !(lr > 0.f)) return fail(EVPP_ERR_INVALID, "bad epochs / lr");
   if (epochs == 0) return 0;
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t moments = (2 * (size_t)kSurrogateParams + 3) & ~(size_t)3;   // keeps the activation workspace 16-byte aligned
   if (h->sg_ws.ensure((moments + surrogate_workspace_floats(N)) * 4)) return fail(EVPP_ERR_CUDA, "surrogate workspace alloc failed");
@@ -679,7 +749,7 @@ int evpp_surrogate_query(evpp_handle* h, const float* params, const float* xyz, 
   if (M < 0 || M > (1ll << 30)) return fail(EVPP_ERR_INVALID, "bad M");
   if (M == 0) return 0;
   if (!xyz || !out) return fail(EVPP_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   const int nl = launch_surrogate_query(params, xyz, (int)M, out, (cudaStream_t)stream);
   if (nl < 0) return fail(EVPP_ERR_CUDA, "surrogate kernel configuration failed");
   h->launches += nl;
@@ -696,7 +766,7 @@ int evpp_tsdf_set_volume(evpp_handle* h, const float* state, const float* nray, 
   if (!h || !state || !nray || !dims || !origin || !aabb_min || !aabb_max) return fail(EVPP_ERR_INVALID, "null argument");
   if (dims[0] < 2 || dims[1] < 2 || dims[2] < 2) return fail(EVPP_ERR_INVALID, "volume dims must be >= 2");
   if (!(voxel_size > 0.f) || !(far_plane > near_plane)) return fail(EVPP_ERR_INVALID, "bad voxel size / bounds");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   const long long n = (long long)dims[0] * dims[1] * dims[2];
   const int S = n_samples;   // the caller evaluates int((far-near)/voxel_res)+1 in double like tsdf_gpu.py:41
   if (S < 2 || S > 4096) return fail(EVPP_ERR_INVALID, "sample count %d out of range", S);
@@ -733,7 +803,7 @@ int evpp_tsdf_render_rays(evpp_handle* h, const float* rays_o, const float* rays
   if (N < 0 || N > 0x7fffffffLL) return fail(EVPP_ERR_INVALID, "bad ray count");
   if (!rays_o || !rays_d) return fail(EVPP_ERR_INVALID, "null rays");
   if (!h->tsdf_ready) return fail(EVPP_ERR_STATE, "no TSDF state volume (evpp_tsdf_set_volume)");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   h->launches += launch_tsdf_march(h->tsdf, rays_o, rays_d, (int)N, uncer, depth, n_unknown, first_hit, voxel_idx,
                                    (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
@@ -752,7 +822,7 @@ int evpp_tsdf_score_views(evpp_handle* h, const float* c2w, int V, int H, int W,
   if (R <= 0) return fail(EVPP_ERR_INVALID, "R must be positive when pix_idx is given");
   const long long N = (long long)V * R;
   if (N > 0x7fffffffLL) return fail(EVPP_ERR_INVALID, "too many rays for one call");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (h->tsdf_ro.ensure((size_t)N * 12) || h->tsdf_rd.ensure((size_t)N * 12) || h->tsdf_u.ensure((size_t)N * 4) ||
       h->tsdf_d.ensure((size_t)N * 4))
@@ -773,7 +843,7 @@ int evpp_tsdf_score_views_host(evpp_handle* h, const float* c2w_host, int V, int
   if (!h) return fail(EVPP_ERR_INVALID, "null handle");
   if (V == 0) return 0;
   if (!c2w_host || !view_uncer_host || !view_depth_host) return fail(EVPP_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (h->st_c2w.ensure((size_t)V * 48) || h->tsdf_vu.ensure((size_t)V * 4) || h->tsdf_vd.ensure((size_t)V * 4))
     return fail(EVPP_ERR_CUDA, "staging alloc failed");
@@ -839,7 +909,7 @@ int evpp_ngp_set_occupancy(evpp_handle* h, const uint8_t* bitfield, int64_t nbyt
   if (!h->ngp_configured) return fail(EVPP_ERR_STATE, "evpp_ngp_configure first");
   const int64_t G = h->ngp.grid_res;
   if (nbytes != G * G * G / 8) return fail(EVPP_ERR_INVALID, "bitfield must hold grid_res^3 bits (%lld bytes)", (long long)(G * G * G / 8));
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   if (h->ngp_bits.ensure((size_t)nbytes)) return fail(EVPP_ERR_CUDA, "bitfield alloc failed");
   CUDA_TRY(cudaMemcpy(h->ngp_bits.p, bitfield, (size_t)nbytes, cudaMemcpyDefault));
   h->ngp.bitfield = h->ngp_bits.as<uint8_t>();
@@ -854,7 +924,7 @@ int evpp_ngp_load_params(evpp_handle* h, const uint16_t* table_fp16, int64_t n_e
   const NgpLevel& last = h->ngp.levels[h->ngp.n_levels - 1];
   if (n_entries != (int64_t)last.offset + last.size) return fail(EVPP_ERR_INVALID, "table has %lld entries, level table needs %lld", (long long)n_entries, (long long)last.offset + last.size);
   if (n_mlp_floats != kNgpMlpFloats) return fail(EVPP_ERR_INVALID, "packed MLP must hold %d floats", kNgpMlpFloats);
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   if (h->ngp_table.ensure((size_t)n_entries * 4) || h->ngp_mlp.ensure((size_t)kNgpMlpFloats * 4))
     return fail(EVPP_ERR_CUDA, "NGP parameter alloc failed");
   CUDA_TRY(cudaMemcpy(h->ngp_table.p, table_fp16, (size_t)n_entries * 4, cudaMemcpyDefault));
@@ -872,7 +942,7 @@ int evpp_tensorf_load_params(evpp_handle* h, const uint16_t* planes_fp16, const 
   if (!h->ngp_configured) return fail(EVPP_ERR_STATE, "evpp_ngp_configure first");
   if (res < 2 || res > 2048) return fail(EVPP_ERR_INVALID, "grid resolution out of range");
   if (n_mlp_floats != kTfMlpFloats) return fail(EVPP_ERR_INVALID, "packed TensoRF colour network must hold %d floats", kTfMlpFloats);
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   const size_t pb = (size_t)3 * res * res * 64 * 2, lb = (size_t)3 * res * 64 * 2;
   if (h->tf_planes.ensure(pb) || h->tf_lines.ensure(lb) || h->tf_mlp.ensure((size_t)kTfMlpFloats * 4))
     return fail(EVPP_ERR_CUDA, "TensoRF parameter alloc failed");
@@ -894,7 +964,7 @@ int evpp_ngp_encode(evpp_handle* h, const float* u, int64_t M, float* enc, int32
   if (!u || M < 0) return fail(EVPP_ERR_INVALID, "bad argument");
   if (!h->ngp_configured || !h->ngp_has_params || h->ngp_tensorf)
     return fail(EVPP_ERR_STATE, "hash-grid encoder not configured / no hash-grid parameters loaded");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   h->launches += launch_ngp_encode(h->ngp, u, M, enc, indices, (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -951,7 +1021,7 @@ int evpp_ngp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_
   if (!rays_o || !rays_d || N < 0) return fail(EVPP_ERR_INVALID, "bad rays");
   int rc = ngp_ready(h);
   if (rc) return rc;
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   const int cap = h->ngp_chunk_rays;
   for (int64_t g0 = 0; g0 < N; g0 += cap) {
     const int n = (int)std::min<int64_t>(cap, N - g0);
@@ -970,7 +1040,7 @@ int evpp_ngp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, 
   if (rc) return rc;
   if (!pix_idx) R = H * W;
   if (R <= 0) return fail(EVPP_ERR_INVALID, "R must be positive when pix_idx is given");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const long long N = (long long)V * R;
   const int cap = (int)std::min<long long>(N, h->ngp_chunk_rays);
@@ -982,7 +1052,7 @@ int evpp_ngp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, 
     rc = ngp_render_device(h, h->ngp_ro.as<float>(), h->ngp_rd.as<float>(), n, nullptr, 0, h->ngp_beta2.as<float>() + g0, st);
     if (rc) return rc;
   }
-  h->launches += launch_view_reduce(h->ngp_beta2.as<float>(), V, R, scores, st);
+  h->launches += launch_view_reduce(h->ngp_beta2.as<float>(), V, R, scores, nullptr, st);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -992,7 +1062,7 @@ int evpp_ngp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int 
   if (!h) return fail(EVPP_ERR_INVALID, "null handle");
   if (V == 0) return 0;
   if (!c2w_host || !scores_host) return fail(EVPP_ERR_INVALID, "null argument");
-  CUDA_TRY(cudaSetDevice(h->device));
+  EVPP_ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (h->st_c2w.ensure((size_t)V * 48) || h->ngp_scores.ensure((size_t)V * 4)) return fail(EVPP_ERR_CUDA, "staging alloc failed");
   CUDA_TRY(cudaMemcpyAsync(h->st_c2w.p, c2w_host, (size_t)V * 48, cudaMemcpyHostToDevice, st));
@@ -1028,15 +1098,16 @@ int evpp_set_profiling(evpp_handle* h, int enabled) {
   for (auto& pr : h->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   h->prof_events.clear();
   h->prof_evals.clear();
+  h->prof_flops.clear();
   h->prof_ms = 0.0;
+  h->prof_total_flops = 0.0;
   h->prof_launches = 0;
   h->prof_total_evals = 0;
   return 0;
 }
 
-int evpp_get_mlp_time_ms(evpp_handle* h, double* total_ms, int64_t* launches, int64_t* evals) {
-  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
-  CUDA_TRY(cudaSetDevice(h->device));
+static int collect_profile(evpp_handle* h) {
+  EVPP_ON_DEVICE(h->device);
   CUDA_TRY(cudaDeviceSynchronize());
   for (size_t i = 0; i < h->prof_events.size(); ++i) {
     float ms = 0.f;
@@ -1044,14 +1115,34 @@ int evpp_get_mlp_time_ms(evpp_handle* h, double* total_ms, int64_t* launches, in
     h->prof_ms += ms;
     h->prof_launches += 1;
     h->prof_total_evals += h->prof_evals[i];
+    h->prof_total_flops += h->prof_flops[i];
     cudaEventDestroy(h->prof_events[i].first);
     cudaEventDestroy(h->prof_events[i].second);
   }
   h->prof_events.clear();
   h->prof_evals.clear();
+  h->prof_flops.clear();
+  return 0;
+}
+
+int evpp_get_mlp_time_ms(evpp_handle* h, double* total_ms, int64_t* launches, int64_t* evals) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  int rc = collect_profile(h);
+  if (rc) return rc;
   if (total_ms) *total_ms = h->prof_ms;
   if (launches) *launches = h->prof_launches;
   if (evals) *evals = h->prof_total_evals;
+  return 0;
+}
+
+int evpp_get_mlp_profile(evpp_handle* h, double* total_ms, int64_t* launches, int64_t* evals, double* flops) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  int rc = collect_profile(h);
+  if (rc) return rc;
+  if (total_ms) *total_ms = h->prof_ms;
+  if (launches) *launches = h->prof_launches;
+  if (evals) *evals = h->prof_total_evals;
+  if (flops) *flops = h->prof_total_flops;
   return 0;
 }
 

@@ -25,6 +25,8 @@
 //                     the second half's MMAs (SPLIT template parameter).
 //
 // Per row the kernel reads 4 B (z) and writes 20 B.
+#include <cmath>
+
 #include "common.cuh"
 
 namespace evpp {
@@ -41,19 +43,14 @@ constexpr int kThreads = 32 * (kEpiWarps + 2);
 // issue slot behind busy epilogue warps.
 constexpr int kProducerWarp = kEpiWarps;
 constexpr int kMmaWarp = kEpiWarps + 1;
-constexpr int kStages = 6;
+constexpr int kMaxStages = 6;
 constexpr int kStageBytes = 32768;
 constexpr int kBlkBytes = 16384;          // 128 rows x 128 B
 constexpr int kLayers = 10;               // pts_linears 0..7, feature_linear (8), views_linears.0 (9)
-constexpr int kOffX = 0;                             // position embedding: 128 rows x 128 B, 128-byte swizzle
-constexpr int kOffXD = kOffX + kBlkBytes;            // direction embedding: 128 rows x 64 B, 64-byte swizzle
-constexpr int kOffRing = kOffXD + kBlkBytes / 2;
-constexpr int kOffBias = kOffRing + kStages * kStageBytes;   // fp32 bias[10][256]
-constexpr int kOffMisc = kOffBias + kLayers * 256 * 4;
 
 struct Misc {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t acc_full[4];   // [accumulator region][column half]
   uint64_t a_ready[4];
   uint64_t x_ready;
@@ -61,8 +58,24 @@ struct Misc {
   uint32_t tmem_base;
   uint32_t pad_;
 };
-constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc);
-static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+
+// Shared-memory layout.  NP = number of tensor-core passes per product (see mlp_tc_kernel): with NP > 1 every
+// operand exists as a (hi, lo) pair of fp16 images, so the embeddings take twice the room and the weight ring
+// gives up one stage for them.
+template <int NP>
+struct Lay {
+  static constexpr int kStages = NP > 1 ? 5 : 6;
+  static constexpr int kOffX = 0;                                     // position embedding (hi): 128 rows x 128 B, 128-byte swizzle
+  static constexpr int kOffXlo = kOffX + kBlkBytes;                   // its lo half (NP > 1 only)
+  static constexpr int kOffXD = NP > 1 ? 2 * kBlkBytes : kBlkBytes;   // direction embedding (hi): 128 rows x 64 B, 64-byte swizzle
+  static constexpr int kOffXDlo = kOffXD + kBlkBytes / 2;             // its lo half (NP > 1 only)
+  static constexpr int kOffRing = kOffXD + (NP > 1 ? kBlkBytes : kBlkBytes / 2);
+  static constexpr int kOffBias = kOffRing + kStages * kStageBytes;   // fp32 bias[10][256]
+  static constexpr int kOffMisc = kOffBias + kLayers * 256 * 4;
+  static constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc);
+  static_assert(kOffRing % 1024 == 0, "weight K-blocks need 1024-byte alignment (128-byte swizzle atoms)");
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+};
 
 // per-tile weight stream: number of 64-wide K-blocks per layer and their size
 __host__ __device__ constexpr int layer_has_x(int l) { return l == 0 || l == 5 || l == 9; }
@@ -250,25 +263,46 @@ __device__ __forceinline__ uint32_t sw128(int row, int ch) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4));
 }
 
-// Frequency encoding of one coordinate triple by angle doubling from an accurate sincosf at the
-// base frequency: the 2^k-th octave carries <= 2^k ulp-level phase error (<= 6e-5 at k = 9), below
-// the 2.4e-4 rounding step of the 16-bit operand it is converted to.
-template <bool BF16, int L, bool SW64>
-__device__ __forceinline__ void encode_store(const float (&p)[3], uint32_t row_base, int row, int nchunks) {
+// fp32 -> (hi, lo) fp16 pair with hi + lo == x to ~22 significant bits (lo is subnormal below |x| ~ 0.25, where its
+// absolute resolution 2^-24 is still at the fp32 rounding level of O(1) activations)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Frequency encoding of one coordinate triple.
+// EXACT = false: angle doubling from an accurate sincosf at the base frequency: the 2^k-th octave carries <= 2^k
+// ulp-level phase error (<= 6e-5 at k = 9), below the 2.4e-4 rounding step of the 16-bit operand it is converted to.
+// EXACT = true (the split-fp16 passes): one accurate sincosf per octave on the exactly scaled argument, like the
+// reference's torch.sin(x * 2^k) (run_nerf_helpers.py:46-49), stored as a (hi, lo) pair of blocks lo_delta bytes apart.
+template <bool BF16, int L, bool SW64, bool EXACT>
+__device__ __forceinline__ void encode_store(const float (&p)[3], uint32_t row_base, uint32_t lo_delta, int row,
+                                             int nchunks) {
   float e[64];
   e[0] = p[0]; e[1] = p[1]; e[2] = p[2];
-  float s[3], c[3];
+  if (EXACT) {
 #pragma unroll
-  for (int i = 0; i < 3; ++i) sincosf(p[i], &s[i], &c[i]);
+    for (int l = 0; l < L; ++l) {
 #pragma unroll
-  for (int l = 0; l < L; ++l) {
+      for (int i = 0; i < 3; ++i) sincosf(p[i] * (float)(1 << l), &e[3 + l * 6 + i], &e[3 + l * 6 + 3 + i]);
+    }
+  } else {
+    float s[3], c[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      e[3 + l * 6 + i] = s[i];
-      e[3 + l * 6 + 3 + i] = c[i];
-      const float s2 = 2.f * s[i] * c[i];
-      const float c2 = fmaf(-2.f * s[i], s[i], 1.f);
-      s[i] = s2; c[i] = c2;
+    for (int i = 0; i < 3; ++i) sincosf(p[i], &s[i], &c[i]);
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        e[3 + l * 6 + i] = s[i];
+        e[3 + l * 6 + 3 + i] = c[i];
+        const float s2 = 2.f * s[i] * c[i];
+        const float c2 = fmaf(-2.f * s[i], s[i], 1.f);
+        s[i] = s2; c[i] = c2;
+      }
     }
   }
 #pragma unroll
@@ -277,9 +311,17 @@ __device__ __forceinline__ void encode_store(const float (&p)[3], uint32_t row_b
   for (int ch = 0; ch < 8; ++ch) {
     if (ch < nchunks) {
       const int sw = SW64 ? (ch ^ ((row >> 1) & 3)) : (ch ^ (row & 7));
-      st_shared_v4(row_base + (sw << 4), pack2<BF16>(e[ch * 8 + 0], e[ch * 8 + 1]),
-                   pack2<BF16>(e[ch * 8 + 2], e[ch * 8 + 3]), pack2<BF16>(e[ch * 8 + 4], e[ch * 8 + 5]),
-                   pack2<BF16>(e[ch * 8 + 6], e[ch * 8 + 7]));
+      if (EXACT) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split2(e[ch * 8 + 2 * j], e[ch * 8 + 2 * j + 1], hi[j], lo[j]);
+        st_shared_v4(row_base + (sw << 4), hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(row_base + lo_delta + (sw << 4), lo[0], lo[1], lo[2], lo[3]);
+      } else {
+        st_shared_v4(row_base + (sw << 4), pack2<BF16>(e[ch * 8 + 0], e[ch * 8 + 1]),
+                     pack2<BF16>(e[ch * 8 + 2], e[ch * 8 + 3]), pack2<BF16>(e[ch * 8 + 4], e[ch * 8 + 5]),
+                     pack2<BF16>(e[ch * 8 + 6], e[ch * 8 + 7]));
+      }
     }
   }
 }
@@ -353,21 +395,37 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return c;
 }
+// two fp32 fused multiply-adds in one instruction: a * s + b
+__device__ __forceinline__ float2 fma2(float2 a, float s, float2 b) {
+  float2 c;
+  asm("{\n\t.reg .b64 ra, rs, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\tmov.b64 rb, {%5, %6};\n\t"
+      "fma.rn.f32x2 rc, ra, rs, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(c.x), "=f"(c.y)
+      : "f"(a.x), "f"(a.y), "f"(s), "f"(b.x), "f"(b.y));
+  return c;
+}
 // Drains one layer's accumulator.  KIND 0: ReLU layer -> next A operand; 1: layer 7 (ReLU + alpha head);
-// 2: feature_linear (no ReLU); 3: view layer (ReLU + rgb / uncertainty heads, nothing stored).
+// 2: feature_linear (no ReLU); 3: view layer (ReLU + rgb / uncertainty heads, nothing stored);
+// 4: layer 7 of a sigma-only pass (ReLU + alpha head, nothing stored: it is the last layer);
+// 5: view layer of a beta-only pass (ReLU + uncertainty head only).
 // A warp owns kColsPerWarp columns of each 64-column chunk of its 32 rows; the TMEM load of chunk k+1 is in
 // flight while chunk k is converted and stored.
 // HFC >= 0 makes the warp's column slice a compile-time constant, so that the head weights of layers 7 and 9 become
 // immediate constant-bank operands of the FFMAs instead of indexed constant loads.
-template <bool BF16, int KIND, bool DBG, bool TR, int HFC = -1>
+// NP > 1: the accumulator carries the layer's power-of-two weight scale (inv_ws undoes it, exactly); NP == 3 stores
+// the activations as a (hi, lo) fp16 pair: hi in the 8 packed columns at c0, lo in the 8 columns behind them.
+template <bool BF16, int KIND, bool DBG, bool TR, int NP, int HFC = -1>
 __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& args, const float* bias_l, int l,
                                             uint32_t t_acc, int hf, int lane, uint32_t bar_a, uint32_t bar_acc_l,
                                             uint32_t acc_parity, const RowData& rd, float& alpha, float (&hd)[4],
                                             long long* tr = nullptr, long long* tr0 = nullptr) {
   if (HFC >= 0) hf = HFC;
-  constexpr int NCH = KIND == 3 ? 2 : 4;
+  constexpr bool kStore = KIND <= 2;
+  constexpr bool kRelu = KIND != 2;
+  constexpr int NCH = (KIND == 3 || KIND == 5) ? 2 : 4;
   constexpr int NC = kColsPerWarp;   // 16
   uint32_t r[2][NC];
+  const float inv_ws = NP > 1 ? cst.inv_wscale[l] : 1.f;
   // the first chunk is on the critical path (the next layer's MMAs wait for it): fetch its biases before the
   // accumulator is ready
   float4 bpre[NC / 4];
@@ -401,12 +459,17 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
 #pragma unroll
     for (int j = 0; j < NC / 4; ++j) {
       const float4 b = kb == 0 ? bpre[j] : b4[j];
-      v[2 * j] = add2(make_float2(__uint_as_float(r[kb & 1][4 * j]), __uint_as_float(r[kb & 1][4 * j + 1])),
-                      make_float2(b.x, b.y));
-      v[2 * j + 1] = add2(make_float2(__uint_as_float(r[kb & 1][4 * j + 2]), __uint_as_float(r[kb & 1][4 * j + 3])),
-                          make_float2(b.z, b.w));
+      const float2 a0 = make_float2(__uint_as_float(r[kb & 1][4 * j]), __uint_as_float(r[kb & 1][4 * j + 1]));
+      const float2 a1 = make_float2(__uint_as_float(r[kb & 1][4 * j + 2]), __uint_as_float(r[kb & 1][4 * j + 3]));
+      if (NP > 1) {
+        v[2 * j] = fma2(a0, inv_ws, make_float2(b.x, b.y));
+        v[2 * j + 1] = fma2(a1, inv_ws, make_float2(b.z, b.w));
+      } else {
+        v[2 * j] = add2(a0, make_float2(b.x, b.y));
+        v[2 * j + 1] = add2(a1, make_float2(b.z, b.w));
+      }
     }
-    if (KIND == 1 || KIND == 3 || (DBG && KIND != 2)) {
+    if (kRelu && (KIND != 0 || DBG || NP == 3)) {
 #pragma unroll
       for (int j = 0; j < NC / 2; ++j) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); }
     }
@@ -419,35 +482,46 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
         }
       }
     }
-    if (KIND == 1) {
+    if (KIND == 1 || KIND == 4) {
 #pragma unroll
       for (int j = 0; j < NC / 2; ++j) {
         alpha = fmaf(v[j].x, cst.w_alpha[c0 + 2 * j], alpha);
         alpha = fmaf(v[j].y, cst.w_alpha[c0 + 2 * j + 1], alpha);
       }
     }
-    if (KIND == 3) {
+    if (KIND == 3 || KIND == 5) {
 #pragma unroll
       for (int j = 0; j < NC / 2; ++j) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const float x = e ? v[j].y : v[j].x;
           const int c = c0 + 2 * j + e;
-          hd[0] = fmaf(x, cst.w_rgb[0][c], hd[0]);
-          hd[1] = fmaf(x, cst.w_rgb[1][c], hd[1]);
-          hd[2] = fmaf(x, cst.w_rgb[2][c], hd[2]);
+          if (KIND == 3) {
+            hd[0] = fmaf(x, cst.w_rgb[0][c], hd[0]);
+            hd[1] = fmaf(x, cst.w_rgb[1][c], hd[1]);
+            hd[2] = fmaf(x, cst.w_rgb[2][c], hd[2]);
+          }
           hd[3] = fmaf(x, cst.w_unc[c], hd[3]);
         }
       }
-    } else {
+    }
+    if (kStore) {
       // next layer's A operand, written IN PLACE over the accumulator columns this thread just read:
       // channels c0..c0+15 of this row -> 8 packed columns at c0 (k-step c0/16 of the next layer's TS MMAs)
       uint32_t pk[NC / 2];
+      if (NP == 3) {
+        uint32_t pl[NC / 2];
 #pragma unroll
-      for (int j = 0; j < NC / 2; ++j) {
-        pk[j] = (KIND == 0 && !DBG) ? pack2_relu<BF16>(v[j].x, v[j].y) : pack2<BF16>(v[j].x, v[j].y);
+        for (int j = 0; j < NC / 2; ++j) split2(v[j].x, v[j].y, pk[j], pl[j]);
+        tmem_st8(t_acc + (uint32_t)c0, pk);
+        tmem_st8(t_acc + (uint32_t)(c0 + NC / 2), pl);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NC / 2; ++j) {
+          pk[j] = (KIND == 0 && !DBG) ? pack2_relu<BF16>(v[j].x, v[j].y) : pack2<BF16>(v[j].x, v[j].y);
+        }
+        tmem_st8(t_acc + (uint32_t)c0, pk);
       }
-      tmem_st8(t_acc + (uint32_t)c0, pk);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -467,21 +541,39 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
 // SPLIT: hidden K-blocks kb >= SPLIT of a 256-wide layer are issued as two N = 128 halves (4 = none)
 // DM: 0 = production, 1 = per-layer activation dumps + pipeline trace (fp32 ReLU path), 2 = pipeline trace only
 // (production arithmetic and timing)
-template <bool BF16, bool RAYS, int C, int DM, int SPLIT>
+// NP: tensor-core passes per product.  1 = plain 16-bit operands (the bulk pass).  With fp16 operands split as
+// x = hi + lo (hi = fp16(x), lo = fp16(x - hi): 22 significant bits), 2 = A_hi * (W_hi + W_lo): weights at
+// fp32-class precision, activations rounded to fp16; 3 = A_hi * W_hi + A_hi * W_lo + A_lo * W_hi: the whole
+// product at fp32-class precision (the dropped lo * lo term is 2^-22 relative), accumulated in fp32 in tensor
+// memory -- the "exact" path the planner uses to re-score near-tied candidates (plannerServer_*/core/
+// interface.py:115-116 must pick the view the fp32 reference picks).  W_lo is a second weight image streamed
+// through the same ring; A_lo lives in the 8 tensor-memory columns that the in-place packing leaves free.
+// HEADS: dead-output elimination for score-only calls.  0 = all five outputs -> out[m * 5 + ..] (render());
+// 1 = sigma only -> out[m] (the coarse pass of Controller.get_uncertainty feeds nothing but sample_pdf's
+// weights: the pass stops after layer 7 + alpha head); 2 = beta only -> out[m] (nerf.py:307-309 reads
+// raw[..., 4] of the fine pass and nothing else: the alpha and rgb heads are skipped).
+template <bool BF16, bool RAYS, int C, int DM, int SPLIT, int NP, int HEADS>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcArgs args) {
+  static_assert(NP == 1 || (!BF16 && SPLIT == 4 && DM == 0), "split passes: fp16 operands, no half-split K-blocks");
+  static_assert(HEADS == 0 || (RAYS && DM == 0), "score-only variants exist for ray batches only");
+  using L_ = Lay<NP>;
+  constexpr int kStages = L_::kStages;
+  constexpr int NB = NP > 1 ? 2 : 1;                  // ring stages per K-block: W_hi (, W_lo)
+  constexpr int kLayersRun = HEADS == 1 ? 8 : kLayers;
   constexpr bool DBG = DM == 1;
   constexpr bool TR = DM != 0;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   const uint32_t smem_base = smem_u32(smem_dyn);
   if (smem_base & 1023u) __trap();   // the 128-byte swizzle atoms need 1024-byte aligned blocks
   uint8_t* smem_gen = smem_dyn;
-  Misc& misc = *reinterpret_cast<Misc*>(smem_gen + kOffMisc);
-  float* partial = reinterpret_cast<float*>(smem_gen + kOffXD);   // [128][kColSplit-1][5] head partial sums; aliases XD,
-                                                                   // which is idle between the view layer and the next tile
-  float* bias_s = reinterpret_cast<float*>(smem_gen + kOffBias);
+  Misc& misc = *reinterpret_cast<Misc*>(smem_gen + L_::kOffMisc);
+  float* partial = reinterpret_cast<float*>(smem_gen + L_::kOffXD);   // [128][kColSplit-1][5] head partial sums; aliases XD,
+                                                                       // which is idle between the view layer and the next tile
+  float* bias_s = reinterpret_cast<float*>(smem_gen + L_::kOffBias);
   for (int i = threadIdx.x; i < kLayers * 256; i += kThreads) bias_s[i] = cst.bias[i >> 8][i & 255];
-  const uint32_t sX = smem_base + kOffX, sXD = smem_base + kOffXD, sRing = smem_base + kOffRing;
+  const uint32_t sX = smem_base + L_::kOffX, sXD = smem_base + L_::kOffXD, sRing = smem_base + L_::kOffRing;
+  constexpr uint32_t kXloDelta = L_::kOffXlo - L_::kOffX, kXDloDelta = L_::kOffXDlo - L_::kOffXD;
   const uint32_t bar_full = smem_u32(&misc.full[0]), bar_empty = smem_u32(&misc.empty[0]);
   const uint32_t bar_acc = smem_u32(&misc.acc_full[0]), bar_a = smem_u32(&misc.a_ready[0]);
   const uint32_t bar_x = smem_u32(&misc.x_ready), bar_xd = smem_u32(&misc.xd_ready);
@@ -534,8 +626,8 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < ntile_iters; ++it) {
         const uint8_t* src = args.image;
-        for (int l = 0; l < kLayers; ++l) {
-          const int nblk = layer_has_x(l) + layer_h_blocks(l);
+        for (int l = 0; l < kLayersRun; ++l) {
+          const int nblk = (layer_has_x(l) + layer_h_blocks(l)) * NB;   // NP > 1: every K-block is a (W_hi, W_lo) pair
           const uint32_t bytes = (uint32_t)layer_n(l) * 128u;
           for (int b = 0; b < nblk; ++b) {
             if (l == 4 && b == 0) EVPP_TRACE(117);
@@ -573,12 +665,59 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
       uint32_t stage = 0, phase = 0, a_phase = 0, x_phase = 0, xd_phase = 0;
       bool pre_full = false;   // the next weight stage's arrival was already awaited (static after unrolling)
       for (int it = 0; it < ntile_iters; ++it) {
-        for (int l = 0; l < kLayers; ++l) {
+        for (int l = 0; l < kLayersRun; ++l) {
           const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 256u;
           const uint32_t a_tmem = tmem + (uint32_t)((l & 1) ^ 1) * 256u;
           const uint32_t idesc = make_idesc(BF16, layer_n(l));
           uint32_t accumulate = 0;
           EVPP_TRACE(l * 4 + 0);
+          if constexpr (NP > 1) {
+            // ---- split passes: per K step A_hi * W_hi (+ A_hi * W_lo (+ A_lo * W_hi)); K-block = 2 ring stages ----
+            const int nblk = layer_has_x(l) + layer_h_blocks(l);
+            for (int b = 0; b < nblk; ++b) {
+              const bool xblk = layer_has_x(l) && b == 0;
+              const int kb = b - layer_has_x(l);
+              uint32_t s_hi = stage, p_hi = phase;
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              uint32_t s_lo = stage, p_lo = phase;
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              mbar_wait(bar_full + 8 * s_hi, p_hi);   // weights first: prefetched long ago
+              mbar_wait(bar_full + 8 * s_lo, p_lo);
+              const uint64_t b_hi = make_desc(sRing + s_hi * kStageBytes), b_lo = make_desc(sRing + s_lo * kStageBytes);
+              if (xblk) {
+                if (l == 0) { mbar_wait(bar_x, x_phase); x_phase ^= 1u; }
+                if (l == 9) { mbar_wait(bar_xd, xd_phase); xd_phase ^= 1u; }
+                tc_fence_after();
+                const int ksteps = l == 9 ? 2 : 4;
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t a_hi = l == 9 ? make_desc_sw64(sXD + k * 32) : make_desc(sX + k * 32);
+                  const uint64_t a_lo = l == 9 ? make_desc_sw64(sXD + kXDloDelta + k * 32) : make_desc(sX + kXloDelta + k * 32);
+                  umma_f16(d_tmem, a_hi, b_hi + (uint64_t)(k * 2), idesc, accumulate);
+                  umma_f16(d_tmem, a_hi, b_lo + (uint64_t)(k * 2), idesc, 1u);
+                  if (NP == 3) umma_f16(d_tmem, a_lo, b_hi + (uint64_t)(k * 2), idesc, 1u);
+                  accumulate = 1;
+                }
+              } else {
+                mbar_wait(bar_a + 8 * kb, a_phase);     // then the activations of this K-block
+                tc_fence_after();
+                const uint32_t a_addr0 = a_tmem + (uint32_t)(kb * 64);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t a_hi = a_addr0 + (uint32_t)(k * 16);
+                  umma_f16_ts(d_tmem, a_hi, b_hi + (uint64_t)(k * 2), idesc, accumulate);
+                  umma_f16_ts(d_tmem, a_hi, b_lo + (uint64_t)(k * 2), idesc, 1u);
+                  if (NP == 3) umma_f16_ts(d_tmem, a_hi + 8u, b_hi + (uint64_t)(k * 2), idesc, 1u);
+                  accumulate = 1;
+                }
+              }
+              if (C == 1) { umma_commit(bar_empty + 8 * s_hi); umma_commit(bar_empty + 8 * s_lo); }
+              else { umma_commit_mcast(bar_empty + 8 * s_hi, mc_mask); umma_commit_mcast(bar_empty + 8 * s_lo, mc_mask); }
+            }
+            umma_commit(bar_acc + 16 * (l & 1));
+            if (l >= 1) a_phase ^= 1u;
+            umma_commit(bar_acc + 16 * (l & 1) + 8);
+            continue;
+          }
           if (layer_has_x(l)) {
             // layers 0 and 5 read the position embedding (X), the view layer the direction embedding (XD)
             if (l == 0) { mbar_wait(bar_x, x_phase); x_phase ^= 1u; }
@@ -637,8 +776,10 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
             // The issuer crawls while the epilogue warps are busy (it loses most issue slots to them), and after
             // the second half it is on the critical path to the next layer: look at the next layer's first
             // weight stage now, while the tensor pipe still has queued work.
-            mbar_wait(bar_full + 8 * s2, p2);
-            pre_full = true;
+            if (l + 1 < kLayersRun || it + 1 < ntile_iters) {
+              mbar_wait(bar_full + 8 * s2, p2);
+              pre_full = true;
+            }
             for (int kb = nfull; kb < 4; ++kb) {
               const uint64_t b_desc0 = make_desc(sRing + stage * kStageBytes + 16384);
               const uint32_t a_addr0 = a_tmem + (uint32_t)(kb * 64);
@@ -668,7 +809,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
     RowData cur, nxt;
     load_row<RAYS>(args, args.tile0 + (long long)blockIdx.x, ntiles, row, cur);
     if (hf == 0) {
-      encode_store<BF16, kLpos, false>(cur.p, sX + row_off, row, 8);
+      encode_store<BF16, kLpos, false, NP == 3>(cur.p, sX + row_off, kXloDelta, row, 8);
       fence_proxy_async();
     }
     __syncwarp();
@@ -677,7 +818,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
       float alpha = 0.f;
       float hd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int l = 0; l < kLayers; ++l) {
+      for (int l = 0; l < kLayersRun; ++l) {
         const int ab = l & 1;
         const uint32_t bar_l = bar_acc + 16 * ab, par_l = acc_phase[ab];
         acc_phase[ab] ^= 1u;
@@ -688,24 +829,27 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
           tr = args.trace + (warp == 0 ? 90 : 95);
         long long* tr0 = (TR && args.trace && blockIdx.x == 0 && it == 2 && l == 3) ? args.trace + 100 + warp : nullptr;
 #define EVPP_DRAIN(KIND_, HFC_) \
-  drain_layer<BF16, KIND_, DBG, TR, HFC_>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd, tr, tr0)
-        if (l == 9) {
-          if (hf == 0) EVPP_DRAIN(3, 0); else if (hf == 1) EVPP_DRAIN(3, 1); else if (hf == 2) EVPP_DRAIN(3, 2); else EVPP_DRAIN(3, 3);
-        } else if (l == 8) {
-          EVPP_DRAIN(2, -1);
+  drain_layer<BF16, KIND_, DBG, TR, NP, HFC_>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd, tr, tr0)
+#define EVPP_DRAIN_HF(KIND_) \
+  do { if (hf == 0) EVPP_DRAIN(KIND_, 0); else if (hf == 1) EVPP_DRAIN(KIND_, 1); else if (hf == 2) EVPP_DRAIN(KIND_, 2); else EVPP_DRAIN(KIND_, 3); } while (0)
+        if (HEADS != 1 && l == 9) {
+          if constexpr (HEADS == 2) EVPP_DRAIN_HF(5); else if constexpr (HEADS == 0) EVPP_DRAIN_HF(3);
+        } else if (HEADS != 1 && l == 8) {
+          if constexpr (HEADS != 1) EVPP_DRAIN(2, -1);
         } else if (l == 7) {
-          if (hf == 0) EVPP_DRAIN(1, 0); else if (hf == 1) EVPP_DRAIN(1, 1); else if (hf == 2) EVPP_DRAIN(1, 2); else EVPP_DRAIN(1, 3);
+          if constexpr (HEADS == 1) EVPP_DRAIN_HF(4); else if constexpr (HEADS == 2) EVPP_DRAIN(0, -1); else EVPP_DRAIN_HF(1);
         } else {
           EVPP_DRAIN(0, -1);
         }
+#undef EVPP_DRAIN_HF
 #undef EVPP_DRAIN
         if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 1);
         // The epilogue warps now idle until the next layer's MMAs finish: use the window to stage operands.
-        if (l == 0) {
+        if (l == 0 && HEADS != 1) {
           // XD <- direction embedding of this tile (the previous tile's view-layer MMAs, its last readers,
           // completed before that tile's final accumulator wait)
           if (hf == 1) {
-            encode_store<BF16, kLdir, true>(cur.dv, sXD + (uint32_t)(row * 64), row, 4);
+            encode_store<BF16, kLdir, true, NP == 3>(cur.dv, sXD + (uint32_t)(row * 64), kXDloDelta, row, 4);
             fence_proxy_async();
           }
           __syncwarp();
@@ -715,7 +859,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
           load_row<RAYS>(args, args.tile0 + (long long)blockIdx.x + (long long)(it + 1) * gridDim.x,
                          it + 1 < ntile_iters ? ntiles : 0, row, nxt);
           if (hf == 0) {
-            encode_store<BF16, kLpos, false>(nxt.p, sX + row_off, row, 8);
+            encode_store<BF16, kLpos, false, NP == 3>(nxt.p, sX + row_off, kXloDelta, row, 8);
             fence_proxy_async();
           }
           __syncwarp();
@@ -723,10 +867,12 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
         }
         if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 2);
       }
-      // ---- heads: combine the two column halves, add biases, exp on the uncertainty ----
+      // ---- heads: combine the column slices, add biases, exp on the uncertainty ----
       if (hf != 0) {
         float* pr = partial + (row * (kColSplit - 1) + hf - 1) * 5;
-        pr[0] = hd[0]; pr[1] = hd[1]; pr[2] = hd[2]; pr[3] = alpha; pr[4] = hd[3];
+        if (HEADS == 0) { pr[0] = hd[0]; pr[1] = hd[1]; pr[2] = hd[2]; }
+        if (HEADS != 2) pr[3] = alpha;
+        if (HEADS != 1) pr[4] = hd[3];
       }
       epi_bar_sync();
       if (hf == 0 && cur.valid) {
@@ -735,14 +881,21 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
         for (int k = 0; k < kColSplit - 1; ++k) {
           const float* pr = partial + (row * (kColSplit - 1) + k) * 5;
 #pragma unroll
-          for (int e = 0; e < 5; ++e) t[e] += pr[e];
+          for (int e = 0; e < 5; ++e)
+            if (HEADS == 0 || (HEADS == 1 && e == 3) || (HEADS == 2 && e == 4)) t[e] += pr[e];
         }
-        float* o = args.out + cur.m * 5;
-        o[0] = t[0] + cst.head_b[1];
-        o[1] = t[1] + cst.head_b[2];
-        o[2] = t[2] + cst.head_b[3];
-        o[3] = t[3] + cst.head_b[0];
-        o[4] = expf(t[4] + cst.head_b[4]);   // run_nerf_helpers.py:128-129
+        if (HEADS == 0) {
+          float* o = args.out + cur.m * 5;
+          o[0] = t[0] + cst.head_b[1];
+          o[1] = t[1] + cst.head_b[2];
+          o[2] = t[2] + cst.head_b[3];
+          o[3] = t[3] + cst.head_b[0];
+          o[4] = expf(t[4] + cst.head_b[4]);   // run_nerf_helpers.py:128-129
+        } else if (HEADS == 1) {
+          args.out[cur.m] = t[3] + cst.head_b[0];
+        } else {
+          args.out[cur.m] = expf(t[4] + cst.head_b[4]);
+        }
       }
       epi_bar_sync();   // partial[] (XD) is rewritten in the next tile's layer-0 window
       cur = nxt;
@@ -768,15 +921,16 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   if (args.pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
-template <bool BF16, bool RAYS, int C, int DM, int SPLIT>
+template <bool BF16, bool RAYS, int C, int DM, int SPLIT, int NP, int HEADS>
 cudaError_t launch_one(const TcConsts& cst, const TcArgs& a, int grid, cudaStream_t st, bool dependent = false) {
-  auto kern = mlp_tc_kernel<BF16, RAYS, C, DM, SPLIT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  auto kern = mlp_tc_kernel<BF16, RAYS, C, DM, SPLIT, NP, HEADS>;
+  constexpr int smem = Lay<NP>::kSmemBytes;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -815,14 +969,22 @@ const TcEnv& tc_env() {
   return env;
 }
 
+// Split-precision passes (fp16x2 / fp16x3) and the score-only variants are built for clusters of 1 and 2 CTAs and
+// one K-block schedule each (the experiment knobs EVPP_TC_CLUSTER=4/42 and EVPP_TC_SPLIT apply to the plain pass).
+template <bool RAYS, int NP, int HEADS>
+cudaError_t launch_np(const TcWeights& w, const TcArgs& a, int C, long long grid, cudaStream_t st) {
+  if (C >= 2) return launch_one<false, RAYS, 2, 0, 4, NP, HEADS>(*w.consts, a, (int)grid, st, false);
+  return launch_one<false, RAYS, 1, 0, 4, NP, HEADS>(*w.consts, a, (int)grid, st, false);
+}
+
 template <bool RAYS, int SPLIT>
 cudaError_t launch_split(const TcWeights& w, const TcArgs& a, int C, long long grid, cudaStream_t st,
                          bool dependent = false) {
   const bool bf = w.dtype == EVPP_PREC_BF16;
   cudaError_t e;
-#define EVPP_TC_DISPATCH(CC, DD)                                                              \
-  e = bf ? launch_one<true, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st, dependent)      \
-         : launch_one<false, RAYS, CC, DD, SPLIT>(*w.consts, a, (int)grid, st, dependent)
+#define EVPP_TC_DISPATCH(CC, DD)                                                                    \
+  e = bf ? launch_one<true, RAYS, CC, DD, SPLIT, 1, 0>(*w.consts, a, (int)grid, st, dependent)      \
+         : launch_one<false, RAYS, CC, DD, SPLIT, 1, 0>(*w.consts, a, (int)grid, st, dependent)
   if (a.dbg) {
     EVPP_TC_DISPATCH(1, RAYS ? 0 : 1);
   } else if (a.trace) {          // production kernel (cluster, packed epilogue) with the clock stamps compiled in
@@ -834,17 +996,28 @@ cudaError_t launch_split(const TcWeights& w, const TcArgs& a, int C, long long g
   return e;
 }
 
+// score-only variants of the plain pass (HEADS 1 / 2), ray batches only
+template <int HEADS>
+cudaError_t launch_heads(const TcWeights& w, const TcArgs& a, int C, long long grid, cudaStream_t st) {
+  const bool bf = w.dtype == EVPP_PREC_BF16;
+  if (C >= 2)
+    return bf ? launch_one<true, true, 2, 0, 2, 1, HEADS>(*w.consts, a, (int)grid, st, false)
+              : launch_one<false, true, 2, 0, 2, 1, HEADS>(*w.consts, a, (int)grid, st, false);
+  return bf ? launch_one<true, true, 1, 0, 2, 1, HEADS>(*w.consts, a, (int)grid, st, false)
+            : launch_one<false, true, 1, 0, 2, 1, HEADS>(*w.consts, a, (int)grid, st, false);
+}
+
 // How many 4-CTA clusters of this kernel are co-resident (they do not tile every GPC: 33 on a 148-SM B200).
 int max_clusters_of_4(int num_sms) {
   static const int max_clusters = [num_sms] {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(148); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.gridDim = dim3(148); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Lay<1>::kSmemBytes;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    auto kern = mlp_tc_kernel<false, true, 4, false, 2>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    auto kern = mlp_tc_kernel<false, true, 4, 0, 2, 1, 0>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<1>::kSmemBytes);
     int mc = 0;
     if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc <= 0) mc = num_sms / 4;
     if (getenv("EVPP_TC_VERBOSE")) fprintf(stderr, "evpp: %d co-resident 4-CTA clusters\n", mc);
@@ -854,7 +1027,7 @@ int max_clusters_of_4(int num_sms) {
 }
 
 template <bool RAYS>
-int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
+int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st, int heads = 0) {
   if (a.M <= 0) return 0;
   const TcEnv& env = tc_env();
   const int g_cluster = env.cluster, g_split = env.split;
@@ -868,11 +1041,14 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   a.tile_end = ntiles;
   a.pdl = 0;
   if ((a.dbg || a.trace) && RAYS) return -1;
+  const int np = w.dtype == EVPP_PREC_FP16X3 ? 3 : w.dtype == EVPP_PREC_FP16X2 ? 2 : 1;
+  if ((np > 1 || heads != 0) && (a.dbg || a.trace)) return -1;
+  if (heads != 0 && !RAYS) return -1;
 
   // Hybrid 4 + 2: 4-CTA clusters share one weight stream four ways (L2 reads quartered) but leave 16 of the 148 SMs
   // idle; a second launch of 2-CTA clusters, released by griddepcontrol.launch_dependents as soon as every 4-CTA
   // cluster is resident, takes those SMs and a proportional slice of the tiles.
-  if (g_cluster == 42 && !a.dbg && !a.trace && ntiles >= 32LL * num_sms) {
+  if (g_cluster == 42 && np == 1 && heads == 0 && !a.dbg && !a.trace && ntiles >= 32LL * num_sms) {
     const long long grid_a = (long long)max_clusters_of_4(num_sms) * 4;
     const long long grid_b = (num_sms - grid_a) / 2 * 2;
     if (grid_a > 0 && grid_b > 0) {
@@ -917,7 +1093,8 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
     }
   }
 
-  const int C = g_cluster == 42 ? 2 : g_cluster;
+  int C = g_cluster == 42 ? 2 : g_cluster;
+  if ((np > 1 || heads != 0) && C > 2) C = 2;
   long long grid = ntiles < num_sms ? ntiles : num_sms;
   grid = (grid + C - 1) / C * C;
   if (grid > num_sms) grid = num_sms / C * C;
@@ -928,9 +1105,21 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st) {
   }
   a.tiles_per_cta = (int)((ntiles + grid - 1) / grid);
   cudaError_t e;
-  switch (g_split) {
-    case 2: e = launch_split<RAYS, 2>(w, a, C, grid, st); break;
-    default: e = launch_split<RAYS, 4>(w, a, C, grid, st); break;
+  if (np > 1) {
+    if constexpr (RAYS) {
+      if (np == 3) e = heads == 1 ? launch_np<true, 3, 1>(w, a, C, grid, st) : heads == 2 ? launch_np<true, 3, 2>(w, a, C, grid, st) : launch_np<true, 3, 0>(w, a, C, grid, st);
+      else e = heads == 1 ? launch_np<true, 2, 1>(w, a, C, grid, st) : heads == 2 ? launch_np<true, 2, 2>(w, a, C, grid, st) : launch_np<true, 2, 0>(w, a, C, grid, st);
+    } else {
+      e = np == 3 ? launch_np<false, 3, 0>(w, a, C, grid, st) : launch_np<false, 2, 0>(w, a, C, grid, st);
+    }
+  } else if (heads != 0) {
+    if constexpr (RAYS) e = heads == 1 ? launch_heads<1>(w, a, C, grid, st) : launch_heads<2>(w, a, C, grid, st);
+    else e = cudaErrorInvalidValue;
+  } else {
+    switch (g_split) {
+      case 2: e = launch_split<RAYS, 2>(w, a, C, grid, st); break;
+      default: e = launch_split<RAYS, 4>(w, a, C, grid, st); break;
+    }
   }
 #ifdef EVPP_TC_DIAG
   {
@@ -993,12 +1182,62 @@ void pack_image(const std::vector<std::vector<float>>& t, std::vector<uint8_t>& 
   for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[16], 128, 283, kb * 64, 64);   // views : feature part
 }
 
+// state_dict tensor of GEMM layer l (0..7 pts_linears, 8 feature_linear, 9 views_linears.0)
+int layer_tensor(int l) { return l < 8 ? 2 * l : l == 8 ? 18 : 16; }
+
+// Power-of-two scale that brings the largest |w| of a layer into [2^13, 2^14): the lo halves of the split weights
+// then sit in fp16's normal range (an unscaled lo of a ~0.06 weight would be subnormal, 2^-21 relative), and the
+// epilogue undoes the scale exactly (TcConsts::inv_wscale).
+float layer_wscale(const std::vector<float>& W) {
+  float m = 0.f;
+  for (float v : W) m = std::fmax(m, std::fabs(v));
+  if (!(m > 0.f)) return 1.f;
+  int e = 0;
+  std::frexp(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+  return std::ldexp(1.f, 14 - e);          // m * scale in [2^13, 2^14)
+}
+
+// Split image: every K-block of pack_image as a (hi, lo) pair, hi = fp16(w * s), lo = fp16(w * s - hi).
+void pack_image_split(const std::vector<std::vector<float>>& t, std::vector<uint8_t>& img) {
+  std::vector<std::vector<float>> hi(t.size()), lo(t.size());
+  for (int l = 0; l < kLayers; ++l) {
+    const int ti = layer_tensor(l);
+    const float s = layer_wscale(t[ti]);
+    hi[ti].resize(t[ti].size());
+    lo[ti].resize(t[ti].size());
+    for (size_t i = 0; i < t[ti].size(); ++i) {
+      const float w = t[ti][i] * s;
+      const float h = __half2float(__float2half_rn(w));
+      hi[ti][i] = h;
+      lo[ti][i] = w - h;
+    }
+  }
+  img.clear();
+  img.reserve(2 * kImageBytes);
+  auto pair = [&](int ti, int n_rows, int in_dim, int col0, int count) {
+    put_block<__half>(img, hi[ti], n_rows, in_dim, col0, count);
+    put_block<__half>(img, lo[ti], n_rows, in_dim, col0, count);
+  };
+  pair(0, 256, 63, 0, 63);
+  for (int l = 1; l <= 4; ++l)
+    for (int kb = 0; kb < 4; ++kb) pair(2 * l, 256, 256, kb * 64, 64);
+  pair(10, 256, 319, 0, 63);
+  for (int kb = 0; kb < 4; ++kb) pair(10, 256, 319, 63 + kb * 64, 64);
+  for (int l = 6; l <= 7; ++l)
+    for (int kb = 0; kb < 4; ++kb) pair(2 * l, 256, 256, kb * 64, 64);
+  for (int kb = 0; kb < 4; ++kb) pair(18, 256, 256, kb * 64, 64);
+  pair(16, 128, 283, 256, 27);
+  for (int kb = 0; kb < 4; ++kb) pair(16, 128, 283, kb * 64, 64);
+}
+
 }  // namespace
 
 size_t tc_weight_image_bytes() { return kImageBytes; }
 
 void tc_pack_weights(const std::vector<std::vector<float>>& t, int dtype, std::vector<uint8_t>& image, TcConsts& c) {
-  if (dtype == EVPP_PREC_BF16) pack_image<__nv_bfloat16>(t, image); else pack_image<__half>(t, image);
+  if (dtype == EVPP_PREC_BF16) pack_image<__nv_bfloat16>(t, image);
+  else if (dtype == EVPP_PREC_FP16X2 || dtype == EVPP_PREC_FP16X3) pack_image_split(t, image);
+  else pack_image<__half>(t, image);
   memset(&c, 0, sizeof(c));
   for (int l = 0; l < 8; ++l) memcpy(c.bias[l], t[2 * l + 1].data(), 256 * 4);
   memcpy(c.bias[8], t[19].data(), 256 * 4);
@@ -1009,16 +1248,15 @@ void tc_pack_weights(const std::vector<std::vector<float>>& t, int dtype, std::v
   c.head_b[0] = t[21][0];
   c.head_b[1] = t[23][0]; c.head_b[2] = t[23][1]; c.head_b[3] = t[23][2];
   c.head_b[4] = t[25][0];
+  for (int l = 0; l < kLayers; ++l) c.inv_wscale[l] = 1.f / layer_wscale(t[layer_tensor(l)]);
 }
 
-int tc_configure() { return 0; }   // attributes are set lazily per instantiation in launch_one
-
-int launch_mlp_tc(const TcWeights& w, const RayBatch& rb, float* raw, int num_sms, cudaStream_t st) {
+int launch_mlp_tc(const TcWeights& w, const RayBatch& rb, float* raw, int num_sms, cudaStream_t st, int heads) {
   TcArgs a{};
   a.rb = rb;
   a.M = (long long)rb.n * rb.S;
   a.out = raw;
-  return launch_any<true>(w, a, num_sms, st);
+  return launch_any<true>(w, a, num_sms, st, heads);
 }
 
 int launch_mlp_tc_points(const TcWeights& w, const float* pts, const float* dirs, int64_t M, float* out,

@@ -107,6 +107,10 @@ __device__ __forceinline__ RayScratch ray_scratch(float* base, int S) {
 }
 
 // raw2outputs (run_nerf.py:344-388) for one ray by one warp.  On return plane 3 holds weights[i].
+// SIGMA_ONLY: `raw` is the [S] row of raw sigmas a score-only coarse pass produces (mlp_tc.cu, HEADS = 1); only the
+// weights are computed (all that sample_pdf needs) -- the alpha / transmittance arithmetic is the same instructions
+// in the same order, so the weights are bit-identical to the full variant's.
+template <bool SIGMA_ONLY>
 __device__ __forceinline__ void composite_ray_warp(const float* __restrict__ raw, const float* __restrict__ z, float dnorm,
                                                    int S, int white_bkgd, long long t, const CompositeOut& co,
                                                    const RayScratch& sc, int lane) {
@@ -123,19 +127,22 @@ __device__ __forceinline__ void composite_ray_warp(const float* __restrict__ raw
 #pragma unroll 2
   for (int i = lane; i < S; i += 32) {
     const float* rw = raw + i * 5;
-    const float x0 = rw[0], x1 = rw[1], x2 = rw[2], x3 = rw[3], x4 = rw[4];
+    const float x3 = SIGMA_ONLY ? raw[i] : rw[3];
     const float zi = sz[i];
     float dist = (i + 1 < S) ? __fsub_rn(sz[i + 1], zi) : 1e10f;
     dist = __fmul_rn(dist, dnorm);
     const float sigma = fmaxf(x3, 0.f);
     const float alpha = __fsub_rn(1.f, expf(__fmul_rn(-sigma, dist)));
     dT[i] = (double)__fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
-    pl[0 * Sp + i] = 1.f / (1.f + expf(-x0));
-    pl[1 * Sp + i] = 1.f / (1.f + expf(-x1));
-    pl[2 * Sp + i] = 1.f / (1.f + expf(-x2));
     pl[3 * Sp + i] = alpha;
-    pl[4 * Sp + i] = x4;
-    if (co.unc) co.unc[t * S + i] = x4;
+    if (!SIGMA_ONLY) {
+      const float x0 = rw[0], x1 = rw[1], x2 = rw[2], x4 = rw[4];
+      pl[0 * Sp + i] = 1.f / (1.f + expf(-x0));
+      pl[1 * Sp + i] = 1.f / (1.f + expf(-x1));
+      pl[2 * Sp + i] = 1.f / (1.f + expf(-x2));
+      pl[4 * Sp + i] = x4;
+      if (co.unc) co.unc[t * S + i] = x4;
+    }
   }
   __syncwarp();
   // stage 2, the transmittance recurrence in double (torch.cumprod's accumulation type on CPU), one lane:
@@ -164,6 +171,7 @@ __device__ __forceinline__ void composite_ray_warp(const float* __restrict__ raw
     if (co.weights) co.weights[t * S + i] = w;
   }
   __syncwarp();
+  if (SIGMA_ONLY) return;
   // stage 3, six fp32 FMA chains in sample order: lane 0 acc (x = 1: fma(w, 1, acc) rounds exactly like acc + w),
   // 1 depth (x = z), 2..4 rgb (x = sigmoid), 5 sum of beta^2 (a = x = beta)
   float accum = 0.f;
@@ -209,7 +217,29 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ z, con
   if (t >= n) return;
   const RayScratch sc = ray_scratch(ray_smem + (size_t)warp * ray_scratch_floats(S), S);
   const float dn = ray_norm(rays_d + t * 3);
-  composite_ray_warp(raw + t * S * 5, z + t * S, dn, S, white_bkgd, t, co, sc, lane);
+  composite_ray_warp<false>(raw + t * S * 5, z + t * S, dn, S, white_bkgd, t, co, sc, lane);
+}
+
+// Score-only final pass: sum over the samples of beta^2 per ray from the [n,S] beta rows of a beta-only fine pass
+// (mlp_tc.cu, HEADS = 2).  One THREAD per ray: the sum is the same fp32 fused-multiply-add chain in sample order as
+// lane 5 of composite_ray_warp runs (bit-identical), 32 independent chains per warp instead of one; a thread walks
+// its row with 16-byte loads, every 128-byte line it touches is consumed from L1 within 8 steps.
+__global__ void __launch_bounds__(128)
+beta2_kernel(const float* __restrict__ beta, int n, int S, float* __restrict__ beta2) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float* b = beta + t * S;
+  float accum = 0.f;
+  int i = 0;
+  if ((S & 3) == 0) {
+    for (; i + 4 <= S; i += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(b + i);
+      accum = __fmaf_rn(v.x, v.x, accum); accum = __fmaf_rn(v.y, v.y, accum);
+      accum = __fmaf_rn(v.z, v.z, accum); accum = __fmaf_rn(v.w, v.w, accum);
+    }
+  }
+  for (; i < S; ++i) accum = __fmaf_rn(b[i], b[i], accum);
+  beta2[t] = accum;
 }
 
 // Coarse compositing + sample_pdf(det) (run_nerf_helpers.py:216-259) + sort(cat) (run_nerf.py:483), one warp per ray.
@@ -221,6 +251,7 @@ composite_kernel(const float* __restrict__ raw, const float* __restrict__ z, con
 // therefore returns the very same values as the reference's serial loops.  The inverse-cdf lookup is
 // searchsorted(right=True) = upper_bound on the non-decreasing cdf; the final sort(cat[...]) is the stable merge
 // of two sorted runs (coarse entries first on ties), whose output positions are ranks found by binary search.
+template <bool SIGMA_ONLY>
 __global__ void __launch_bounds__(32 * kRayWarps)
 coarse_resample_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                        const float* __restrict__ u_vals, int n, int Sc, int Ni, int white_bkgd, CompositeOut co,
@@ -239,7 +270,7 @@ coarse_resample_kernel(const float* __restrict__ raw, const float* __restrict__ 
   const float* wts = sc.pl + 3 * sc.Sp;          // coarse weights after composite_ray_warp
   const float* zc = sc.sz;
   const float dn = ray_norm(rays_d + t * 3);
-  composite_ray_warp(raw + t * Sc * 5, z + t * Sc, dn, Sc, white_bkgd, t, co, sc, lane);
+  composite_ray_warp<SIGMA_ONLY>(raw + t * Sc * (SIGMA_ONLY ? 1 : 5), z + t * Sc, dn, Sc, white_bkgd, t, co, sc, lane);
   __syncwarp();
 
   // pdf over weights[1:-1] + 1e-5, cdf = [0, cumsum(pdf)]  -> nb = Sc-1 entries; lane L owns entries
@@ -387,7 +418,9 @@ __global__ void pixel_subset_kernel(uint64_t seed, int V, int R, uint32_t n, int
 }
 
 // score[v] = sum_rays beta2 / R   (nerf.py:307-309); fp64 tree, deterministic.
-__global__ void view_reduce_kernel(const float* __restrict__ beta2, int R, float* __restrict__ scores) {
+// A score that is not finite (16-bit activations overflowed somewhere upstream) raises *nonfinite.
+__global__ void view_reduce_kernel(const float* __restrict__ beta2, int R, float* __restrict__ scores,
+                                   int* __restrict__ nonfinite) {
   __shared__ double sh[256];
   const int v = blockIdx.x;
   double a = 0.0;
@@ -398,7 +431,11 @@ __global__ void view_reduce_kernel(const float* __restrict__ beta2, int R, float
     if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
     __syncthreads();
   }
-  if (threadIdx.x == 0) scores[v] = (float)(sh[0] / (double)R);
+  if (threadIdx.x == 0) {
+    const float sc = (float)(sh[0] / (double)R);
+    scores[v] = sc;
+    if (nonfinite && !isfinite(sc)) atomicAdd(nonfinite, 1);
+  }
 }
 
 // plannerServer_Object/core/vpp.py:199-220 + interface.py:115-116, single CTA.
@@ -487,12 +524,24 @@ static bool ray_kernel_smem(K kern, size_t bytes) {
 
 int launch_coarse_resample(const float* raw, const float* z, const float* rays_d, const float* u_vals, int n,
                            int Sc, int Ni, int white_bkgd, CompositeOut co, float* z_fine, float* cdf_dump,
-                           int32_t* inds_dump, float* zs_dump, cudaStream_t st) {
+                           int32_t* inds_dump, float* zs_dump, cudaStream_t st, bool sigma_only) {
   if (n <= 0) return 0;
   const size_t smem = (size_t)kRayWarps * resample_scratch_floats(Sc, Ni) * sizeof(float);
-  if (!ray_kernel_smem(coarse_resample_kernel, smem)) return -1;
-  coarse_resample_kernel<<<(n + kRayWarps - 1) / kRayWarps, 32 * kRayWarps, smem, st>>>(
-      raw, z, rays_d, u_vals, n, Sc, Ni, white_bkgd, co, z_fine, cdf_dump, inds_dump, zs_dump);
+  if (sigma_only) {
+    if (!ray_kernel_smem(coarse_resample_kernel<true>, smem)) return -1;
+    coarse_resample_kernel<true><<<(n + kRayWarps - 1) / kRayWarps, 32 * kRayWarps, smem, st>>>(
+        raw, z, rays_d, u_vals, n, Sc, Ni, white_bkgd, co, z_fine, cdf_dump, inds_dump, zs_dump);
+  } else {
+    if (!ray_kernel_smem(coarse_resample_kernel<false>, smem)) return -1;
+    coarse_resample_kernel<false><<<(n + kRayWarps - 1) / kRayWarps, 32 * kRayWarps, smem, st>>>(
+        raw, z, rays_d, u_vals, n, Sc, Ni, white_bkgd, co, z_fine, cdf_dump, inds_dump, zs_dump);
+  }
+  return 1;
+}
+
+int launch_beta2(const float* beta, int n, int S, float* beta2, cudaStream_t st) {
+  if (n <= 0) return 0;
+  beta2_kernel<<<(n + 127) / 128, 128, 0, st>>>(beta, n, S, beta2);
   return 1;
 }
 
@@ -514,9 +563,9 @@ int launch_pixel_subset(uint64_t seed, int V, int R, int n_pixels, int32_t* out,
   return 1;
 }
 
-int launch_view_reduce(const float* beta2, int V, int R, float* scores, cudaStream_t st) {
+int launch_view_reduce(const float* beta2, int V, int R, float* scores, int* nonfinite, cudaStream_t st) {
   if (V <= 0) return 0;
-  view_reduce_kernel<<<V, 256, 0, st>>>(beta2, R, scores);
+  view_reduce_kernel<<<V, 256, 0, st>>>(beta2, R, scores, nonfinite);
   return 1;
 }
 

@@ -22,13 +22,16 @@ int launch_coarse_z(const float* t_vals, int n, int S, float near_plane, float f
 // raw2outputs on the coarse pass + sample_pdf + sort (run_nerf.py:473-484)
 int launch_coarse_resample(const float* raw, const float* z, const float* rays_d, const float* u_vals, int n,
                            int Sc, int Ni, int white_bkgd, CompositeOut co, float* z_fine, float* cdf_dump,
-                           int32_t* inds_dump, float* zs_dump, cudaStream_t st);
+                           int32_t* inds_dump, float* zs_dump, cudaStream_t st, bool sigma_only = false);
+// score-only final pass: per-ray sum of beta^2 from beta rows [n,S] (bit-identical to launch_composite's beta2)
+int launch_beta2(const float* beta, int n, int S, float* beta2, cudaStream_t st);
 // raw2outputs on the final pass, fused with the per-ray sum of beta^2
 int launch_composite(const float* raw, const float* z, const float* rays_d, int n, int S, int white_bkgd,
                      CompositeOut co, cudaStream_t st);
 // R distinct pseudo-random pixel ids in [0, n_pixels) per view (keyed Feistel permutation), out [V,R]
 int launch_pixel_subset(uint64_t seed, int V, int R, int n_pixels, int32_t* out, cudaStream_t st);
-int launch_view_reduce(const float* beta2, int V, int R, float* scores, cudaStream_t st);
+// nonfinite (optional, device int): incremented for every view whose score is inf / NaN
+int launch_view_reduce(const float* beta2, int V, int R, float* scores, int* nonfinite, cudaStream_t st);
 int launch_select_nbv(const float* scores, const float* weight, int V, int dirs, float* norm_scores,
                       int32_t* best_dir, int32_t* winner, cudaStream_t st);
 

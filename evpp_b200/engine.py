@@ -44,11 +44,13 @@ class Engine:
         self.n_samples, self.n_importance = n_samples, n_importance
         self.S_f = n_samples + n_importance
         self._h = C.c_void_p()
-        check(self.lib.evpp_create(self.device.index, C.byref(self.cfg), C.byref(self._h)))
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_create(self.device.index, C.byref(self.cfg), C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            self.lib.evpp_destroy(self._h)
+            with torch.cuda.device(self.device):
+                self.lib.evpp_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -75,8 +77,9 @@ class Engine:
             off += t.numel()
         packed = torch.cat(flat).contiguous()
         offs = np.asarray(offsets, dtype=np.int64)
-        check(self.lib.evpp_load_nerf_weights(self._h, which, C.c_void_p(packed.data_ptr()),
-                                              offs.ctypes.data_as(C.c_void_p), len(offsets)))
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_load_nerf_weights(self._h, which, C.c_void_p(packed.data_ptr()),
+                                                  offs.ctypes.data_as(C.c_void_p), len(offsets)))
 
     # ---- scoring (Controller.get_uncertainty, nerf.py:266-309) -------------------------------------
     def score_views(self, c2w, H, W, fx, fy, cx, cy, pix_idx=None):
@@ -108,14 +111,26 @@ class Engine:
                                                  _ptr(pix_idx_host), R, _ptr(out), _stream_ptr(self.device)))
         return out
 
-    def rescore_views_fp32(self, c2w_host, view_ids, H, W, fx, fy, cx, cy, pix_idx_host=None):
+    def rescore_views(self, c2w_host, view_ids, H, W, fx, fy, cx, cy, pix_idx_host=None, precision="fp16x3"):
+        """Scores of the views ``view_ids`` (indices into the HOST pose array) at ``precision`` regardless of the
+        engine's bulk precision.  "fp16x3" = the tensor-core exact path (split-fp16 operands, three MMAs per
+        product, fp32-class results), "fp32" = the FFMA kernel (numerical anchor).  Returns a host tensor [K]."""
         ids = torch.as_tensor(np.asarray(view_ids), dtype=torch.int32).contiguous()
         R = 0 if pix_idx_host is None else pix_idx_host.shape[1]
         out = torch.empty(len(ids), dtype=torch.float32)
+        prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
         with torch.cuda.device(self.device):
-            check(self.lib.evpp_rescore_views_fp32(self._h, _ptr(c2w_host), _ptr(ids), len(ids), H, W, fx, fy, cx,
-                                                   cy, _ptr(pix_idx_host), R, _ptr(out), _stream_ptr(self.device)))
+            check(self.lib.evpp_rescore_views(self._h, _ptr(c2w_host), _ptr(ids), len(ids), H, W, fx, fy, cx, cy,
+                                              _ptr(pix_idx_host), R, prec, _ptr(out), _stream_ptr(self.device)))
         return out
+
+    def rescore_views_fp32(self, c2w_host, view_ids, H, W, fx, fy, cx, cy, pix_idx_host=None):
+        return self.rescore_views(c2w_host, view_ids, H, W, fx, fy, cx, cy, pix_idx_host, precision="fp32")
+
+    def set_score_mode(self, full_outputs):
+        """False (default): scoring calls skip the network outputs the score does not depend on (bit-identical
+        scores); True: they evaluate the full network like render()."""
+        check(self.lib.evpp_set_score_mode(self._h, int(bool(full_outputs))))
 
     # ---- rendering (render / render_rays, run_nerf.py:131-196, 391-509) -----------------------------
     def render_rays(self, rays_o, rays_d, near, far, precision=None, want=("rgb", "disp", "acc", "depth", "unc"),
@@ -261,5 +276,13 @@ class Engine:
 
     def mlp_time(self):
         ms, n, ev = C.c_double(0), C.c_int64(0), C.c_int64(0)
-        check(self.lib.evpp_get_mlp_time_ms(self._h, C.byref(ms), C.byref(n), C.byref(ev)))
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_get_mlp_time_ms(self._h, C.byref(ms), C.byref(n), C.byref(ev)))
         return ms.value, n.value, ev.value
+
+    def mlp_profile(self):
+        """(total ms, launches, evaluations, executed FLOPs) of the MLP launches recorded since set_profiling(True)."""
+        ms, n, ev, fl = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_double(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_get_mlp_profile(self._h, C.byref(ms), C.byref(n), C.byref(ev), C.byref(fl)))
+        return ms.value, n.value, ev.value, fl.value

@@ -27,20 +27,24 @@
 extern "C" {
 #endif
 
-#define EVPP_ABI_VERSION 1
+#define EVPP_ABI_VERSION 2
 
 typedef enum evpp_status {
   EVPP_OK = 0,
   EVPP_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
   EVPP_ERR_CUDA = -2,      /* a CUDA runtime call or kernel failed */
   EVPP_ERR_STATE = -3,     /* e.g. weights not loaded */
-  EVPP_ERR_NO_DEVICE = -4  /* no usable sm_100 device: there is NO CPU fallback */
+  EVPP_ERR_NO_DEVICE = -4, /* no usable sm_100 device: there is NO CPU fallback */
+  EVPP_ERR_NONFINITE = -5  /* a score came out inf / NaN (16-bit activations overflowed): retry in bf16 */
 } evpp_status;
 
 typedef enum evpp_precision {
   EVPP_PREC_FP32 = 0,  /* fp32 FFMA MLP (exact mode; used for the top-K re-score)            */
   EVPP_PREC_FP16 = 1,  /* tcgen05.mma kind::f16, fp16 operands, fp32 accumulation in TMEM   */
-  EVPP_PREC_BF16 = 2   /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulation in TMEM   */
+  EVPP_PREC_BF16 = 2,  /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulation in TMEM   */
+  EVPP_PREC_FP16X2 = 3, /* tcgen05, weights as an fp16 (hi, lo) pair = 22 bits, activations fp16: 2 MMAs per product */
+  EVPP_PREC_FP16X3 = 4  /* tcgen05, weights AND activations as (hi, lo) pairs, 3 MMAs per product, fp32 accumulate:
+                           fp32-class results on the tensor cores (the exact path of the NBV re-score)            */
 } evpp_precision;
 
 typedef enum evpp_net { EVPP_NET_COARSE = 0, EVPP_NET_FINE = 1 } evpp_net;
@@ -100,6 +104,19 @@ int evpp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int H, i
 int evpp_rescore_views_fp32(evpp_handle* h, const float* c2w_host, const int32_t* view_ids, int K,
                             int H, int W, float fx, float fy, float cx, float cy,
                             const int32_t* pix_idx_host, int R, float* scores_host, void* stream);
+
+/* The same re-score at any precision.  EVPP_PREC_FP16X3 is the tensor-core exact path: fp16 (hi, lo) split of
+ * weights and activations, three tcgen05 MMAs per product, fp32 accumulation -- fp32-class scores (<= 2e-5
+ * relative to the reference) at about a third of the bulk pass's rate instead of the FFMA kernel's 1/26. */
+int evpp_rescore_views(evpp_handle* h, const float* c2w_host, const int32_t* view_ids, int K, int H, int W,
+                       float fx, float fy, float cx, float cy, const int32_t* pix_idx_host, int R,
+                       int precision, float* scores_host, void* stream);
+
+/* Scoring calls (evpp_score_views*, evpp_rescore_views*) compute only what Controller.get_uncertainty's result
+ * depends on (nerf.py:307-309 reads raw[..., 4] of the final pass): the coarse network stops at its sigma, the fine
+ * network skips its alpha / rgb heads.  The scores are bit-identical to the full evaluation;
+ * full_outputs != 0 switches the elimination off (parity tests, like-for-like timing).  Default 0. */
+int evpp_set_score_mode(evpp_handle* h, int full_outputs);
 
 /* Replaces render(rays=...) / batchify_rays / render_rays (run_nerf.py:116-196, 391-509) with
  * use_viewdirs=True, ndc=False, perturb=0, raw_noise_std=0.  All device pointers; any output
@@ -293,6 +310,9 @@ int evpp_get_counters(evpp_handle* h, int64_t* kernel_launches, int64_t* mlp_eva
  * stream) since the last reset; enable with evpp_set_profiling(h, 1). Synchronises. */
 int evpp_set_profiling(evpp_handle* h, int enabled);
 int evpp_get_mlp_time_ms(evpp_handle* h, double* total_ms, int64_t* launches, int64_t* evals);
+/* Same, plus the FLOPs those launches really executed (a score-only coarse evaluation is 982,528 FLOP, a
+ * score-only fine evaluation 1,185,792, a full evaluation 1,187,072: SURVEY.md section 8). */
+int evpp_get_mlp_profile(evpp_handle* h, double* total_ms, int64_t* launches, int64_t* evals, double* flops);
 
 #ifdef __cplusplus
 }

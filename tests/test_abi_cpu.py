@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(build_lib):
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.evpp_abi_version() == 1
+    assert lib.evpp_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -80,6 +80,70 @@ def test_mlp_tensor_core_vs_oracle(engine_factory, weights, prec):
 
 
 # ---------------------------------------------------------------- full render, per stage --------
+@pytest.mark.parametrize("prec,tol", [("fp16x3", 2e-6), ("fp16x2", 2e-3)])
+def test_mlp_split_precision_vs_oracle(engine_factory, weights, prec, tol):
+    """The tensor-core exact path: fp16 (hi, lo) split operands, 3 MMAs per product (fp16x3), fp32 accumulation.
+    Raw outputs must sit at the fp32 rounding level of the oracle (the FFMA kernel's tolerance is 3e-5);
+    fp16x2 (weights split only) keeps fp16 activation noise."""
+    torch.manual_seed(4)
+    M = 128 * 37 + 5   # ragged tail
+    pts = (torch.rand(M, 3) - 0.5) * 10
+    dirs = torch.nn.functional.normalize(torch.randn(M, 3), dim=-1)
+    x = torch.cat([O.embed(pts, 10), O.embed(dirs, 4)], -1)
+    for variant, net in (("plain", 0), ("spread", 1)):
+        with torch.no_grad():
+            ref = O.nerf_forward(weights[variant][net], x).numpy()
+        y = engine_factory(variant).mlp_forward(net, pts, dirs, precision=prec).cpu().numpy()
+        err = np.abs(y - ref).max(0) / (np.abs(ref).max(0) + 1e-6)
+        print(prec, variant, "max err / max |ref| per channel", err)
+        assert (err < tol).all(), err
+        assert np.isfinite(y).all()
+    g = load_golden("mlp_kat.npz")
+    if prec == "fp16x3":
+        y = engine_factory().mlp_forward(0, torch.from_numpy(g["pts"]), torch.from_numpy(g["dirs"]), precision=prec).cpu().numpy()
+        np.testing.assert_allclose(y, g["out"], rtol=3e-5, atol=3e-6)       # same bar as the fp32 FFMA kernel
+
+
+def test_mlp_split_precision_large_coordinates(engine_factory, weights):
+    """far=80 live bounds on the exact tensor-core path: one accurate sincosf per octave, arguments up to ~4e4."""
+    torch.manual_seed(3)
+    pts = (torch.rand(1000, 3) - 0.5) * 160
+    dirs = torch.nn.functional.normalize(torch.randn(1000, 3), dim=-1)
+    x = torch.cat([O.embed(pts, 10), O.embed(dirs, 4)], -1)
+    with torch.no_grad():
+        ref = O.nerf_forward(weights["spread"][1], x).numpy()
+    y = engine_factory("spread").mlp_forward(1, pts, dirs, precision="fp16x3").cpu().numpy()
+    np.testing.assert_allclose(y, ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16", "fp16x2", "fp16x3"])
+def test_score_only_passes_are_bit_identical(engine_factory, prec):
+    """Dead-output elimination (evpp_set_score_mode): scoring calls stop the coarse network at its sigma and skip
+    the fine network's alpha / rgb heads; every score must equal the full evaluation's bit for bit
+    (Controller.get_uncertainty reads raw[..., 4] of the fine pass only, nerf.py:307-309)."""
+    eng = engine_factory("spread", prec, max_chunk_rays=1000)      # several chunks, ragged last one
+    H, W = 30, 40
+    K = O.make_K(H, W, 30.0)
+    poses = torch.Tensor(np.asarray(O.views_to_poses(O.hemisphere_views(3, seed=11))))[:, :3, :4].contiguous().cuda()
+    try:
+        eng.set_score_mode(True)
+        full = eng.score_views(poses, H, W, *_intr(K)).cpu()
+        eng.set_score_mode(False)
+        lean = eng.score_views(poses, H, W, *_intr(K)).cpu()
+    finally:
+        eng.set_score_mode(False)
+    assert torch.isfinite(full).all()
+    assert torch.equal(full, lean), (full, lean)
+    # coarse-only engines (N_importance = 0) score from the coarse network's beta
+    e0 = engine_factory("spread", prec, n_importance=0)
+    try:
+        e0.set_score_mode(True)
+        full0 = e0.score_views(poses, H, W, *_intr(K)).cpu()
+    finally:
+        e0.set_score_mode(False)
+    assert torch.equal(full0, e0.score_views(poses, H, W, *_intr(K)).cpu())
+
+
 @pytest.mark.parametrize("variant", ["plain", "spread"])
 def test_render_fp32_matches_reference_golden(engine_factory, variant):
     g = load_golden(f"render_small_{variant}.npz")
@@ -182,7 +246,7 @@ def test_sampling_stages_on_reference_tensors(engine_factory, variant):
 
 
 @pytest.mark.parametrize("variant", ["plain", "spread"])
-@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("fp16", 1e-3), ("bf16", 1e-3)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("fp16x3", 2e-5), ("fp16x2", 2e-4), ("fp16", 1e-3), ("bf16", 1e-3)])
 def test_scores_match_reference_golden(engine_factory, variant, prec, tol):
     g = load_golden(f"render_small_{variant}.npz")
     eng = engine_factory(variant, precision=prec)
@@ -194,7 +258,7 @@ def test_scores_match_reference_golden(engine_factory, variant, prec, tol):
 
 
 @pytest.mark.parametrize("variant", ["plain", "spread"])
-@pytest.mark.parametrize("prec,tol", [("fp32", 5e-5), ("fp16", 1e-3), ("bf16", 1e-3)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 5e-5), ("fp16x3", 5e-5), ("fp16", 1e-3), ("bf16", 1e-3)])
 def test_scores_far80_pixel_subset(engine_factory, variant, prec, tol):
     """Live bounds near 0.5 / far 80 (nerf.py:100-101) and an explicit pixel subset (nerf.py:284-290),
     through the HOST-buffer entry point."""

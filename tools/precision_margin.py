@@ -15,7 +15,7 @@ torch.manual_seed(0)
 c0, f0 = O.init_nerf_state_dict(), O.init_nerf_state_dict()
 W8 = {"plain": (c0, f0), "spread": (O.spread_variant(c0), O.spread_variant(f0))}
 G = os.path.join(ROOT, "tests", "golden")
-for prec in ("fp16", "bf16"):
+for prec in ("fp32", "fp16x3", "fp16x2", "fp16", "bf16"):
     for name, variant, far in (("render_small_plain", "plain", 6.0), ("render_small_spread", "spread", 6.0),
                                ("score_far80_plain", "plain", 80.0), ("score_far80_spread", "spread", 80.0),
                                ("config1_spread", "spread", 6.0)):
