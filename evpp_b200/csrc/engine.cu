@@ -551,8 +551,8 @@ int evpp_set_score_mode(evpp_handle* h, int full_outputs) {
   return 0;
 }
 
-int evpp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, int64_t N, float near_plane,
-                     float far_plane, int precision, const evpp_render_out* out, void* stream) {
+int evpp_render_rays_ex(evpp_handle* h, const float* rays_o, const float* rays_d, const float* viewdirs, int64_t N,
+                        float near_plane, float far_plane, int precision, const evpp_render_out* out, void* stream) {
   if (!h || !out) return fail(EVPP_ERR_INVALID, "null argument");
   if (N < 0) return fail(EVPP_ERR_INVALID, "negative N");
   if (N == 0) return 0;
@@ -568,12 +568,23 @@ int evpp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, i
     const int n = (int)std::min<int64_t>(cap, N - g0);
     CUDA_TRY(cudaMemcpyAsync(h->rays_o.p, rays_o + g0 * 3, (size_t)n * 12, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->rays_d.p, rays_d + g0 * 3, (size_t)n * 12, cudaMemcpyDeviceToDevice, st));
-    // viewdirs = rays_d / ||rays_d|| (run_nerf.py:165-171): reuse the ray kernel's normalisation
-    h->launches += launch_normalize_dirs(h->rays_d.as<float>(), n, h->viewdirs.as<float>(), st);
+    if (viewdirs) {
+      // caller-provided view directions, used as they are (Controller.get_rays_depth hands batchify_rays the raw,
+      // un-normalised directions: nerf.py:364-366)
+      CUDA_TRY(cudaMemcpyAsync(h->viewdirs.p, viewdirs + g0 * 3, (size_t)n * 12, cudaMemcpyDeviceToDevice, st));
+    } else {
+      // viewdirs = rays_d / ||rays_d|| (run_nerf.py:165-171): reuse the ray kernel's normalisation
+      h->launches += launch_normalize_dirs(h->rays_d.as<float>(), n, h->viewdirs.as<float>(), st);
+    }
     rc = render_chunk(h, n, near_plane, far_plane, precision, out, g0, nullptr, st);
     if (rc) return rc;
   }
   return 0;
+}
+
+int evpp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, int64_t N, float near_plane,
+                     float far_plane, int precision, const evpp_render_out* out, void* stream) {
+  return evpp_render_rays_ex(h, rays_o, rays_d, nullptr, N, near_plane, far_plane, precision, out, stream);
 }
 
 int evpp_get_rays(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx, float cy,

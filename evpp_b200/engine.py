@@ -44,8 +44,8 @@ class Engine:
         self.n_samples, self.n_importance = n_samples, n_importance
         self.S_f = n_samples + n_importance
         self._h = C.c_void_p()
-        with torch.cuda.device(self.device):
-            check(self.lib.evpp_create(self.device.index, C.byref(self.cfg), C.byref(self._h)))
+        # (no torch.cuda.device here: the C side validates the ordinal and restores the caller's current device)
+        check(self.lib.evpp_create(self.device.index, C.byref(self.cfg), C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -81,6 +81,20 @@ class Engine:
             check(self.lib.evpp_load_nerf_weights(self._h, which, C.c_void_p(packed.data_ptr()),
                                                   offs.ctypes.data_as(C.c_void_p), len(offsets)))
 
+    def load_checkpoint(self, ckpt):
+        """Both networks from a checkpoint of the reference: the ``.tar`` written by ``Controller.save_model``
+        (nerfServer/core/nerf.py:612-621; reloaded by create_nerf, run_nerf.py:292-312) or the dict inside it, keys
+        ``network_fn_state_dict`` / ``network_fine_state_dict`` (``global_step`` and ``optimizer_state_dict`` are
+        ignored).  Returns ``global_step``."""
+        if isinstance(ckpt, (str, bytes)):
+            ckpt = torch.load(ckpt, map_location="cpu", weights_only=True)
+        for key in ("network_fn_state_dict", "network_fine_state_dict"):
+            if key not in ckpt or ckpt[key] is None:
+                raise KeyError(f"checkpoint lacks {key} (expected the dict of Controller.save_model, nerf.py:612-621)")
+        self.load_weights(0, ckpt["network_fn_state_dict"])
+        self.load_weights(1, ckpt["network_fine_state_dict"])
+        return ckpt.get("global_step")
+
     # ---- scoring (Controller.get_uncertainty, nerf.py:266-309) -------------------------------------
     def score_views(self, c2w, H, W, fx, fy, cx, cy, pix_idx=None):
         """c2w: cuda float32 [V,3,4]; pix_idx: cuda int32 [V,R] or None.  Returns cuda float32 [V]."""
@@ -96,8 +110,10 @@ class Engine:
                                             _ptr(scores), _stream_ptr(self.device)))
         return scores
 
-    def score_views_host(self, c2w_host, H, W, fx, fy, cx, cy, pix_idx_host=None, out=None):
-        """HOST in / HOST out (pinned torch CPU tensors recommended).  Synchronises."""
+    def score_views_host(self, c2w_host, H, W, fx, fy, cx, cy, pix_idx_host=None, out=None, precision=None):
+        """HOST in / HOST out (pinned torch CPU tensors recommended).  Synchronises.  Raises EvppError(-5,
+        EVPP_ERR_NONFINITE) when a score is inf / NaN (16-bit activations overflowed); ``out`` is filled anyway.
+        precision: None = the engine's bulk precision, else any precision name / code for this call."""
         assert c2w_host.device.type == "cpu" and c2w_host.dtype == torch.float32 and c2w_host.is_contiguous()
         V = c2w_host.shape[0]
         R = 0
@@ -107,8 +123,14 @@ class Engine:
         if out is None:
             out = torch.empty(V, dtype=torch.float32).pin_memory()
         with torch.cuda.device(self.device):
-            check(self.lib.evpp_score_views_host(self._h, _ptr(c2w_host), V, H, W, fx, fy, cx, cy,
-                                                 _ptr(pix_idx_host), R, _ptr(out), _stream_ptr(self.device)))
+            if precision is None:
+                check(self.lib.evpp_score_views_host(self._h, _ptr(c2w_host), V, H, W, fx, fy, cx, cy,
+                                                     _ptr(pix_idx_host), R, _ptr(out), _stream_ptr(self.device)))
+            else:
+                prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+                ids = torch.arange(V, dtype=torch.int32)
+                check(self.lib.evpp_rescore_views(self._h, _ptr(c2w_host), _ptr(ids), V, H, W, fx, fy, cx, cy,
+                                                  _ptr(pix_idx_host), R, prec, _ptr(out), _stream_ptr(self.device)))
         return out
 
     def rescore_views(self, c2w_host, view_ids, H, W, fx, fy, cx, cy, pix_idx_host=None, precision="fp16x3"):
@@ -134,9 +156,13 @@ class Engine:
 
     # ---- rendering (render / render_rays, run_nerf.py:131-196, 391-509) -----------------------------
     def render_rays(self, rays_o, rays_d, near, far, precision=None, want=("rgb", "disp", "acc", "depth", "unc"),
-                    capture_stages=False):
+                    capture_stages=False, viewdirs=None):
+        """viewdirs: optional [N,3] view directions used as given (None = rays_d / ||rays_d||, run_nerf.py:170)."""
         rays_o = rays_o.to(self.device, torch.float32).reshape(-1, 3).contiguous()
         rays_d = rays_d.to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        if viewdirs is not None:
+            viewdirs = viewdirs.to(self.device, torch.float32).reshape(-1, 3).contiguous()
+            assert viewdirs.shape == rays_d.shape
         N = rays_o.shape[0]
         S = self.S_f if self.n_importance > 0 else self.n_samples
         shapes = {"rgb": (N, 3), "disp": (N,), "acc": (N,), "depth": (N,), "unc": (N, S), "raw": (N, S, 5),
@@ -147,8 +173,8 @@ class Engine:
         prec = self.precision if precision is None else (PRECISIONS[precision] if isinstance(precision, str) else precision)
         with torch.cuda.device(self.device):
             check(self.lib.evpp_set_stage_capture(self._h, int(capture_stages)))
-            check(self.lib.evpp_render_rays(self._h, _ptr(rays_o), _ptr(rays_d), N, float(near), float(far), prec,
-                                            C.byref(ro), _stream_ptr(self.device)))
+            check(self.lib.evpp_render_rays_ex(self._h, _ptr(rays_o), _ptr(rays_d), _ptr(viewdirs), N, float(near),
+                                               float(far), prec, C.byref(ro), _stream_ptr(self.device)))
         return outs
 
     def stage(self, name):

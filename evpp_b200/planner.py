@@ -4,6 +4,7 @@ identical to the fp32 reference when the bulk pass runs on fp16/bf16 tensor core
 import numpy as np
 import torch
 
+from ._lib import PRECISIONS
 from .run_nerf import _intrinsics, get_pose
 
 
@@ -36,27 +37,54 @@ def select_nbv(views, uncers, dirs_per_location=3, depth_clip=None):
     return data, data[win], int(idx[win])
 
 
-def score_and_select(engine, views, H, W, K, dirs_per_location=1, depth_clip=None, pix_idx=None, topk=16):
-    """Fast pass on the engine's configured precision for all views, then re-score the ``topk``
-    best (after weighting) with the fp32 MLP and select among the corrected scores.
-    Returns dict(scores, data, nbv, winner, margin)."""
+def contenders(scores, weight=None, margin=2e-3):
+    """Sorted indices (int32) of the views whose weighted fast score is within ``margin`` (relative) of the best.
+    With a bulk pass accurate to tol = margin / 2 per view (north_star: 1e-3), no view outside this band can be the
+    true arg-max: true_v <= fast_v (1 + tol) < best_fast (1 - 2 tol)(1 + tol) <= true_leader (1 + tol)^2 (1 - 2 tol)
+    < true_leader."""
+    s = np.asarray(scores, dtype=np.float64)
+    if weight is not None:
+        s = s * np.asarray(weight, dtype=np.float64)
+    best = np.max(s)
+    return np.flatnonzero(s >= best - margin * abs(best)).astype(np.int32)
+
+
+def score_and_select(engine, views, H, W, K, dirs_per_location=1, depth_clip=None, pix_idx=None, topk=0, margin=2e-3,
+                     exact="fp16x3"):
+    """Fast pass at the engine's bulk precision for all views, then the views that could still be the arg-max are
+    scored again on the exact path (``exact``: "fp16x3" = split-fp16 tensor-core passes, fp32-class; "fp32" = the
+    FFMA kernel) and the selection runs on the corrected scores, so that the next-best view is the fp32
+    reference's (plannerServer_*/core/interface.py:115-116).
+
+    Candidates = every view whose weighted fast score is within ``margin`` of the best (``contenders``) plus the
+    ``topk`` best.  After the re-score the guard loop adds any view left outside whose weighted fast score, inflated
+    by the bulk pass's tolerance margin / 2, still reaches the best exact score, and repeats until there is none:
+    a non-candidate can therefore never win on an inflated 16-bit score.
+    Returns dict(scores, data, nbv, winner, margin, rescored)."""
     views = np.asarray(views, dtype=np.float64)
     poses = torch.Tensor(np.asarray([get_pose(list(v[0:3]), v[3], v[4]) for v in views]))[:, :3, :4].contiguous()
     fx, fy, cx, cy = _intrinsics(K)
     pix_t = None if pix_idx is None else torch.as_tensor(np.ascontiguousarray(pix_idx, dtype=np.int32))
     scores = engine.score_views_host(poses, H, W, fx, fy, cx, cy, pix_t).clone().numpy().astype(np.float64)
     w = np.ones_like(scores) if depth_clip is None else np.asarray(depth_clip, dtype=np.float64)
-    if topk and engine.precision != 0:
-        cand = np.argsort(scores * w, kind="stable")[::-1][:min(topk, len(scores))]
-        cand = np.sort(cand).astype(np.int32)
-        exact = engine.rescore_views_fp32(poses, cand, H, W, fx, fy, cx, cy, pix_t).numpy().astype(np.float64)
-        # guard: a view outside the candidate set must not beat the re-scored winner spuriously;
-        # its fast score carries <=1e-3 relative error, so demote ties inside that band
-        scores[cand] = exact
+    done = np.zeros(len(scores), dtype=bool)
+    exact_code = PRECISIONS[exact] if isinstance(exact, str) else int(exact)
+    if engine.precision not in (PRECISIONS["fp32"], exact_code) and len(scores) > 1:
+        fast = scores.copy()
+        cand = set(contenders(fast, w, margin).tolist())
+        if topk:
+            cand |= set(np.argsort(fast * w, kind="stable")[::-1][:min(topk, len(fast))].tolist())
+        tol = 0.5 * margin
+        while cand:
+            ids = np.sort(np.fromiter(cand, dtype=np.int32))
+            scores[ids] = engine.rescore_views(poses, ids, H, W, fx, fy, cx, cy, pix_t, precision=exact).numpy().astype(np.float64)
+            done[ids] = True
+            best = np.max((scores * w)[done])
+            cand = set(np.flatnonzero(~done & (fast * w * (1.0 + tol) >= best)).tolist())
     data, nbv, win = select_nbv(views, scores, dirs_per_location, depth_clip)
-    ws = np.sort(scores * w)
-    margin = float((ws[-1] - ws[-2]) / ws[-1]) if len(ws) > 1 else float("inf")
-    return {"scores": scores, "data": data, "nbv": nbv, "winner": win, "margin": margin}
+    ws = np.sort((scores * w)[done]) if done.sum() > 1 else np.sort(scores * w)
+    margin_out = float((ws[-1] - ws[-2]) / ws[-1]) if len(ws) > 1 else float("inf")
+    return {"scores": scores, "data": data, "nbv": nbv, "winner": win, "margin": margin_out, "rescored": int(done.sum())}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -175,7 +203,7 @@ def sample_direction(locations, tsdf, get_uncertainty, object_center, scene="obj
     """Drop-in for ``Viewpath_planner.sample_direction(locations)``: stage 1 scores the whole direction fan with the
     TSDF occupancy ray cast (``tsdf.get_uncertainty_tsdf``, evpp_b200.TSDF), keeps the 3 best directions per location,
     stage 2 scores those with the NeRF uncertainty (``get_uncertainty(locations, us, vs) -> (uncers, _, _)``, the
-    reference's interface2 signature; pass ``evpp_b200.views.get_uncertainty`` or an Engine-backed callable), the
+    reference's interface2 signature: ``evpp_b200.views.planner_client(controller)`` builds it from a Controller), the
     Object scene weights by the depth clip, the best direction per location is kept and the gains are normalised by
     their maximum.  Returns data [L, 6] = (x, y, z, u, v, gain) like the reference."""
     locations = np.asarray(locations, dtype=np.float64)

@@ -5,12 +5,16 @@ structure as nerfServer/core/run_nerf.py (render, :131-196) and run_nerf_helpers
 Supported configuration = what the server runs at inference (nerf.py:727-752): ndc=False,
 use_viewdirs=True, perturb=0, raw_noise_std=0.  Anything else raises (no silent fallback).
 """
+import hashlib
+
 import numpy as np
 import torch
 
 from .engine import Engine
 
-_ENGINE_CACHE = {}
+_ENGINE_CACHE = {}             # insertion-ordered: least recently used first
+_FINGERPRINT_MEMO = {}
+_ENGINE_CACHE_MAX = 2          # e.g. one snapshot per scoring device of the reference's uncertainty_kargs list
 
 
 def get_pose(location, u, v):
@@ -55,6 +59,34 @@ def make_render_kwargs(network_fn, network_fine, N_samples=64, N_importance=128,
             "raw_noise_std": 0., "device": eng.device, "ndc": False, "lindisp": lindisp, "engine": eng}
 
 
+def _weights_fingerprint(net):
+    """Content hash of a network's parameters (module or state_dict): the cache must notice new weights behind a
+    recycled id() and must not pin one engine per deep copy of the same weights (copy_model, nerf.py:718-757,
+    deep-copies the training networks at every hand-off)."""
+    if net is None:
+        return None
+    sd = net.state_dict() if hasattr(net, "state_dict") else net
+    # unchanged tensors (same storage, same in-place version counters) -> the fingerprint computed last time
+    quick = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+    memo = _FINGERPRINT_MEMO.get(id(net))
+    if memo is not None and memo[0] == quick:
+        return memo[1]
+    fp = _hash_state_dict(sd)
+    if len(_FINGERPRINT_MEMO) > 16:
+        _FINGERPRINT_MEMO.clear()
+    _FINGERPRINT_MEMO[id(net)] = (quick, fp)
+    return fp
+
+
+def _hash_state_dict(sd):
+    h = hashlib.blake2b(digest_size=16)
+    for k in sorted(sd.keys()):
+        t = sd[k].detach().to("cpu", torch.float32).contiguous()
+        h.update(k.encode())
+        h.update(t.numpy().tobytes())
+    return h.hexdigest()
+
+
 def _engine_from_kwargs(kwargs, near, far):
     eng = kwargs.get("engine")
     if eng is not None:
@@ -64,13 +96,21 @@ def _engine_from_kwargs(kwargs, near, far):
         raise ValueError("render(): kwargs need 'engine' (make_render_kwargs) or 'network_fn'")
     dev = kwargs.get("device", 0)
     dev = dev.index if isinstance(dev, torch.device) else dev
-    key = (id(net), id(fine), kwargs.get("N_samples", 64), kwargs.get("N_importance", 128),
+    key = (_weights_fingerprint(net), _weights_fingerprint(fine), kwargs.get("N_samples", 64), kwargs.get("N_importance", 128),
            bool(kwargs.get("white_bkgd", False)), bool(kwargs.get("lindisp", False)), dev)
-    if key not in _ENGINE_CACHE:
+    eng = _ENGINE_CACHE.get(key)
+    if eng is None:
+        # new weights replace the engine that held this configuration's previous snapshot: at most
+        # _ENGINE_CACHE_MAX engines (0.7 GB of workspace each) stay alive, least recently used first out
+        while len(_ENGINE_CACHE) >= _ENGINE_CACHE_MAX:
+            _ENGINE_CACHE.pop(next(iter(_ENGINE_CACHE))).close()
         kw = make_render_kwargs(net, fine, N_samples=key[2], N_importance=key[3], white_bkgd=key[4], lindisp=key[5],
                                 device=dev or 0, near=near, far=far)
-        _ENGINE_CACHE[key] = kw["engine"]
-    return _ENGINE_CACHE[key]
+        eng = kw["engine"]
+    else:
+        del _ENGINE_CACHE[key]          # re-insert: most recently used last
+    _ENGINE_CACHE[key] = eng
+    return eng
 
 
 def get_rays(H, W, K, c2w, dev=None, engine=None):

@@ -36,3 +36,15 @@ def get_ray_depth(controller, body, method="POST"):
     data = json.loads(body) if isinstance(body, (bytes, str)) else body
     depths = controller.get_rays_depth(data["locations"], data["directions"])
     return {"depths": depths.cpu().numpy().tolist()}
+
+
+def planner_client(controller):
+    """The planner side of the wire (plannerServer_*/core/interface2.py:46-60) without the HTTP hop:
+    ``get_uncertainty(locations, us, vs) -> (uncers, [], [])`` built on ``controller``, encoding and decoding the
+    same JSON bodies the two services exchange.  This is the callable ``planner.sample_direction`` expects."""
+    def client(locations, us, vs):
+        body = json.dumps({"locations": [list(map(float, x)) for x in locations], "us": [float(u) for u in us],
+                           "vs": [float(v) for v in vs]})
+        reply = json.loads(json.dumps(get_uncertainty(controller, body)))
+        return reply["uncers"], [], []
+    return client

@@ -133,6 +133,13 @@ int evpp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_d, i
                      float near_plane, float far_plane, int precision,
                      const evpp_render_out* out, void* stream);
 
+/* Same with explicit view directions (device [N,3], used as given; NULL = rays_d / ||rays_d|| like render()).
+ * Replaces batchify_rays on a caller-built [N,11] ray batch: Controller.get_rays_depth (nerf.py:353-392) appends
+ * the raw, un-normalised directions as viewdirs. */
+int evpp_render_rays_ex(evpp_handle* h, const float* rays_o, const float* rays_d, const float* viewdirs,
+                        int64_t N, float near_plane, float far_plane, int precision,
+                        const evpp_render_out* out, void* stream);
+
 /* get_rays (run_nerf_helpers.py:173-182) + viewdir normalisation (run_nerf.py:170).
  * device out: rays_o/rays_d/viewdirs [V*R,3] (any may be NULL). */
 int evpp_get_rays(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy,

@@ -147,6 +147,18 @@ def spread_variant(sd):
     return sd
 
 
+def sparse_variant(sd, k=2000.0, q=0.03):
+    """Random-init weights reshaped into a scene with empty space and solid blobs: sigma_raw' = k * (sigma_raw - q)
+    (random-init sigma_raw spans about +-0.04, so ~2 % of space is dense) and rgb logits x 30 (saturated colours).
+    Rays then miss everything (white background), stop early or stop late: all three masks of the depth /
+    surface queries (nerf.py:344-350, 386-391) get exercised."""
+    sd = {k_: v.clone() for k_, v in sd.items()}
+    sd["alpha_linear.weight"] = sd["alpha_linear.weight"] * k
+    sd["alpha_linear.bias"] = sd["alpha_linear.bias"] * k - k * q
+    sd["rgb_linear.weight"] = sd["rgb_linear.weight"] * 30
+    return sd
+
+
 def nerf_forward(sd, x, input_ch=63, input_ch_views=27, skips=SKIPS, D=NETDEPTH):
     """nerfServer/core/run_nerf_helpers.py:108-134 (use_viewdirs=True branch)."""
     input_pts, input_views = torch.split(x, [input_ch, input_ch_views], dim=-1)
@@ -350,6 +362,74 @@ def score_views(poses, H, W, K, near, far, sd_coarse, sd_fine, pix_idx=None, chu
         uncers = uncertainty.reshape((V, R * S_f))
         uncers = torch.sum(uncers, -1) / R
     return uncers
+
+
+# ----------------------------------------------------------------------------
+# f2: depth / surface queries through the same renderer
+# ----------------------------------------------------------------------------
+def sphere_dirs(step):
+    """Ray fan of Controller.get_surface_points (nerfServer/core/nerf.py:332-336)."""
+    rays_d = []
+    for u in np.arange(0, 2 * np.pi, step):
+        for v in np.arange(0, np.pi, step):
+            rays_d.append([np.cos(u), np.sin(u) * np.cos(v), np.sin(u) * np.sin(v)])
+    return torch.Tensor(rays_d)
+
+
+def get_surface_points(location, radius, step, H, W, K, near, far, sd_coarse, sd_fine, chunk=CHUNK,
+                       return_all=False):
+    """nerfServer/core/nerf.py:325-351: sphere of rays from ``location``; white pixels (mean(rgb)*255 > 250) get
+    depth 0; keep the points with near < depth < radius."""
+    rays_d = sphere_dirs(step)
+    location = torch.Tensor(location)
+    rays_o = location.expand([rays_d.shape[0], rays_d.shape[1]])
+    batch_rays = torch.stack([rays_o, rays_d], 0)
+    with torch.no_grad():
+        rgb, disp, acc, uncertainty, depth, extras = render(H, W, K, chunk=chunk, rays=batch_rays, near=near, far=far,
+                                                            sd_coarse=sd_coarse, sd_fine=sd_fine, retraw=True)
+        depth_raw = depth.clone()
+        rgbs = torch.mean(rgb, -1) * 255
+        depth[rgbs > 250] = 0
+        white = rgbs > 250
+        points = rays_o + rays_d * depth[..., None]
+        keep = (depth < radius) & (depth > near)
+        points = points[depth < radius]
+        depth = depth[depth < radius]
+        points = points[depth > near]
+    if return_all:
+        return points, {"depth_raw": depth_raw, "white": white, "keep": keep, "rgb": rgb}
+    return points
+
+
+def get_rays_depth(locations, dirs, near, far, sd_coarse, sd_fine, chunk=CHUNK, return_all=False):
+    """nerfServer/core/nerf.py:353-392: depth along caller rays through batchify_rays on a hand-built [N,11] batch
+    whose view directions are the RAW ``dirs`` (not normalised: ``rays = torch.cat([rays, dirs], -1)``, :365);
+    white pixels and depths below near are zeroed."""
+    inputs = torch.Tensor(locations)
+    dirs = torch.Tensor(dirs)
+    with torch.no_grad():
+        sh = dirs.shape
+        rays_o = torch.reshape(inputs, [-1, 3]).float()
+        rays_d = torch.reshape(dirs, [-1, 3]).float()
+        near_t, far_t = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+        rays = torch.cat([rays_o, rays_d, near_t, far_t], -1)
+        rays = torch.cat([rays, dirs.reshape(-1, 3)], -1)
+        all_ret = {}
+        for i in range(0, rays.shape[0], chunk):
+            ret = render_rays(rays[i:i + chunk], sd_coarse, sd_fine, retraw=True)
+            for k in ret:
+                all_ret.setdefault(k, []).append(ret[k])
+        all_ret = {k: torch.cat(all_ret[k], 0) for k in all_ret}
+        for k in all_ret:
+            all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+        rgb_map, depth_map = all_ret["rgb_map"], all_ret["depth_map"]
+        depth_raw = depth_map.clone()
+        rgbs = torch.mean(rgb_map, -1) * 255
+        depth_map[rgbs > 250] = 0
+    depth_map[depth_map < near] = 0
+    if return_all:
+        return depth_map, {"depth_raw": depth_raw, "white": rgbs > 250, "rgb": rgb_map}
+    return depth_map
 
 
 # ----------------------------------------------------------------------------

@@ -162,3 +162,29 @@ def test_two_rank_ray_sharded_view_sweep(n_pixels):
         np.testing.assert_array_equal(maps, full.numpy())
         np.testing.assert_allclose(scores, ref_scores, rtol=1e-6)
         np.testing.assert_allclose(scores, one_scores.numpy(), rtol=1e-6)
+
+
+def test_planner_client_is_the_callable_sample_direction_expects():
+    """views.planner_client: interface2.get_uncertainty's call shape (locations, us, vs) -> (uncers, [], []) over the
+    JSON bodies of the two services (plannerServer_*/core/interface2.py:46-60, nerfServer/core/views.py:94-113)."""
+    import evpp_b200
+    from evpp_b200 import views
+
+    class FakeController:
+        def get_uncertainty(self, poses):
+            p = np.asarray(poses)
+            return torch.tensor(1.0 + p[:, 0, 3] ** 2 + 0.1 * p[:, 1, 1])
+
+    client = views.planner_client(FakeController())
+    u, a, b = client([[1.0, 2.0, 3.0], [0.5, 0.0, 1.0]], [0.1, 0.2], [0.3, 0.4])
+    assert a == [] and b == [] and len(u) == 2 and abs(u[0] - (2.0 + 0.1 * np.cos(0.1))) < 1e-6
+
+    class Tsdf:
+        @staticmethod
+        def get_uncertainty_tsdf(locs, us, vs):
+            a = np.asarray(locs)
+            return list(0.5 + 0.5 * np.sin(a[:, 0] + np.asarray(us))), list(2.0 + np.cos(np.asarray(vs)))
+
+    locs = np.random.RandomState(1).uniform(-1, 1, (5, 3))
+    data = evpp_b200.sample_direction(locs, Tsdf, client, [0.0, 1.0, 0.0], scene="room")
+    assert data.shape == (5, 6) and data[:, 5].max() == 1.0

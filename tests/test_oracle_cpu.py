@@ -308,3 +308,111 @@ def test_get_poses_equals_get_pose():
     assert np.array_equal(ref, evpp_b200.get_poses(loc, u, v))
     assert np.array_equal(ref[:50], evpp_b200.get_poses(loc[:50].tolist(), u[:50].tolist(), v[:50].tolist()))
     assert np.array_equal(ref, np.array([O.get_pose(list(loc[i]), u[i], v[i]) for i in range(n)], dtype=np.float64))
+
+
+# ---------------------------------------------------------------- Controller seam (a1, a11, f2) ----------------
+def test_controller_queries_oracle_matches_golden(weights):
+    """tests/golden/controller_queries.npz holds outputs of the UNMODIFIED bodies of Controller.get_uncertainty /
+    get_surface_points / get_rays_depth and views.get_pose (oracle/make_golden_queries.py): the oracle restatements
+    must reproduce them bit for bit, including the reference's np.random.choice pixel protocol."""
+    g = load_golden("controller_queries.npz")
+    H, W, near, far = int(g["H"]), int(g["W"]), float(g["near"]), float(g["far"])
+    K = O.make_K(H, W, float(g["focal"]))
+    c, f = weights["spread"]
+    assert np.array_equal(np.asarray(O.views_to_poses(g["views"])), g["poses"])
+    np.random.seed(0)
+    pix = np.stack([np.random.choice(H * W, size=[1000], replace=False) for _ in range(len(g["views"]))]).astype(np.int32)
+    assert np.array_equal(pix, g["pix"])
+    assert np.array_equal(O.score_views(g["poses"], H, W, K, near, far, c, f, pix_idx=pix).numpy(), g["uncers"])
+    torch.manual_seed(0)
+    cs, fs = O.sparse_variant(O.init_nerf_state_dict()), O.sparse_variant(O.init_nerf_state_dict())
+    pts, ex = O.get_surface_points(g["sp_location"].tolist(), float(g["sp_radius"]), float(g["sp_step"]), H, W, K, near, far,
+                                   cs, fs, return_all=True)
+    assert np.array_equal(pts.numpy(), g["sp_points"]) and np.array_equal(ex["white"].numpy(), g["sp_white"])
+    assert 0 < g["sp_white"].sum() < g["sp_white"].size and 0 < g["sp_keep"].sum() < g["sp_keep"].size   # masks are exercised
+    d = O.get_rays_depth(g["rd_locations"].tolist(), g["rd_dirs"].tolist(), near, far, cs, fs)
+    assert np.array_equal(d.numpy(), g["rd_depths"])
+    assert 0 < g["rd_white"].sum() < g["rd_white"].size
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference"), reason="reference tree not present")
+def test_controller_queries_golden_is_the_reference():
+    """Re-runs the ast-extracted reference methods and compares with the committed fixture (the fixture is not stale)."""
+    from oracle import make_golden_queries as M, ref_import
+    g = load_golden("controller_queries.npz")
+    ns, Hm, Rm = M.reference_controller_methods()
+    torch.manual_seed(0)
+    c, f = O.init_nerf_state_dict(), O.init_nerf_state_dict()
+    kw = ref_import.make_reference_kwargs(Hm, Rm, O.spread_variant(c), O.spread_variant(f))
+    kw.update({"near": float(g["near"]), "far": float(g["far"])})
+    ctl = M.stand_in_controller(int(g["H"]), int(g["W"]), float(g["focal"]), float(g["near"]), float(g["far"]), kw)
+    poses = [ns["get_pose"](list(v[0:3]), v[3], v[4]) for v in g["views"]]
+    assert np.array_equal(np.asarray(poses), g["poses"])
+    np.random.seed(0)
+    assert np.array_equal(ns["get_uncertainty"](ctl, poses).numpy(), g["uncers"])
+    kw = ref_import.make_reference_kwargs(Hm, Rm, O.sparse_variant(c), O.sparse_variant(f))
+    kw.update({"near": float(g["near"]), "far": float(g["far"])})
+    ctl = M.stand_in_controller(int(g["H"]), int(g["W"]), float(g["focal"]), float(g["near"]), float(g["far"]), kw)
+    assert np.array_equal(ns["get_rays_depth"](ctl, g["rd_locations"].tolist(), g["rd_dirs"].tolist()).numpy(), g["rd_depths"])
+    assert np.array_equal(ns["get_surface_points"](ctl, g["sp_location"].tolist(), float(g["sp_radius"]), float(g["sp_step"])).numpy(),
+                          g["sp_points"])
+
+
+# ---------------------------------------------------------------- NBV identity guard (planner.score_and_select) ----
+class _FakeEngine:
+    """Stands in for the CUDA engine on the host: a bulk pass with a bounded relative error and an exact re-score."""
+    precision = 1          # fp16
+
+    def __init__(self, exact, fast):
+        self.exact, self.fast, self.rescored = np.asarray(exact, np.float32), np.asarray(fast, np.float32), []
+
+    def score_views_host(self, poses, H, W, fx, fy, cx, cy, pix=None):
+        return torch.from_numpy(self.fast.copy())
+
+    def rescore_views(self, poses, ids, H, W, fx, fy, cx, cy, pix=None, precision="fp16x3"):
+        self.rescored.append(np.asarray(ids).copy())
+        return torch.from_numpy(self.exact[np.asarray(ids)])
+
+
+def test_score_and_select_guard_near_ties_across_the_topk_boundary():
+    """a view ranked just outside the re-scored set must not win on an inflated 16-bit score.
+    Near-tied leaders, bulk errors up to +-5e-4 (inside the 1e-3 tolerance): the winner must be the exact arg-max
+    for every error pattern, with and without weights, and views far from the lead must not be re-scored."""
+    from evpp_b200 import planner
+    rng = np.random.RandomState(0)
+    V = 48
+    views = np.concatenate([rng.uniform(-1, 1, (V, 3)), rng.uniform(-0.5, 0.5, (V, 2))], 1)
+    K = O.make_K(6, 8, 6.0)
+    for trial in range(200):
+        exact = 100.0 * (1.0 + 4e-4 * rng.standard_normal(V))          # leaders within a few 1e-4 of each other
+        exact[rng.choice(V, 24, replace=False)] *= rng.uniform(0.5, 0.99, 24)      # the rest well below
+        fast = exact * (1.0 + rng.uniform(-5e-4, 5e-4, V))
+        w = rng.uniform(0.3, 1.0, V) if trial % 2 else None
+        eng = _FakeEngine(exact, fast)
+        res = planner.score_and_select(eng, views, 6, 8, K, dirs_per_location=1, depth_clip=w, topk=4 if trial % 3 == 0 else 0)
+        truth = np.asarray(exact, np.float32).astype(np.float64) * (1.0 if w is None else w)
+        assert res["winner"] == int(np.argsort(truth, kind="stable")[-1]), trial
+        assert res["rescored"] < V                                      # the far-below half is never touched
+        s = fast.astype(np.float32).astype(np.float64) * (1.0 if w is None else w)
+        band = s >= s.max() * (1 - 2e-3)
+        assert set(np.flatnonzero(band)) <= set(np.concatenate(eng.rescored).tolist())
+
+
+def test_contenders_band():
+    from evpp_b200.planner import contenders
+    s = np.array([100.0, 99.9, 99.79, 50.0, 100.1])
+    assert contenders(s, None, 2e-3).tolist() == [0, 1, 4]
+    assert contenders(s, np.array([1, 1, 1, 2.01, 1.0]), 2e-3).tolist() == [3]      # weights move the band
+    assert contenders(np.array([5.0]), None, 2e-3).tolist() == [0]
+
+
+def test_weight_fingerprint_tracks_content_not_identity():
+    """render()'s engine cache (evpp_b200/run_nerf.py) keys on the weights' content: equal copies share an engine,
+    an in-place update (a training step) does not."""
+    from evpp_b200 import run_nerf as R
+    torch.manual_seed(0)
+    sd = O.init_nerf_state_dict()
+    a = R._weights_fingerprint(sd)
+    assert a == R._weights_fingerprint(sd) == R._weights_fingerprint({k: v.clone() for k, v in sd.items()})
+    sd["alpha_linear.bias"].add_(1.0)
+    assert R._weights_fingerprint(sd) != a
