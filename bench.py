@@ -2,13 +2,20 @@
 """Benchmark of the candidate-view scoring hot path (BASELINE.json metric: candidate views scored/sec).
 
   python bench.py --gpus N --steps K --warmup W            # the CUDA engine (this repo)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host CPU cores
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own renderer on the host CPU cores
 
-A step = one pass of the hot path over one batch of synthetic candidate views: configs[1] of
-BASELINE.json (Object scene, 512 hemisphere views x 80x60 rays, 64+128 samples, random-init
-reference NeRF x2), in reference-parity mode (frequency encoding + 8x256 NeRF + NeurAR head --
-the only scorer the reference implements).  With N ranks every rank scores
-its own 512-view block (weak scaling) and the per-view scores are all-gathered over NCCL.
+A step = one pass of the hot path over the north-star workload, configs[2] of BASELINE.json: the 4096-view Room
+sweep (1024 positions x 4 directions of the Room fan, 128x96 rays per view, 64+128 samples per ray, random-init
+reference NeRF x2) in reference-parity mode (frequency encoding + 8x256 NeRF + NeurAR head -- the only scorer the
+reference implements).  The 4096 views are split over the N ranks (STRONG scaling).  A step
+is everything the planner needs from the sweep, i.e. an NBV identical to the fp32 reference's:
+
+  bulk pass (fp16 tensor cores, score-only network outputs) -> all_gather of the 4096 scores -> every view within
+  2e-3 of the leader re-scored on the tensor-core exact path (fp16x3), dealt out over the ranks -> all_gather ->
+  the planner's selection tail on the device -> winner,
+
+and the winner is checked against tests/golden/room_sweep_nbv.json (the fp32 oracle's arg-max over the leaders).
+`--workload object` keeps round 1's weak-scaled configs[1] (512 views x 80x60 rays per GPU).
 """
 import argparse
 import json
@@ -25,11 +32,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_EVAL = 1187072.0
-V_PER_RANK, IMG_H, IMG_W, FOCAL = 512, 60, 80, 60.0
-WORKLOAD = "object"
+V_TOTAL, IMG_H, IMG_W, FOCAL = 4096, 96, 128, 96.0       # room: views of the whole sweep; object: views PER GPU
+WORKLOAD = "room"
 NEAR, FAR = 0.5, 6.0
 S_C, S_I = 64, 128
 EVALS_PER_RAY = S_C + (S_C + S_I)
+MARGIN = 2e-3
+NBV_FIXTURE = os.path.join(ROOT, "tests", "golden", "room_sweep_nbv.json")
 
 
 def peaks():
@@ -76,76 +85,139 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_workload(rank):
+def make_workload(rank, world=1):
+    """Weights (seed 0) and the candidate views.  room: the SAME 4096 views on every rank (seed 0; each rank scores a
+    block of them); object: 512 views per rank, seeded by the rank (weak scaling)."""
     from evpp_b200 import synthetic as S
     torch.manual_seed(0)
     c = S.init_nerf_state_dict()
     f = S.init_nerf_state_dict()
-    views = S.room_views(V_PER_RANK, seed=rank) if WORKLOAD == "room" else S.hemisphere_views(V_PER_RANK, seed=rank)
+    views = S.room_views(V_TOTAL, seed=0) if WORKLOAD == "room" else S.hemisphere_views(V_TOTAL, seed=rank)
     poses = torch.Tensor(np.asarray(S.views_to_poses(views)))[:, :3, :4].contiguous()
     return c, f, views, poses
 
 
-def cpu_reference_rate(c, f, views, seconds_budget=20.0, max_views=8):
-    """Times the oracle port (== the reference's render() + sum(beta^2)/R, bit-identical on CPU) on a
-    bounded sample of the same workload with all host threads."""
-    from oracle import evpp_oracle as O
-    K = O.make_K(IMG_H, IMG_W, FOCAL)
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    poses = O.views_to_poses(views)
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown CPU"
+
+
+class HostReference:
+    """The reference path on the host cores: the UNMODIFIED reference render() (oracle/_ref or /root/reference,
+    kind 'reference') when it can be imported, else the oracle port (bit-identical to it on CPU, kind 'port').
+    score(view_ids, n_pix) = Controller.get_uncertainty's arithmetic (nerf.py:278-309) on a pixel subset."""
+
+    def __init__(self, c, f, views):
+        from oracle import evpp_oracle as O, ref_import
+        self.O, self.views, self.c, self.f = O, views, c, f
+        self.K = O.make_K(IMG_H, IMG_W, FOCAL)
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        self.kind, self.kwargs, self.R = "port", None, None
+        if ref_import.available():
+            try:
+                H, R = ref_import.load()
+                self.kwargs = ref_import.make_reference_kwargs(H, R, c, f, N_samples=S_C, N_importance=S_I, white_bkgd=True)
+                self.R, self.Hm = R, H
+                self.kind = "reference"
+            except Exception as e:      # e.g. cv2 missing on the box: fall back to the port, say so
+                print(f"bench: reference import failed ({e}); timing the oracle port", file=sys.stderr)
+        self.desc = ("unmodified reference render() (nerfServer/core/run_nerf.py:131, vendored by oracle/build_ref.py) + sum(beta^2)/R (nerf.py:307-309)"
+                     if self.kind == "reference" else "oracle port, bit-identical to the reference's render() on CPU (oracle/make_golden.py)")
+
+    def score(self, ids, pix):
+        """ids: view indices; pix: int [len(ids), R] flat pixel ids (or None = full grid).  Returns scores [len(ids)]."""
+        O = self.O
+        poses = O.views_to_poses([self.views[i] for i in ids])
+        with torch.no_grad():
+            if self.kind == "port":
+                return O.score_views(poses, IMG_H, IMG_W, self.K, NEAR, FAR, self.c, self.f, pix_idx=pix)
+            rays = O.build_view_rays(poses, IMG_H, IMG_W, self.K, pix)           # get_rays + row subset, nerf.py:282-296
+            R = rays.shape[1] // len(ids)
+            out = self.R.render(IMG_H, IMG_W, self.K, chunk=1024 * 32, rays=rays, retraw=True, dev=torch.device("cpu"),
+                                near=NEAR, far=FAR, **{k: v for k, v in self.kwargs.items() if k not in ("near", "far")})
+            unc = out[3] ** 2
+            return torch.sum(unc.reshape(len(ids), R * (S_C + S_I)), -1) / R
+
+
+def reference_sample(step):
+    """Bounded sample of the sweep for one host step: 32 views of the workload x 1/32 of each view's pixels = one
+    view-equivalent of rays (work is exactly linear in rays: views and rays share no state)."""
+    n_pix = IMG_H * IMG_W
+    rng = np.random.RandomState(1000 + step)
+    ids = rng.choice(V_TOTAL, size=32, replace=False)
+    per = n_pix // 32
+    pix = np.stack([rng.choice(n_pix, size=per, replace=False) for _ in ids]).astype(np.int32)
+    return ids, pix, 32 * per / n_pix
+
+
+def cpu_reference_rate(c, f, views, seconds_budget=20.0):
+    """cpu_baseline leg of the default line: the reference on a bounded sample (about 20 s), all host threads."""
+    ref = HostReference(c, f, views)
+    ids, pix, veq = reference_sample(0)
     t0 = time.time()
-    with torch.no_grad():
-        O.score_views(poses[:1], IMG_H, IMG_W, K, NEAR, FAR, c, f)
+    ref.score(ids, pix)
     t1 = time.time() - t0
-    nv = int(max(1, min(max_views, seconds_budget // max(t1, 1e-3))))
-    t0 = time.time()
-    with torch.no_grad():
-        O.score_views(poses[:nv], IMG_H, IMG_W, K, NEAR, FAR, c, f)
-    dt = time.time() - t0
-    return nv / dt, threads, f"{nv} of {V_PER_RANK} views x {IMG_W}x{IMG_H} rays, 64+128 samples, {dt:.1f} s wall (1 warm-up view {t1:.1f} s)"
+    n = int(max(1, min(8, seconds_budget // max(t1, 1e-3))))
+    best, tot = 1e30, 0.0
+    for k in range(n):
+        ids, pix, veq = reference_sample(1 + k)
+        t0 = time.time()
+        ref.score(ids, pix)
+        dt = time.time() - t0
+        best, tot = min(best, dt), tot + dt
+    return veq * n / tot, ref.threads, ref.kind, (
+        f"{n} samples of {int(veq * IMG_H * IMG_W)} rays (32 views of the {V_TOTAL}-view sweep x {IMG_H * IMG_W // 32} pixels each = {veq:.2f} "
+        f"view-equivalents), 64+128 samples/ray, {tot:.1f} s wall (warm-up {t1:.1f} s, best sample {best:.1f} s); {ref.desc}; "
+        f"{ref.threads} threads of {cpu_model()}; rate extrapolated linearly in rays")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from oracle import evpp_oracle as O
-    c, f, views, _ = make_workload(0)
-    K = O.make_K(IMG_H, IMG_W, FOCAL)
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    poses = O.views_to_poses(views)
+    c, f, views, _ = make_workload(0, world)
+    ref = HostReference(c, f, views)
     on_gpu = args.ref_device == "cuda"
     if on_gpu:
         # informational: the reference's torch path (same ops, same order) with its tensors on cuda:0
         import warnings
+        from oracle import evpp_oracle as O
         warnings.simplefilter("ignore")
         torch.set_default_device("cuda")
         torch.set_default_tensor_type(torch.cuda.FloatTensor)      # the legacy torch.Tensor(...) constructors too
         c = {k: v.cuda() for k, v in c.items()}
         f = {k: v.cuda() for k, v in f.items()}
-    per_step = 8 if on_gpu else 1                            # bounded sample: 1 view (4800 rays) per step on the host
-    times = []
-    with torch.no_grad():
-        for s in range(args.warmup + args.steps):
-            if on_gpu:
-                torch.cuda.synchronize()
-            t0 = time.time()
-            sc = O.score_views(poses[(s % 8) * per_step:(s % 8) * per_step + per_step], IMG_H, IMG_W, K, NEAR, FAR, c, f)
-            if on_gpu:
-                sc = sc.cpu()
-            if s >= args.warmup:
-                times.append(time.time() - t0)
+        ref.kind, ref.c, ref.f = "port", c, f
+    times, veq = [], 1.0
+    for s in range(args.warmup + args.steps):
+        ids, pix, veq = reference_sample(s)
+        if on_gpu:
+            torch.cuda.synchronize()
+        t0 = time.time()
+        sc = ref.score(ids, pix)
+        if on_gpu:
+            sc = sc.cpu()
+        if s >= args.warmup:
+            times.append(time.time() - t0)
     ms = 1e3 * float(np.mean(times))
-    val = per_step / (ms / 1e3)
-    kind = "port"
+    val = veq / (ms / 1e3)
+    best3 = veq / min(times[:3]) if times else None
+    sample = (f"per step 32 views of the {V_TOTAL}-view workload x {IMG_H * IMG_W // 32} pixels each = {veq:.2f} view-equivalents of rays "
+              f"({int(veq * IMG_H * IMG_W)} rays x 256 MLP evaluations), rate extrapolated linearly in rays (BASELINE.md section 3); {ref.desc}; "
+              f"{ref.threads} threads of {cpu_model()}; best of the first 3 timed steps: {best3:.4f} views/s"
+              + ("; THIS RUN: the same torch ops on cuda:0, not the host" if on_gpu else ""))
     line = {"impl": "reference", "metric": "candidate views scored/sec", "value": val, "unit": "views/s",
             "rays_per_s": val * IMG_H * IMG_W, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(world, "reference torch path on cuda:0 (informational)" if on_gpu else "host CPU, torch fp32"),
-            "cpu_baseline": {"value": val, "unit": "views/s", "cores": threads, "kind": kind,
-                             "sample": f"{per_step} view(s) x {IMG_W}x{IMG_H} rays per step of the {V_PER_RANK}-view workload; oracle port, bit-identical to the reference's render() on CPU (oracle/make_golden.py)"
-                                       + ("; THIS RUN: the same torch ops on cuda:0, not the host" if on_gpu else "")},
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if WORKLOAD == "room" else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world, "reference torch path on cuda:0 (informational)" if on_gpu else "host CPU, torch fp32"),
+            "cpu_baseline": {"value": val, "unit": "views/s", "cores": ref.threads, "kind": ref.kind, "sample": sample,
+                             "cpu": cpu_model(), "best_of_3": best3},
             "e2e": {"value": val, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -512,40 +584,65 @@ def planner_cpu_baseline(c, f, locations, center, state, nray, ts):
 
 
 def workload_config(world, engine_desc):
-    name = ("BASELINE configs[2] Room scene sweep (4096 poses at 8 GPUs), reference-parity scorer" if WORKLOAD == "room"
-            else "BASELINE configs[1] Object scene")
-    return {"workload": f"{name}: {V_PER_RANK} candidate views x {IMG_W}x{IMG_H} rays per GPU, "
+    if WORKLOAD == "room":
+        return {"workload": f"BASELINE configs[2] Room scene sweep (north star): {V_TOTAL} candidate poses x {IMG_W}x{IMG_H} rays, split over "
+                            f"{world} GPU(s), {S_C}+{S_I} samples/ray ({EVALS_PER_RAY} MLP evals/ray), reference-parity scorer "
+                            "(freq. encoding + 8x256 NeRF + NeurAR uncertainty head, random-init seed 0); a step = bulk pass + exact "
+                            "re-score of the near-tied leaders + NBV selection",
+                "views": V_TOTAL, "views_per_gpu": (V_TOTAL + world - 1) // world, "rays_per_view": IMG_H * IMG_W, "near": NEAR, "far": FAR,
+                "parallelism": f"{V_TOTAL} views sharded over {world} GPU(s) in contiguous blocks, all_gather of the scores, contenders "
+                               "dealt out round robin for the exact pass, second all_gather, replicated selection",
+                "engine": engine_desc,
+                "l2": "per-step working set (~0.7 GB of streamed ray/sample intermediates per 131072-ray chunk, >300 chunks) exceeds L2; "
+                      "256 MB L2 flush between timed steps"}
+    return {"workload": f"BASELINE configs[1] Object scene: {V_TOTAL} candidate views x {IMG_W}x{IMG_H} rays per GPU, "
                         f"{S_C}+{S_I} samples/ray ({EVALS_PER_RAY} MLP evals/ray), reference-parity scorer "
                         "(freq. encoding + 8x256 NeRF + NeurAR uncertainty head, random-init seed 0)",
-            "views_per_gpu": V_PER_RANK, "rays_per_view": IMG_H * IMG_W, "near": NEAR, "far": FAR,
+            "views_per_gpu": V_TOTAL, "rays_per_view": IMG_H * IMG_W, "near": NEAR, "far": FAR,
             "parallelism": f"views sharded over {world} GPU(s), all_gather of scores", "engine": engine_desc,
             "l2": "per-step working set (~14 GB of streamed ray/sample intermediates) exceeds L2; 256 MB L2 flush between timed steps"}
+
+
+def measured_traffic_per_eval():
+    """DRAM bytes per MLP evaluation from the committed ncu --set full capture of one benchmark-sized launch
+    (profiles/r2_mlp_tc_dram.json, written by tools/ncu_metrics.py from the .ncu-rep); None when absent."""
+    path = os.path.join(ROOT, "profiles", "r2_mlp_tc_dram.json")
+    try:
+        d = json.load(open(path))
+        return float(d["dram_bytes"]) / float(d["evals"]), d
+    except Exception:
+        return None, None
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="evpp_b200")
-    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16", "fp16x2", "fp16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rescore", action="store_true", help="bulk pass only (no exact re-score of the leaders, no NBV identity)")
+    ap.add_argument("--full-outputs", action="store_true", help="scoring calls evaluate the full network like render() (round-1 behaviour)")
     ap.add_argument("--pixel-sampler", default="device", choices=["device", "numpy"],
                     help="--mode planner only: where the random pixel subsets of the live protocol are drawn")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' runs the same reference torch path on cuda:0 (informational row; "
                          "the reference arm the driver compares against is the CPU one)")
-    ap.add_argument("--workload", default="object", choices=["object", "room"],
-                    help="object: BASELINE configs[1] (512 hemisphere views x 80x60 rays per GPU, the headline); room: the "
-                         "4096-view Room sweep of configs[2] in reference-parity mode (512 views x 128x96 rays per GPU)")
+    ap.add_argument("--workload", default="room", choices=["object", "room"],
+                    help="room (default): the 4096-view Room sweep of BASELINE configs[2], strong-scaled over the ranks, with NBV "
+                         "selection inside the step; object: BASELINE configs[1], 512 hemisphere views x 80x60 rays per GPU (weak)")
+    ap.add_argument("--views", type=int, default=0, help="override the number of views (room: whole sweep; object: per GPU)")
     ap.add_argument("--mode", default="parity", choices=["parity", "ngp", "tensorf", "planner", "fullres"],
-                    help="parity: the reference's scorer (headline, BASELINE configs[1]); ngp: occupancy grid + hash grid "
+                    help="parity: the reference's scorer (headline); ngp: occupancy grid + hash grid "
                          "scorer on the Room sweep shape (BASELINE configs[2]; no reference counterpart); fullres: BASELINE configs[4], "
                          "640x480 renders with the rays of every image sharded over the ranks (strong scaling)")
     args = ap.parse_args()
-    if args.workload == "room":
-        global IMG_H, IMG_W, FOCAL, WORKLOAD
-        IMG_H, IMG_W, FOCAL, WORKLOAD = 96, 128, 96.0, "room"
+    global IMG_H, IMG_W, FOCAL, WORKLOAD, V_TOTAL
+    if args.workload == "object":
+        IMG_H, IMG_W, FOCAL, WORKLOAD, V_TOTAL = 60, 80, 60.0, "object", 512
+    if args.views > 0:
+        V_TOTAL = args.views
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -579,30 +676,46 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     dev = torch.device("cuda", local_rank)
-    c, f, views, poses_host = make_workload(rank)
+    c, f, views, poses_host = make_workload(rank, world)
     K = np.array([[FOCAL, 0, 0.5 * IMG_W], [0, FOCAL, 0.5 * IMG_H], [0, 0, 1]])
     fx, fy, cx, cy = _intrinsics(K)
     eng = evpp_b200.Engine(device=local_rank, n_samples=S_C, n_importance=S_I, near=NEAR, far=FAR,
                            white_bkgd=True, precision=args.precision)
     eng.load_weights(0, c)
     eng.load_weights(1, f)
+    eng.set_score_mode(args.full_outputs)
+    room = WORKLOAD == "room"
+    V = V_TOTAL                                   # views this rank holds poses for (room: the whole sweep)
+    V_job = V_TOTAL if room else V_TOTAL * world  # views scored per step by the whole job
     poses_dev = poses_host.to(dev)
     poses_pinned = poses_host.pin_memory()
-    scores_pinned = torch.empty(V_PER_RANK, dtype=torch.float32).pin_memory()
+    out_pinned = torch.empty(V_job + 1, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    V_total = V_PER_RANK * world
+    margin = 0.0 if args.no_rescore else MARGIN
+    state = {"winner": None, "band": 0, "scores": None}
+
+    def sweep(poses, host_out):
+        if room:
+            s, win, band = edist.sweep_select(eng, poses, IMG_H, IMG_W, fx, fy, cx, cy, rank, world, margin=margin, host_out=host_out)
+        else:       # weak scaling: every rank scores its own 512 views, then the same gather / selection tail
+            pd = poses.to(dev, non_blocking=True) if poses.device.type == "cpu" else poses
+            s = eng.score_views(pd, IMG_H, IMG_W, fx, fy, cx, cy)
+            if world > 1:
+                s = edist.gather_scores(s, V_job, rank, world)
+            _, _, w = eng.select_nbv(s, None, 1)
+            if host_out is not None:
+                host_out[:V_job].copy_(s, non_blocking=True)
+                host_out[V_job:].copy_(w.to(torch.float32), non_blocking=True)
+                torch.cuda.synchronize()
+            win, band = int(w.item()), 0
+        state.update(winner=win, band=band, scores=s)
+        return s
 
     def step_device():
-        s = eng.score_views(poses_dev, IMG_H, IMG_W, fx, fy, cx, cy)
-        if world > 1:
-            s = edist.gather_scores(s, V_total, rank, world)
-        return s
+        return sweep(poses_dev, None)
 
     def step_e2e():
-        s = eng.score_views_host(poses_pinned, IMG_H, IMG_W, fx, fy, cx, cy, out=scores_pinned)
-        if world > 1:
-            s = edist.gather_scores(s.to(dev, non_blocking=True), V_total, rank, world).cpu()
-        return s
+        return sweep(poses_pinned, out_pinned)
 
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
@@ -639,44 +752,63 @@ def main():
     if rank == 0:
         sampler.start()
     ms_dev, _, launches, evals = timed(step_device, args.steps, args.warmup, profile=True)
-    mlp_ms, mlp_launches, mlp_evals = eng.mlp_time()
+    mlp_ms, mlp_launches, mlp_evals, mlp_flops = eng.mlp_profile()
     eng.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
     _, ms_e2e_wall, _, _ = timed(step_e2e, max(2, min(args.steps, 3)), 1)
 
     if rank == 0:
         sustained, burst, src = peaks()
-        value = V_total / (ms_dev / 1e3)
-        e2e_val = V_total / (ms_e2e_wall / 1e3)
-        flops_per_launch = FLOP_PER_EVAL * mlp_evals / max(1, mlp_launches)
+        value = V_job / (ms_dev / 1e3)
+        e2e_val = V_job / (ms_e2e_wall / 1e3)
         avg_launch_ms = mlp_ms / max(1, mlp_launches)
-        achieved = flops_per_launch / (avg_launch_ms / 1e3) / 1e12 if avg_launch_ms > 0 else 0.0
+        achieved = mlp_flops / (mlp_ms / 1e3) / 1e12 if mlp_ms > 0 else 0.0            # FLOPs the launches really executed
+        nominal = FLOP_PER_EVAL * mlp_evals / (mlp_ms / 1e3) / 1e12 if mlp_ms > 0 else 0.0
         tensor = args.precision != "fp32"
+        bpe, cap = measured_traffic_per_eval()
+        # NBV check: the winner of the timed sweep against the stored fp32-oracle winner of this exact workload
+        check = {"winner": state["winner"], "rescored_views": state["band"], "expected": None, "ok": None}
+        if room and os.path.exists(NBV_FIXTURE):
+            fx_ = json.load(open(NBV_FIXTURE))
+            if fx_.get("views") == V_TOTAL and fx_.get("H") == IMG_H and fx_.get("W") == IMG_W:
+                check["expected"] = fx_["winner"]
+                check["ok"] = bool(state["winner"] == fx_["winner"]) if not args.no_rescore else None
+                check["source"] = fx_.get("source")
+        if check["ok"] is False:
+            sys.exit(f"bench.py: NBV mismatch: the sweep selected view {state['winner']}, the fp32 oracle selects {check['expected']}")
         line = {"metric": "candidate views scored/sec", "value": value, "unit": "views/s",
                 "rays_per_s": value * IMG_H * IMG_W, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fp16": "f16 operands, f32 accumulate (tcgen05)", "bf16": "bf16 operands, f32 accumulate (tcgen05)",
+                "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong" if room else "weak", "vs_baseline": None,
+                "dtype": {"fp16": "f16 operands, f32 accumulate (tcgen05); leaders re-scored with split-f16 operands (3 MMAs per product, f32-class)",
+                          "bf16": "bf16 operands, f32 accumulate (tcgen05); leaders re-scored with split-f16 operands",
+                          "fp16x2": "split-f16 weights, f16 activations, f32 accumulate (tcgen05)", "fp16x3": "split-f16 operands, f32 accumulate (tcgen05)",
                           "fp32": "f32"}[args.precision],
-                "data": "synthetic", "config": workload_config(world, f"evpp_b200 CUDA engine, precision={args.precision}"),
-                "e2e": {"value": e2e_val, "unit": "views/s", "h2d_bytes_per_step": int(V_PER_RANK * 12 * 4),
-                        "d2h_bytes_per_step": int(V_PER_RANK * 4), "ms_per_step": ms_e2e_wall,
-                        "api": "Engine.score_views_host == evpp_score_views_host (pinned host poses in, host scores out)"},
+                "data": "synthetic", "config": workload_config(world, f"evpp_b200 CUDA engine, precision={args.precision}, "
+                                                                      f"{'full' if args.full_outputs else 'score-only'} network outputs, rescore margin {margin:g}"),
+                "e2e": {"value": e2e_val, "unit": "views/s", "h2d_bytes_per_step": int(V * 12 * 4),
+                        "d2h_bytes_per_step": int(V_job * 4 + 4 + (V_job * 4 if room else 0)), "ms_per_step": ms_e2e_wall,
+                        "api": "evpp_b200.dist.sweep_select (pinned host poses in every step; scores + winner id land in pinned host memory; the "
+                               "contender logic reads the gathered scores on the host)" if room else
+                               "Engine.score_views + select_nbv (pinned host poses in, host scores + winner out)"},
                 "gpu_launches": int(launches),
+                "nbv_check": check,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                              "frac": achieved / sustained,
-                             # DRAM bytes per launch: 11.97 B per MLP evaluation measured by ncu --set full
-                             # (profiles/r1_mlp_tc_ncu_metrics.txt: 51.8 MB for a 4.33 M-evaluation launch) x the
-                             # evaluations of an average launch of this run; algorithmic = 24 B/evaluation + 36 B/ray
-                             "traffic": (11.97 * mlp_evals / max(1, mlp_launches)) if tensor else None,
-                             "traffic_unit": "bytes/launch (ncu dram__bytes_read+write per evaluation x evaluations per launch)",
+                             "traffic": (bpe * mlp_evals / max(1, mlp_launches)) if (tensor and bpe) else None,
+                             "traffic_unit": "bytes/launch: DRAM bytes per evaluation of the committed ncu --set full capture of one 131072-ray fine "
+                                             "launch (profiles/r2_mlp_tc_dram.json) x the evaluations of an average launch of this run" if bpe else None,
                              "peak_source": f"{src} bf16_tflops_sustained (cuBLAS bf16 under the power cap; the kernel is timed inside a long step)",
-                             "kernel": "mlp_tc_kernel (fused encode + 10-layer NeRF/NeurAR MLP, tcgen05 TS-mode, activations in tensor memory)" if tensor else "mlp_simt_kernel (fp32 FFMA; tensor peak shown for scale only)",
-                             "flop_per_launch": flops_per_launch, "avg_launch_ms": avg_launch_ms,
+                             "kernel": "mlp_tc_kernel (fused encode + NeRF/NeurAR MLP, tcgen05 TS-mode, activations in tensor memory; all launches of the "
+                                       "step: bulk fp16 and exact fp16x3, score-only variants)" if tensor else "mlp_simt_kernel (fp32 FFMA; tensor peak shown for scale only)",
+                             "achieved_definition": "FLOPs the launches executed (score-only coarse evaluation 982,528, fine 1,185,792; an fp16x3 launch "
+                                                    "counts its evaluations once, not its three MMA passes) / CUDA-event time of the launches",
+                             "achieved_at_1187072_flop_per_eval": nominal,
+                             "flop_per_launch": mlp_flops / max(1, mlp_launches), "avg_launch_ms": avg_launch_ms,
                              "mlp_share_of_step": mlp_ms / (ms_dev * args.steps) if ms_dev > 0 else None},
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_reference_rate(c, f, views)
-            line["cpu_baseline"] = {"value": v, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample}
+            v, cores, kind, sample = cpu_reference_rate(c, f, views)
+            line["cpu_baseline"] = {"value": v, "unit": "views/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

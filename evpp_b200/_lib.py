@@ -48,6 +48,8 @@ SIGNATURES = {
     "evpp_destroy": (_I, [_P]),
     "evpp_load_nerf_weights": (_I, [_P, _I, _P, _P, _I]),
     "evpp_score_views": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
+    "evpp_score_views_ex": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _I, _P, _P]),
+    "evpp_get_nonfinite": (_I, [_P, C.POINTER(C.c_int32), _P]),
     "evpp_score_views_host": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
     "evpp_rescore_views_fp32": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
     "evpp_rescore_views": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _I, _P, _P]),

@@ -472,14 +472,30 @@ int evpp_load_nerf_weights(evpp_handle* h, int which, const float* packed, const
   return 0;
 }
 
-int evpp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx,
-                     float cy, const int32_t* pix_idx, int R, float* scores, void* stream) {
+int evpp_score_views_ex(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx,
+                        float cy, const int32_t* pix_idx, int R, int precision, float* scores, void* stream) {
   if (!h) return fail(EVPP_ERR_INVALID, "null handle");
   if (V == 0) return 0;   // empty candidate list: nothing to score (empty tensors carry null pointers)
   if (!c2w || !scores) return fail(EVPP_ERR_INVALID, "null argument");
+  if (precision < 0) precision = h->cfg.precision;
+  if (precision >= kNumPrec) return fail(EVPP_ERR_INVALID, "bad precision %d", precision);
   EVPP_ON_DEVICE(h->device);
-  return score_views_device(h, c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, scores, h->cfg.precision,
-                            (cudaStream_t)stream);
+  return score_views_device(h, c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, scores, precision, (cudaStream_t)stream);
+}
+
+int evpp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy, float cx,
+                     float cy, const int32_t* pix_idx, int R, float* scores, void* stream) {
+  return evpp_score_views_ex(h, c2w, V, H, W, fx, fy, cx, cy, pix_idx, R, -1, scores, stream);
+}
+
+int evpp_get_nonfinite(evpp_handle* h, int32_t* count, void* stream) {
+  if (!h || !count) return fail(EVPP_ERR_INVALID, "null argument");
+  *count = 0;
+  if (!h->nonfinite.p) return 0;
+  EVPP_ON_DEVICE(h->device);
+  CUDA_TRY(cudaMemcpyAsync(count, h->nonfinite.p, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
 }
 
 static int score_host_impl(evpp_handle* h, const float* c2w_host, int V, int H, int W, float fx, float fy,

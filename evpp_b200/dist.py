@@ -113,3 +113,67 @@ def render_views_ray_sharded(render_block, V, n_pixels, rank, world, device="cpu
     partial = pad[..., -1].sum(1, dtype=torch.float64)        # the padding rows are zero
     dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
     return maps, (partial / n_pixels).to(torch.float32)
+
+
+def scatter_round_robin(ids, rank, world):
+    """The share of ``ids`` (sorted global view ids of the contenders) that ``rank`` re-scores: every world-th one.
+    Contenders cluster wherever the scene is uncertain, i.e. inside one rank's contiguous block of the sweep;
+    dealing them out keeps the exact pass balanced (strong scaling) whatever their positions."""
+    return ids[rank::world]
+
+
+def sweep_select(engine, poses, H, W, fx, fy, cx, cy, rank=0, world=1, margin=2e-3, exact="fp16x3", weight=None,
+                 dirs_per_location=1, group=None, host_out=None):
+    """One candidate sweep with identical-NBV guarantee, sharded over ``world`` ranks:
+
+      1. bulk pass: rank r scores its contiguous block of the V poses at the engine's 16-bit precision;
+      2. all_gather of the V scores (NCCL on the GPU box; 16 KB at V = 4096);
+      3. contenders = views whose (weighted) score is within ``margin`` of the best (planner.contenders) -- the same
+         set on every rank; they are dealt out round robin and re-scored on the tensor-core exact path (``exact``);
+      4. all_gather of the exact scores, written over the fast ones;
+      5. the planner's selection tail (vpp.py:199-220 + interface.py:115-116) on the device (evpp_select_nbv).
+
+    poses: float32 [V,3,4] on the engine's device (already resident) or on the host (pinned: copied every call).
+    Returns (scores [V] on the device, winner view id, number of re-scored views).  With ``host_out`` (a pinned
+    float32 [V + 1] tensor) the scores and the winner id are also landed in host memory before returning."""
+    from .planner import contenders
+    dev = engine.device
+    V = poses.shape[0]
+    b, e = shard_range(V, rank, world)
+    on_host = poses.device.type == "cpu"
+    poses_dev = poses.to(dev, non_blocking=True) if on_host else poses
+    local = engine.score_views(poses_dev[b:e], H, W, fx, fy, cx, cy) if e > b else torch.empty(0, device=dev)
+    scores = gather_scores(local, V, rank, world, group) if world > 1 else local
+    fast_host = scores.cpu().numpy().astype(np.float64)
+    if not np.isfinite(fast_host).all():
+        raise FloatingPointError("non-finite view scores in the bulk pass (16-bit activations overflowed): use precision='bf16'")
+    band = contenders(fast_host, None if weight is None else weight.cpu().numpy(), margin) if margin > 0 else np.zeros(0, np.int32)
+    n_band = len(band)
+    if margin > 0 and engine.precision not in (0, 4) and V > 1:
+        mine = scatter_round_robin(band, rank, world)
+        per = (n_band + world - 1) // world
+        ex = torch.full((per,), float("-inf"), device=dev)
+        if len(mine):
+            ids = torch.from_numpy(mine.astype(np.int64)).to(dev)
+            ex[:len(mine)] = engine.score_views(poses_dev[ids], H, W, fx, fy, cx, cy, precision=exact)
+        if world > 1:
+            allx = torch.empty(world * per, device=dev)
+            dist.all_gather_into_tensor(allx, ex, group=group) if dev.type == "cuda" else _all_gather_list(allx, ex, world, group)
+            # allx[r * per + k] is the exact score of band[r + k * world]
+            k = torch.arange(per, device=dev)[None, :].expand(world, per)
+            r = torch.arange(world, device=dev)[:, None].expand(world, per)
+            slot = (r + k * world).reshape(-1)
+            ok = slot < n_band
+            band_t = torch.from_numpy(band.astype(np.int64)).to(dev)
+            scores = scores.clone()
+            scores[band_t[slot[ok]]] = allx[ok]
+        else:
+            scores = scores.clone()
+            scores[torch.from_numpy(band.astype(np.int64)).to(dev)] = ex[:n_band]
+    _, _, win = engine.select_nbv(scores, weight, dirs_per_location)
+    if host_out is not None:
+        host_out[:V].copy_(scores, non_blocking=True)
+        host_out[V:V + 1].copy_(win.to(torch.float32), non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return scores, int(host_out[V].item()), n_band
+    return scores, int(win.item()), n_band

@@ -96,8 +96,9 @@ class Engine:
         return ckpt.get("global_step")
 
     # ---- scoring (Controller.get_uncertainty, nerf.py:266-309) -------------------------------------
-    def score_views(self, c2w, H, W, fx, fy, cx, cy, pix_idx=None):
-        """c2w: cuda float32 [V,3,4]; pix_idx: cuda int32 [V,R] or None.  Returns cuda float32 [V]."""
+    def score_views(self, c2w, H, W, fx, fy, cx, cy, pix_idx=None, precision=None):
+        """c2w: cuda float32 [V,3,4]; pix_idx: cuda int32 [V,R] or None.  Returns cuda float32 [V] (asynchronous:
+        a non-finite score is not reported here, see nonfinite_count()).  precision: None = the bulk precision."""
         c2w = c2w.to(self.device, torch.float32).contiguous()
         V = c2w.shape[0]
         R = 0
@@ -105,10 +106,18 @@ class Engine:
             pix_idx = pix_idx.to(self.device, torch.int32).contiguous()
             R = pix_idx.shape[1]
         scores = torch.empty(V, device=self.device, dtype=torch.float32)
+        prec = -1 if precision is None else (PRECISIONS[precision] if isinstance(precision, str) else int(precision))
         with torch.cuda.device(self.device):
-            check(self.lib.evpp_score_views(self._h, _ptr(c2w), V, H, W, fx, fy, cx, cy, _ptr(pix_idx), R,
-                                            _ptr(scores), _stream_ptr(self.device)))
+            check(self.lib.evpp_score_views_ex(self._h, _ptr(c2w), V, H, W, fx, fy, cx, cy, _ptr(pix_idx), R, prec,
+                                               _ptr(scores), _stream_ptr(self.device)))
         return scores
+
+    def nonfinite_count(self):
+        """Number of inf / NaN scores of the last device-side scoring call (synchronises)."""
+        n = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_get_nonfinite(self._h, C.byref(n), _stream_ptr(self.device)))
+        return n.value
 
     def score_views_host(self, c2w_host, H, W, fx, fy, cx, cy, pix_idx_host=None, out=None, precision=None):
         """HOST in / HOST out (pinned torch CPU tensors recommended).  Synchronises.  Raises EvppError(-5,

@@ -92,6 +92,17 @@ int evpp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, floa
                      float cx, float cy, const int32_t* pix_idx, int R, float* scores,
                      void* stream);
 
+/* Same at an explicit precision (< 0 = cfg.precision) -- e.g. EVPP_PREC_FP16X3 to re-score the contenders of a sweep
+ * whose poses are already on the device. */
+int evpp_score_views_ex(evpp_handle* h, const float* c2w, int V, int H, int W, float fx, float fy,
+                        float cx, float cy, const int32_t* pix_idx, int R, int precision,
+                        float* scores, void* stream);
+
+/* How many scores of the LAST device-side scoring call on this handle were not finite (inf / NaN: 16-bit
+ * activations overflowed).  Synchronises `stream`.  The host entry points check this themselves and return
+ * EVPP_ERR_NONFINITE. */
+int evpp_get_nonfinite(evpp_handle* h, int32_t* count, void* stream);
+
 /* Same with HOST buffers (what the HTTP view nerfServer/core/views.py:94-113 holds):
  * host->device copy of poses / pixel indices and device->host copy of the scores included. */
 int evpp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int H, int W, float fx,

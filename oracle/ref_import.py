@@ -1,9 +1,9 @@
-"""Import the UNMODIFIED reference renderer from /root/reference (build container only).
+"""Import the UNMODIFIED reference renderer: from /root/reference in the build container, from the byte-identical
+vendored copy ``oracle/_ref/`` (written by ``oracle/build_ref.py``, git-ignored, shipped like the ``.so``) elsewhere.
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so nothing in
-``-m gpu`` tests, ``smoke()`` or ``bench.py`` may call this; it is used by
-``oracle/make_golden.py`` (and by a ``not gpu`` test that is skipped when the reference
-is absent) to pin ``oracle/evpp_oracle.py`` against the real code.
+TEST / BENCH INFRASTRUCTURE.  Used by ``oracle/make_golden*.py`` and the ``not gpu`` tests that pin
+``oracle/evpp_oracle.py`` against the real code, and by ``bench.py --impl reference`` / its ``cpu_baseline`` leg to
+time the reference itself on the host cores.  Never imported by the product, ``smoke()`` or the ``-m gpu`` tests.
 
 Recipe: ``run_nerf.py`` imports imageio / matplotlib.pyplot /
 colorlog and opens ``./logs/test.log`` at import time, so three empty stub modules are
@@ -15,11 +15,20 @@ import sys
 import tempfile
 import types
 
-REF_ROOT = "/root/reference/nerfServer"
+REF_ROOTS = ["/root/reference/nerfServer",
+             os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "nerfServer")]   # vendored copy (build_ref.py)
+REF_ROOT = next((r for r in REF_ROOTS if os.path.isfile(os.path.join(r, "core", "run_nerf.py"))), REF_ROOTS[0])
 
 
 def available():
-    return os.path.isdir(REF_ROOT)
+    return os.path.isfile(os.path.join(REF_ROOT, "core", "run_nerf.py"))
+
+
+def source():
+    """'tree' = /root/reference itself, 'vendored' = the byte-identical copy under oracle/_ref (GPU box), None."""
+    if not available():
+        return None
+    return "tree" if REF_ROOT == REF_ROOTS[0] else "vendored"
 
 
 def load():

@@ -1133,7 +1133,7 @@ def test_unchanged_seam_picks_the_fp32_next_best_view_on_plain_weights(weights, 
 
 def test_fp16_overflow_is_reported_and_retried_in_bf16(weights, caplog):
     """a checkpoint whose pre-activations exceed 65504 must not yield silent inf / NaN
-    scores.  pts_linears weights x 64: the C ABI returns EVPP_ERR_NONFINITE (-5) from the host entry point, the
+    scores.  pts_linears.1-3 weights x 64: the C ABI returns EVPP_ERR_NONFINITE (-5) from the host entry point, the
     Controller retries the call in bf16 once, logs it, and returns finite scores within bf16 tolerance of the oracle."""
     import logging
     import evpp_b200
@@ -1142,10 +1142,12 @@ def test_fp16_overflow_is_reported_and_retried_in_bf16(weights, caplog):
 
     def blow(sd):
         sd = {k: v.clone() for k, v in sd.items()}
-        for i in (1, 2):
-            sd[f"pts_linears.{i}.weight"] = sd[f"pts_linears.{i}.weight"] * 64
-        sd["pts_linears.3.weight"] = sd["pts_linears.3.weight"] / 64
-        sd["pts_linears.4.weight"] = sd["pts_linears.4.weight"] / 64
+        total = 1.0
+        for i, k in ((1, 64.0), (2, 64.0), (3, 256.0)):      # activations up to ~2 x 2^20 / 64 >> 65504 after layer 3
+            total *= k
+            sd[f"pts_linears.{i}.weight"] = sd[f"pts_linears.{i}.weight"] * k
+            sd[f"pts_linears.{i}.bias"] = sd[f"pts_linears.{i}.bias"] * total
+        sd["pts_linears.4.weight"] = sd["pts_linears.4.weight"] / total      # back to O(1) for the rest of the network
         return sd
 
     cb, fb = blow(c), blow(f)
