@@ -82,6 +82,8 @@ SIGNATURES = {
     "evpp_ngp_score_views": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
     "evpp_ngp_score_views_host": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
     "evpp_ngp_get_sample_count": (_I, [_P, C.POINTER(_L)]),
+    "evpp_check_guards": (_I, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "evpp_poison_workspace": (_I, [_P]),
     "evpp_get_counters": (_I, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "evpp_set_profiling": (_I, [_P, _I]),
     "evpp_get_mlp_time_ms": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_L), C.POINTER(_L)]),

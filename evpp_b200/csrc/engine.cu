@@ -40,23 +40,41 @@ int fail(int code, const char* fmt, ...) {
                   __LINE__);                                                                        \
   } while (0)
 
+// Device buffer with guard bands.  compute-sanitizer is closed on the GPU pool this engine is developed on, so every
+// buffer the engine owns carries kGuard bytes of a known pattern before and after the payload; evpp_check_guards()
+// verifies them (a write past either end of any workspace, by any kernel, shows up there) -- see tests and
+// tools/selfcheck.py.
+constexpr size_t kGuard = 256;
+constexpr int kGuardByte = 0xA5;
 struct DevBuf {
-  void* p = nullptr;
+  void* p = nullptr;       // payload (256-byte aligned: cudaMalloc alignment + kGuard)
   size_t bytes = 0;
   int ensure(size_t need) {
     if (need <= bytes) return 0;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-    cudaError_t e = cudaMalloc(&p, need);
+    release();
+    void* base = nullptr;
+    cudaError_t e = cudaMalloc(&base, need + 2 * kGuard);
     if (e != cudaSuccess) return (int)e;
+    cudaMemset(base, kGuardByte, kGuard);
+    cudaMemset(static_cast<char*>(base) + kGuard + need, kGuardByte, kGuard);
+    p = static_cast<char*>(base) + kGuard;
     bytes = need;
     return 0;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFree(static_cast<char*>(p) - kGuard);
     p = nullptr;
     bytes = 0;
+  }
+  // number of corrupted guard bytes (device must be idle)
+  int check() const {
+    if (!p) return 0;
+    unsigned char host[2 * kGuard];
+    if (cudaMemcpy(host, static_cast<char*>(p) - kGuard, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (cudaMemcpy(host + kGuard, static_cast<char*>(p) + bytes, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int bad = 0;
+    for (size_t i = 0; i < 2 * kGuard; ++i) bad += host[i] != kGuardByte;
+    return bad;
   }
   template <typename T>
   T* as() const { return reinterpret_cast<T*>(p); }
@@ -295,6 +313,21 @@ int render_chunk(evpp_handle* h, int n, float near_plane, float far_plane, int p
   return 0;
 }
 
+std::vector<DevBuf*> all_buffers(evpp_handle* h) {
+  std::vector<DevBuf*> v = {&h->t_vals, &h->u_vals, &h->rays_o, &h->rays_d, &h->viewdirs, &h->z_c, &h->raw_c, &h->z_f,
+                            &h->raw_f, &h->beta2, &h->nonfinite, &h->st_c2w, &h->st_pix, &h->st_scores, &h->w_c, &h->cdf, &h->inds, &h->zs,
+                            &h->tsdf_state, &h->tsdf_nray, &h->tsdf_t, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d,
+                            &h->tsdf_vu, &h->tsdf_vd, &h->ngp_table, &h->ngp_mlp, &h->ngp_bits, &h->ngp_ro, &h->ngp_rd,
+                            &h->ngp_counts, &h->ngp_offsets, &h->ngp_total, &h->ngp_masks, &h->ngp_tiles, &h->ngp_t0, &h->ngp_t, &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2,
+                            &h->ngp_scores, &h->tf_planes, &h->tf_lines, &h->tf_mlp, &h->sg_ws};
+  for (int i = 0; i < 2; ++i) {
+    NetWeights& nw = h->net[i];
+    for (DevBuf* b : {&nw.simt_stream, &nw.bias, &nw.head_w, &nw.head_b}) v.push_back(b);
+    for (auto& b : nw.tc_image) v.push_back(&b);
+  }
+  return v;
+}
+
 int check_device_ok(int device) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
@@ -394,18 +427,7 @@ int evpp_destroy(evpp_handle* h) {
   DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   for (auto& pr : h->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-  for (int i = 0; i < 2; ++i) {
-    NetWeights& nw = h->net[i];
-    nw.simt_stream.release(); nw.bias.release(); nw.head_w.release(); nw.head_b.release();
-    for (auto& b : nw.tc_image) b.release();
-  }
-  for (DevBuf* b : {&h->t_vals, &h->u_vals, &h->rays_o, &h->rays_d, &h->viewdirs, &h->z_c, &h->raw_c, &h->z_f,
-                    &h->raw_f, &h->beta2, &h->nonfinite, &h->st_c2w, &h->st_pix, &h->st_scores, &h->w_c, &h->cdf, &h->inds, &h->zs,
-                    &h->tsdf_state, &h->tsdf_nray, &h->tsdf_t, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d,
-                    &h->tsdf_vu, &h->tsdf_vd, &h->ngp_table, &h->ngp_mlp, &h->ngp_bits, &h->ngp_ro, &h->ngp_rd,
-                    &h->ngp_counts, &h->ngp_offsets, &h->ngp_total, &h->ngp_masks, &h->ngp_tiles, &h->ngp_t0, &h->ngp_t, &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2,
-                    &h->ngp_scores, &h->tf_planes, &h->tf_lines, &h->tf_mlp, &h->sg_ws})
-    b->release();
+  for (DevBuf* b : all_buffers(h)) b->release();
   delete h;
   return 0;
 }
@@ -1109,6 +1131,36 @@ int evpp_ngp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int 
 int evpp_ngp_get_sample_count(evpp_handle* h, int64_t* samples) {
   if (!h || !samples) return fail(EVPP_ERR_INVALID, "null argument");
   *samples = h->ngp_samples;
+  return 0;
+}
+
+int evpp_check_guards(evpp_handle* h, int32_t* corrupted_bytes, int32_t* buffers_checked) {
+  if (!h || !corrupted_bytes) return fail(EVPP_ERR_INVALID, "null argument");
+  EVPP_ON_DEVICE(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  int bad = 0, n = 0;
+  for (DevBuf* b : all_buffers(h)) {
+    if (!b->p) continue;
+    const int c = b->check();
+    if (c < 0) return fail(EVPP_ERR_CUDA, "guard read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+    bad += c;
+    ++n;
+  }
+  *corrupted_bytes = bad;
+  if (buffers_checked) *buffers_checked = n;
+  return 0;
+}
+
+int evpp_poison_workspace(evpp_handle* h) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  EVPP_ON_DEVICE(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  // 0xFF bytes = NaN as fp32, -1 as int32: a kernel that reads a workspace element nobody wrote in THIS call shows it
+  for (DevBuf* b : {&h->rays_o, &h->rays_d, &h->viewdirs, &h->z_c, &h->raw_c, &h->z_f, &h->raw_f, &h->beta2, &h->st_scores,
+                    &h->w_c, &h->cdf, &h->inds, &h->zs, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d, &h->tsdf_vu, &h->tsdf_vd,
+                    &h->ngp_ro, &h->ngp_rd, &h->ngp_counts, &h->ngp_offsets, &h->ngp_masks, &h->ngp_tiles, &h->ngp_t0, &h->ngp_t,
+                    &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2, &h->ngp_scores})
+    if (b->p) CUDA_TRY(cudaMemset(b->p, 0xFF, b->bytes));
   return 0;
 }
 

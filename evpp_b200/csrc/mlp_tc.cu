@@ -386,14 +386,12 @@ __device__ __forceinline__ void load_row(const TcArgs& args, long long tile, lon
   }
 }
 
-// two fp32 adds in one instruction (sm_100 packed fp32 pipe)
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  float2 c;
-  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-      "add.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
-      : "=f"(c.x), "=f"(c.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return c;
+// ReLU that keeps NaN (fmaxf(NaN, 0) would return 0 and hide an overflow of the 16-bit activations upstream: the
+// non-finite score check of the engine relies on NaN / inf reaching the outputs)
+__device__ __forceinline__ float relu_nan(float x) {
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+  return r;
 }
 // two fp32 fused multiply-adds in one instruction: a * s + b
 __device__ __forceinline__ float2 fma2(float2 a, float s, float2 b) {
@@ -412,8 +410,9 @@ __device__ __forceinline__ float2 fma2(float2 a, float s, float2 b) {
 // flight while chunk k is converted and stored.
 // HFC >= 0 makes the warp's column slice a compile-time constant, so that the head weights of layers 7 and 9 become
 // immediate constant-bank operands of the FFMAs instead of indexed constant loads.
-// NP > 1: the accumulator carries the layer's power-of-two weight scale (inv_ws undoes it, exactly); NP == 3 stores
-// the activations as a (hi, lo) fp16 pair: hi in the 8 packed columns at c0, lo in the 8 columns behind them.
+// The accumulator carries the layer's power-of-two weight scale (inv_ws undoes it, exactly, in the same FMA that adds
+// the bias).  NP == 3 stores the activations as a (hi, lo) fp16 pair: hi in the 8 packed columns at c0, lo in the
+// 8 columns behind them.
 template <bool BF16, int KIND, bool DBG, bool TR, int NP, int HFC = -1>
 __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& args, const float* bias_l, int l,
                                             uint32_t t_acc, int hf, int lane, uint32_t bar_a, uint32_t bar_acc_l,
@@ -425,7 +424,7 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
   constexpr int NCH = (KIND == 3 || KIND == 5) ? 2 : 4;
   constexpr int NC = kColsPerWarp;   // 16
   uint32_t r[2][NC];
-  const float inv_ws = NP > 1 ? cst.inv_wscale[l] : 1.f;
+  const float inv_ws = cst.inv_wscale[l];
   // the first chunk is on the critical path (the next layer's MMAs wait for it): fetch its biases before the
   // accumulator is ready
   float4 bpre[NC / 4];
@@ -461,17 +460,12 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
       const float4 b = kb == 0 ? bpre[j] : b4[j];
       const float2 a0 = make_float2(__uint_as_float(r[kb & 1][4 * j]), __uint_as_float(r[kb & 1][4 * j + 1]));
       const float2 a1 = make_float2(__uint_as_float(r[kb & 1][4 * j + 2]), __uint_as_float(r[kb & 1][4 * j + 3]));
-      if (NP > 1) {
-        v[2 * j] = fma2(a0, inv_ws, make_float2(b.x, b.y));
-        v[2 * j + 1] = fma2(a1, inv_ws, make_float2(b.z, b.w));
-      } else {
-        v[2 * j] = add2(a0, make_float2(b.x, b.y));
-        v[2 * j + 1] = add2(a1, make_float2(b.z, b.w));
-      }
+      v[2 * j] = fma2(a0, inv_ws, make_float2(b.x, b.y));
+      v[2 * j + 1] = fma2(a1, inv_ws, make_float2(b.z, b.w));
     }
     if (kRelu && (KIND != 0 || DBG || NP == 3)) {
 #pragma unroll
-      for (int j = 0; j < NC / 2; ++j) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); }
+      for (int j = 0; j < NC / 2; ++j) { v[j].x = relu_nan(v[j].x); v[j].y = relu_nan(v[j].y); }
     }
     if (DBG) {
       if (l == args.dbg_layer && rd.valid) {
@@ -1154,40 +1148,26 @@ __nv_bfloat16 to_op<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 // Appends one pre-swizzled K-block: n_rows x 64 channels; channel k of row n = W[n*in_dim + col0 + k]
 // for k < count, else 0.  Layout = what make_desc()/SWIZZLE_128B expects (see sw128()).
 template <typename T>
-void put_block(std::vector<uint8_t>& img, const std::vector<float>& W, int n_rows, int in_dim, int col0, int count) {
+void put_block(std::vector<uint8_t>& img, const std::vector<float>& W, int n_rows, int in_dim, int col0, int count,
+               float scale = 1.f) {
   const size_t base = img.size();
   img.resize(base + (size_t)n_rows * 128, 0);
   for (int n = 0; n < n_rows; ++n)
     for (int k = 0; k < 64; ++k) {
-      const float v = k < count ? W[(size_t)n * in_dim + col0 + k] : 0.f;
+      const float v = k < count ? W[(size_t)n * in_dim + col0 + k] * scale : 0.f;
       const T hv = to_op<T>(v);
       const size_t off = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
       memcpy(&img[base + off], &hv, 2);
     }
 }
 
-template <typename T>
-void pack_image(const std::vector<std::vector<float>>& t, std::vector<uint8_t>& img) {
-  img.clear();
-  img.reserve(kImageBytes);
-  put_block<T>(img, t[0], 256, 63, 0, 63);                                   // layer 0 : X
-  for (int l = 1; l <= 4; ++l)
-    for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[2 * l], 256, 256, kb * 64, 64);
-  put_block<T>(img, t[10], 256, 319, 0, 63);                                 // layer 5 : X part of cat[pts, h]
-  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[10], 256, 319, 63 + kb * 64, 64);
-  for (int l = 6; l <= 7; ++l)
-    for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[2 * l], 256, 256, kb * 64, 64);
-  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[18], 256, 256, kb * 64, 64);   // feature_linear
-  put_block<T>(img, t[16], 128, 283, 256, 27);                               // views : direction part
-  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[16], 128, 283, kb * 64, 64);   // views : feature part
-}
-
 // state_dict tensor of GEMM layer l (0..7 pts_linears, 8 feature_linear, 9 views_linears.0)
 int layer_tensor(int l) { return l < 8 ? 2 * l : l == 8 ? 18 : 16; }
 
-// Power-of-two scale that brings the largest |w| of a layer into [2^13, 2^14): the lo halves of the split weights
-// then sit in fp16's normal range (an unscaled lo of a ~0.06 weight would be subnormal, 2^-21 relative), and the
-// epilogue undoes the scale exactly (TcConsts::inv_wscale).
+// Power-of-two scale that brings the largest |w| of a layer into [2^13, 2^14): a trained layer with tiny weights
+// does not flush to zero in fp16 (subnormals start at 6e-5), a layer with weights beyond 65504 does not overflow,
+// the lo halves of the split weights sit in fp16's normal range, and the epilogue undoes the scale exactly
+// (TcConsts::inv_wscale, folded into the bias FMA).
 float layer_wscale(const std::vector<float>& W) {
   float m = 0.f;
   for (float v : W) m = std::fmax(m, std::fabs(v));
@@ -1195,6 +1175,24 @@ float layer_wscale(const std::vector<float>& W) {
   int e = 0;
   std::frexp(m, &e);                       // m = f * 2^e, f in [0.5, 1)
   return std::ldexp(1.f, 14 - e);          // m * scale in [2^13, 2^14)
+}
+
+template <typename T>
+void pack_image(const std::vector<std::vector<float>>& t, std::vector<uint8_t>& img) {
+  img.clear();
+  img.reserve(kImageBytes);
+  float sc[kLayers];
+  for (int l = 0; l < kLayers; ++l) sc[l] = layer_wscale(t[layer_tensor(l)]);
+  put_block<T>(img, t[0], 256, 63, 0, 63, sc[0]);                            // layer 0 : X
+  for (int l = 1; l <= 4; ++l)
+    for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[2 * l], 256, 256, kb * 64, 64, sc[l]);
+  put_block<T>(img, t[10], 256, 319, 0, 63, sc[5]);                          // layer 5 : X part of cat[pts, h]
+  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[10], 256, 319, 63 + kb * 64, 64, sc[5]);
+  for (int l = 6; l <= 7; ++l)
+    for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[2 * l], 256, 256, kb * 64, 64, sc[l]);
+  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[18], 256, 256, kb * 64, 64, sc[8]);   // feature_linear
+  put_block<T>(img, t[16], 128, 283, 256, 27, sc[9]);                        // views : direction part
+  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[16], 128, 283, kb * 64, 64, sc[9]);   // views : feature part
 }
 
 // Split image: every K-block of pack_image as a (hi, lo) pair, hi = fp16(w * s), lo = fp16(w * s - hi).

@@ -300,6 +300,19 @@ class Engine:
                                               _stream_ptr(self.device)))
         return out
 
+    def check_guards(self):
+        """(corrupted guard bytes, buffers checked): every engine-owned device buffer has guard bands on both sides;
+        a non-zero count means some kernel wrote out of bounds (evpp_check_guards).  Synchronises."""
+        bad, n = C.c_int32(0), C.c_int32(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_check_guards(self._h, C.byref(bad), C.byref(n)))
+        return bad.value, n.value
+
+    def poison_workspace(self):
+        """Fill the per-call workspace with NaN bit patterns (self-check hook, evpp_poison_workspace)."""
+        with torch.cuda.device(self.device):
+            check(self.lib.evpp_poison_workspace(self._h))
+
     # ---- counters -----------------------------------------------------------------------------------
     def counters(self):
         a, b = C.c_int64(0), C.c_int64(0)

@@ -324,6 +324,15 @@ int evpp_ngp_get_sample_count(evpp_handle* h, int64_t* samples);
  * evaluations issued (for bench.py's gpu_launches and roofline accounting). */
 int evpp_get_counters(evpp_handle* h, int64_t* kernel_launches, int64_t* mlp_evals);
 
+/* Self-check (compute-sanitizer is not available on the development pool): every device buffer the engine owns is
+ * allocated with 256-byte guard bands of a known pattern on both sides; this synchronises the device and counts the
+ * guard bytes any kernel has overwritten since the buffers were allocated (0 = no out-of-bounds write). */
+int evpp_check_guards(evpp_handle* h, int32_t* corrupted_bytes, int32_t* buffers_checked);
+
+/* Self-check hook: fills every per-call workspace buffer with 0xFF bytes (NaN as fp32), so that a kernel reading an
+ * element that was not written earlier in the same call produces a visibly wrong result. */
+int evpp_poison_workspace(evpp_handle* h);
+
 /* Average duration in ms of the MLP kernel launches recorded (CUDA events on the launching
  * stream) since the last reset; enable with evpp_set_profiling(h, 1). Synchronises. */
 int evpp_set_profiling(evpp_handle* h, int enabled);

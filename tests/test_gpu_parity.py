@@ -1201,3 +1201,23 @@ def test_render_engine_cache_is_bounded_and_content_keyed(weights):
     for e in R._ENGINE_CACHE.values():
         e.close()
     R._ENGINE_CACHE.clear()
+
+
+def test_guard_bands_poisoned_workspace_and_run_to_run_determinism(engine_factory):
+    """Stand-in for compute-sanitizer (closed on the GPU pool), small edition of tools/selfcheck.py: scoring on a
+    NaN-poisoned workspace gives the same bits every time (no read of stale / unwritten elements, no race between the
+    producer, MMA and epilogue roles), and no kernel has touched the guard bands around the engine's buffers."""
+    H, W = 12, 16
+    K = O.make_K(H, W, 12.0)
+    poses = torch.Tensor(np.asarray(O.views_to_poses(O.hemisphere_views(7, seed=1))))[:, :3, :4].contiguous().cuda()
+    for prec in ("fp16", "fp16x3", "fp32"):
+        eng = engine_factory("spread", prec, max_chunk_rays=500)
+        ref = None
+        for r in range(6):
+            eng.poison_workspace()
+            s = eng.score_views(poses, H, W, *_intr(K)).cpu()
+            assert torch.isfinite(s).all()
+            ref = s if ref is None else ref
+            assert torch.equal(ref, s), (prec, r)
+        bad, n = eng.check_guards()
+        assert bad == 0 and n >= 10, (prec, bad, n)
