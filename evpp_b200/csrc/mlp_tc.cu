@@ -287,7 +287,12 @@ __device__ __forceinline__ void encode_store(const float (&p)[3], uint32_t row_b
 #pragma unroll
     for (int l = 0; l < L; ++l) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) sincosf(p[i] * (float)(1 << l), &e[3 + l * 6 + i], &e[3 + l * 6 + 3 + i]);
+      for (int i = 0; i < 3; ++i) {
+        float sn, cs;      // (not &e[..]: taking the array's address would pin all of e[] in local memory)
+        sincosf(p[i] * (float)(1 << l), &sn, &cs);
+        e[3 + l * 6 + i] = sn;
+        e[3 + l * 6 + 3 + i] = cs;
+      }
     }
   } else {
     float s[3], c[3];
@@ -423,7 +428,10 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
   constexpr bool kRelu = KIND != 2;
   constexpr int NCH = (KIND == 3 || KIND == 5) ? 2 : 4;
   constexpr int NC = kColsPerWarp;   // 16
-  uint32_t r[2][NC];
+  // The tensor-memory load of chunk k+1 is in flight while chunk k is converted (two register buffers).  Measured for
+  // the fp16x3 pass too: a single buffer saves its ~80 bytes of spills and costs 9 % (115 vs 126 views/s).
+  constexpr bool kPrefetch = true;
+  uint32_t r[kPrefetch ? 2 : 1][NC];
   const float inv_ws = cst.inv_wscale[l];
   // the first chunk is on the critical path (the next layer's MMAs wait for it): fetch its biases before the
   // accumulator is ready
@@ -440,16 +448,17 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
   bool half1_early = false;
 #pragma unroll
   for (int kb = 0; kb < NCH; ++kb) {
+    const int rb = kPrefetch ? (kb & 1) : 0;
     tmem_ld_wait();
-    if (kb + 1 < NCH) {
+    if (kPrefetch && kb + 1 < NCH) {
       if (kb + 1 == 2) {
         half1_early = __all_sync(0xffffffffu, mbar_test(bar_acc_l + 8, acc_parity));
         if (half1_early) {
           tc_fence_after();
-          tmem_ld16(t_acc + (uint32_t)((kb + 1) * 64 + hf * NC), r[(kb + 1) & 1]);
+          tmem_ld16(t_acc + (uint32_t)((kb + 1) * 64 + hf * NC), r[kPrefetch ? ((kb + 1) & 1) : 0]);
         }
       } else {
-        tmem_ld16(t_acc + (uint32_t)((kb + 1) * 64 + hf * NC), r[(kb + 1) & 1]);
+        tmem_ld16(t_acc + (uint32_t)((kb + 1) * 64 + hf * NC), r[kPrefetch ? ((kb + 1) & 1) : 0]);
       }
     }
     const int c0 = kb * 64 + hf * NC;
@@ -458,8 +467,8 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
 #pragma unroll
     for (int j = 0; j < NC / 4; ++j) {
       const float4 b = kb == 0 ? bpre[j] : b4[j];
-      const float2 a0 = make_float2(__uint_as_float(r[kb & 1][4 * j]), __uint_as_float(r[kb & 1][4 * j + 1]));
-      const float2 a1 = make_float2(__uint_as_float(r[kb & 1][4 * j + 2]), __uint_as_float(r[kb & 1][4 * j + 3]));
+      const float2 a0 = make_float2(__uint_as_float(r[rb][4 * j]), __uint_as_float(r[rb][4 * j + 1]));
+      const float2 a1 = make_float2(__uint_as_float(r[rb][4 * j + 2]), __uint_as_float(r[rb][4 * j + 3]));
       v[2 * j] = fma2(a0, inv_ws, make_float2(b.x, b.y));
       v[2 * j + 1] = fma2(a1, inv_ws, make_float2(b.z, b.w));
     }
@@ -523,10 +532,18 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
       if (TR && tr && lane == 0) tr[1 + kb] = clk();
       if (TR && tr0 && lane == 0 && kb == 0) tr0[0] = clk();
     }
-    if (kb == 1 && NCH > 2 && !half1_early) {
-      mbar_wait(bar_acc_l + 8, acc_parity);
-      tc_fence_after();
-      tmem_ld16(t_acc + (uint32_t)(2 * 64 + hf * NC), r[0]);
+    if (kPrefetch) {
+      if (kb == 1 && NCH > 2 && !half1_early) {
+        mbar_wait(bar_acc_l + 8, acc_parity);
+        tc_fence_after();
+        tmem_ld16(t_acc + (uint32_t)(2 * 64 + hf * NC), r[0]);
+      }
+    } else if (kb + 1 < NCH) {
+      if (kb + 1 == 2) {
+        mbar_wait(bar_acc_l + 8, acc_parity);
+        tc_fence_after();
+      }
+      tmem_ld16(t_acc + (uint32_t)((kb + 1) * 64 + hf * NC), r[0]);
     }
   }
   if (NCH == 2) mbar_wait(bar_acc_l + 8, acc_parity);   // keeps the phase of the (unused) second-half barrier in step
@@ -799,7 +816,8 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
     const int row = q * 32 + lane;
     const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-    uint32_t acc_phase[2] = {0u, 0u};
+    uint32_t acc_phase = 0u;   // bit r = phase of accumulator region r (NOT an array: l & 1 is a runtime index, and a
+                               // dynamically indexed array would live in local memory -- 320 LDL / STL per tile)
     RowData cur, nxt;
     load_row<RAYS>(args, args.tile0 + (long long)blockIdx.x, ntiles, row, cur);
     if (hf == 0) {
@@ -814,8 +832,8 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
 #pragma unroll 1
       for (int l = 0; l < kLayersRun; ++l) {
         const int ab = l & 1;
-        const uint32_t bar_l = bar_acc + 16 * ab, par_l = acc_phase[ab];
-        acc_phase[ab] ^= 1u;
+        const uint32_t bar_l = bar_acc + 16 * ab, par_l = (acc_phase >> ab) & 1u;
+        acc_phase ^= 1u << ab;
         if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 0);   // (before the accumulator wait)
         const uint32_t t_acc = t_lane + (uint32_t)(ab * 256);
         long long* tr = nullptr;
