@@ -590,7 +590,8 @@ def workload_config(world, engine_desc):
                             "(freq. encoding + 8x256 NeRF + NeurAR uncertainty head, random-init seed 0); a step = bulk pass + exact "
                             "re-score of the near-tied leaders + NBV selection",
                 "views": V_TOTAL, "views_per_gpu": (V_TOTAL + world - 1) // world, "rays_per_view": IMG_H * IMG_W, "near": NEAR, "far": FAR,
-                "parallelism": f"{V_TOTAL} views sharded over {world} GPU(s) in contiguous blocks, all_gather of the scores, contenders "
+                "parallelism": f"{V_TOTAL} views sharded over {world} GPU(s) in contiguous blocks (sized in proportion to each rank's measured "
+                               "speed after two calibration sweeps), all_gather of the scores, contenders "
                                "dealt out round robin for the exact pass, second all_gather, replicated selection",
                 "engine": engine_desc,
                 "l2": "per-step working set (~0.7 GB of streamed ray/sample intermediates per 131072-ray chunk, >300 chunks) exceeds L2; "
@@ -622,6 +623,7 @@ def main():
     ap.add_argument("--impl", default="evpp_b200")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16", "fp16x2", "fp16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="equal view blocks per rank (no speed-proportional split)")
     ap.add_argument("--no-rescore", action="store_true", help="bulk pass only (no exact re-score of the leaders, no NBV identity)")
     ap.add_argument("--full-outputs", action="store_true", help="scoring calls evaluate the full network like render() (round-1 behaviour)")
     ap.add_argument("--pixel-sampler", default="device", choices=["device", "numpy"],
@@ -692,11 +694,18 @@ def main():
     out_pinned = torch.empty(V_job + 1, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     margin = 0.0 if args.no_rescore else MARGIN
-    state = {"winner": None, "band": 0, "scores": None}
+    state = {"winner": None, "band": 0, "scores": None, "ranges": None, "calibrating": world > 1 and not args.no_balance}
 
     def sweep(poses, host_out):
         if room:
-            s, win, band = edist.sweep_select(eng, poses, IMG_H, IMG_W, fx, fy, cx, cy, rank, world, margin=margin, host_out=host_out)
+            timing = {} if state["calibrating"] else None
+            s, win, band = edist.sweep_select(eng, poses, IMG_H, IMG_W, fx, fy, cx, cy, rank, world, margin=margin, host_out=host_out,
+                                              ranges=state["ranges"], timing=timing)
+            if timing:
+                # load balance: the next sweep's blocks are proportional to the speeds the ranks
+                # just measured on their own bulk pass (the GPUs of a box run 1-3 % apart under the power cap)
+                sp = edist.exchange_speeds(timing["bulk_views"], timing["bulk_ms"], rank, world, dev)
+                state["ranges"] = edist.balanced_ranges(V_TOTAL, sp)
         else:       # weak scaling: every rank scores its own 512 views, then the same gather / selection tail
             pd = poses.to(dev, non_blocking=True) if poses.device.type == "cpu" else poses
             s = eng.score_views(pd, IMG_H, IMG_W, fx, fy, cx, cy)
@@ -751,6 +760,10 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    if state["calibrating"]:
+        for _ in range(2):          # two untimed calibration sweeps fix the block sizes; the timed steps do not re-balance
+            step_device()
+        state["calibrating"] = False
     ms_dev, _, launches, evals = timed(step_device, args.steps, args.warmup, profile=True)
     mlp_ms, mlp_launches, mlp_evals, mlp_flops = eng.mlp_profile()
     eng.set_profiling(False)
@@ -792,6 +805,7 @@ def main():
                                "Engine.score_views + select_nbv (pinned host poses in, host scores + winner out)"},
                 "gpu_launches": int(launches),
                 "nbv_check": check,
+                "view_blocks": [e_ - b_ for b_, e_ in state["ranges"]] if state["ranges"] else None,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                              "frac": achieved / sustained,
                              "traffic": (bpe * mlp_evals / max(1, mlp_launches)) if (tensor and bpe) else None,

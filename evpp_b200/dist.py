@@ -115,6 +115,42 @@ def render_views_ray_sharded(render_block, V, n_pixels, rank, world, device="cpu
     return maps, (partial / n_pixels).to(torch.float32)
 
 
+def balanced_ranges(V, speeds):
+    """Contiguous view blocks proportional to per-rank speeds (views / ms measured on each rank's own previous pass):
+    the GPUs of one box settle at different clocks under the power cap (1-3 % apart), and a strong-scaled sweep ends
+    when the slowest rank does.  Returns [(begin, end)] per rank covering [0, V) exactly."""
+    sp = np.asarray(speeds, dtype=np.float64)
+    if len(sp) == 0 or not np.all(np.isfinite(sp)) or np.any(sp <= 0):
+        return [shard_range(V, r, len(sp)) for r in range(len(sp))]
+    edges = np.rint(np.concatenate([[0.0], np.cumsum(sp / sp.sum())]) * V).astype(np.int64)
+    edges[0], edges[-1] = 0, V
+    edges = np.maximum.accumulate(edges)
+    return [(int(edges[r]), int(edges[r + 1])) for r in range(len(sp))]
+
+
+def gather_blocks(local, ranges, V, rank, world, group=None):
+    """all_gather of per-rank score blocks of UNEQUAL sizes (ranges[r] = (begin, end) of rank r) -> full [V] tensor."""
+    per = max(e - b for b, e in ranges)
+    pad = torch.full((per,), float("-inf"), dtype=torch.float32, device=local.device)
+    pad[:local.numel()] = local.to(torch.float32)
+    out = torch.empty(world * per, dtype=torch.float32, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group) if hasattr(dist, "all_gather_into_tensor") and \
+        local.device.type == "cuda" else _all_gather_list(out, pad, world, group)
+    full = torch.empty(V, dtype=torch.float32, device=local.device)
+    for r, (b, e) in enumerate(ranges):
+        full[b:e] = out[r * per:r * per + (e - b)]
+    return full
+
+
+def exchange_speeds(local_views, local_ms, rank, world, device, group=None):
+    """Every rank's bulk-pass speed (views / ms) on every rank: the input of balanced_ranges."""
+    t = torch.zeros(world, dtype=torch.float64, device=device)
+    t[rank] = (local_views / local_ms) if local_ms > 0 and local_views > 0 else 0.0
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
 def scatter_round_robin(ids, rank, world):
     """The share of ``ids`` (sorted global view ids of the contenders) that ``rank`` re-scores: every world-th one.
     Contenders cluster wherever the scene is uncertain, i.e. inside one rank's contiguous block of the sweep;
@@ -123,7 +159,7 @@ def scatter_round_robin(ids, rank, world):
 
 
 def sweep_select(engine, poses, H, W, fx, fy, cx, cy, rank=0, world=1, margin=2e-3, exact="fp16x3", weight=None,
-                 dirs_per_location=1, group=None, host_out=None):
+                 dirs_per_location=1, group=None, host_out=None, ranges=None, timing=None):
     """One candidate sweep with identical-NBV guarantee, sharded over ``world`` ranks:
 
       1. bulk pass: rank r scores its contiguous block of the V poses at the engine's 16-bit precision;
@@ -134,17 +170,32 @@ def sweep_select(engine, poses, H, W, fx, fy, cx, cy, rank=0, world=1, margin=2e
       5. the planner's selection tail (vpp.py:199-220 + interface.py:115-116) on the device (evpp_select_nbv).
 
     poses: float32 [V,3,4] on the engine's device (already resident) or on the host (pinned: copied every call).
+    ranges: optional [(begin, end)] per rank (balanced_ranges) instead of equal blocks; timing: optional dict that
+    receives 'bulk_ms' (CUDA-event time of this rank's bulk pass) and 'bulk_views' for the next call's balancing.
     Returns (scores [V] on the device, winner view id, number of re-scored views).  With ``host_out`` (a pinned
     float32 [V + 1] tensor) the scores and the winner id are also landed in host memory before returning."""
     from .planner import contenders
     dev = engine.device
     V = poses.shape[0]
-    b, e = shard_range(V, rank, world)
+    b, e = ranges[rank] if ranges is not None else shard_range(V, rank, world)
     on_host = poses.device.type == "cpu"
     poses_dev = poses.to(dev, non_blocking=True) if on_host else poses
+    ev = None
+    if timing is not None and dev.type == "cuda":
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     local = engine.score_views(poses_dev[b:e], H, W, fx, fy, cx, cy) if e > b else torch.empty(0, device=dev)
-    scores = gather_scores(local, V, rank, world, group) if world > 1 else local
+    if ev is not None:
+        ev[1].record()
+    if world == 1:
+        scores = local
+    elif ranges is not None:
+        scores = gather_blocks(local, ranges, V, rank, world, group)
+    else:
+        scores = gather_scores(local, V, rank, world, group)
     fast_host = scores.cpu().numpy().astype(np.float64)
+    if ev is not None:
+        timing["bulk_ms"], timing["bulk_views"] = ev[0].elapsed_time(ev[1]), e - b
     if not np.isfinite(fast_host).all():
         raise FloatingPointError("non-finite view scores in the bulk pass (16-bit activations overflowed): use precision='bf16'")
     band = contenders(fast_host, None if weight is None else weight.cpu().numpy(), margin) if margin > 0 else np.zeros(0, np.int32)

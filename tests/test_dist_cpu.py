@@ -218,28 +218,44 @@ class _SweepEngine:
         return None, None, torch.tensor([int(best)], dtype=torch.int32)
 
 
-def _sweep_select_worker(rank, world, port, V, q):
+def _sweep_select_worker(rank, world, port, V, q, speeds=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     poses = torch.zeros(V, 3, 4)
     poses[:, 0, 3] = torch.arange(V, dtype=torch.float32)
     eng = _SweepEngine()
-    scores, win, band = edist.sweep_select(eng, poses, 6, 8, 6.0, 6.0, 4.0, 3.0, rank, world, margin=2e-3)
+    ranges = None
+    if speeds is not None:        # unequal, speed-proportional blocks; the speeds travel through the collective
+        sp = edist.exchange_speeds(speeds[rank], 1.0, rank, world, "cpu")
+        ranges = edist.balanced_ranges(V, sp)
+        assert ranges[0][0] == 0 and ranges[-1][1] == V and ranges[0][1] == ranges[1][0]
+    scores, win, band = edist.sweep_select(eng, poses, 6, 8, 6.0, 6.0, 4.0, 3.0, rank, world, margin=2e-3, ranges=ranges)
     q.put((rank, scores.numpy(), win, band, eng.exact_calls))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("V", [41, 200])
-def test_two_rank_sweep_select_matches_single_process_and_exact_argmax(V):
+def test_balanced_ranges_cover_exactly_and_follow_the_speeds():
+    for V in (1, 7, 4096):
+        for sp in ([1.0], [1.0, 1.0], [1.0, 1.03, 0.98, 1.0], [3.0, 1.0], [1.0] * 8):
+            r = edist.balanced_ranges(V, sp)
+            assert r[0][0] == 0 and r[-1][1] == V and all(r[i][1] == r[i + 1][0] for i in range(len(r) - 1))
+            assert all(e >= b for b, e in r)
+    r = edist.balanced_ranges(4096, [1.0, 1.02])
+    assert r[1][1] - r[1][0] > r[0][1] - r[0][0] and abs((r[1][1] - r[1][0]) / (r[0][1] - r[0][0]) - 1.02) < 2e-3
+    assert edist.balanced_ranges(10, [0.0, 1.0]) == [edist.shard_range(10, 0, 2), edist.shard_range(10, 1, 2)]   # bad timing: equal blocks
+
+
+@pytest.mark.parametrize("V,speeds", [(41, None), (200, None), (200, (1.0, 1.7))])
+def test_two_rank_sweep_select_matches_single_process_and_exact_argmax(V, speeds):
     """dist.sweep_select at world size 2 (gloo): bulk pass sharded in blocks, contenders dealt out round robin for
     the exact pass, both gathers, replicated selection -- every rank ends with the single-process scores and with
     the arg-max of the EXACT scores although the leaders are closer than the bulk pass's error."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_sweep_select_worker, args=(r, 2, port, V, q)) for r in range(2)]
+    procs = [ctx.Process(target=_sweep_select_worker, args=(r, 2, port, V, q, speeds)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(2)]
