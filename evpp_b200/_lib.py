@@ -24,12 +24,13 @@ class EvppRenderOut(C.Structure):
 class EvppNgpConfig(C.Structure):
     _fields_ = [("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3), ("grid_res", C.c_int32),
                 ("near_plane", C.c_float), ("far_plane", C.c_float), ("dt", C.c_float), ("max_steps", C.c_int32),
-                ("max_samples", C.c_int32), ("n_levels", C.c_int32), ("white_bkgd", C.c_int32)]
+                ("max_samples", C.c_int32), ("n_levels", C.c_int32), ("white_bkgd", C.c_int32),
+                ("march_mode", C.c_int32), ("cascades", C.c_int32), ("dt_gamma", C.c_float), ("min_near", C.c_float)]
 
 
 class EvppNgpOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("rgb", "depth", "acc", "beta2", "counts", "t", "raw", "enc")] + \
-               [("sample_capacity", C.c_int64), ("total_so_far", C.c_int64)]
+               [("sample_capacity", C.c_int64), ("total_so_far", C.c_int64), ("delta", C.c_void_p), ("cell", C.c_void_p)]
 
 
 class EvppError(RuntimeError):

@@ -141,8 +141,8 @@ struct evpp_handle {
   DevBuf tf_planes, tf_lines, tf_mlp;
   NgpParams ngp{};
   DevBuf ngp_table, ngp_mlp, ngp_bits, ngp_ro, ngp_rd, ngp_counts, ngp_offsets, ngp_total, sg_ws, ngp_masks, ngp_tiles, ngp_t0, ngp_t, ngp_ray, ngp_raw,
-      ngp_beta2, ngp_scores;
-  int64_t ngp_samples = 0;       // kept samples since handle creation
+      ngp_beta2, ngp_scores, ngp_delta, ngp_cell, ngp_counter;
+  int64_t ngp_samples = 0;       // kept samples since handle creation (host-visible part; the device counter holds the rest)
   int ngp_chunk_rays = 1 << 20;  // rays per marching chunk (one count -> scan -> fill round trip each)
   // counters / profiling
   int64_t launches = 0, evals = 0;
@@ -319,7 +319,7 @@ std::vector<DevBuf*> all_buffers(evpp_handle* h) {
                             &h->tsdf_state, &h->tsdf_nray, &h->tsdf_t, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d,
                             &h->tsdf_vu, &h->tsdf_vd, &h->ngp_table, &h->ngp_mlp, &h->ngp_bits, &h->ngp_ro, &h->ngp_rd,
                             &h->ngp_counts, &h->ngp_offsets, &h->ngp_total, &h->ngp_masks, &h->ngp_tiles, &h->ngp_t0, &h->ngp_t, &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2,
-                            &h->ngp_scores, &h->tf_planes, &h->tf_lines, &h->tf_mlp, &h->sg_ws};
+                            &h->ngp_scores, &h->ngp_delta, &h->ngp_cell, &h->ngp_counter, &h->tf_planes, &h->tf_lines, &h->tf_mlp, &h->sg_ws};
   for (int i = 0; i < 2; ++i) {
     NetWeights& nw = h->net[i];
     for (DevBuf* b : {&nw.simt_stream, &nw.bias, &nw.head_w, &nw.head_b}) v.push_back(b);
@@ -921,8 +921,19 @@ int evpp_ngp_configure(evpp_handle* h, const evpp_ngp_config* cfg, const float* 
   if (cfg->n_levels < 1 || cfg->n_levels > kNgpMaxLevels) return fail(EVPP_ERR_INVALID, "n_levels must be 1..%d", kNgpMaxLevels);
   if (cfg->n_levels != 16) return fail(EVPP_ERR_INVALID, "the fused field kernel is built for 16 levels x 2 features (32 inputs)");
   if (cfg->grid_res < 8 || cfg->grid_res > 1024 || (cfg->grid_res & 7)) return fail(EVPP_ERR_INVALID, "grid_res must be a multiple of 8 in [8,1024]");
-  if (!(cfg->dt > 0.f) || !(cfg->far_plane > cfg->near_plane) || cfg->max_steps < 1 || cfg->max_samples < 1)
+  if (cfg->march_mode != 0 && cfg->march_mode != 1) return fail(EVPP_ERR_INVALID, "march_mode must be 0 (uniform) or 1 (torch-ngp)");
+  if (cfg->max_steps < 1 || cfg->max_samples < 1) return fail(EVPP_ERR_INVALID, "bad marching parameters");
+  if (cfg->march_mode == 0 && (!(cfg->dt > 0.f) || !(cfg->far_plane > cfg->near_plane)))
     return fail(EVPP_ERR_INVALID, "bad marching parameters");
+  if (cfg->march_mode == 1) {
+    if (cfg->grid_res & (cfg->grid_res - 1)) return fail(EVPP_ERR_INVALID, "torch-ngp marching needs a power-of-two grid_res (Morton order)");
+    if (cfg->cascades < 1 || cfg->cascades > 8) return fail(EVPP_ERR_INVALID, "cascades must be in [1,8]");
+    if (!(cfg->dt_gamma >= 0.f) || !(cfg->min_near >= 0.f)) return fail(EVPP_ERR_INVALID, "dt_gamma and min_near must be >= 0");
+    const float sx = cfg->aabb_max[0] - cfg->aabb_min[0];
+    for (int c = 1; c < 3; ++c)
+      if (std::fabs((cfg->aabb_max[c] - cfg->aabb_min[c]) - sx) > 1e-5f * sx)
+        return fail(EVPP_ERR_INVALID, "torch-ngp marching needs a cubic scene box");
+  }
   NgpParams& P = h->ngp;
   P.n_levels = cfg->n_levels;
   for (int l = 0; l < cfg->n_levels; ++l) {
@@ -948,6 +959,26 @@ int evpp_ngp_configure(evpp_handle* h, const evpp_ngp_config* cfg, const float* 
   }
   P.near_plane = cfg->near_plane; P.far_plane = cfg->far_plane; P.dt = cfg->dt;
   P.max_steps = cfg->max_steps; P.max_samples = cfg->max_samples; P.white_bkgd = cfg->white_bkgd;
+  P.march_mode = cfg->march_mode;
+  P.cascades = cfg->march_mode == 1 ? cfg->cascades : 1;
+  if (cfg->march_mode == 1) {
+    // fp32 constants exactly as the restatement computes them (the test suite holds the same arithmetic in numpy)
+    P.bound = (float)(1 << (cfg->cascades - 1));
+    const float half = 0.5f * (cfg->aabb_max[0] - cfg->aabb_min[0]);
+    P.scale = P.bound / half;
+    for (int c = 0; c < 3; ++c) P.center[c] = 0.5f * (cfg->aabb_min[c] + cfg->aabb_max[c]);
+    const float two_sqrt3 = 2.f * 1.7320508075688772f;
+    P.dt_gamma = cfg->dt_gamma;
+    P.dt_min = two_sqrt3 / (float)cfg->max_steps;
+    P.dt_max = two_sqrt3 * (float)(1 << (cfg->cascades - 1)) / (float)cfg->grid_res;
+    P.min_near = cfg->min_near;
+  }
+  if (h->ngp_counter.ensure(8)) return fail(EVPP_ERR_CUDA, "counter alloc failed");
+  {
+    DeviceGuard guard(h->device);
+    cudaMemset(h->ngp_counter.p, 0, 8);
+  }
+  h->ngp_samples = 0;
   h->ngp_configured = true;
   h->ngp_has_occ = h->ngp_has_params = false;
   return 0;
@@ -957,7 +988,9 @@ int evpp_ngp_set_occupancy(evpp_handle* h, const uint8_t* bitfield, int64_t nbyt
   if (!h || !bitfield) return fail(EVPP_ERR_INVALID, "null argument");
   if (!h->ngp_configured) return fail(EVPP_ERR_STATE, "evpp_ngp_configure first");
   const int64_t G = h->ngp.grid_res;
-  if (nbytes != G * G * G / 8) return fail(EVPP_ERR_INVALID, "bitfield must hold grid_res^3 bits (%lld bytes)", (long long)(G * G * G / 8));
+  const int64_t want = G * G * G / 8 * (h->ngp.march_mode == 1 ? h->ngp.cascades : 1);
+  if (nbytes != want) return fail(EVPP_ERR_INVALID, "bitfield must hold %sgrid_res^3 bits (%lld bytes)",
+                                  h->ngp.march_mode == 1 ? "cascades x " : "", (long long)want);
   EVPP_ON_DEVICE(h->device);
   if (h->ngp_bits.ensure((size_t)nbytes)) return fail(EVPP_ERR_CUDA, "bitfield alloc failed");
   CUDA_TRY(cudaMemcpy(h->ngp_bits.p, bitfield, (size_t)nbytes, cudaMemcpyDefault));
@@ -1019,42 +1052,73 @@ int evpp_ngp_encode(evpp_handle* h, const float* u, int64_t M, float* enc, int32
   return 0;
 }
 
-// march -> scan -> fill -> field -> composite for rays already on the device; leaves per-ray beta2 in `beta2`
+// march -> scan -> fill -> field -> composite for rays already on the device; leaves per-ray beta2 in `beta2`.
+// No host round trip: the sample buffers are sized for the worst case (rays x max_samples) once, and the kernels
+// after the scan read the chunk's sample total from device memory.  Only a caller that asks for per-sample dumps
+// (evpp_ngp_render_rays with t / raw / enc / delta / cell) makes the host wait for the total.
 static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, int n, evpp_ngp_out* out, long long off,
                              float* beta2, cudaStream_t st) {
+  const NgpParams& P = h->ngp;
+  const bool tngp = P.march_mode == 1;
+  const long long cap = (long long)n * P.max_samples + 1;
   if (h->ngp_counts.ensure((size_t)n * 4) || h->ngp_offsets.ensure((size_t)n * 4) || h->ngp_total.ensure(4) ||
-      h->ngp_masks.ensure((size_t)n * ngp_mask_words(h->ngp) * 4) || h->ngp_tiles.ensure((size_t)2 * ngp_scan_tiles(n) * 4) || h->ngp_t0.ensure((size_t)n * 4))
-    return fail(EVPP_ERR_CUDA, "NGP workspace alloc failed");
+      h->ngp_tiles.ensure((size_t)2 * ngp_scan_tiles(n) * 4) ||
+      (!tngp && (h->ngp_masks.ensure((size_t)n * ngp_mask_words(P) * 4) || h->ngp_t0.ensure((size_t)n * 4))) ||
+      (tngp && h->ngp_delta.ensure((size_t)cap * 4)) ||
+      h->ngp_t.ensure((size_t)cap * 4) || h->ngp_ray.ensure((size_t)cap * 4) || h->ngp_raw.ensure((size_t)cap * 20))
+    return fail(EVPP_ERR_CUDA, "NGP workspace alloc failed (%d rays x %d samples)", n, P.max_samples);
+  const bool want_cells = tngp && out && out->cell;
+  if (want_cells && h->ngp_cell.ensure((size_t)cap * 4)) return fail(EVPP_ERR_CUDA, "NGP workspace alloc failed");
   int32_t* counts = out && out->counts ? out->counts + off : h->ngp_counts.as<int32_t>();
   int32_t* offsets = h->ngp_offsets.as<int32_t>();
-  h->launches += launch_ngp_march_count(h->ngp, ro, rd, n, counts, h->ngp_masks.as<uint32_t>(), h->ngp_t0.as<float>(), st);
-  h->launches += launch_ngp_scan(counts, n, offsets, h->ngp_total.as<int32_t>(), h->ngp_tiles.as<int32_t>(), st);
-  int32_t total = 0;
-  CUDA_TRY(cudaMemcpyAsync(&total, h->ngp_total.p, 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  const long long M = total;
-  if (h->ngp_t.ensure((size_t)(M + 1) * 4) || h->ngp_ray.ensure((size_t)(M + 1) * 4) || h->ngp_raw.ensure((size_t)(M + 1) * 20))
-    return fail(EVPP_ERR_CUDA, "NGP sample workspace alloc failed (%lld samples)", M);
-  h->launches += launch_ngp_march_fill(h->ngp, n, counts, offsets, h->ngp_masks.as<uint32_t>(), h->ngp_t0.as<float>(),
-                                        h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), st);
-  float* enc_dump = out && out->enc && out->sample_capacity >= out->total_so_far + M ? out->enc + out->total_so_far * 32 : nullptr;
-  if (h->ngp_tensorf)
-    h->launches += launch_tensorf_field(h->ngp, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), M, h->ngp_raw.as<float>(),
-                                        h->num_sms, st);
+  const int32_t* total_dev = h->ngp_total.as<int32_t>();
+  if (tngp)
+    h->launches += launch_tngp_march_count(P, ro, rd, n, counts, st);
   else
-    h->launches += launch_ngp_field(h->ngp, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), M, h->ngp_raw.as<float>(),
-                                    enc_dump, h->num_sms, h->cfg.precision != EVPP_PREC_FP32, st);
-  h->launches += launch_ngp_composite(h->ngp, h->ngp_raw.as<float>(), h->ngp_t.as<float>(), counts, offsets, n,
+    h->launches += launch_ngp_march_count(P, ro, rd, n, counts, h->ngp_masks.as<uint32_t>(), h->ngp_t0.as<float>(), st);
+  h->launches += launch_ngp_scan(counts, n, offsets, h->ngp_total.as<int32_t>(), h->ngp_tiles.as<int32_t>(),
+                                 h->ngp_counter.as<unsigned long long>(), st);
+  if (tngp)
+    h->launches += launch_tngp_march_fill(P, ro, rd, n, counts, offsets, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(),
+                                          h->ngp_delta.as<float>(), want_cells ? h->ngp_cell.as<int32_t>() : nullptr, st);
+  else
+    h->launches += launch_ngp_march_fill(P, n, counts, offsets, h->ngp_masks.as<uint32_t>(), h->ngp_t0.as<float>(),
+                                          h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), st);
+  const bool dumps = out && (out->t || out->raw || out->enc || out->delta || out->cell);
+  long long M = -1;
+  if (dumps) {      // diagnostics path: the host needs the total to place the per-sample dumps
+    int32_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, h->ngp_total.p, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    M = total;
+  }
+  const bool room = dumps && out->sample_capacity >= out->total_so_far + M;
+  float* enc_dump = room && out->enc ? out->enc + out->total_so_far * 32 : nullptr;
+  if (h->ngp_tensorf)
+    h->launches += launch_tensorf_field(P, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), cap - 1, total_dev,
+                                        h->ngp_raw.as<float>(), h->num_sms, st);
+  else
+    h->launches += launch_ngp_field(P, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), cap - 1, total_dev,
+                                    h->ngp_raw.as<float>(), enc_dump, h->num_sms, h->cfg.precision != EVPP_PREC_FP32, st);
+  h->launches += launch_ngp_composite(P, h->ngp_raw.as<float>(), h->ngp_t.as<float>(), tngp ? h->ngp_delta.as<float>() : nullptr,
+                                      counts, offsets, n,
                                       out && out->rgb ? out->rgb + off * 3 : nullptr, out && out->depth ? out->depth + off : nullptr,
                                       out && out->acc ? out->acc + off : nullptr, beta2, st);
-  if (out && out->sample_capacity >= out->total_so_far + M) {
+  if (room) {
     if (out->t) CUDA_TRY(cudaMemcpyAsync(out->t + out->total_so_far, h->ngp_t.p, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
     if (out->raw) CUDA_TRY(cudaMemcpyAsync(out->raw + out->total_so_far * 5, h->ngp_raw.p, (size_t)M * 20, cudaMemcpyDeviceToDevice, st));
+    if (out->delta && tngp) CUDA_TRY(cudaMemcpyAsync(out->delta + out->total_so_far, h->ngp_delta.p, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
+    if (want_cells) CUDA_TRY(cudaMemcpyAsync(out->cell + out->total_so_far, h->ngp_cell.p, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
   }
-  if (out) out->total_so_far += M;
-  h->ngp_samples += M;
+  if (dumps) out->total_so_far += M;
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+// rays per marching chunk: the worst-case sample buffers (rays x max_samples x 32 B) stay below ~8.6 GB
+static int ngp_chunk_cap(evpp_handle* h) {
+  const long long by_samples = (1ll << 28) / std::max(1, h->ngp.max_samples);
+  return (int)std::max<long long>(1, std::min<long long>(h->ngp_chunk_rays, by_samples));
 }
 
 static int ngp_ready(evpp_handle* h) {
@@ -1071,7 +1135,7 @@ int evpp_ngp_render_rays(evpp_handle* h, const float* rays_o, const float* rays_
   int rc = ngp_ready(h);
   if (rc) return rc;
   EVPP_ON_DEVICE(h->device);
-  const int cap = h->ngp_chunk_rays;
+  const int cap = ngp_chunk_cap(h);
   for (int64_t g0 = 0; g0 < N; g0 += cap) {
     const int n = (int)std::min<int64_t>(cap, N - g0);
     rc = ngp_render_device(h, rays_o + g0 * 3, rays_d + g0 * 3, n, out, g0, out->beta2 ? out->beta2 + g0 : nullptr, (cudaStream_t)stream);
@@ -1092,7 +1156,7 @@ int evpp_ngp_score_views(evpp_handle* h, const float* c2w, int V, int H, int W, 
   EVPP_ON_DEVICE(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const long long N = (long long)V * R;
-  const int cap = (int)std::min<long long>(N, h->ngp_chunk_rays);
+  const int cap = (int)std::min<long long>(N, ngp_chunk_cap(h));
   if (h->ngp_ro.ensure((size_t)cap * 12) || h->ngp_rd.ensure((size_t)cap * 12) || h->ngp_beta2.ensure((size_t)N * 4))
     return fail(EVPP_ERR_CUDA, "NGP ray workspace alloc failed");
   for (long long g0 = 0; g0 < N; g0 += cap) {
@@ -1130,7 +1194,13 @@ int evpp_ngp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int 
 
 int evpp_ngp_get_sample_count(evpp_handle* h, int64_t* samples) {
   if (!h || !samples) return fail(EVPP_ERR_INVALID, "null argument");
-  *samples = h->ngp_samples;
+  *samples = 0;
+  if (!h->ngp_counter.p) return 0;
+  EVPP_ON_DEVICE(h->device);
+  unsigned long long v = 0;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(&v, h->ngp_counter.p, 8, cudaMemcpyDeviceToHost));
+  *samples = (int64_t)v;
   return 0;
 }
 
@@ -1159,7 +1229,7 @@ int evpp_poison_workspace(evpp_handle* h) {
   for (DevBuf* b : {&h->rays_o, &h->rays_d, &h->viewdirs, &h->z_c, &h->raw_c, &h->z_f, &h->raw_f, &h->beta2, &h->st_scores,
                     &h->w_c, &h->cdf, &h->inds, &h->zs, &h->tsdf_ro, &h->tsdf_rd, &h->tsdf_u, &h->tsdf_d, &h->tsdf_vu, &h->tsdf_vd,
                     &h->ngp_ro, &h->ngp_rd, &h->ngp_counts, &h->ngp_offsets, &h->ngp_masks, &h->ngp_tiles, &h->ngp_t0, &h->ngp_t,
-                    &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2, &h->ngp_scores})
+                    &h->ngp_ray, &h->ngp_raw, &h->ngp_beta2, &h->ngp_scores, &h->ngp_delta, &h->ngp_cell})
     if (b->p) CUDA_TRY(cudaMemset(b->p, 0xFF, b->bytes));
   return 0;
 }

@@ -213,6 +213,120 @@ __global__ void ngp_fill_kernel(NgpParams P, int n, const int32_t* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------- torch-ngp marcher (march_mode 1) ----------
+// Restatement of the PUBLISHED ray-marching rule of ashawkey/torch-ngp (`raymarching`: near_far_from_aabb +
+// march_rays): the scene cube is [-bound, bound]^3 in normalised coordinates, rays have unit directions and t is a
+// normalised distance; `cascades` nested occupancy grids of H^3 cells (cascade c covers [-2^c, 2^c]^3, capped at the
+// bound), each stored as a Morton-ordered bitfield; the step is dt = clamp(t * dt_gamma, dt_min, dt_max) with
+// dt_min = 2 sqrt(3) / max_steps, dt_max = 2 sqrt(3) 2^(C-1) / H; the cascade of a sample is the larger of the one
+// its position falls in and the one whose cells are at least dt wide; an occupied cell yields a sample and advances
+// by dt, an empty cell is skipped to its far face in dt-sized steps.  The dependency is not in the reference tree
+// (README.md:25 only links it): parity is UNPINNED; the test suite restates the same arithmetic in numpy,
+// operation by operation (every product and sum below is a separately rounded fp32 operation for that reason) and
+// the tests demand bit-equal counts, cell indices and sample positions.
+// One THREAD per ray: the step recurrence is serial (dt depends on t); the count pass and the fill pass (after the
+// exclusive scan of the counts -- a deterministic layout instead of torch-ngp's atomicAdd order) walk it twice.
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+__device__ __forceinline__ uint32_t morton3d(uint32_t x, uint32_t y, uint32_t z) {
+  return expand_bits10(x) | (expand_bits10(y) << 1) | (expand_bits10(z) << 2);
+}
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+__device__ __forceinline__ int mip_of(float mx, int C) {      // frexp exponent clamped to [0, C-1]
+  int e;
+  frexpf(mx, &e);
+  return min(C - 1, max(0, e));
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+tngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n,
+                  int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, float* __restrict__ t_out,
+                  int32_t* __restrict__ ray_of_sample, float* __restrict__ delta_out, int32_t* __restrict__ cell_out) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= n) return;
+  const int limit = FILL ? counts[ray] : min(P.max_steps, P.max_samples);
+  if (FILL && limit == 0) return;
+  float o[3], d[3], rd[3];
+  const float wx = rays_d[(long long)ray * 3], wy = rays_d[(long long)ray * 3 + 1], wz = rays_d[(long long)ray * 3 + 2];
+  const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(wx, wx), __fmul_rn(wy, wy)), __fmul_rn(wz, wz)));
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o[c] = __fmul_rn(__fsub_rn(rays_o[(long long)ray * 3 + c], P.center[c]), P.scale);
+    d[c] = __fdiv_rn(rays_d[(long long)ray * 3 + c], len);
+    rd[c] = __fdiv_rn(1.f, d[c]);
+  }
+  // near_far_from_aabb on the cube [-bound, bound]^3 (slab test axis by axis, a miss leaves no samples)
+  float near = 0.f, far = 0.f;
+  bool hit = true;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float a = __fmul_rn(__fsub_rn(-P.bound, o[c]), rd[c]);
+    float b = __fmul_rn(__fsub_rn(P.bound, o[c]), rd[c]);
+    if (a > b) { const float tmp = a; a = b; b = tmp; }
+    if (c == 0) {
+      near = a; far = b;
+    } else {
+      if (near > b || a > far) hit = false;
+      if (a > near) near = a;
+      if (b < far) far = b;
+    }
+  }
+  if (near < P.min_near) near = P.min_near;
+  int steps = 0;
+  if (hit) {
+    const int H = P.grid_res, C = P.cascades;
+    const float fH = (float)H, rH = __fdiv_rn(1.f, fH);
+    const uint32_t H3 = (uint32_t)H * H * H;
+    const float t_to_world = __fdiv_rn(1.f, __fmul_rn(P.scale, len));    // world parameter along the un-normalised ray
+    const long long base_out = FILL ? offsets[ray] : 0;
+    float t = near;
+    while (t < far && steps < limit) {
+      float x[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) x[c] = clampf(__fadd_rn(o[c], __fmul_rn(t, d[c])), -P.bound, P.bound);
+      const float dt = clampf(__fmul_rn(t, P.dt_gamma), P.dt_min, P.dt_max);
+      const int level = max(mip_of(fmaxf(fabsf(x[0]), fmaxf(fabsf(x[1]), fabsf(x[2]))), C),
+                            mip_of(__fmul_rn(__fmul_rn(dt, fH), 0.5f), C));
+      const float mip_bound = fminf(scalbnf(1.f, level), P.bound);
+      const float mip_rbound = __fdiv_rn(1.f, mip_bound);
+      int nc[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        nc[c] = (int)clampf(__fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn(x[c], mip_rbound), 1.f), 0.5f), fH), 0.f, (float)(H - 1));
+      const uint32_t index = (uint32_t)level * H3 + morton3d((uint32_t)nc[0], (uint32_t)nc[1], (uint32_t)nc[2]);
+      const bool occ = (P.bitfield[index >> 3] >> (index & 7u)) & 1;
+      if (occ) {
+        if (FILL) {
+          t_out[base_out + steps] = __fmul_rn(t, t_to_world);
+          ray_of_sample[base_out + steps] = ray;
+          delta_out[base_out + steps] = dt;
+          if (cell_out) cell_out[base_out + steps] = (int32_t)index;
+        }
+        ++steps;
+        t = __fadd_rn(t, dt);
+      } else {
+        float tt = 3.4e38f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float face = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nc[c], 0.5f), copysignf(0.5f, d[c])), rH), 2.f), 1.f), mip_bound);
+          tt = fminf(tt, __fmul_rn(__fsub_rn(face, x[c]), rd[c]));       // fminf drops the NaN of an axis-parallel ray
+        }
+        tt = __fadd_rn(t, fmaxf(0.f, tt));
+        do {
+          t = __fadd_rn(t, clampf(__fmul_rn(t, P.dt_gamma), P.dt_min, P.dt_max));
+        } while (t < tt && t < far);      // (t < far: same outputs -- nothing is emitted past far -- and no endless walk when tt = inf)
+      }
+    }
+  }
+  if (!FILL) counts[ray] = steps;
+}
+
 // Exclusive scan of the per-ray counts in three small launches: per-tile sums (4096 counts per block), a single
 // block scanning the (<= a few hundred) tile sums with the kernel below, and per-tile local scans.
 constexpr int kScanTile = 4096;   // 256 threads x 16 counts
@@ -265,7 +379,7 @@ __global__ void __launch_bounds__(256) ngp_tile_scan_kernel(const int32_t* __res
 
 // exclusive scan by ONE block: tiles of 4096 entries, warp-shuffle scans, running carry (used on the tile sums)
 __global__ void ngp_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets,
-                                int32_t* __restrict__ total) {
+                                int32_t* __restrict__ total, unsigned long long* __restrict__ sample_counter) {
   __shared__ int warp_sum[32];
   __shared__ int carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -305,7 +419,10 @@ __global__ void ngp_scan_kernel(const int32_t* __restrict__ counts, int n, int32
     if (threadIdx.x == 1023) carry_s = run;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry_s;
+  if (threadIdx.x == 0) {
+    *total = carry_s;
+    if (sample_counter) *sample_counter += (unsigned long long)carry_s;   // single block, stream-ordered: no atomics needed
+  }
 }
 
 // ---------------------------------------------------------------- field (encode + MLP) -------------
@@ -350,9 +467,10 @@ constexpr int kFieldSmemBytes = (kNgpMlpFloats + 3) / 4 * 16 + 2 * 64 * kFieldTh
 
 __global__ void __launch_bounds__(kFieldThreads, 2)
 ngp_field_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                 const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M,
-                 float* __restrict__ raw, float* __restrict__ enc_dump) {
+                 const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M_cap,
+                 const int32_t* __restrict__ total_dev, float* __restrict__ raw, float* __restrict__ enc_dump) {
   extern __shared__ __align__(16) float smem_w[];
+  const long long M = total_dev ? (((long long)*total_dev) < M_cap ? (long long)*total_dev : M_cap) : M_cap;   // the marcher's total, read on the device
   float* WT_s0 = smem_w;                     // [32][64]
   float* WT_s1 = WT_s0 + 32 * 64;            // [64][16]
   float* WT_c0 = WT_s1 + 64 * 16;            // [32][64] (input 31 is the zero pad)
@@ -543,9 +661,10 @@ __device__ __forceinline__ void load_a(const __half* st, int ks, int g, int t, u
 
 __global__ void __launch_bounds__(32 * kTcWarps, 2)
 ngp_field_tc_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                    const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M,
-                    float* __restrict__ raw, float* __restrict__ enc_dump) {
+                    const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M_cap,
+                    const int32_t* __restrict__ total_dev, float* __restrict__ raw, float* __restrict__ enc_dump) {
   extern __shared__ __align__(16) __half smem_h[];
+  const long long M = total_dev ? (((long long)*total_dev) < M_cap ? (long long)*total_dev : M_cap) : M_cap;   // the marcher's total, read on the device
   {   // fp32 packed weights -> padded fp16 [out][in]
     const float* g = P.mlp;
     for (int i = threadIdx.x; i < kTcW_end; i += blockDim.x) smem_h[i] = __float2half_rn(0.f);
@@ -704,9 +823,10 @@ __device__ __forceinline__ void h8_to_f(const uint4& v, float (&f)[8]) {
 
 __global__ void __launch_bounds__(32 * kTfWarps, 1)
 tensorf_field_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                     const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M,
-                     float* __restrict__ raw) {
+                     const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M_cap,
+                     const int32_t* __restrict__ total_dev, float* __restrict__ raw) {
   extern __shared__ __align__(16) __half smem_h[];
+  const long long M = total_dev ? (((long long)*total_dev) < M_cap ? (long long)*total_dev : M_cap) : M_cap;   // the marcher's total, read on the device
   {
     const float* g = P.tf_mlp;
     for (int i = threadIdx.x; i < kTfW_end; i += blockDim.x) smem_h[i] = __float2half_rn(0.f);
@@ -862,7 +982,7 @@ tensorf_field_kernel(NgpParams P, const float* __restrict__ rays_o, const float*
 // idle most lanes.  Transmittance = exclusive product of (1 - alpha + 1e-10) by an 8-wide shuffle scan, carried
 // across groups of eight samples in T.
 __global__ void ngp_composite_kernel(NgpParams P, const float* __restrict__ raw, const float* __restrict__ t_s,
-                                     const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, int n,
+                                     const float* __restrict__ delta, const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, int n,
                                      float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ acc,
                                      float* __restrict__ beta2) {
   const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -881,7 +1001,7 @@ __global__ void ngp_composite_kernel(NgpParams P, const float* __restrict__ raw,
     if (s < cnt) {
       const float* r = raw + (off + s) * 5;
       r0 = r[0]; r1 = r[1]; r2 = r[2];
-      alpha = 1.f - expf(-r[3] * P.dt);
+      alpha = 1.f - expf(-r[3] * (delta ? delta[off + s] : P.dt));
       beta = r[4];
       tt = t_s[off + s];
     }
@@ -943,11 +1063,12 @@ int launch_ngp_march_count(const NgpParams& P, const float* ro, const float* rd,
 }
 
 // tile_ws: 2 * ngp_scan_tiles(n) ints
-int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* total, int32_t* tile_ws, cudaStream_t st) {
+int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* total, int32_t* tile_ws,
+                    unsigned long long* sample_counter, cudaStream_t st) {
   if (n <= 0) return 0;
   const int tiles = ngp_scan_tiles(n);
   ngp_tile_sum_kernel<<<tiles, 256, 0, st>>>(counts, n, tile_ws);
-  ngp_scan_kernel<<<1, 1024, 0, st>>>(tile_ws, tiles, tile_ws + tiles, total);
+  ngp_scan_kernel<<<1, 1024, 0, st>>>(tile_ws, tiles, tile_ws + tiles, total, sample_counter);
   ngp_tile_scan_kernel<<<tiles, 256, 0, st>>>(counts, n, tile_ws + tiles, offsets);
   return 3;
 }
@@ -961,38 +1082,54 @@ int launch_ngp_march_fill(const NgpParams& P, int n, const int32_t* counts, cons
 }
 
 int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
-                     long long M, float* raw, float* enc_dump, int num_sms, bool tensor_cores, cudaStream_t st) {
+                     long long M, const int32_t* total_dev, float* raw, float* enc_dump, int num_sms, bool tensor_cores,
+                     cudaStream_t st) {
   if (M <= 0) return 0;
   if (tensor_cores) {
     cudaFuncSetAttribute(ngp_field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFieldTcSmemBytes);
     long long blocks = ((M + 31) / 32 + kTcWarps - 1) / kTcWarps;
     const long long cap = (long long)num_sms * 2;
     if (blocks > cap) blocks = cap;
-    ngp_field_tc_kernel<<<(unsigned)blocks, 32 * kTcWarps, kFieldTcSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, raw, enc_dump);
+    ngp_field_tc_kernel<<<(unsigned)blocks, 32 * kTcWarps, kFieldTcSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, total_dev, raw, enc_dump);
     return 1;
   }
   cudaFuncSetAttribute(ngp_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFieldSmemBytes);
   long long blocks = (M + 2 * kFieldThreads - 1) / (2 * kFieldThreads);
   const long long cap = (long long)num_sms * 2;      // 2 resident CTAs per SM, grid-stride over the rest
   if (blocks > cap) blocks = cap;
-  ngp_field_kernel<<<(unsigned)blocks, kFieldThreads, kFieldSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, raw, enc_dump);
+  ngp_field_kernel<<<(unsigned)blocks, kFieldThreads, kFieldSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, total_dev, raw, enc_dump);
   return 1;
 }
 
 int launch_tensorf_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
-                         long long M, float* raw, int num_sms, cudaStream_t st) {
+                         long long M, const int32_t* total_dev, float* raw, int num_sms, cudaStream_t st) {
   if (M <= 0) return 0;
   cudaFuncSetAttribute(tensorf_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTensorfSmemBytes);
   long long blocks = ((M + 31) / 32 + kTfWarps - 1) / kTfWarps;
   if (blocks > num_sms) blocks = num_sms;
-  tensorf_field_kernel<<<(unsigned)blocks, 32 * kTfWarps, kTensorfSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, raw);
+  tensorf_field_kernel<<<(unsigned)blocks, 32 * kTfWarps, kTensorfSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, total_dev, raw);
   return 1;
 }
 
-int launch_ngp_composite(const NgpParams& P, const float* raw, const float* t, const int32_t* counts,
+int launch_ngp_composite(const NgpParams& P, const float* raw, const float* t, const float* delta, const int32_t* counts,
                          const int32_t* offsets, int n, float* rgb, float* depth, float* acc, float* beta2, cudaStream_t st) {
   if (n <= 0) return 0;
-  ngp_composite_kernel<<<(unsigned)(((long long)n * 8 + 255) / 256), 256, 0, st>>>(P, raw, t, counts, offsets, n, rgb, depth, acc, beta2);
+  ngp_composite_kernel<<<(unsigned)(((long long)n * 8 + 255) / 256), 256, 0, st>>>(P, raw, t, delta, counts, offsets, n, rgb, depth, acc, beta2);
+  return 1;
+}
+
+int launch_tngp_march_count(const NgpParams& P, const float* ro, const float* rd, int n, int32_t* counts, cudaStream_t st) {
+  if (n <= 0) return 0;
+  tngp_march_kernel<false><<<(n + 127) / 128, 128, 0, st>>>(P, ro, rd, n, counts, nullptr, nullptr, nullptr, nullptr, nullptr);
+  return 1;
+}
+
+int launch_tngp_march_fill(const NgpParams& P, const float* ro, const float* rd, int n, const int32_t* counts,
+                           const int32_t* offsets, float* t, int32_t* ray_of_sample, float* delta, int32_t* cell_index,
+                           cudaStream_t st) {
+  if (n <= 0) return 0;
+  tngp_march_kernel<true><<<(n + 127) / 128, 128, 0, st>>>(P, ro, rd, n, const_cast<int32_t*>(counts), offsets, t, ray_of_sample, delta,
+                                                           cell_index);
   return 1;
 }
 

@@ -37,6 +37,12 @@ struct NgpParams {      // device pointers + configuration, passed to kernels by
   float near_plane, far_plane, dt;
   int max_steps, max_samples;
   int white_bkgd;
+  // march_mode 1 (torch-ngp raymarching semantics): cubic scene box mapped to [-bound, bound]^3, `cascades` nested
+  // Morton-ordered H^3 bitfields, dt = clamp(t * dt_gamma, dt_min, dt_max), empty cells skipped to their far face
+  int march_mode;
+  int cascades;
+  float bound, scale, center[3];   // x_n = (x_world - center) * scale
+  float dt_gamma, dt_min, dt_max, min_near;
 };
 
 int launch_ngp_encode(const NgpParams& P, const float* u, long long M, float* enc, int32_t* idx, cudaStream_t st);
@@ -44,14 +50,26 @@ int ngp_mask_words(const NgpParams& P);   // ballot words per ray kept between t
 int ngp_scan_tiles(int n);                // the scan needs a workspace of 2 * ngp_scan_tiles(n) ints
 int launch_ngp_march_count(const NgpParams& P, const float* ro, const float* rd, int n, int32_t* counts, uint32_t* masks,
                            float* t0, cudaStream_t st);
-int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* total, int32_t* tile_ws, cudaStream_t st);
+// total: device int (samples of this chunk); sample_counter: optional device int64 running sum over chunks
+int launch_ngp_scan(const int32_t* counts, int n, int32_t* offsets, int32_t* total, int32_t* tile_ws,
+                    unsigned long long* sample_counter, cudaStream_t st);
+// torch-ngp marcher (march_mode 1): thread per ray, count pass then (after the scan) fill pass; delta [M] = step
+// length of every kept sample in normalised units
+int launch_tngp_march_count(const NgpParams& P, const float* ro, const float* rd, int n, int32_t* counts, cudaStream_t st);
+int launch_tngp_march_fill(const NgpParams& P, const float* ro, const float* rd, int n, const int32_t* counts,
+                           const int32_t* offsets, float* t, int32_t* ray_of_sample, float* delta, int32_t* cell_index,
+                           cudaStream_t st);
 int launch_ngp_march_fill(const NgpParams& P, int n, const int32_t* counts, const int32_t* offsets, const uint32_t* masks,
                           const float* t0, float* t, int32_t* ray_of_sample, cudaStream_t st);
+// M = upper bound of the sample count (the buffers' capacity); total_dev (optional, device) = the actual count, read
+// by the kernel itself, so that the host never has to wait for the marcher's total
 int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
-                     long long M, float* raw, float* enc_dump, int num_sms, bool tensor_cores, cudaStream_t st);
+                     long long M, const int32_t* total_dev, float* raw, float* enc_dump, int num_sms, bool tensor_cores,
+                     cudaStream_t st);
 int launch_tensorf_field(const NgpParams& P, const float* ro, const float* rd, const float* t, const int32_t* ray_of_sample,
-                         long long M, float* raw, int num_sms, cudaStream_t st);
-int launch_ngp_composite(const NgpParams& P, const float* raw, const float* t, const int32_t* counts,
+                         long long M, const int32_t* total_dev, float* raw, int num_sms, cudaStream_t st);
+// delta: optional per-sample step lengths (march_mode 1); null = the constant P.dt
+int launch_ngp_composite(const NgpParams& P, const float* raw, const float* t, const float* delta, const int32_t* counts,
                          const int32_t* offsets, int n, float* rgb, float* depth, float* acc, float* beta2, cudaStream_t st);
 
 }  // namespace evpp

@@ -57,12 +57,46 @@ def pack_mlp(p):
                            heads.reshape(-1), np.asarray(p["unc.b"], np.float32).reshape(-1)]).astype(np.float32)
 
 
+def morton3d(x, y, z):
+    """Interleave the low 10 bits of x, y, z (x in bit 0): torch-ngp's cell order inside one cascade."""
+    def expand(v):
+        v = np.asarray(v, dtype=np.uint32)
+        v = (v * np.uint32(0x00010001)) & np.uint32(0xFF0000FF)
+        v = (v * np.uint32(0x00000101)) & np.uint32(0x0F00F00F)
+        v = (v * np.uint32(0x00000011)) & np.uint32(0xC30C30C3)
+        v = (v * np.uint32(0x00000005)) & np.uint32(0x49249249)
+        return v
+    with np.errstate(over="ignore"):
+        return expand(x) | (expand(y) << np.uint32(1)) | (expand(z) << np.uint32(2))
+
+
+def pack_cascade_bitfield(occ):
+    """bool [C, H, H, H] (cascade, x, y, z) -> uint8 [C*H^3/8] bitfield in torch-ngp's layout: bit (index & 7) of byte
+    index >> 3 with index = cascade * H^3 + morton3d(x, y, z)."""
+    occ = np.asarray(occ, dtype=bool)
+    Cc, H = occ.shape[0], occ.shape[1]
+    g = np.arange(H, dtype=np.uint32)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    m = morton3d(X, Y, Z).reshape(-1).astype(np.int64)
+    flat = np.zeros((Cc, H ** 3), dtype=bool)
+    for c in range(Cc):
+        flat[c, m] = occ[c].reshape(-1)
+    return np.packbits(flat.reshape(-1), bitorder="little")
+
+
 class NGPScorer:
     def __init__(self, engine=None, device=0, H=400, W=400, focal=300.0, aabb_min=(-5.0, 0.01, -5.0),
                  aabb_max=(5.0, 5.01, 6.0), grid_res=128, near=0.5, far=6.0, dt=0.02, max_steps=1024, max_samples=256,
                  n_levels=16, base_res=16, log2_hashmap=19, desired_res=2048, white_bkgd=True, max_chunk_rays=0,
-                 precision="fp16"):
-        """precision: "fp16" = small MLP on the tensor cores (fp16 operands, fp32 accumulate); "fp32" = exact FFMA."""
+                 precision="fp16", march="uniform", cascades=1, dt_gamma=0.0, min_near=0.2):
+        """precision: "fp16" = small MLP on the tensor cores (fp16 operands, fp32 accumulate); "fp32" = exact FFMA.
+        march: "uniform" = constant step dt over one x-major grid_res^3 bitfield, one warp per ray with ballot / popc
+        compaction; "torch_ngp" = the published torch-ngp marching rule (cubic scene box = [-2^(cascades-1), ..]^3,
+        ``cascades`` Morton-ordered bitfields -- see pack_cascade_bitfield --, dt = clamp(t * dt_gamma, dt_min, dt_max),
+        empty cells skipped to their far face, rays start at max(box entry, min_near) in normalised units)."""
+        if march not in ("uniform", "torch_ngp"):
+            raise ValueError("march must be 'uniform' or 'torch_ngp'")
+        self.march, self.cascades = march, cascades
         self.engine = engine if engine is not None else Engine(device=device, precision=precision, near=near, far=far,
                                                                max_chunk_rays=max_chunk_rays)
         self.H, self.W, self.focal = H, W, focal
@@ -70,7 +104,8 @@ class NGPScorer:
         self.grid_res, self.dt, self.max_samples = grid_res, dt, max_samples
         self.levels = level_table(n_levels, base_res, log2_hashmap, desired_res)
         self.cfg = EvppNgpConfig((C.c_float * 3)(*aabb_min), (C.c_float * 3)(*aabb_max), grid_res, near, far, dt,
-                                 max_steps, max_samples, n_levels, int(bool(white_bkgd)))
+                                 max_steps, max_samples, n_levels, int(bool(white_bkgd)),
+                                 1 if march == "torch_ngp" else 0, int(cascades), float(dt_gamma), float(min_near))
         e = self.engine
         sc, rs, of, sz, _ = self.levels
         check(e.lib.evpp_ngp_configure(e._h, C.byref(self.cfg), sc.ctypes.data_as(C.c_void_p), rs.ctypes.data_as(C.c_void_p),
@@ -101,7 +136,7 @@ class NGPScorer:
         return (enc, idx) if want_indices else enc
 
     def render_rays(self, rays_o, rays_d, want_samples=False):
-        """Returns dict(rgb, depth, acc, beta2, counts[, t, raw, enc, total])."""
+        """Returns dict(rgb, depth, acc, beta2, counts[, t, raw, enc, total; torch_ngp march: delta, cell])."""
         e = self.engine
         ro = torch.as_tensor(rays_o).to(e.device, torch.float32).reshape(-1, 3).contiguous()
         rd = torch.as_tensor(rays_d).to(e.device, torch.float32).reshape(-1, 3).contiguous()
@@ -113,14 +148,17 @@ class NGPScorer:
         if want_samples:
             o.update(t=torch.empty(cap, device=e.device), raw=torch.empty(cap, 5, device=e.device),
                      enc=torch.empty(cap, 32, device=e.device))
+            if self.march == "torch_ngp":
+                o.update(delta=torch.empty(cap, device=e.device), cell=torch.empty(cap, device=e.device, dtype=torch.int32))
         out = EvppNgpOut(*[(o[k].data_ptr() if k in o else None) for k in ("rgb", "depth", "acc", "beta2", "counts", "t", "raw", "enc")],
-                         cap, 0)
+                         cap, 0, o["delta"].data_ptr() if "delta" in o else None, o["cell"].data_ptr() if "cell" in o else None)
         with torch.cuda.device(e.device):
             check(e.lib.evpp_ngp_render_rays(e._h, _ptr(ro), _ptr(rd), n, C.byref(out), _stream_ptr(e.device)))
         o["total"] = int(out.total_so_far)
         if want_samples:
-            for k in ("t", "raw", "enc"):
-                o[k] = o[k][:o["total"]]
+            for k in ("t", "raw", "enc", "delta", "cell"):
+                if k in o:
+                    o[k] = o[k][:o["total"]]
         return o
 
     def get_uncertainty(self, poses, pix_idx=None):

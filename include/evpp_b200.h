@@ -285,14 +285,26 @@ typedef struct evpp_ngp_config {
   int32_t max_steps, max_samples;   /* steps walked / samples kept per ray at most                       */
   int32_t n_levels;                 /* hash-grid levels (16; 2 features each)                            */
   int32_t white_bkgd;
+  /* march_mode 0: uniform steps over one x-major G^3 bitfield, warp-per-ray ballot / popc compaction (above).
+   * march_mode 1: the published torch-ngp `raymarching` rule: the (cubic) scene box is [-bound, bound]^3 with
+   *   bound = 2^(cascades-1), `cascades` nested Morton-ordered grid_res^3 bitfields (cascades*G^3 bits),
+   *   dt = clamp(t*dt_gamma, 2 sqrt3 / max_steps, 2 sqrt3 * 2^(cascades-1) / G) in normalised units, occupied cell ->
+   *   sample + step dt, empty cell -> skip to its far face; rays start at max(box entry, min_near).  near_plane,
+   *   far_plane and dt are not used in this mode. */
+  int32_t march_mode;
+  int32_t cascades;
+  float dt_gamma;
+  float min_near;
 } evpp_ngp_config;
 
 typedef struct evpp_ngp_out {       /* device pointers, any may be NULL                                  */
   float* rgb; float* depth; float* acc; float* beta2;   /* per ray [N,3] / [N]                           */
   int32_t* counts;                  /* kept samples per ray [N] (integer, bit-exact vs the restatement)  */
   float* t; float* raw; float* enc; /* per kept sample, packed ray after ray: [cap], [cap,5], [cap,32]   */
-  int64_t sample_capacity;          /* capacity of t / raw / enc in samples                              */
+  int64_t sample_capacity;          /* capacity of t / raw / enc / delta / cell in samples               */
   int64_t total_so_far;             /* out: kept samples of the call                                     */
+  float* delta;                     /* march_mode 1: step length of every kept sample [cap] (normalised) */
+  int32_t* cell;                    /* march_mode 1: bitfield index (cascade*G^3 + Morton) of the sample's cell [cap] */
 } evpp_ngp_out;
 
 /* level tables computed by the caller (torch-ngp gridencoder): scale_l = 2^(l*log2 b)*base - 1,

@@ -155,6 +155,140 @@ def march(rays_o, rays_d, bitfield, G, aabb_min, aabb_max, near, far, dt, max_st
 
 
 # ---------------------------------------------------------------------------------------------------
+# torch-ngp marching (march_mode 1)
+# ---------------------------------------------------------------------------------------------------
+# Restatement of the PUBLISHED algorithm of ashawkey/torch-ngp's `raymarching` extension (near_far_from_aabb +
+# march_rays; README.md:25 of the reference links the project, nothing of it is in the reference tree and it is not
+# installed here: PARITY UNPINNED -- there is no copy to execute or diff against).  What is restated: the scene cube
+# [-bound, bound]^3 with bound = 2^(C-1); C nested occupancy grids of H^3 cells, Morton-ordered bitfield with
+# index = cascade * H^3 + morton3D(x, y, z); the step dt = clamp(t * dt_gamma, dt_min, dt_max),
+# dt_min = 2 sqrt3 / max_steps, dt_max = 2 sqrt3 * 2^(C-1) / H; the cascade of a sample =
+# max(frexp-exponent of max|x|, frexp-exponent of dt * H / 2) clamped to [0, C-1]; an occupied cell gives a sample and
+# advances by dt; an empty cell is left through its far face in dt-sized steps.  Every fp32 operation is rounded
+# separately, in the order of evpp_b200/csrc/ngp.cu::tngp_march_kernel, so counts, cell indices, sample positions and
+# step lengths can be compared bit for bit.
+def morton3d(x, y, z):
+    def expand(v):
+        v = np.uint32(v)
+        v = np.uint32((int(v) * 0x00010001) & 0xFF0000FF)
+        v = np.uint32((int(v) * 0x00000101) & 0x0F00F00F)
+        v = np.uint32((int(v) * 0x00000011) & 0xC30C30C3)
+        v = np.uint32((int(v) * 0x00000005) & 0x49249249)
+        return int(v)
+    return expand(x) | (expand(y) << 1) | (expand(z) << 2)
+
+
+def tngp_constants(aabb_min, aabb_max, H, cascades, max_steps, dt_gamma, min_near):
+    amin, amax = np.asarray(aabb_min, dtype=F), np.asarray(aabb_max, dtype=F)
+    bound = F(1 << (cascades - 1))
+    half = F(0.5) * (amax[0] - amin[0])
+    two_sqrt3 = F(2.0) * F(1.7320508075688772)
+    return dict(bound=bound, scale=F(bound / half), center=(F(0.5) * (amin + amax)).astype(F), H=int(H), C=int(cascades),
+                dt_gamma=F(dt_gamma), dt_min=F(two_sqrt3 / F(max_steps)), dt_max=F(F(two_sqrt3 * F(1 << (cascades - 1))) / F(H)),
+                min_near=F(min_near), max_steps=int(max_steps))
+
+
+def cascade_occupancy(H=32, cascades=2, seed=0, fill=0.03):
+    """Synthetic nested occupancy: a solid blob shell + specks, bool [C, H, H, H] in (x, y, z) order per cascade;
+    cascade c covers [-2^c, 2^c]^3 (capped at the bound)."""
+    rng = np.random.RandomState(seed)
+    occ = np.zeros((cascades, H, H, H), dtype=bool)
+    g = (np.arange(H) + 0.5) / H * 2 - 1
+    for c in range(cascades):
+        b = min(2.0 ** c, 2.0 ** (cascades - 1))
+        X, Y, Z = np.meshgrid(g * b, g * b, g * b, indexing="ij")
+        r = np.sqrt(X ** 2 + Y ** 2 + Z ** 2)
+        occ[c] = (np.abs(r - 0.6) < 0.08) | ((np.abs(X - 0.3) < 0.15) & (np.abs(Y) < 0.4) & (np.abs(Z + 0.2) < 0.1))
+        occ[c] |= rng.rand(H, H, H) < fill
+    return occ
+
+
+def _mip(mx, C):
+    e = int(np.frexp(F(mx))[1])
+    return min(C - 1, max(0, e))
+
+
+def march_tngp(rays_o, rays_d, bitfield, K, max_samples):
+    """rays in WORLD coordinates (un-normalised directions).  Returns (counts int32 [N], and per ray the lists
+    t_world fp32, delta fp32 (normalised step), cell int (bitfield index))."""
+    o_w, d_w = rays_o.astype(F), rays_d.astype(F)
+    N = o_w.shape[0]
+    H, C = K["H"], K["C"]
+    fH, rH = F(H), F(F(1) / F(H))
+    H3 = H * H * H
+    bound = K["bound"]
+    counts = np.zeros(N, dtype=np.int32)
+    ts, deltas, cells = [], [], []
+    limit = min(K["max_steps"], max_samples)
+
+    def clampf(v, lo, hi):
+        return F(min(max(F(v), F(lo)), F(hi)))
+
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        for r in range(N):
+            wx, wy, wz = d_w[r]
+            ln = F(np.sqrt(F(F(F(wx * wx) + F(wy * wy)) + F(wz * wz))))
+            o = [F(F(o_w[r][c] - K["center"][c]) * K["scale"]) for c in range(3)]
+            d = [F(d_w[r][c] / ln) for c in range(3)]
+            rd = [F(F(1) / d[c]) for c in range(3)]
+            near = far = F(0)
+            hit = True
+            for c in range(3):
+                a = F(F(-bound - o[c]) * rd[c])
+                b = F(F(bound - o[c]) * rd[c])
+                if a > b:
+                    a, b = b, a
+                if c == 0:
+                    near, far = a, b
+                else:
+                    if near > b or a > far:
+                        hit = False
+                    if a > near:
+                        near = a
+                    if b < far:
+                        far = b
+            if near < K["min_near"]:
+                near = K["min_near"]
+            t_list, dl_list, ce_list = [], [], []
+            if hit:
+                t_to_world = F(F(1) / F(K["scale"] * ln))
+                t = F(near)
+                while t < far and len(t_list) < limit:
+                    x = [clampf(F(o[c] + F(t * d[c])), -bound, bound) for c in range(3)]
+                    dt = clampf(F(t * K["dt_gamma"]), K["dt_min"], K["dt_max"])
+                    level = max(_mip(max(abs(x[0]), abs(x[1]), abs(x[2])), C), _mip(F(F(dt * fH) * F(0.5)), C))
+                    mip_bound = F(min(F(2.0 ** level), bound))
+                    mip_rbound = F(F(1) / mip_bound)
+                    nc = [int(clampf(F(F(F(F(x[c] * mip_rbound) + F(1)) * F(0.5)) * fH), 0.0, F(H - 1))) for c in range(3)]
+                    index = level * H3 + morton3d(nc[0], nc[1], nc[2])
+                    occ = (int(bitfield[index >> 3]) >> (index & 7)) & 1
+                    if occ:
+                        t_list.append(F(t * t_to_world))
+                        dl_list.append(dt)
+                        ce_list.append(index)
+                        t = F(t + dt)
+                    else:
+                        tt = F(3.4e38)
+                        for c in range(3):
+                            sg = F(np.copysign(F(0.5), d[c]))
+                            face = F(F(F(F(F(F(nc[c]) + F(0.5)) + sg) * rH) * F(2)) - F(1))
+                            face = F(face * mip_bound)
+                            cand = F(F(face - x[c]) * rd[c])
+                            if not np.isnan(cand):
+                                tt = F(min(tt, cand))
+                        tt = F(t + F(max(F(0), tt)))
+                        while True:
+                            t = F(t + clampf(F(t * K["dt_gamma"]), K["dt_min"], K["dt_max"]))
+                            if not (t < tt and t < far):
+                                break
+            counts[r] = len(t_list)
+            ts.append(np.asarray(t_list, dtype=F))
+            deltas.append(np.asarray(dl_list, dtype=F))
+            cells.append(np.asarray(ce_list, dtype=np.int64))
+    return counts, ts, deltas, cells
+
+
+# ---------------------------------------------------------------------------------------------------
 # networks
 # ---------------------------------------------------------------------------------------------------
 def sh16(dirs):

@@ -713,6 +713,78 @@ def test_ngp_render_and_scores_vs_restatement(precision, tol):
     assert sc.get_uncertainty(np.zeros((0, 4, 4))).numel() == 0
 
 
+@pytest.mark.parametrize("cascades,dt_gamma,max_samples", [(1, 0.0, 64), (2, 1.0 / 128, 64), (3, 1.0 / 64, 7)])
+def test_ngp_torch_ngp_marching_bit_exact(cascades, dt_gamma, max_samples):
+    """march="torch_ngp" (missing #3): the published torch-ngp rule -- Morton-ordered cascaded
+    bitfield, dt = clamp(t * dt_gamma, dt_min, dt_max), cascade chosen from position and step size, empty cells
+    skipped to their far face -- restated in oracle/ngp_oracle.py::march_tngp (parity unpinned: the dependency is
+    not in the reference tree).  Per-ray counts, the bitfield index of every sample's cell, the sample positions
+    and the step lengths are bit-exact; compositing with the per-sample step length matches the restatement."""
+    import evpp_b200
+    from evpp_b200 import ngp
+    from oracle import ngp_oracle as N
+    Hg = 32
+    half = float(2 ** (cascades - 1)) * 1.25                    # world half-extent: normalised = world / 1.25
+    amin, amax = (-half, 1.0 - half, -half), (half, 1.0 + half, half)
+    occ = N.cascade_occupancy(Hg, cascades, seed=cascades)
+    bits = ngp.pack_cascade_bitfield(occ)
+    p, levels = N.init_ngp_params(0)
+    p = N.spread_params(p)
+    sc = evpp_b200.NGPScorer(device=0, H=12, W=16, focal=12.0, aabb_min=amin, aabb_max=amax, grid_res=Hg, max_steps=256,
+                             max_samples=max_samples, precision="fp32", march="torch_ngp", cascades=cascades, dt_gamma=dt_gamma,
+                             min_near=0.05)
+    sc.set_occupancy(bits)
+    sc.load_params(p)
+    rng = np.random.RandomState(7)
+    views = O.hemisphere_views(3, seed=4, center=(0., 1., 0.), rmin=0.8 * half, rmax=1.6 * half)
+    ro, rd = O.build_view_rays(O.views_to_poses(views), 12, 16, O.make_K(12, 16, 12.0))
+    extra_o = torch.tensor([[0., 1., -3. * half], [0.1, 1.2, 0.3], [20., 1., 0.], [0., 1., 0.2]])
+    extra_d = torch.tensor([[0., 0., 1.], [1., 0., 0.], [1., 0., 0.], [0., -2., 0.]])        # axis-parallel, inside, outside
+    ro, rd = torch.cat([ro, extra_o]), torch.cat([rd, extra_d])
+    K = N.tngp_constants(amin, amax, Hg, cascades, 256, dt_gamma, 0.05)
+    counts, ts, deltas, cells = N.march_tngp(ro.numpy(), rd.numpy(), bits, K, max_samples)
+    out = sc.render_rays(ro, rd, want_samples=True)
+    assert np.array_equal(out["counts"].cpu().numpy(), counts)
+    assert out["total"] == int(counts.sum()) and counts.sum() > 300 and (counts == 0).any()
+    assert np.array_equal(out["cell"].cpu().numpy().astype(np.int64), np.concatenate(cells))
+    assert np.array_equal(out["t"].cpu().numpy(), np.concatenate(ts))
+    assert np.array_equal(out["delta"].cpu().numpy(), np.concatenate(deltas))
+    if cascades > 1:
+        assert len(np.unique(np.concatenate(cells) // Hg ** 3)) > 1           # more than one cascade is really visited
+    # field + compositing on the marched samples: alpha = 1 - exp(-sigma * delta_i), score = sum(beta^2) / rays
+    amin_f, inv_size = np.asarray(amin, np.float32), (np.float32(1) / (np.asarray(amax, np.float32) - np.asarray(amin, np.float32)))
+    beta2 = np.zeros(len(counts))
+    acc = np.zeros(len(counts))
+    raw_gpu = out["raw"].cpu().numpy()
+    off = 0
+    for r in range(len(counts)):
+        n = int(counts[r])
+        if n:
+            t = ts[r]
+            pts = ro[r].numpy()[None, :] + rd[r].numpy()[None, :] * t[:, None]
+            u = (pts - amin_f) * inv_size
+            vd = (rd[r] / rd[r].norm()).numpy()
+            raw = N.mlp_forward(N.grid_encode(u.astype(np.float32), p["table"], levels), np.repeat(vd[None, :], n, 0), p)
+            np.testing.assert_allclose(raw_gpu[off:off + n], raw, rtol=3e-4, atol=2e-6)
+            alpha = 1.0 - np.exp(-raw[:, 3] * deltas[r].astype(np.float64))
+            T = np.cumprod(np.concatenate([[1.0], 1.0 - alpha + 1e-10]))[:-1]
+            acc[r] = (alpha * T).sum()
+            beta2[r] = (raw[:, 4] ** 2).sum()
+        off += n
+    np.testing.assert_allclose(out["acc"].cpu().numpy(), acc, atol=2e-5)
+    np.testing.assert_allclose(out["beta2"].cpu().numpy(), beta2, rtol=3e-4, atol=1e-6)
+    s = sc.get_uncertainty(O.views_to_poses(views)).cpu().numpy()
+    np.testing.assert_allclose(s, beta2[:3 * 192].reshape(3, 192).sum(-1) / 192, rtol=3e-4)
+    # error behaviour of the mode's configuration
+    with pytest.raises(evpp_b200.EvppError):
+        evpp_b200.NGPScorer(engine=sc.engine, H=12, W=16, focal=12.0, aabb_min=(-1, -1, -1), aabb_max=(1, 2, 1), grid_res=32,
+                            march="torch_ngp")                                  # not a cube
+    with pytest.raises(evpp_b200.EvppError):
+        evpp_b200.NGPScorer(engine=sc.engine, H=12, W=16, focal=12.0, aabb_min=(-1, -1, -1), aabb_max=(1, 1, 1), grid_res=24,
+                            march="torch_ngp")                                  # Morton order needs a power of two
+    sc.engine.close()
+
+
 def test_tensorf_backbone_vs_restatement():
     """TensoRF VM backbone (BASELINE configs[3], parity unpinned): same integer-exact marching, VM features + colour
     network on the tensor cores within the 16-bit operand tolerance, per-view scores within 1e-3."""
