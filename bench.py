@@ -290,12 +290,23 @@ def run_ngp(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    sc.engine.set_profiling(True)
     ms_dev, _, samples, launches = run(step_dev, args.steps, args.warmup)
+    field_ms, field_launches, _, _ = sc.engine.mlp_profile()          # CUDA events around the field kernel launches
+    sc.engine.set_profiling(False)
+    field_ms_per_step = field_ms / max(1, args.steps + args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     _, ms_e2e, _, _ = run(step_e2e, max(2, min(args.steps, 3)), 1)
     if rank == 0:
         d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         gather_gbs = samples * bytes_per_sample / (ms_dev / 1e3) / 1e9
+        field_gbs = samples * bytes_per_sample / (field_ms_per_step / 1e3) / 1e9 if field_ms_per_step > 0 else None
+        # ceilings measured on this chip for 4-byte gathers from an L2-resident table (tools/gather_bw.cu + the stand-alone
+        # encode kernel, profiles/r1_microbench.txt): the hash-grid table (24.5 MB) and the VM grids (34.6 MB) live in the
+        # 126 MB L2, so HBM bandwidth is not the bound of this mode
+        peaks_g = {"random_pairs_GBs": 1763.0, "ray_coherent_GBs": 3411.0, "source": "profiles/r1_microbench.txt (440.8 G random-pair "
+                   "gathers/s x 4 B; stand-alone encode kernel on ray-coherent points 3411 GB/s)"}
+        peak_gather = peaks_g["ray_coherent_GBs"]
         line = {"metric": "candidate views scored/sec", "value": V_total / (ms_dev / 1e3), "unit": "views/s",
                 "rays_per_s": V_total * H * W / (ms_dev / 1e3), "samples_per_s": samples * world / (ms_dev / 1e3),
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
@@ -309,11 +320,17 @@ def run_ngp(args, rank, local_rank, world):
                 "e2e": {"value": V_total / (ms_e2e / 1e3), "unit": "views/s", "h2d_bytes_per_step": V * 48, "d2h_bytes_per_step": V * 4,
                         "api": "NGPScorer.get_uncertainty == evpp_ngp_score_views_host"},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": gather_gbs, "peak": d.get("hbm_gbs", 6650.0), "unit": "GB/s",
-                             "frac": gather_gbs / d.get("hbm_gbs", 6650.0), "traffic": None,
-                             "note": "algorithmic feature-gather bytes (hash grid: 512 B, VM grids: 2304 B per kept sample) over the WHOLE step; the 24.5 MB table is "
-                                     "L2-resident, so the relevant ceiling is the measured random-gather rate (profiles/r1_microbench.txt), "
-                                     "which the stand-alone encode kernel reaches to 87 %; the fused step also runs the marching, the MLP (warp-level tensor-core MMA) and the compositing"},
+                "roofline": {"bound": "hbm", "achieved": field_gbs if field_gbs else gather_gbs, "peak": peak_gather, "unit": "GB/s",
+                             "frac": (field_gbs if field_gbs else gather_gbs) / peak_gather, "traffic": None,
+                             "kernel": "tensorf_field_kernel" if tensorf else "ngp_field_tc_kernel (hash-grid gathers + small MLP on warp-level tensor-core MMA)",
+                             "achieved_whole_step": gather_gbs, "achieved_field_kernel_only": field_gbs,
+                             "field_kernel_ms_per_step": field_ms_per_step, "field_share_of_step": field_ms_per_step / ms_dev if ms_dev > 0 else None,
+                             "peak_definition": "memory-system bound, but by the L2 gather rate, not HBM: measured rate of the stand-alone encode kernel on "
+                                                "ray-coherent points (the access pattern of this step)", "peaks_measured": peaks_g,
+                             "frac_of_random_pair_rate": (field_gbs if field_gbs else gather_gbs) / peaks_g["random_pairs_GBs"],
+                             "hbm_peak_GBs": d.get("hbm_gbs", 6650.0),
+                             "note": "algorithmic feature-gather bytes (hash grid: 16 levels x 8 corners x 4 B = 512 B, VM grids: 2304 B per kept sample) / "
+                                     "CUDA-event time of the field kernel; the kernel also evaluates the MLP and writes 20 B per sample"},
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

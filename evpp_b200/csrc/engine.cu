@@ -1094,12 +1094,24 @@ static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, i
   }
   const bool room = dumps && out->sample_capacity >= out->total_so_far + M;
   float* enc_dump = room && out->enc ? out->enc + out->total_so_far * 32 : nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profiling) {       // the field kernel (encode + MLP) is this mode's dominant kernel: timed like the NeRF MLP
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+  }
   if (h->ngp_tensorf)
     h->launches += launch_tensorf_field(P, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), cap - 1, total_dev,
                                         h->ngp_raw.as<float>(), h->num_sms, st);
   else
     h->launches += launch_ngp_field(P, ro, rd, h->ngp_t.as<float>(), h->ngp_ray.as<int32_t>(), cap - 1, total_dev,
                                     h->ngp_raw.as<float>(), enc_dump, h->num_sms, h->cfg.precision != EVPP_PREC_FP32, st);
+  if (h->profiling) {
+    cudaEventRecord(e1, st);
+    h->prof_events.emplace_back(e0, e1);
+    h->prof_evals.push_back(0);      // the sample count lives on the device (evpp_ngp_get_sample_count)
+    h->prof_flops.push_back(0.0);
+  }
   h->launches += launch_ngp_composite(P, h->ngp_raw.as<float>(), h->ngp_t.as<float>(), tngp ? h->ngp_delta.as<float>() : nullptr,
                                       counts, offsets, n,
                                       out && out->rgb ? out->rgb + off * 3 : nullptr, out && out->depth ? out->depth + off : nullptr,
