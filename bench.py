@@ -840,6 +840,17 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, cores, kind, sample = cpu_reference_rate(c, f, views)
             line["cpu_baseline"] = {"value": v, "unit": "views/s", "cores": cores, "kind": kind, "sample": sample}
+            # informational: the reference's own torch path with its tensors on this GPU -- what the
+            # reference delivers in deployment -- so that the speed-up decomposes into "GPU vs CPU" and "fused sm_100a
+            # vs PyTorch eager" (BASELINE.md section 3).  Bounded sample, separate process.
+            try:
+                res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-device", "cuda", "--steps", "3",
+                                      "--warmup", "1", "--workload", WORKLOAD], capture_output=True, text=True, timeout=300)
+                rl = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+                line["reference_torch_on_this_gpu"] = {"value": rl["value"], "unit": "views/s", "sample": rl["cpu_baseline"]["sample"],
+                                                       "note": "informational; the reference arm the driver compares against is the host-CPU one"}
+            except Exception as e:
+                line["reference_torch_on_this_gpu"] = {"value": None, "note": f"not measured: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

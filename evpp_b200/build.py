@@ -69,7 +69,7 @@ def build(force=False, verbose=False):
                 if verbose:
                     print(res.stderr)
     res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] +
-                         [_obj(s) for s in SOURCES], capture_output=True, text=True)
+                         [_obj(s) for s in SOURCES] + ["-ldl"], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     open(LIB + ".hash", "w").write(want)

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in nsys / ncu --nvtx, cost nothing without a tool attached
+
 #include "common.cuh"
 #include "sampling.cuh"
 #include "tsdf.cuh"
@@ -90,6 +92,12 @@ constexpr double kFlopBetaOnly = kFlopPerEval - 2.0 * (256 + 3 * 128);
 
 // Every entry point runs on the handle's device and leaves the caller's current device as it found it
 // (one process may drive several GPUs, nerf.py:269-273).
+// NVTX range over a scope (tracing).  Names: evpp:score_views, evpp:chunk, evpp:mlp_coarse, ...
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct DeviceGuard {
   int prev = -1;
   cudaError_t err = cudaSuccess;
@@ -219,6 +227,7 @@ TcWeights tc_of(const NetWeights& nw, int prec, float* dbg = nullptr, int dbg_la
 int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw, cudaStream_t st, int heads = 0) {
   NetWeights& nw = h->net[which];
   if (!nw.loaded) return fail(EVPP_ERR_STATE, "weights of net %d not loaded (evpp_load_nerf_weights)", which);
+  NvtxRange nvtx_mlp(which == EVPP_NET_COARSE ? "evpp:mlp_coarse" : "evpp:mlp_fine");
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling) {
     cudaEventCreate(&e0);
@@ -256,6 +265,7 @@ int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw,
 int render_chunk(evpp_handle* h, int n, float near_plane, float far_plane, int prec, const evpp_render_out* out,
                  long long off, float* beta2, cudaStream_t st) {
   const int Sc = h->Sc, Ni = h->Ni, Sf = h->Sf;
+  NvtxRange nvtx_chunk("evpp:chunk");
   const bool score_only = !out && beta2 && !h->capture && !h->score_full_outputs && prec != EVPP_PREC_FP32;
   h->launches += launch_coarse_z(h->t_vals.as<float>(), n, Sc, near_plane, far_plane, h->cfg.lindisp,
                                  h->z_c.as<float>(), st);
@@ -348,6 +358,7 @@ int score_views_device(evpp_handle* h, const float* c2w, int V, int H, int W, fl
   if (V == 0) return 0;
   if (!pix_idx) R = H * W;
   if (R <= 0) return fail(EVPP_ERR_INVALID, "R must be positive when pix_idx is given");
+  NvtxRange nvtx_score("evpp:score_views");
   const long long N = (long long)V * R;
   const int cap = (int)std::min<long long>(N, h->cfg.max_chunk_rays);
   int rc = ensure_workspace(h, cap);
@@ -1058,6 +1069,7 @@ int evpp_ngp_encode(evpp_handle* h, const float* u, int64_t M, float* enc, int32
 // (evpp_ngp_render_rays with t / raw / enc / delta / cell) makes the host wait for the total.
 static int ngp_render_device(evpp_handle* h, const float* ro, const float* rd, int n, evpp_ngp_out* out, long long off,
                              float* beta2, cudaStream_t st) {
+  NvtxRange nvtx_chunk("evpp:ngp_chunk");
   const NgpParams& P = h->ngp;
   const bool tngp = P.march_mode == 1;
   const long long cap = (long long)n * P.max_samples + 1;
