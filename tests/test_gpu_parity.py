@@ -810,6 +810,15 @@ def test_tensorf_backbone_vs_restatement():
     assert int(np.argmax(s)) == int(np.argmax(sref))
     with pytest.raises(Exception):
         sc.encode(torch.rand(4, 3))        # the hash-grid encoder is not available on a TensoRF scorer
+    # the benchmarked resolution (BASELINE configs[3]: res 300, 34.6 MB of grids), a subset of the rays
+    p300 = N.init_tensorf_params(1, R=300)
+    sc.load_params(p300)
+    sel = np.r_[0:768:7, 768:772]
+    ref = N.render_rays(ro.numpy()[sel], rd.numpy()[sel], p300, None, bits, NGP_CFG)
+    out = sc.render_rays(ro[sel], rd[sel], want_samples=True)
+    assert np.array_equal(out["counts"].cpu().numpy(), ref["counts"]) and ref["counts"].sum() > 200
+    np.testing.assert_allclose(out["raw"].cpu().numpy(), ref["raw"], rtol=6e-3, atol=3e-4)
+    np.testing.assert_allclose(out["beta2"].cpu().numpy(), ref["beta2"], rtol=6e-3, atol=1e-4)
 
 
 @pytest.mark.parametrize("lindisp,white,ns,ni", [(True, True, 64, 128), (False, False, 64, 128), (False, True, 32, 16),
