@@ -1302,3 +1302,35 @@ def test_guard_bands_poisoned_workspace_and_run_to_run_determinism(engine_factor
             assert torch.equal(ref, s), (prec, r)
         bad, n = eng.check_guards()
         assert bad == 0 and n >= 10, (prec, bad, n)
+
+
+def test_room_sweep_selects_the_stored_reference_winner():
+    """The north-star workload at full size (BASELINE configs[2]: 4096 Room poses x 128x96 rays, plain random-init
+    weights) through dist.sweep_select, the call bench.py times: bulk fp16 pass, exact re-score of the views within
+    2e-3 of the leader, selection on the device.  The two best views are 2.9e-5 apart -- closer than the bulk pass's
+    error -- and the winner must be the one the UNMODIFIED reference picks (tests/golden/room_sweep_nbv.json: the
+    reference's render() run on the host over the leaders); the exact-path scores of those leaders must agree with
+    the reference's to 2e-5."""
+    import json
+    import bench
+    from evpp_b200 import Engine, dist as edist
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "room_sweep_nbv.json")))
+    assert (bench.V_TOTAL, bench.IMG_H, bench.IMG_W) == (g["views"], g["H"], g["W"])
+    c, f, views, poses = bench.make_workload(0, 1)
+    eng = Engine(device=0, near=bench.NEAR, far=bench.FAR, precision="fp16")
+    eng.load_weights(0, c)
+    eng.load_weights(1, f)
+    intr = (bench.FOCAL, bench.FOCAL, 0.5 * bench.IMG_W, 0.5 * bench.IMG_H)
+    scores, win, band = edist.sweep_select(eng, poses.cuda(), bench.IMG_H, bench.IMG_W, *intr, 0, 1, margin=bench.MARGIN)
+    assert win == g["winner"]
+    assert 2 <= band <= 64
+    s = scores.cpu().numpy().astype(np.float64)
+    ids = np.asarray(g["oracle_ids"])
+    in_band = s[ids] >= s.max() * (1 - bench.MARGIN)
+    assert in_band.sum() >= 2
+    np.testing.assert_allclose(s[ids][in_band], np.asarray(g["oracle_scores"])[in_band], rtol=2e-5)      # re-scored on the exact path
+    np.testing.assert_allclose(s[ids], np.asarray(g["oracle_scores"]), rtol=1e-3)                         # the rest: bulk tolerance
+    assert int(np.argmax(s)) == g["winner"]
+    bad, _ = eng.check_guards()
+    assert bad == 0
+    eng.close()
