@@ -858,6 +858,21 @@ def main():
                                                        "note": "informational; the reference arm the driver compares against is the host-CPU one"}
             except Exception as e:
                 line["reference_torch_on_this_gpu"] = {"value": None, "note": f"not measured: {e}"}
+            # informational: the north_star's NGP-mode scorer (occupancy bitfield + hash grid; no reference counterpart, parity
+            # unpinned) and its TensoRF variant on the same sweep shape, so that the driver-run line carries them too
+            line["other_modes"] = {}
+            for mode in ("ngp", "tensorf"):
+                try:
+                    res = subprocess.run([sys.executable, os.path.abspath(__file__), "--mode", mode, "--steps", "3", "--warmup", "3"],
+                                         capture_output=True, text=True, timeout=300)
+                    ml = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+                    line["other_modes"][mode] = {"value": ml["value"], "unit": "views/s", "samples_per_s": ml.get("samples_per_s"),
+                                                 "e2e": ml["e2e"]["value"], "workload": ml["config"]["workload"],
+                                                 "field_kernel_gather_GBs": ml["roofline"].get("achieved_field_kernel_only"),
+                                                 "roofline_frac": ml["roofline"]["frac"], "roofline_peak_GBs": ml["roofline"]["peak"],
+                                                 "cmd": f"python bench.py --mode {mode} --steps 3 --warmup 3"}
+                except Exception as e:
+                    line["other_modes"][mode] = {"value": None, "note": f"not measured: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

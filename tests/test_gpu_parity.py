@@ -1334,3 +1334,42 @@ def test_room_sweep_selects_the_stored_reference_winner():
     bad, _ = eng.check_guards()
     assert bad == 0
     eng.close()
+
+
+def test_round2_entry_points_edge_cases(engine_factory, weights):
+    """Empty and degenerate inputs through the round-2 entry points: no views, one view (nothing to order), an empty
+    re-score list, explicit precisions, bad precision codes."""
+    import ctypes as C
+    import evpp_b200
+    from evpp_b200 import EvppError, dist as edist
+    eng = engine_factory("spread", "fp16")
+    H, W = 6, 8
+    K = O.make_K(H, W, 6.0)
+    intr = _intr(K)
+    poses = torch.Tensor(np.asarray(O.views_to_poses(O.circle_views(3))))[:, :3, :4].contiguous()
+    assert eng.rescore_views(poses, [], H, W, *intr).numel() == 0
+    assert eng.score_views(poses[:0].cuda(), H, W, *intr, precision="fp16x3").numel() == 0
+    one = eng.rescore_views(poses, [2], H, W, *intr, precision="fp16x3")
+    allv = eng.score_views_host(poses, H, W, *intr, precision="fp16x3")
+    assert torch.equal(one, allv[2:3])                               # a view's score does not depend on its neighbours
+    with pytest.raises(EvppError) as ei:
+        eng.score_views(poses.cuda(), H, W, *intr, precision=9)
+    assert ei.value.code == -1
+    with pytest.raises(EvppError) as ei:
+        eng.rescore_views(poses, [-1], H, W, *intr)
+    assert ei.value.code == -1
+    s, win, band = edist.sweep_select(eng, poses[:1].cuda(), H, W, *intr, 0, 1)
+    assert win == 0 and s.numel() == 1
+    s, win, band = edist.sweep_select(eng, poses.cuda(), H, W, *intr, 0, 1, margin=0.0)     # bulk pass only
+    assert band == 0 and win == int(torch.argmax(s))
+    host_out = torch.empty(4, dtype=torch.float32).pin_memory()
+    s2, win2, _ = edist.sweep_select(eng, poses.pin_memory(), H, W, *intr, 0, 1, host_out=host_out)      # host poses in, host results out
+    assert win2 == int(host_out[3].item()) and torch.equal(host_out[:3], s2.cpu())
+    ctl = evpp_b200.Controller(H=H, W=W, focal=6.0, near=0.5, far=6.0, precision="fp16", sample_num=None)
+    ctl.copy_model(*weights["spread"])
+    assert ctl.get_uncertainty(np.zeros((0, 4, 4))).numel() == 0
+    assert ctl.get_uncertainty(O.views_to_poses(O.circle_views(1))).numel() == 1 and ctl.last_rescored == 0
+    with pytest.raises(ValueError):
+        evpp_b200.Controller(rescore="sometimes")
+    assert eng.nonfinite_count() == 0
+    ctl.engine.close()
