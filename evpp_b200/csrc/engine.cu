@@ -571,9 +571,10 @@ int evpp_score_views_host(evpp_handle* h, const float* c2w_host, int V, int H, i
 int evpp_rescore_views(evpp_handle* h, const float* c2w_host, const int32_t* view_ids, int K, int H, int W,
                        float fx, float fy, float cx, float cy, const int32_t* pix_idx_host, int R, int precision,
                        float* scores_host, void* stream) {
-  if (!h || !c2w_host || !view_ids || !scores_host) return fail(EVPP_ERR_INVALID, "null argument");
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
   if (precision < 0 || precision >= kNumPrec) return fail(EVPP_ERR_INVALID, "bad precision %d", precision);
-  if (K <= 0) return 0;
+  if (K <= 0) return 0;      // an empty re-score list (empty tensors carry null pointers)
+  if (!c2w_host || !view_ids || !scores_host) return fail(EVPP_ERR_INVALID, "null argument");
   EVPP_ON_DEVICE(h->device);
   std::vector<float> poses((size_t)K * 12);
   std::vector<int32_t> pix;
