@@ -17,7 +17,7 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libevpp_b200.so")
 SOURCES = ["engine.cu", "sampling.cu", "mlp_simt.cu", "mlp_tc.cu", "tsdf.cu", "ngp.cu", "surrogate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--split-compile", "0"]
+              "-Xcompiler", "-fPIC", "--split-compile", "0"] + os.environ.get("EVPP_NVCC_EXTRA", "").split()   # experiments: -D...
 
 
 def _headers():

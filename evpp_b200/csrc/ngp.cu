@@ -584,6 +584,9 @@ ngp_field_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __r
 // padded by 8 halves (conflict-free 32-bit fragment loads).
 // (These small GEMMs -- N <= 64, K <= 64 -- cannot fill a 128-row tcgen05 tile without a second staging pass
 // through shared or tensor memory per layer; the warp-level MMA keeps the chain in registers instead.)
+#ifndef EVPP_NGP_TC_CTAS
+#define EVPP_NGP_TC_CTAS 2
+#endif
 constexpr int kTcWarps = 8;
 constexpr int kLd32 = 40, kLd64 = 72;            // padded row strides (halves) for K = 32 / K = 64 matrices
 constexpr int kTcW_s0 = 0;                       // [64][kLd32]
@@ -659,7 +662,7 @@ __device__ __forceinline__ void load_a(const __half* st, int ks, int g, int t, u
   }
 }
 
-__global__ void __launch_bounds__(32 * kTcWarps, 2)
+__global__ void __launch_bounds__(32 * kTcWarps, EVPP_NGP_TC_CTAS)
 ngp_field_tc_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                     const float* __restrict__ t_s, const int32_t* __restrict__ ray_of_sample, long long M_cap,
                     const int32_t* __restrict__ total_dev, float* __restrict__ raw, float* __restrict__ enc_dump) {
@@ -1088,7 +1091,7 @@ int launch_ngp_field(const NgpParams& P, const float* ro, const float* rd, const
   if (tensor_cores) {
     cudaFuncSetAttribute(ngp_field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFieldTcSmemBytes);
     long long blocks = ((M + 31) / 32 + kTcWarps - 1) / kTcWarps;
-    const long long cap = (long long)num_sms * 2;
+    const long long cap = (long long)num_sms * EVPP_NGP_TC_CTAS;
     if (blocks > cap) blocks = cap;
     ngp_field_tc_kernel<<<(unsigned)blocks, 32 * kTcWarps, kFieldTcSmemBytes, st>>>(P, ro, rd, t, ray_of_sample, M, total_dev, raw, enc_dump);
     return 1;
