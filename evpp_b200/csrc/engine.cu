@@ -985,9 +985,9 @@ int evpp_ngp_configure(evpp_handle* h, const evpp_ngp_config* cfg, const float* 
     P.dt_max = two_sqrt3 * (float)(1 << (cfg->cascades - 1)) / (float)cfg->grid_res;
     P.min_near = cfg->min_near;
   }
-  if (h->ngp_counter.ensure(8)) return fail(EVPP_ERR_CUDA, "counter alloc failed");
   {
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h->device);      // (allocations must land on the handle's device, whatever the caller's current one is)
+    if (guard.err != cudaSuccess || h->ngp_counter.ensure(8)) return fail(EVPP_ERR_CUDA, "counter alloc failed");
     cudaMemset(h->ngp_counter.p, 0, 8);
   }
   h->ngp_samples = 0;
