@@ -649,6 +649,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-balance", action="store_true", help="equal view blocks per rank (no speed-proportional split)")
     ap.add_argument("--no-rescore", action="store_true", help="bulk pass only (no exact re-score of the leaders, no NBV identity)")
+    ap.add_argument("--no-fold", action="store_true", help="score-only passes in the reference's layer order (feature_linear not folded into the view layer)")
     ap.add_argument("--full-outputs", action="store_true", help="scoring calls evaluate the full network like render() (round-1 behaviour)")
     ap.add_argument("--pixel-sampler", default="device", choices=["device", "numpy"],
                     help="--mode planner only: where the random pixel subsets of the live protocol are drawn")
@@ -709,7 +710,7 @@ def main():
                            white_bkgd=True, precision=args.precision)
     eng.load_weights(0, c)
     eng.load_weights(1, f)
-    eng.set_score_mode(args.full_outputs)
+    eng.set_score_mode(1 if args.full_outputs else 2 if args.no_fold else 0)
     room = WORKLOAD == "room"
     V = V_TOTAL                                   # views this rank holds poses for (room: the whole sweep)
     V_job = V_TOTAL if room else V_TOTAL * world  # views scored per step by the whole job
@@ -821,7 +822,7 @@ def main():
                           "fp16x2": "split-f16 weights, f16 activations, f32 accumulate (tcgen05)", "fp16x3": "split-f16 operands, f32 accumulate (tcgen05)",
                           "fp32": "f32"}[args.precision],
                 "data": "synthetic", "config": workload_config(world, f"evpp_b200 CUDA engine, precision={args.precision}, "
-                                                                      f"{'full' if args.full_outputs else 'score-only'} network outputs, rescore margin {margin:g}"),
+                                                                      f"{'full' if args.full_outputs else 'score-only'} network outputs{'' if args.full_outputs or args.no_fold else ', feature_linear folded into the view layer'}, rescore margin {margin:g}"),
                 "e2e": {"value": e2e_val, "unit": "views/s", "h2d_bytes_per_step": int(V * 12 * 4),
                         "d2h_bytes_per_step": int(V_job * 4 + 4 + (V_job * 4 if room else 0)), "ms_per_step": ms_e2e_wall,
                         "api": "evpp_b200.dist.sweep_select (pinned host poses in every step; scores + winner id land in pinned host memory; the "
@@ -838,7 +839,7 @@ def main():
                              "peak_source": f"{src} bf16_tflops_sustained (cuBLAS bf16 under the power cap; the kernel is timed inside a long step)",
                              "kernel": "mlp_tc_kernel (fused encode + NeRF/NeurAR MLP, tcgen05 TS-mode, activations in tensor memory; all launches of the "
                                        "step: bulk fp16 and exact fp16x3, score-only variants)" if tensor else "mlp_simt_kernel (fp32 FFMA; tensor peak shown for scale only)",
-                             "achieved_definition": "FLOPs the launches executed (score-only coarse evaluation 982,528, fine 1,185,792; an fp16x3 launch "
+                             "achieved_definition": "FLOPs the launches executed (score-only coarse evaluation 982,528, fine 1,054,720 with the folded feature layer; an fp16x3 launch "
                                                     "counts its evaluations once, not its three MMA passes) / CUDA-event time of the launches",
                              "achieved_at_1187072_flop_per_eval": nominal,
                              "flop_per_launch": mlp_flops / max(1, mlp_launches), "avg_launch_ms": avg_launch_ms,

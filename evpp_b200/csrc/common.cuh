@@ -54,6 +54,7 @@ struct TcWeights {
   float* dbg;                 // optional device [M,256] dump of one layer's activations (parity tests)
   int dbg_layer;
   long long* trace;           // optional device [128] clock64 stamps of one tile's pipeline (diagnostics)
+  int folded;                 // image / consts hold feature_linear folded into views_linears.0 (score-only fine pass, heads = 3)
 };
 
 struct RayBatch {             // device pointers of one chunk
@@ -69,13 +70,15 @@ struct RayBatch {             // device pointers of one chunk
 int launch_mlp_simt(const SimtWeights& w, const RayBatch& rb, float* raw, cudaStream_t st);
 int launch_mlp_simt_points(const SimtWeights& w, const float* pts, const float* dirs, int64_t M, float* out,
                            cudaStream_t st);
-// heads: 0 = raw [n,S,5]; 1 = sigma only -> raw [n,S] (pass stops after layer 7); 2 = beta only -> raw [n,S]
+// heads: 0 = raw [n,S,5]; 1 = sigma only -> raw [n,S] (pass stops after layer 7); 2 = beta only -> raw [n,S];
+// 3 = beta only with feature_linear folded into the view layer (needs weights packed with fold = true)
 int launch_mlp_tc(const TcWeights& w, const RayBatch& rb, float* raw, int num_sms, cudaStream_t st, int heads = 0);
 int launch_mlp_tc_points(const TcWeights& w, const float* pts, const float* dirs, int64_t M, float* out,
                          int num_sms, cudaStream_t st);
 size_t tc_weight_image_bytes();
 // host-side repack of one network: fills `image` (tc_weight_image_bytes()) from fp32 state_dict tensors
-void tc_pack_weights(const std::vector<std::vector<float>>& tensors, int dtype, std::vector<uint8_t>& image,
+// fold: multiply feature_linear into views_linears.0 (nine GEMM layers; the image of the score-only fine pass)
+void tc_pack_weights(const std::vector<std::vector<float>>& tensors, int dtype, bool fold, std::vector<uint8_t>& image,
                      TcConsts& consts);
 
 }  // namespace evpp

@@ -89,6 +89,7 @@ constexpr int kNumPrec = 5;   // evpp_precision values
 constexpr double kFlopFull = kFlopPerEval;
 constexpr double kFlopSigmaOnly = 2.0 * (63 * 256 + 4 * 256 * 256 + 319 * 256 + 2 * 256 * 256 + 256);
 constexpr double kFlopBetaOnly = kFlopPerEval - 2.0 * (256 + 3 * 128);
+constexpr double kFlopBetaOnlyFolded = kFlopBetaOnly - 2.0 * 256 * 256;      // feature_linear multiplied into the view layer
 
 // Every entry point runs on the handle's device and leaves the caller's current device as it found it
 // (one process may drive several GPUs, nerf.py:269-273).
@@ -116,9 +117,9 @@ struct DeviceGuard {
 
 struct NetWeights {
   bool loaded = false;
-  DevBuf simt_stream, bias, head_w, head_b, tc_image[kNumPrec];   // tc_image indexed by precision (1..4)
-  bool tc_ready[kNumPrec] = {false, false, false, false, false};
-  TcConsts tc_consts{};
+  DevBuf simt_stream, bias, head_w, head_b, tc_image[kNumPrec][2];   // tc_image[precision 1..4][folded feature layer]
+  bool tc_ready[kNumPrec][2] = {};
+  TcConsts tc_consts[2] = {};
   std::vector<std::vector<float>> host;                   // fp32 state_dict tensors (for lazy tc repack)
 };
 
@@ -135,7 +136,8 @@ struct evpp_handle {
   int chunk_cap = 0;
   DevBuf rays_o, rays_d, viewdirs, z_c, raw_c, z_f, raw_f;
   DevBuf beta2, st_c2w, st_pix, st_scores, nonfinite;
-  bool score_full_outputs = false;   // evpp_set_score_mode: scoring calls run the full network like render()
+  int score_mode = 0;   // evpp_set_score_mode: 0 score-only passes + folded feature layer, 1 full network like render(),
+                        // 2 score-only passes in the reference's layer order (bit-identical to 1)
   // stage capture
   bool capture = false;
   DevBuf w_c, cdf, inds, zs;
@@ -205,25 +207,27 @@ int ensure_workspace(evpp_handle* h, int cap) {
   return 0;
 }
 
-int ensure_tc(evpp_handle* h, int which, int prec) {
+int ensure_tc(evpp_handle* h, int which, int prec, bool fold = false) {
   NetWeights& nw = h->net[which];
-  if (nw.tc_ready[prec]) return 0;
+  if (nw.tc_ready[prec][fold]) return 0;
   std::vector<uint8_t> image;
-  tc_pack_weights(nw.host, prec, image, nw.tc_consts);
-  if (nw.tc_image[prec].ensure(image.size())) return fail(EVPP_ERR_CUDA, "tc weight image alloc failed");
-  CUDA_TRY(cudaMemcpy(nw.tc_image[prec].p, image.data(), image.size(), cudaMemcpyHostToDevice));
-  nw.tc_ready[prec] = true;
+  tc_pack_weights(nw.host, prec, fold, image, nw.tc_consts[fold]);
+  if (nw.tc_image[prec][fold].ensure(image.size())) return fail(EVPP_ERR_CUDA, "tc weight image alloc failed");
+  CUDA_TRY(cudaMemcpy(nw.tc_image[prec][fold].p, image.data(), image.size(), cudaMemcpyHostToDevice));
+  nw.tc_ready[prec][fold] = true;
   return 0;
 }
 
 SimtWeights simt_of(const NetWeights& nw) {
   return SimtWeights{nw.simt_stream.as<float>(), nw.bias.as<float>(), nw.head_w.as<float>(), nw.head_b.as<float>()};
 }
-TcWeights tc_of(const NetWeights& nw, int prec, float* dbg = nullptr, int dbg_layer = -1, long long* trace = nullptr) {
-  return TcWeights{nw.tc_image[prec].p, &nw.tc_consts, prec, dbg, dbg_layer, trace};
+TcWeights tc_of(const NetWeights& nw, int prec, float* dbg = nullptr, int dbg_layer = -1, long long* trace = nullptr,
+                bool fold = false) {
+  return TcWeights{nw.tc_image[prec][fold].p, &nw.tc_consts[fold], prec, dbg, dbg_layer, trace, fold ? 1 : 0};
 }
 
-// heads: 0 = raw [n,S,5]; 1 = sigma only, 2 = beta only -> raw [n,S] (tensor-core precisions only)
+// heads: 0 = raw [n,S,5]; 1 = sigma only, 2 = beta only, 3 = beta only with the folded feature layer -> raw [n,S]
+// (tensor-core precisions only)
 int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw, cudaStream_t st, int heads = 0) {
   NetWeights& nw = h->net[which];
   if (!nw.loaded) return fail(EVPP_ERR_STATE, "weights of net %d not loaded (evpp_load_nerf_weights)", which);
@@ -239,16 +243,17 @@ int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw,
     if (heads != 0) return fail(EVPP_ERR_INVALID, "internal: the fp32 FFMA kernel has no score-only variant");
     nl = launch_mlp_simt(simt_of(nw), rb, raw, st);
   } else {
-    int rc = ensure_tc(h, which, prec);
+    const bool fold = heads == 3;
+    int rc = ensure_tc(h, which, prec, fold);
     if (rc) return rc;
-    nl = launch_mlp_tc(tc_of(nw, prec), rb, raw, h->num_sms, st, heads);
+    nl = launch_mlp_tc(tc_of(nw, prec, nullptr, -1, nullptr, fold), rb, raw, h->num_sms, st, heads);
     if (nl < 0) return fail(EVPP_ERR_CUDA, "tcgen05 MLP launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (h->profiling) {
     cudaEventRecord(e1, st);
     h->prof_events.emplace_back(e0, e1);
     h->prof_evals.push_back((int64_t)rb.n * rb.S);
-    h->prof_flops.push_back((double)rb.n * rb.S * (heads == 1 ? kFlopSigmaOnly : heads == 2 ? kFlopBetaOnly : kFlopFull));
+    h->prof_flops.push_back((double)rb.n * rb.S * (heads == 1 ? kFlopSigmaOnly : heads == 2 ? kFlopBetaOnly : heads == 3 ? kFlopBetaOnlyFolded : kFlopFull));
   }
   h->launches += nl;
   h->evals += (int64_t)rb.n * rb.S;
@@ -266,11 +271,12 @@ int render_chunk(evpp_handle* h, int n, float near_plane, float far_plane, int p
                  long long off, float* beta2, cudaStream_t st) {
   const int Sc = h->Sc, Ni = h->Ni, Sf = h->Sf;
   NvtxRange nvtx_chunk("evpp:chunk");
-  const bool score_only = !out && beta2 && !h->capture && !h->score_full_outputs && prec != EVPP_PREC_FP32;
+  const bool score_only = !out && beta2 && !h->capture && h->score_mode != 1 && prec != EVPP_PREC_FP32;
+  const int beta_heads = h->score_mode == 0 ? 3 : 2;      // the beta-only pass: with / without the folded feature layer
   h->launches += launch_coarse_z(h->t_vals.as<float>(), n, Sc, near_plane, far_plane, h->cfg.lindisp,
                                  h->z_c.as<float>(), st);
   RayBatch rb{h->rays_o.as<float>(), h->rays_d.as<float>(), h->viewdirs.as<float>(), h->z_c.as<float>(), n, Sc};
-  int rc = run_mlp(h, EVPP_NET_COARSE, prec, rb, h->raw_c.as<float>(), st, score_only ? (Ni > 0 ? 1 : 2) : 0);
+  int rc = run_mlp(h, EVPP_NET_COARSE, prec, rb, h->raw_c.as<float>(), st, score_only ? (Ni > 0 ? 1 : beta_heads) : 0);
   if (rc) return rc;
   int nl;
   CompositeOut co{};
@@ -291,7 +297,7 @@ int render_chunk(evpp_handle* h, int n, float near_plane, float far_plane, int p
     if (nl < 0) return fail(EVPP_ERR_CUDA, "resampling kernel configuration failed (shared memory for %d + %d samples)", Sc, Ni);
     h->launches += nl;
     RayBatch rf{h->rays_o.as<float>(), h->rays_d.as<float>(), h->viewdirs.as<float>(), h->z_f.as<float>(), n, Sf};
-    rc = run_mlp(h, EVPP_NET_FINE, prec, rf, h->raw_f.as<float>(), st, score_only ? 2 : 0);
+    rc = run_mlp(h, EVPP_NET_FINE, prec, rf, h->raw_f.as<float>(), st, score_only ? beta_heads : 0);
     if (rc) return rc;
   }
   const float* raw = Ni > 0 ? h->raw_f.as<float>() : h->raw_c.as<float>();
@@ -333,7 +339,7 @@ std::vector<DevBuf*> all_buffers(evpp_handle* h) {
   for (int i = 0; i < 2; ++i) {
     NetWeights& nw = h->net[i];
     for (DevBuf* b : {&nw.simt_stream, &nw.bias, &nw.head_w, &nw.head_b}) v.push_back(b);
-    for (auto& b : nw.tc_image) v.push_back(&b);
+    for (auto& pr : nw.tc_image) { v.push_back(&pr[0]); v.push_back(&pr[1]); }
   }
   return v;
 }
@@ -496,7 +502,7 @@ int evpp_load_nerf_weights(evpp_handle* h, int which, const float* packed, const
   CUDA_TRY(cudaMemcpy(nw.bias.p, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(nw.head_w.p, head_w.data(), head_w.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(nw.head_b.p, head_b.data(), head_b.size() * 4, cudaMemcpyHostToDevice));
-  for (bool& b : nw.tc_ready) b = false;
+  for (auto& pr : nw.tc_ready) pr[0] = pr[1] = false;
   nw.loaded = true;
   if (h->cfg.precision != EVPP_PREC_FP32) {
     int rc = ensure_tc(h, which, h->cfg.precision);
@@ -595,9 +601,10 @@ int evpp_rescore_views_fp32(evpp_handle* h, const float* c2w_host, const int32_t
                             scores_host, stream);
 }
 
-int evpp_set_score_mode(evpp_handle* h, int full_outputs) {
+int evpp_set_score_mode(evpp_handle* h, int mode) {
   if (!h) return fail(EVPP_ERR_INVALID, "null handle");
-  h->score_full_outputs = full_outputs != 0;
+  if (mode < 0 || mode > 2) return fail(EVPP_ERR_INVALID, "score mode must be 0 (lean, folded), 1 (full outputs) or 2 (lean, reference layer order)");
+  h->score_mode = mode;
   return 0;
 }
 

@@ -78,9 +78,10 @@ struct Lay {
 };
 
 // per-tile weight stream: number of 64-wide K-blocks per layer and their size
-__host__ __device__ constexpr int layer_has_x(int l) { return l == 0 || l == 5 || l == 9; }
+// `view` = index of the view layer: 9 in the reference's layer order, 8 when feature_linear is folded into it
+__host__ __device__ constexpr int layer_has_x(int l, int view = 9) { return l == 0 || l == 5 || l == view; }
 __host__ __device__ constexpr int layer_h_blocks(int l) { return l == 0 ? 0 : 4; }
-__host__ __device__ constexpr int layer_n(int l) { return l == 9 ? 128 : 256; }
+__host__ __device__ constexpr int layer_n(int l, int view = 9) { return l == view ? 128 : 256; }
 constexpr size_t kImageBytes = (size_t)34 * 32768 + (size_t)5 * 16384;
 
 // ---------------------------------------------------------------- PTX helpers --------------------
@@ -562,16 +563,24 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
 // HEADS: dead-output elimination for score-only calls.  0 = all five outputs -> out[m * 5 + ..] (render());
 // 1 = sigma only -> out[m] (the coarse pass of Controller.get_uncertainty feeds nothing but sample_pdf's
 // weights: the pass stops after layer 7 + alpha head); 2 = beta only -> out[m] (nerf.py:307-309 reads
-// raw[..., 4] of the fine pass and nothing else: the alpha and rgb heads are skipped).
+// raw[..., 4] of the fine pass and nothing else: the alpha and rgb heads are skipped); 3 = like 2 with feature_linear
+// FOLDED into views_linears.0: the reference applies no activation between them (run_nerf_helpers.py:119-122:
+// feature = feature_linear(h); h = relu(views_linears[0](cat[feature, dirs]))), so
+// W_v[:, :256] (W_f h + b_f) + W_v[:, 256:] d + b_v = (W_v[:, :256] W_f) h + W_v[:, 256:] d + (W_v[:, :256] b_f + b_v):
+// one 283 -> 128 layer whose weights are multiplied out on the host in fp64 (tc_pack_weights, fold = true).  The
+// pass runs 9 GEMM layers instead of 10 (11 % fewer tensor cycles per fine evaluation) and skips one rounding of
+// the activations to 16 bits; it is the same function of its inputs, equal to the unfolded pass at rounding level.
 template <bool BF16, bool RAYS, int C, int DM, int SPLIT, int NP, int HEADS>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcArgs args) {
   static_assert(NP == 1 || (!BF16 && SPLIT == 4 && DM == 0), "split passes: fp16 operands, no half-split K-blocks");
   static_assert(HEADS == 0 || (RAYS && DM == 0), "score-only variants exist for ray batches only");
+  static_assert(HEADS >= 0 && HEADS <= 3, "HEADS: 0 full, 1 sigma only, 2 beta only, 3 beta only with the folded feature layer");
   using L_ = Lay<NP>;
   constexpr int kStages = L_::kStages;
   constexpr int NB = NP > 1 ? 2 : 1;                  // ring stages per K-block: W_hi (, W_lo)
-  constexpr int kLayersRun = HEADS == 1 ? 8 : kLayers;
+  constexpr int kView = HEADS == 3 ? 8 : 9;            // index of the view layer (feature_linear folded into it: 8)
+  constexpr int kLayersRun = HEADS == 1 ? 8 : kView + 1;
   constexpr bool DBG = DM == 1;
   constexpr bool TR = DM != 0;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -638,8 +647,8 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
       for (int it = 0; it < ntile_iters; ++it) {
         const uint8_t* src = args.image;
         for (int l = 0; l < kLayersRun; ++l) {
-          const int nblk = (layer_has_x(l) + layer_h_blocks(l)) * NB;   // NP > 1: every K-block is a (W_hi, W_lo) pair
-          const uint32_t bytes = (uint32_t)layer_n(l) * 128u;
+          const int nblk = (layer_has_x(l, kView) + layer_h_blocks(l)) * NB;   // NP > 1: every K-block is a (W_hi, W_lo) pair
+          const uint32_t bytes = (uint32_t)layer_n(l, kView) * 128u;
           for (int b = 0; b < nblk; ++b) {
             if (l == 4 && b == 0) EVPP_TRACE(117);
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
@@ -677,17 +686,22 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
       bool pre_full = false;   // the next weight stage's arrival was already awaited (static after unrolling)
       for (int it = 0; it < ntile_iters; ++it) {
         for (int l = 0; l < kLayersRun; ++l) {
-          const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 256u;
-          const uint32_t a_tmem = tmem + (uint32_t)((l & 1) ^ 1) * 256u;
-          const uint32_t idesc = make_idesc(BF16, layer_n(l));
+          // Accumulator region of layer l.  With an ODD number of layers per tile (the folded pass runs nine) the first
+          // and the last layer of a tile would share a region, and the next tile's layer 0 -- which depends on nothing
+          // but its staged embedding -- could overwrite the accumulator the epilogue is still draining: the parity
+          // alternates from tile to tile there, so that a tile's first layer always lands in the other region.
+          const uint32_t reg = (uint32_t)((l + ((kLayersRun & 1) ? it : 0)) & 1);
+          const uint32_t d_tmem = tmem + reg * 256u;
+          const uint32_t a_tmem = tmem + (reg ^ 1u) * 256u;
+          const uint32_t idesc = make_idesc(BF16, layer_n(l, kView));
           uint32_t accumulate = 0;
           EVPP_TRACE(l * 4 + 0);
           if constexpr (NP > 1) {
             // ---- split passes: per K step A_hi * W_hi (+ A_hi * W_lo (+ A_lo * W_hi)); K-block = 2 ring stages ----
-            const int nblk = layer_has_x(l) + layer_h_blocks(l);
+            const int nblk = layer_has_x(l, kView) + layer_h_blocks(l);
             for (int b = 0; b < nblk; ++b) {
-              const bool xblk = layer_has_x(l) && b == 0;
-              const int kb = b - layer_has_x(l);
+              const bool xblk = layer_has_x(l, kView) && b == 0;
+              const int kb = b - layer_has_x(l, kView);
               uint32_t s_hi = stage, p_hi = phase;
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
               uint32_t s_lo = stage, p_lo = phase;
@@ -697,12 +711,12 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
               const uint64_t b_hi = make_desc(sRing + s_hi * kStageBytes), b_lo = make_desc(sRing + s_lo * kStageBytes);
               if (xblk) {
                 if (l == 0) { mbar_wait(bar_x, x_phase); x_phase ^= 1u; }
-                if (l == 9) { mbar_wait(bar_xd, xd_phase); xd_phase ^= 1u; }
+                if (l == kView) { mbar_wait(bar_xd, xd_phase); xd_phase ^= 1u; }
                 tc_fence_after();
-                const int ksteps = l == 9 ? 2 : 4;
+                const int ksteps = l == kView ? 2 : 4;
                 for (int k = 0; k < ksteps; ++k) {
-                  const uint64_t a_hi = l == 9 ? make_desc_sw64(sXD + k * 32) : make_desc(sX + k * 32);
-                  const uint64_t a_lo = l == 9 ? make_desc_sw64(sXD + kXDloDelta + k * 32) : make_desc(sX + kXloDelta + k * 32);
+                  const uint64_t a_hi = l == kView ? make_desc_sw64(sXD + k * 32) : make_desc(sX + k * 32);
+                  const uint64_t a_lo = l == kView ? make_desc_sw64(sXD + kXDloDelta + k * 32) : make_desc(sX + kXloDelta + k * 32);
                   umma_f16(d_tmem, a_hi, b_hi + (uint64_t)(k * 2), idesc, accumulate);
                   umma_f16(d_tmem, a_hi, b_lo + (uint64_t)(k * 2), idesc, 1u);
                   if (NP == 3) umma_f16(d_tmem, a_lo, b_hi + (uint64_t)(k * 2), idesc, 1u);
@@ -724,29 +738,29 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
               if (C == 1) { umma_commit(bar_empty + 8 * s_hi); umma_commit(bar_empty + 8 * s_lo); }
               else { umma_commit_mcast(bar_empty + 8 * s_hi, mc_mask); umma_commit_mcast(bar_empty + 8 * s_lo, mc_mask); }
             }
-            umma_commit(bar_acc + 16 * (l & 1));
+            umma_commit(bar_acc + 16 * reg);
             if (l >= 1) a_phase ^= 1u;
-            umma_commit(bar_acc + 16 * (l & 1) + 8);
+            umma_commit(bar_acc + 16 * reg + 8);
             continue;
           }
-          if (layer_has_x(l)) {
+          if (layer_has_x(l, kView)) {
             // layers 0 and 5 read the position embedding (X), the view layer the direction embedding (XD)
             if (l == 0) { mbar_wait(bar_x, x_phase); x_phase ^= 1u; }
-            if (l == 9) { mbar_wait(bar_xd, xd_phase); xd_phase ^= 1u; }
+            if (l == kView) { mbar_wait(bar_xd, xd_phase); xd_phase ^= 1u; }
             if (!pre_full) mbar_wait(bar_full + 8 * stage, phase);
             pre_full = false;
             tc_fence_after();
-            const int ksteps = l == 9 ? 2 : 4;
-            const uint32_t xa = l == 9 ? sXD : sX;
+            const int ksteps = l == kView ? 2 : 4;
+            const uint32_t xa = l == kView ? sXD : sX;
             for (int k = 0; k < ksteps; ++k) {
-              umma_f16(d_tmem, l == 9 ? make_desc_sw64(xa + k * 32) : make_desc(xa + k * 32),
+              umma_f16(d_tmem, l == kView ? make_desc_sw64(xa + k * 32) : make_desc(xa + k * 32),
                        make_desc(sRing + stage * kStageBytes + k * 32), idesc, accumulate);
               accumulate = 1;
             }
             if (C == 1) umma_commit(bar_empty + 8 * stage); else umma_commit_mcast(bar_empty + 8 * stage, mc_mask);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          const int nfull = (layer_n(l) == 256 && layer_h_blocks(l) == 4) ? SPLIT : layer_h_blocks(l);
+          const int nfull = (layer_n(l, kView) == 256 && layer_h_blocks(l) == 4) ? SPLIT : layer_h_blocks(l);
           for (int kb = 0; kb < nfull; ++kb) {
             if (!pre_full) mbar_wait(bar_full + 8 * stage, phase);   // weights first: prefetched long ago, off the critical path
             pre_full = false;
@@ -783,7 +797,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
                 umma_f16_ts(d_tmem, a_addr0 + (uint32_t)(k * 16), b_desc0 + (uint64_t)(k * 2), idesc_h, 1u);
               if (++s2 == kStages) { s2 = 0; p2 ^= 1u; }
             }
-            umma_commit(bar_acc + 16 * (l & 1));
+            umma_commit(bar_acc + 16 * reg);
             // The issuer crawls while the epilogue warps are busy (it loses most issue slots to them), and after
             // the second half it is on the critical path to the next layer: look at the next layer's first
             // weight stage now, while the tensor pipe still has queued work.
@@ -801,10 +815,10 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           } else {
-            umma_commit(bar_acc + 16 * (l & 1));
+            umma_commit(bar_acc + 16 * reg);
           }
           if (l >= 1) a_phase ^= 1u;
-          umma_commit(bar_acc + 16 * (l & 1) + 8);
+          umma_commit(bar_acc + 16 * reg + 8);
           EVPP_TRACE(l * 4 + 3);
         }
       }
@@ -831,7 +845,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
       float hd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int l = 0; l < kLayersRun; ++l) {
-        const int ab = l & 1;
+        const int ab = (l + ((kLayersRun & 1) ? it : 0)) & 1;      // accumulator region, see the MMA issuer
         const uint32_t bar_l = bar_acc + 16 * ab, par_l = (acc_phase >> ab) & 1u;
         acc_phase ^= 1u << ab;
         if (warp == 0 && lane == 0) EVPP_TRACE(40 + l * 3 + 0);   // (before the accumulator wait)
@@ -844,12 +858,12 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
   drain_layer<BF16, KIND_, DBG, TR, NP, HFC_>(cst, args, bias_s + l * 256, l, t_acc, hf, lane, bar_a, bar_l, par_l, cur, alpha, hd, tr, tr0)
 #define EVPP_DRAIN_HF(KIND_) \
   do { if (hf == 0) EVPP_DRAIN(KIND_, 0); else if (hf == 1) EVPP_DRAIN(KIND_, 1); else if (hf == 2) EVPP_DRAIN(KIND_, 2); else EVPP_DRAIN(KIND_, 3); } while (0)
-        if (HEADS != 1 && l == 9) {
-          if constexpr (HEADS == 2) EVPP_DRAIN_HF(5); else if constexpr (HEADS == 0) EVPP_DRAIN_HF(3);
-        } else if (HEADS != 1 && l == 8) {
-          if constexpr (HEADS != 1) EVPP_DRAIN(2, -1);
+        if (HEADS != 1 && l == kView) {
+          if constexpr (HEADS >= 2) EVPP_DRAIN_HF(5); else if constexpr (HEADS == 0) EVPP_DRAIN_HF(3);
+        } else if (HEADS != 1 && HEADS != 3 && l == 8) {
+          if constexpr (HEADS == 0 || HEADS == 2) EVPP_DRAIN(2, -1);
         } else if (l == 7) {
-          if constexpr (HEADS == 1) EVPP_DRAIN_HF(4); else if constexpr (HEADS == 2) EVPP_DRAIN(0, -1); else EVPP_DRAIN_HF(1);
+          if constexpr (HEADS == 1) EVPP_DRAIN_HF(4); else if constexpr (HEADS >= 2) EVPP_DRAIN(0, -1); else EVPP_DRAIN_HF(1);
         } else {
           EVPP_DRAIN(0, -1);
         }
@@ -883,7 +897,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
       if (hf != 0) {
         float* pr = partial + (row * (kColSplit - 1) + hf - 1) * 5;
         if (HEADS == 0) { pr[0] = hd[0]; pr[1] = hd[1]; pr[2] = hd[2]; }
-        if (HEADS != 2) pr[3] = alpha;
+        if (HEADS < 2) pr[3] = alpha;
         if (HEADS != 1) pr[4] = hd[3];
       }
       epi_bar_sync();
@@ -894,7 +908,7 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
           const float* pr = partial + (row * (kColSplit - 1) + k) * 5;
 #pragma unroll
           for (int e = 0; e < 5; ++e)
-            if (HEADS == 0 || (HEADS == 1 && e == 3) || (HEADS == 2 && e == 4)) t[e] += pr[e];
+            if (HEADS == 0 || (HEADS == 1 && e == 3) || (HEADS >= 2 && e == 4)) t[e] += pr[e];
         }
         if (HEADS == 0) {
           float* o = args.out + cur.m * 5;
@@ -1056,6 +1070,7 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st, int h
   const int np = w.dtype == EVPP_PREC_FP16X3 ? 3 : w.dtype == EVPP_PREC_FP16X2 ? 2 : 1;
   if ((np > 1 || heads != 0) && (a.dbg || a.trace)) return -1;
   if (heads != 0 && !RAYS) return -1;
+  if ((heads == 3) != (w.folded != 0)) return -1;      // the folded pass needs the folded weight image, and only that pass may use it
 
   // Hybrid 4 + 2: 4-CTA clusters share one weight stream four ways (L2 reads quartered) but leave 16 of the 148 SMs
   // idle; a second launch of 2-CTA clusters, released by griddepcontrol.launch_dependents as soon as every 4-CTA
@@ -1119,13 +1134,15 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st, int h
   cudaError_t e;
   if (np > 1) {
     if constexpr (RAYS) {
-      if (np == 3) e = heads == 1 ? launch_np<true, 3, 1>(w, a, C, grid, st) : heads == 2 ? launch_np<true, 3, 2>(w, a, C, grid, st) : launch_np<true, 3, 0>(w, a, C, grid, st);
-      else e = heads == 1 ? launch_np<true, 2, 1>(w, a, C, grid, st) : heads == 2 ? launch_np<true, 2, 2>(w, a, C, grid, st) : launch_np<true, 2, 0>(w, a, C, grid, st);
+      if (np == 3) e = heads == 1 ? launch_np<true, 3, 1>(w, a, C, grid, st) : heads == 2 ? launch_np<true, 3, 2>(w, a, C, grid, st)
+                     : heads == 3 ? launch_np<true, 3, 3>(w, a, C, grid, st) : launch_np<true, 3, 0>(w, a, C, grid, st);
+      else e = heads == 1 ? launch_np<true, 2, 1>(w, a, C, grid, st) : heads == 2 ? launch_np<true, 2, 2>(w, a, C, grid, st)
+               : heads == 3 ? launch_np<true, 2, 3>(w, a, C, grid, st) : launch_np<true, 2, 0>(w, a, C, grid, st);
     } else {
       e = np == 3 ? launch_np<false, 3, 0>(w, a, C, grid, st) : launch_np<false, 2, 0>(w, a, C, grid, st);
     }
   } else if (heads != 0) {
-    if constexpr (RAYS) e = heads == 1 ? launch_heads<1>(w, a, C, grid, st) : launch_heads<2>(w, a, C, grid, st);
+    if constexpr (RAYS) e = heads == 1 ? launch_heads<1>(w, a, C, grid, st) : heads == 2 ? launch_heads<2>(w, a, C, grid, st) : launch_heads<3>(w, a, C, grid, st);
     else e = cudaErrorInvalidValue;
   } else {
     switch (g_split) {
@@ -1179,8 +1196,34 @@ void put_block(std::vector<uint8_t>& img, const std::vector<float>& W, int n_row
     }
 }
 
-// state_dict tensor of GEMM layer l (0..7 pts_linears, 8 feature_linear, 9 views_linears.0)
-int layer_tensor(int l) { return l < 8 ? 2 * l : l == 8 ? 18 : 16; }
+// One K-block of a weight image: rows [0, n_rows) of state_dict tensor `tensor` ([n_rows][in_dim]), input columns
+// [col0, col0 + count), belonging to GEMM layer `layer` (its power-of-two scale applies).
+struct Blk { int tensor, n_rows, in_dim, col0, count, layer; };
+
+// Consumption order of the kernel.  fold = false: the reference's ten GEMM layers (pts_linears 0..7, feature_linear,
+// views_linears.0).  fold = true: nine layers, feature_linear multiplied into views_linears.0 (tensor 16 then holds
+// [W_v[:, :256] W_f | W_v[:, 256:]], see fold_feature_layer) as layer 8.
+std::vector<Blk> image_blocks(bool fold) {
+  std::vector<Blk> v;
+  v.push_back({0, 256, 63, 0, 63, 0});                                          // layer 0 : X
+  for (int l = 1; l <= 4; ++l)
+    for (int kb = 0; kb < 4; ++kb) v.push_back({2 * l, 256, 256, kb * 64, 64, l});
+  v.push_back({10, 256, 319, 0, 63, 5});                                        // layer 5 : X part of cat[pts, h]
+  for (int kb = 0; kb < 4; ++kb) v.push_back({10, 256, 319, 63 + kb * 64, 64, 5});
+  for (int l = 6; l <= 7; ++l)
+    for (int kb = 0; kb < 4; ++kb) v.push_back({2 * l, 256, 256, kb * 64, 64, l});
+  const int lv = fold ? 8 : 9;
+  if (!fold)
+    for (int kb = 0; kb < 4; ++kb) v.push_back({18, 256, 256, kb * 64, 64, 8});   // feature_linear
+  v.push_back({16, 128, 283, 256, 27, lv});                                     // views : direction part
+  for (int kb = 0; kb < 4; ++kb) v.push_back({16, 128, 283, kb * 64, 64, lv});  // views : feature part
+  return v;
+}
+
+// state_dict tensor of GEMM layer l (0..7 pts_linears, then feature_linear (8) and views_linears.0 (9), or the folded
+// view layer as 8)
+int layer_tensor(int l, bool fold) { return l < 8 ? 2 * l : (l == 8 && !fold) ? 18 : 16; }
+int n_layers(bool fold) { return fold ? 9 : 10; }
 
 // Power-of-two scale that brings the largest |w| of a layer into [2^13, 2^14): a trained layer with tiny weights
 // does not flush to zero in fp16 (subnormals start at 6e-5), a layer with weights beyond 65504 does not overflow,
@@ -1195,29 +1238,41 @@ float layer_wscale(const std::vector<float>& W) {
   return std::ldexp(1.f, 14 - e);          // m * scale in [2^13, 2^14)
 }
 
-template <typename T>
-void pack_image(const std::vector<std::vector<float>>& t, std::vector<uint8_t>& img) {
-  img.clear();
-  img.reserve(kImageBytes);
-  float sc[kLayers];
-  for (int l = 0; l < kLayers; ++l) sc[l] = layer_wscale(t[layer_tensor(l)]);
-  put_block<T>(img, t[0], 256, 63, 0, 63, sc[0]);                            // layer 0 : X
-  for (int l = 1; l <= 4; ++l)
-    for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[2 * l], 256, 256, kb * 64, 64, sc[l]);
-  put_block<T>(img, t[10], 256, 319, 0, 63, sc[5]);                          // layer 5 : X part of cat[pts, h]
-  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[10], 256, 319, 63 + kb * 64, 64, sc[5]);
-  for (int l = 6; l <= 7; ++l)
-    for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[2 * l], 256, 256, kb * 64, 64, sc[l]);
-  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[18], 256, 256, kb * 64, 64, sc[8]);   // feature_linear
-  put_block<T>(img, t[16], 128, 283, 256, 27, sc[9]);                        // views : direction part
-  for (int kb = 0; kb < 4; ++kb) put_block<T>(img, t[16], 128, 283, kb * 64, 64, sc[9]);   // views : feature part
+// feature_linear folded into views_linears.0 (exact algebra, products accumulated in double):
+//   W'[o][k] = sum_j W_v[o][j] W_f[j][k]   (k < 256),   W'[o][256 + k] = W_v[o][256 + k],   b'[o] = sum_j W_v[o][j] b_f[j] + b_v[o]
+void fold_feature_layer(std::vector<std::vector<float>>& t) {
+  const std::vector<float>&Wv = t[16], &bv = t[17], &Wf = t[18], &bf = t[19];
+  std::vector<float> W2(Wv.size()), b2(bv.size());
+  for (int o = 0; o < 128; ++o) {
+    std::vector<double> acc(256, 0.0);
+    double bacc = (double)bv[o];
+    for (int j = 0; j < 256; ++j) {
+      const double w = (double)Wv[(size_t)o * 283 + j];
+      bacc += w * (double)bf[j];
+      const float* row = &Wf[(size_t)j * 256];
+      for (int k = 0; k < 256; ++k) acc[k] += w * (double)row[k];
+    }
+    for (int k = 0; k < 256; ++k) W2[(size_t)o * 283 + k] = (float)acc[k];
+    for (int k = 256; k < 283; ++k) W2[(size_t)o * 283 + k] = Wv[(size_t)o * 283 + k];
+    b2[o] = (float)bacc;
+  }
+  t[16] = W2;
+  t[17] = b2;
 }
 
-// Split image: every K-block of pack_image as a (hi, lo) pair, hi = fp16(w * s), lo = fp16(w * s - hi).
-void pack_image_split(const std::vector<std::vector<float>>& t, std::vector<uint8_t>& img) {
+template <typename T>
+void pack_image(const std::vector<std::vector<float>>& t, bool fold, std::vector<uint8_t>& img) {
+  img.clear();
+  float sc[kLayers];
+  for (int l = 0; l < n_layers(fold); ++l) sc[l] = layer_wscale(t[layer_tensor(l, fold)]);
+  for (const Blk& b : image_blocks(fold)) put_block<T>(img, t[b.tensor], b.n_rows, b.in_dim, b.col0, b.count, sc[b.layer]);
+}
+
+// Split image: every K-block as a (hi, lo) pair, hi = fp16(w * s), lo = fp16(w * s - hi).
+void pack_image_split(const std::vector<std::vector<float>>& t, bool fold, std::vector<uint8_t>& img) {
   std::vector<std::vector<float>> hi(t.size()), lo(t.size());
-  for (int l = 0; l < kLayers; ++l) {
-    const int ti = layer_tensor(l);
+  for (int l = 0; l < n_layers(fold); ++l) {
+    const int ti = layer_tensor(l, fold);
     const float s = layer_wscale(t[ti]);
     hi[ti].resize(t[ti].size());
     lo[ti].resize(t[ti].size());
@@ -1229,42 +1284,37 @@ void pack_image_split(const std::vector<std::vector<float>>& t, std::vector<uint
     }
   }
   img.clear();
-  img.reserve(2 * kImageBytes);
-  auto pair = [&](int ti, int n_rows, int in_dim, int col0, int count) {
-    put_block<__half>(img, hi[ti], n_rows, in_dim, col0, count);
-    put_block<__half>(img, lo[ti], n_rows, in_dim, col0, count);
-  };
-  pair(0, 256, 63, 0, 63);
-  for (int l = 1; l <= 4; ++l)
-    for (int kb = 0; kb < 4; ++kb) pair(2 * l, 256, 256, kb * 64, 64);
-  pair(10, 256, 319, 0, 63);
-  for (int kb = 0; kb < 4; ++kb) pair(10, 256, 319, 63 + kb * 64, 64);
-  for (int l = 6; l <= 7; ++l)
-    for (int kb = 0; kb < 4; ++kb) pair(2 * l, 256, 256, kb * 64, 64);
-  for (int kb = 0; kb < 4; ++kb) pair(18, 256, 256, kb * 64, 64);
-  pair(16, 128, 283, 256, 27);
-  for (int kb = 0; kb < 4; ++kb) pair(16, 128, 283, kb * 64, 64);
+  for (const Blk& b : image_blocks(fold)) {
+    put_block<__half>(img, hi[b.tensor], b.n_rows, b.in_dim, b.col0, b.count);
+    put_block<__half>(img, lo[b.tensor], b.n_rows, b.in_dim, b.col0, b.count);
+  }
 }
 
 }  // namespace
 
 size_t tc_weight_image_bytes() { return kImageBytes; }
 
-void tc_pack_weights(const std::vector<std::vector<float>>& t, int dtype, std::vector<uint8_t>& image, TcConsts& c) {
-  if (dtype == EVPP_PREC_BF16) pack_image<__nv_bfloat16>(t, image);
-  else if (dtype == EVPP_PREC_FP16X2 || dtype == EVPP_PREC_FP16X3) pack_image_split(t, image);
-  else pack_image<__half>(t, image);
+void tc_pack_weights(const std::vector<std::vector<float>>& t_in, int dtype, bool fold, std::vector<uint8_t>& image, TcConsts& c) {
+  std::vector<std::vector<float>> t = t_in;
+  if (fold) fold_feature_layer(t);
+  if (dtype == EVPP_PREC_BF16) pack_image<__nv_bfloat16>(t, fold, image);
+  else if (dtype == EVPP_PREC_FP16X2 || dtype == EVPP_PREC_FP16X3) pack_image_split(t, fold, image);
+  else pack_image<__half>(t, fold, image);
   memset(&c, 0, sizeof(c));
   for (int l = 0; l < 8; ++l) memcpy(c.bias[l], t[2 * l + 1].data(), 256 * 4);
-  memcpy(c.bias[8], t[19].data(), 256 * 4);
-  memcpy(c.bias[9], t[17].data(), 128 * 4);
+  if (fold) {
+    memcpy(c.bias[8], t[17].data(), 128 * 4);     // layer 8 = the folded view layer
+  } else {
+    memcpy(c.bias[8], t[19].data(), 256 * 4);
+    memcpy(c.bias[9], t[17].data(), 128 * 4);
+  }
   memcpy(c.w_alpha, t[20].data(), 256 * 4);
   memcpy(c.w_rgb, t[22].data(), 384 * 4);
   memcpy(c.w_unc, t[24].data(), 128 * 4);
   c.head_b[0] = t[21][0];
   c.head_b[1] = t[23][0]; c.head_b[2] = t[23][1]; c.head_b[3] = t[23][2];
   c.head_b[4] = t[25][0];
-  for (int l = 0; l < kLayers; ++l) c.inv_wscale[l] = 1.f / layer_wscale(t[layer_tensor(l)]);
+  for (int l = 0; l < n_layers(fold); ++l) c.inv_wscale[l] = 1.f / layer_wscale(t[layer_tensor(l, fold)]);
 }
 
 int launch_mlp_tc(const TcWeights& w, const RayBatch& rb, float* raw, int num_sms, cudaStream_t st, int heads) {

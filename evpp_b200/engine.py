@@ -158,12 +158,14 @@ class Engine:
     def rescore_views_fp32(self, c2w_host, view_ids, H, W, fx, fy, cx, cy, pix_idx_host=None):
         return self.rescore_views(c2w_host, view_ids, H, W, fx, fy, cx, cy, pix_idx_host, precision="fp32")
 
-    def set_score_mode(self, full_outputs):
-        """False (default): scoring calls skip the network outputs the score does not depend on (bit-identical
-        scores); True: they evaluate the full network like render()."""
-        check(self.lib.evpp_set_score_mode(self._h, int(bool(full_outputs))))
+    def set_score_mode(self, mode):
+        """What scoring calls evaluate (evpp_set_score_mode).  False / 0 / "lean" (default): only what the score
+        depends on, with feature_linear folded into the view layer (same function, one GEMM layer less);
+        2 / "lean_unfolded": the same elimination in the reference's layer order (bit-identical to the full
+        evaluation); True / 1 / "full": the full network like render()."""
+        code = {"lean": 0, "full": 1, "lean_unfolded": 2}.get(mode, mode) if isinstance(mode, str) else int(mode)
+        check(self.lib.evpp_set_score_mode(self._h, int(code)))
 
-    # ---- rendering (render / render_rays, run_nerf.py:131-196, 391-509) -----------------------------
     def render_rays(self, rays_o, rays_d, near, far, precision=None, want=("rgb", "disp", "acc", "depth", "unc"),
                     capture_stages=False, viewdirs=None):
         """viewdirs: optional [N,3] view directions used as given (None = rays_d / ||rays_d||, run_nerf.py:170)."""

@@ -123,11 +123,15 @@ int evpp_rescore_views(evpp_handle* h, const float* c2w_host, const int32_t* vie
                        float fx, float fy, float cx, float cy, const int32_t* pix_idx_host, int R,
                        int precision, float* scores_host, void* stream);
 
-/* Scoring calls (evpp_score_views*, evpp_rescore_views*) compute only what Controller.get_uncertainty's result
- * depends on (nerf.py:307-309 reads raw[..., 4] of the final pass): the coarse network stops at its sigma, the fine
- * network skips its alpha / rgb heads.  The scores are bit-identical to the full evaluation;
- * full_outputs != 0 switches the elimination off (parity tests, like-for-like timing).  Default 0. */
-int evpp_set_score_mode(evpp_handle* h, int full_outputs);
+/* How much of the network scoring calls (evpp_score_views*, evpp_rescore_views*) evaluate.  Controller.get_uncertainty's
+ * result depends on raw[..., 4] of the final pass only (nerf.py:307-309):
+ *   mode 0 (default)  the coarse network stops at its sigma, the fine network skips its alpha / rgb heads, and
+ *                     feature_linear is multiplied into views_linears.0 on the host -- the reference applies no
+ *                     activation between them (run_nerf_helpers.py:119-122), so the two are ONE linear map; the pass is
+ *                     the same function of its inputs, equal to the reference's layer order at rounding level;
+ *   mode 2            the same dead-output elimination in the reference's layer order: scores bit-identical to mode 1;
+ *   mode 1            the full network like render() (parity tests, like-for-like timing). */
+int evpp_set_score_mode(evpp_handle* h, int mode);
 
 /* Replaces render(rays=...) / batchify_rays / render_rays (run_nerf.py:116-196, 391-509) with
  * use_viewdirs=True, ndc=False, perturb=0, raw_noise_std=0.  All device pointers; any output
@@ -350,7 +354,8 @@ int evpp_poison_workspace(evpp_handle* h);
 int evpp_set_profiling(evpp_handle* h, int enabled);
 int evpp_get_mlp_time_ms(evpp_handle* h, double* total_ms, int64_t* launches, int64_t* evals);
 /* Same, plus the FLOPs those launches really executed (a score-only coarse evaluation is 982,528 FLOP, a
- * score-only fine evaluation 1,185,792, a full evaluation 1,187,072: SURVEY.md section 8). */
+ * score-only fine evaluation 1,054,720 with the folded feature layer (1,185,792 without), a full evaluation
+ * 1,187,072: SURVEY.md section 8). */
 int evpp_get_mlp_profile(evpp_handle* h, double* total_ms, int64_t* launches, int64_t* evals, double* flops);
 
 #ifdef __cplusplus

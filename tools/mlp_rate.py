@@ -18,7 +18,7 @@ H, W, focal, V = 96, 128, 96.0, int(os.environ.get("V", 64))
 views = S.room_views(V, seed=0)
 poses = torch.Tensor(np.asarray(S.views_to_poses(views)))[:, :3, :4].contiguous().cuda()
 for prec in sys.argv[1:] or ("fp16", "bf16", "fp16x2", "fp16x3"):
-    for full in (True, False):
+    for full in (1, 2, 0):
         eng = Engine(device=0, near=0.5, far=6.0, precision=prec)
         eng.load_weights(0, c)
         eng.load_weights(1, f)
@@ -32,6 +32,6 @@ for prec in sys.argv[1:] or ("fp16", "bf16", "fp16x2", "fp16x3"):
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / 3
         ms, n, ev, fl = eng.mlp_profile()
-        print(f"{prec:7s} {'full outputs' if full else 'score-only  '}: {V / dt:8.1f} views/s  step {1e3 * dt:8.1f} ms  MLP {ms / 3:8.1f} ms "
+        print(f"{prec:7s} { {1: 'full outputs ', 2: 'score-only   ', 0: 'score-only+fold'}[full] }: {V / dt:8.1f} views/s  step {1e3 * dt:8.1f} ms  MLP {ms / 3:8.1f} ms "
               f"({fl / ms / 1e9:7.1f} TFLOP/s executed, {ev * 1187072.0 / ms / 1e9:7.1f} at 1,187,072 FLOP/eval)  score[0] {float(s[0]):.6f}", flush=True)
         eng.close()
