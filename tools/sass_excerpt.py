@@ -12,9 +12,10 @@ OBJ = os.path.join(ROOT, "evpp_b200", "lib", "obj", "mlp_tc.o")
 WANT = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "FENCE.VIEW.ASYNC", "UTCATOMSWS", "F2FP", "FFMA2", "FMNMX", "HMMA", "MUFU"]
 VARIANTS = {
     "ILb0ELb1ELi2ELi0ELi2ELi1ELi1E": "bulk fp16, 2-CTA cluster, sigma-only coarse pass (HEADS=1)",
-    "ILb0ELb1ELi2ELi0ELi2ELi1ELi2E": "bulk fp16, 2-CTA cluster, beta-only fine pass (HEADS=2)",
+    "ILb0ELb1ELi2ELi0ELi2ELi1ELi3E": "bulk fp16, 2-CTA cluster, beta-only fine pass with the folded feature layer (HEADS=3, the production fine pass)",
+    "ILb0ELb1ELi2ELi0ELi2ELi1ELi2E": "bulk fp16, 2-CTA cluster, beta-only fine pass in the reference's layer order (HEADS=2)",
     "ILb0ELb1ELi2ELi0ELi2ELi1ELi0E": "bulk fp16, 2-CTA cluster, full outputs (render())",
-    "ILb0ELb1ELi2ELi0ELi4ELi3ELi2E": "exact fp16x3 (3 MMAs per product), 2-CTA cluster, beta-only fine pass",
+    "ILb0ELb1ELi2ELi0ELi4ELi3ELi3E": "exact fp16x3 (3 MMAs per product), 2-CTA cluster, beta-only fine pass with the folded feature layer",
     "ILb0ELb1ELi2ELi0ELi4ELi3ELi1E": "exact fp16x3, 2-CTA cluster, sigma-only coarse pass",
 }
 sass = subprocess.run(["cuobjdump", "-sass", OBJ], capture_output=True, text=True, check=True).stdout
