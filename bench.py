@@ -794,6 +794,13 @@ def main():
     eng.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
     _, ms_e2e_wall, _, _ = timed(step_e2e, max(2, min(args.steps, 3)), 1)
+    # transparency: the same step with the score-only passes in the reference's ten-layer order (feature_linear NOT folded
+    # into the view layer), one untimed + one timed sweep
+    ms_unfolded = None
+    if not args.full_outputs and not args.no_fold and args.precision != "fp32":
+        eng.set_score_mode(2)
+        ms_unfolded, _, _, _ = timed(step_device, 1, 1)
+        eng.set_score_mode(0)
 
     if rank == 0:
         sustained, burst, src = peaks()
@@ -830,6 +837,10 @@ def main():
                                "Engine.score_views + select_nbv (pinned host poses in, host scores + winner out)"},
                 "gpu_launches": int(launches),
                 "nbv_check": check,
+                "variants": {"score_only_reference_layer_order": {"value": V_job / (ms_unfolded / 1e3), "unit": "views/s", "ms_per_step": ms_unfolded,
+                                                                  "note": "1 warm-up + 1 timed sweep with --no-fold: ten GEMM layers per fine evaluation as in the reference; "
+                                                                          "the headline folds feature_linear into views_linears.0 (no activation between them: one linear map)"}}
+                if ms_unfolded else None,
                 "view_blocks": [e_ - b_ for b_, e_ in state["ranges"]] if state["ranges"] else None,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                              "frac": achieved / sustained,
