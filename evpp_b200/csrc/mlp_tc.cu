@@ -24,7 +24,18 @@
 //                     run as two N = 128 halves (columns 0..127 first), so the drain of the first half overlaps
 //                     the second half's MMAs (SPLIT template parameter).
 //
-// Per row the kernel reads 4 B (z) and writes 20 B.
+// Per row the kernel reads 4 B (z) and writes 20 B (render()) or 4 B (scoring calls).
+//
+// Template axes added in round 2 (documented at mlp_tc_kernel):
+//   NP     1 = plain 16-bit operands (bulk pass); 2 / 3 = split-fp16 passes (W = W_hi + W_lo, A = A_hi + A_lo, two / three
+//          MMAs per product, fp32 accumulate): fp32-class results on the tensor cores -- the exact path that re-scores the
+//          near-tied candidate views so that the planner's arg-max is the fp32 reference's.  A_lo lives in the 8 tensor-
+//          memory columns the in-place packing leaves free, W_lo is a second weight image in the same ring (5 stages).
+//   HEADS  score-only variants for Controller.get_uncertainty (nerf.py:307-309 reads raw[..., 4] of the fine pass only):
+//          1 = sigma only (coarse pass, stops after layer 7), 2 = beta only, 3 = beta only with feature_linear multiplied
+//          into views_linears.0 on the host (no activation between them: one linear map, nine GEMM layers).
+// Every weight image is scaled per layer by a power of two (undone in the epilogue's bias FMA) and the epilogue's ReLU
+// keeps NaN, so neither an underflow of tiny trained weights nor an overflow of fp16 activations can pass silently.
 #include <cmath>
 
 #include "common.cuh"
