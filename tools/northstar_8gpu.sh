@@ -1,4 +1,4 @@
-# BASELINE configs[2]: the 4096-view Room sweep on 8 GPUs (512 views per GPU), reference-parity scorer and NGP mode,
+# BASELINE configs[2]: the 4096-view Room sweep on 8 GPUs (strong-scaled: 512 views per GPU), reference-parity scorer and NGP mode,
 # next to the host-CPU reference on the same box.  Lines go to gpurun_out/northstar_*.json
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531"
 timeout 600 $TR bench.py --gpus 8 --workload room --steps 2 --warmup 3 > gpurun_out/northstar_room_n8.json 2> gpurun_out/northstar_room_n8.err
