@@ -5,7 +5,7 @@ import collections
 import os
 import re
 import subprocess
-import sys
+
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "evpp_b200", "lib", "obj", "mlp_tc.o")
