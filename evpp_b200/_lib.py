@@ -55,6 +55,7 @@ SIGNATURES = {
     "evpp_rescore_views_fp32": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P]),
     "evpp_rescore_views": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _I, _P, _P]),
     "evpp_set_score_mode": (_I, [_P, _I]),
+    "evpp_set_render_mode": (_I, [_P, _I]),
     "evpp_render_rays": (_I, [_P, _P, _P, _L, _F, _F, _I, C.POINTER(EvppRenderOut), _P]),
     "evpp_render_rays_ex": (_I, [_P, _P, _P, _P, _L, _F, _F, _I, C.POINTER(EvppRenderOut), _P]),
     "evpp_get_rays": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _F, _P, _I, _P, _P, _P, _P]),

@@ -71,7 +71,8 @@ int launch_mlp_simt(const SimtWeights& w, const RayBatch& rb, float* raw, cudaSt
 int launch_mlp_simt_points(const SimtWeights& w, const float* pts, const float* dirs, int64_t M, float* out,
                            cudaStream_t st);
 // heads: 0 = raw [n,S,5]; 1 = sigma only -> raw [n,S] (pass stops after layer 7); 2 = beta only -> raw [n,S];
-// 3 = beta only with feature_linear folded into the view layer (needs weights packed with fold = true)
+// 3 = beta only with feature_linear folded into the view layer (needs weights packed with fold = true);
+// 4 = raw [n,S,5] with the folded view layer
 int launch_mlp_tc(const TcWeights& w, const RayBatch& rb, float* raw, int num_sms, cudaStream_t st, int heads = 0);
 int launch_mlp_tc_points(const TcWeights& w, const float* pts, const float* dirs, int64_t M, float* out,
                          int num_sms, cudaStream_t st);

@@ -90,6 +90,7 @@ constexpr double kFlopFull = kFlopPerEval;
 constexpr double kFlopSigmaOnly = 2.0 * (63 * 256 + 4 * 256 * 256 + 319 * 256 + 2 * 256 * 256 + 256);
 constexpr double kFlopBetaOnly = kFlopPerEval - 2.0 * (256 + 3 * 128);
 constexpr double kFlopBetaOnlyFolded = kFlopBetaOnly - 2.0 * 256 * 256;      // feature_linear multiplied into the view layer
+constexpr double kFlopFullFolded = kFlopFull - 2.0 * 256 * 256;
 
 // Every entry point runs on the handle's device and leaves the caller's current device as it found it
 // (one process may drive several GPUs, nerf.py:269-273).
@@ -136,6 +137,7 @@ struct evpp_handle {
   int chunk_cap = 0;
   DevBuf rays_o, rays_d, viewdirs, z_c, raw_c, z_f, raw_f;
   DevBuf beta2, st_c2w, st_pix, st_scores, nonfinite;
+  bool render_fold = true;   // evpp_set_render_mode: render() evaluates feature_linear folded into the view layer
   int score_mode = 0;   // evpp_set_score_mode: 0 score-only passes + folded feature layer, 1 full network like render(),
                         // 2 score-only passes in the reference's layer order (bit-identical to 1)
   // stage capture
@@ -243,7 +245,7 @@ int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw,
     if (heads != 0) return fail(EVPP_ERR_INVALID, "internal: the fp32 FFMA kernel has no score-only variant");
     nl = launch_mlp_simt(simt_of(nw), rb, raw, st);
   } else {
-    const bool fold = heads == 3;
+    const bool fold = heads == 3 || heads == 4;
     int rc = ensure_tc(h, which, prec, fold);
     if (rc) return rc;
     nl = launch_mlp_tc(tc_of(nw, prec, nullptr, -1, nullptr, fold), rb, raw, h->num_sms, st, heads);
@@ -253,7 +255,7 @@ int run_mlp(evpp_handle* h, int which, int prec, const RayBatch& rb, float* raw,
     cudaEventRecord(e1, st);
     h->prof_events.emplace_back(e0, e1);
     h->prof_evals.push_back((int64_t)rb.n * rb.S);
-    h->prof_flops.push_back((double)rb.n * rb.S * (heads == 1 ? kFlopSigmaOnly : heads == 2 ? kFlopBetaOnly : heads == 3 ? kFlopBetaOnlyFolded : kFlopFull));
+    h->prof_flops.push_back((double)rb.n * rb.S * (heads == 1 ? kFlopSigmaOnly : heads == 2 ? kFlopBetaOnly : heads == 3 ? kFlopBetaOnlyFolded : heads == 4 ? kFlopFullFolded : kFlopFull));
   }
   h->launches += nl;
   h->evals += (int64_t)rb.n * rb.S;
@@ -273,10 +275,12 @@ int render_chunk(evpp_handle* h, int n, float near_plane, float far_plane, int p
   NvtxRange nvtx_chunk("evpp:chunk");
   const bool score_only = !out && beta2 && !h->capture && h->score_mode != 1 && prec != EVPP_PREC_FP32;
   const int beta_heads = h->score_mode == 0 ? 3 : 2;      // the beta-only pass: with / without the folded feature layer
+  // all five outputs (render(), or a scoring call in score mode 1 = like-for-like with the reference's layer order)
+  const int full_heads = (out && h->render_fold && !h->capture && prec != EVPP_PREC_FP32) ? 4 : 0;
   h->launches += launch_coarse_z(h->t_vals.as<float>(), n, Sc, near_plane, far_plane, h->cfg.lindisp,
                                  h->z_c.as<float>(), st);
   RayBatch rb{h->rays_o.as<float>(), h->rays_d.as<float>(), h->viewdirs.as<float>(), h->z_c.as<float>(), n, Sc};
-  int rc = run_mlp(h, EVPP_NET_COARSE, prec, rb, h->raw_c.as<float>(), st, score_only ? (Ni > 0 ? 1 : beta_heads) : 0);
+  int rc = run_mlp(h, EVPP_NET_COARSE, prec, rb, h->raw_c.as<float>(), st, score_only ? (Ni > 0 ? 1 : beta_heads) : full_heads);
   if (rc) return rc;
   int nl;
   CompositeOut co{};
@@ -297,7 +301,7 @@ int render_chunk(evpp_handle* h, int n, float near_plane, float far_plane, int p
     if (nl < 0) return fail(EVPP_ERR_CUDA, "resampling kernel configuration failed (shared memory for %d + %d samples)", Sc, Ni);
     h->launches += nl;
     RayBatch rf{h->rays_o.as<float>(), h->rays_d.as<float>(), h->viewdirs.as<float>(), h->z_f.as<float>(), n, Sf};
-    rc = run_mlp(h, EVPP_NET_FINE, prec, rf, h->raw_f.as<float>(), st, score_only ? beta_heads : 0);
+    rc = run_mlp(h, EVPP_NET_FINE, prec, rf, h->raw_f.as<float>(), st, score_only ? beta_heads : full_heads);
     if (rc) return rc;
   }
   const float* raw = Ni > 0 ? h->raw_f.as<float>() : h->raw_c.as<float>();
@@ -599,6 +603,12 @@ int evpp_rescore_views_fp32(evpp_handle* h, const float* c2w_host, const int32_t
                             float* scores_host, void* stream) {
   return evpp_rescore_views(h, c2w_host, view_ids, K, H, W, fx, fy, cx, cy, pix_idx_host, R, EVPP_PREC_FP32,
                             scores_host, stream);
+}
+
+int evpp_set_render_mode(evpp_handle* h, int fold_feature_layer) {
+  if (!h) return fail(EVPP_ERR_INVALID, "null handle");
+  h->render_fold = fold_feature_layer != 0;
+  return 0;
 }
 
 int evpp_set_score_mode(evpp_handle* h, int mode) {

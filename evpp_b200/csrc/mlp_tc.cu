@@ -581,16 +581,20 @@ __device__ __forceinline__ void drain_layer(const TcConsts& cst, const TcArgs& a
 // one 283 -> 128 layer whose weights are multiplied out on the host in fp64 (tc_pack_weights, fold = true).  The
 // pass runs 9 GEMM layers instead of 10 (11 % fewer tensor cycles per fine evaluation) and skips one rounding of
 // the activations to 16 bits; it is the same function of its inputs, equal to the unfolded pass at rounding level.
+// 4 = all five outputs with the same folded view layer (render() when evpp_set_render_mode allows it).
 template <bool BF16, bool RAYS, int C, int DM, int SPLIT, int NP, int HEADS>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcArgs args) {
   static_assert(NP == 1 || (!BF16 && SPLIT == 4 && DM == 0), "split passes: fp16 operands, no half-split K-blocks");
   static_assert(HEADS == 0 || (RAYS && DM == 0), "score-only variants exist for ray batches only");
-  static_assert(HEADS >= 0 && HEADS <= 3, "HEADS: 0 full, 1 sigma only, 2 beta only, 3 beta only with the folded feature layer");
+  static_assert(HEADS >= 0 && HEADS <= 4, "HEADS: 0 full, 1 sigma only, 2 beta only, 3 beta only + folded feature layer, 4 full + folded");
   using L_ = Lay<NP>;
   constexpr int kStages = L_::kStages;
   constexpr int NB = NP > 1 ? 2 : 1;                  // ring stages per K-block: W_hi (, W_lo)
-  constexpr int kView = HEADS == 3 ? 8 : 9;            // index of the view layer (feature_linear folded into it: 8)
+  constexpr bool kFold = HEADS == 3 || HEADS == 4;     // feature_linear multiplied into the view layer on the host
+  constexpr bool kAll = HEADS == 0 || HEADS == 4;      // all five outputs (render())
+  constexpr bool kBeta = HEADS == 2 || HEADS == 3;     // beta only
+  constexpr int kView = kFold ? 8 : 9;                 // index of the view layer
   constexpr int kLayersRun = HEADS == 1 ? 8 : kView + 1;
   constexpr bool DBG = DM == 1;
   constexpr bool TR = DM != 0;
@@ -870,11 +874,11 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
 #define EVPP_DRAIN_HF(KIND_) \
   do { if (hf == 0) EVPP_DRAIN(KIND_, 0); else if (hf == 1) EVPP_DRAIN(KIND_, 1); else if (hf == 2) EVPP_DRAIN(KIND_, 2); else EVPP_DRAIN(KIND_, 3); } while (0)
         if (HEADS != 1 && l == kView) {
-          if constexpr (HEADS >= 2) EVPP_DRAIN_HF(5); else if constexpr (HEADS == 0) EVPP_DRAIN_HF(3);
-        } else if (HEADS != 1 && HEADS != 3 && l == 8) {
-          if constexpr (HEADS == 0 || HEADS == 2) EVPP_DRAIN(2, -1);
+          if constexpr (kBeta) EVPP_DRAIN_HF(5); else if constexpr (kAll) EVPP_DRAIN_HF(3);
+        } else if (HEADS != 1 && !kFold && l == 8) {
+          if constexpr (HEADS != 1 && !kFold) EVPP_DRAIN(2, -1);
         } else if (l == 7) {
-          if constexpr (HEADS == 1) EVPP_DRAIN_HF(4); else if constexpr (HEADS >= 2) EVPP_DRAIN(0, -1); else EVPP_DRAIN_HF(1);
+          if constexpr (HEADS == 1) EVPP_DRAIN_HF(4); else if constexpr (kBeta) EVPP_DRAIN(0, -1); else EVPP_DRAIN_HF(1);
         } else {
           EVPP_DRAIN(0, -1);
         }
@@ -907,8 +911,8 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
       // ---- heads: combine the column slices, add biases, exp on the uncertainty ----
       if (hf != 0) {
         float* pr = partial + (row * (kColSplit - 1) + hf - 1) * 5;
-        if (HEADS == 0) { pr[0] = hd[0]; pr[1] = hd[1]; pr[2] = hd[2]; }
-        if (HEADS < 2) pr[3] = alpha;
+        if (kAll) { pr[0] = hd[0]; pr[1] = hd[1]; pr[2] = hd[2]; }
+        if (kAll || HEADS == 1) pr[3] = alpha;
         if (HEADS != 1) pr[4] = hd[3];
       }
       epi_bar_sync();
@@ -919,9 +923,9 @@ mlp_tc_kernel(const __grid_constant__ TcConsts cst, const __grid_constant__ TcAr
           const float* pr = partial + (row * (kColSplit - 1) + k) * 5;
 #pragma unroll
           for (int e = 0; e < 5; ++e)
-            if (HEADS == 0 || (HEADS == 1 && e == 3) || (HEADS >= 2 && e == 4)) t[e] += pr[e];
+            if (kAll || (HEADS == 1 && e == 3) || (kBeta && e == 4)) t[e] += pr[e];
         }
-        if (HEADS == 0) {
+        if (kAll) {
           float* o = args.out + cur.m * 5;
           o[0] = t[0] + cst.head_b[1];
           o[1] = t[1] + cst.head_b[2];
@@ -1081,7 +1085,7 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st, int h
   const int np = w.dtype == EVPP_PREC_FP16X3 ? 3 : w.dtype == EVPP_PREC_FP16X2 ? 2 : 1;
   if ((np > 1 || heads != 0) && (a.dbg || a.trace)) return -1;
   if (heads != 0 && !RAYS) return -1;
-  if ((heads == 3) != (w.folded != 0)) return -1;      // the folded pass needs the folded weight image, and only that pass may use it
+  if ((heads == 3 || heads == 4) != (w.folded != 0)) return -1;      // the folded passes need the folded weight image, and only they may use it
 
   // Hybrid 4 + 2: 4-CTA clusters share one weight stream four ways (L2 reads quartered) but leave 16 of the 148 SMs
   // idle; a second launch of 2-CTA clusters, released by griddepcontrol.launch_dependents as soon as every 4-CTA
@@ -1146,14 +1150,17 @@ int launch_any(const TcWeights& w, TcArgs a, int num_sms, cudaStream_t st, int h
   if (np > 1) {
     if constexpr (RAYS) {
       if (np == 3) e = heads == 1 ? launch_np<true, 3, 1>(w, a, C, grid, st) : heads == 2 ? launch_np<true, 3, 2>(w, a, C, grid, st)
-                     : heads == 3 ? launch_np<true, 3, 3>(w, a, C, grid, st) : launch_np<true, 3, 0>(w, a, C, grid, st);
+                     : heads == 3 ? launch_np<true, 3, 3>(w, a, C, grid, st) : heads == 4 ? launch_np<true, 3, 4>(w, a, C, grid, st)
+                     : launch_np<true, 3, 0>(w, a, C, grid, st);
       else e = heads == 1 ? launch_np<true, 2, 1>(w, a, C, grid, st) : heads == 2 ? launch_np<true, 2, 2>(w, a, C, grid, st)
-               : heads == 3 ? launch_np<true, 2, 3>(w, a, C, grid, st) : launch_np<true, 2, 0>(w, a, C, grid, st);
+               : heads == 3 ? launch_np<true, 2, 3>(w, a, C, grid, st) : heads == 4 ? launch_np<true, 2, 4>(w, a, C, grid, st)
+               : launch_np<true, 2, 0>(w, a, C, grid, st);
     } else {
       e = np == 3 ? launch_np<false, 3, 0>(w, a, C, grid, st) : launch_np<false, 2, 0>(w, a, C, grid, st);
     }
   } else if (heads != 0) {
-    if constexpr (RAYS) e = heads == 1 ? launch_heads<1>(w, a, C, grid, st) : heads == 2 ? launch_heads<2>(w, a, C, grid, st) : launch_heads<3>(w, a, C, grid, st);
+    if constexpr (RAYS) e = heads == 1 ? launch_heads<1>(w, a, C, grid, st) : heads == 2 ? launch_heads<2>(w, a, C, grid, st)
+                          : heads == 3 ? launch_heads<3>(w, a, C, grid, st) : launch_heads<4>(w, a, C, grid, st);
     else e = cudaErrorInvalidValue;
   } else {
     switch (g_split) {

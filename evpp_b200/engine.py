@@ -81,6 +81,11 @@ class Engine:
             check(self.lib.evpp_load_nerf_weights(self._h, which, C.c_void_p(packed.data_ptr()),
                                                   offs.ctypes.data_as(C.c_void_p), len(offsets)))
 
+    def set_render_mode(self, fold_feature_layer):
+        """True (default): render_rays on the tensor-core precisions evaluates feature_linear folded into the view
+        layer (same function, nine GEMM layers); False: the reference's ten layers (evpp_set_render_mode)."""
+        check(self.lib.evpp_set_render_mode(self._h, int(bool(fold_feature_layer))))
+
     def load_checkpoint(self, ckpt):
         """Both networks from a checkpoint of the reference: the ``.tar`` written by ``Controller.save_model``
         (nerfServer/core/nerf.py:612-621; reloaded by create_nerf, run_nerf.py:292-312) or the dict inside it, keys

@@ -133,6 +133,11 @@ int evpp_rescore_views(evpp_handle* h, const float* c2w_host, const int32_t* vie
  *   mode 1            the full network like render() (parity tests, like-for-like timing). */
 int evpp_set_score_mode(evpp_handle* h, int mode);
 
+/* evpp_render_rays(_ex) on the tensor-core precisions evaluates feature_linear multiplied into views_linears.0 as well
+ * (default 1: the same function with nine GEMM layers, outputs equal to the reference's layer order at the operand
+ * type's rounding level); 0 = the reference's ten layers.  Stage capture and the fp32 FFMA kernel always use ten. */
+int evpp_set_render_mode(evpp_handle* h, int fold_feature_layer);
+
 /* Replaces render(rays=...) / batchify_rays / render_rays (run_nerf.py:116-196, 391-509) with
  * use_viewdirs=True, ndc=False, perturb=0, raw_noise_std=0.  All device pointers; any output
  * may be NULL.  S_f = n_samples + n_importance (or n_samples when n_importance == 0).

@@ -157,6 +157,29 @@ def test_score_only_passes_are_bit_identical(engine_factory, prec, fold_tol):
         eng.set_score_mode(7)
 
 
+@pytest.mark.parametrize("prec,tol", [("fp16", 2e-3), ("fp16x3", 2e-5)])
+def test_render_with_folded_feature_layer_equals_reference_layer_order(engine_factory, prec, tol):
+    """evpp_render_rays folds feature_linear into views_linears.0 by default (evpp_set_render_mode): every output of
+    render() must agree with the reference's ten-layer order at the operand type's rounding level, and the coarse
+    outputs / sample positions (no feature layer on that path before the fine pass) must be unaffected in kind."""
+    eng = engine_factory("spread", prec)
+    H, W = 12, 16
+    K = O.make_K(H, W, 12.0)
+    ro, rd = O.build_view_rays(O.views_to_poses(O.hemisphere_views(2, seed=9)), H, W, K)
+    want = ("rgb", "disp", "acc", "depth", "unc", "raw", "rgb0", "depth0", "unc0")
+    a = eng.render_rays(ro, rd, 0.5, 6.0, want=want)
+    try:
+        eng.set_render_mode(False)
+        b = eng.render_rays(ro, rd, 0.5, 6.0, want=want)
+    finally:
+        eng.set_render_mode(True)
+    for k in want:
+        x, y = a[k].cpu().numpy(), b[k].cpu().numpy()
+        scale = np.abs(y).max() + 1e-6
+        assert np.abs(x - y).max() <= tol * scale, (k, np.abs(x - y).max() / scale)
+    assert not torch.equal(a["raw"], b["raw"])                  # the fold is really taken
+
+
 @pytest.mark.parametrize("variant", ["plain", "spread"])
 def test_render_fp32_matches_reference_golden(engine_factory, variant):
     g = load_golden(f"render_small_{variant}.npz")
@@ -526,21 +549,28 @@ def test_full_resolution_view_spans_chunks(engine_factory, weights):
     K = O.make_K(H, W, 480.0)
     views = O.hemisphere_views(2, seed=3)[:1]
     poses = torch.Tensor(np.asarray(O.views_to_poses(views)))[:, :3, :4].contiguous().cuda()
-    eng.set_score_mode("lean_unfolded")      # the reference's layer order: comparable with render() to the last bits
-    try:
-        s = eng.score_views(poses, H, W, *_intr(K))
-    finally:
-        eng.set_score_mode("lean")
-    s_folded = eng.score_views(poses, H, W, *_intr(K))      # default: feature_linear folded into the view layer
-    assert abs(float(s_folded[0]) - float(s[0])) < 3e-4 * float(s[0])
+    s = eng.score_views(poses, H, W, *_intr(K))              # default: score-only passes, feature_linear folded into the view layer
     ro, rd, _ = eng.get_rays(poses, H, W, *_intr(K))
     assert ro.shape[0] == H * W
-    total = 0.0
-    for b in range(0, H * W, 100_000):                      # ragged blocks, as two or more ranks would render them
-        o = eng.render_rays(ro[b:b + 100_000], rd[b:b + 100_000], 0.5, 6.0, want=("unc", "depth"))
-        total += float(o["unc"].double().square().sum())
-        assert torch.isfinite(o["depth"]).all()
-    np.testing.assert_allclose(float(s[0]), total / (H * W), rtol=2e-6)
+
+    def render_sum():
+        total = 0.0
+        for b in range(0, H * W, 100_000):                      # ragged blocks, as two or more ranks would render them
+            o = eng.render_rays(ro[b:b + 100_000], rd[b:b + 100_000], 0.5, 6.0, want=("unc", "depth"))
+            total += float(o["unc"].double().square().sum())
+            assert torch.isfinite(o["depth"]).all()
+        return total / (H * W)
+
+    np.testing.assert_allclose(float(s[0]), render_sum(), rtol=2e-6)          # render() folds the same way by default
+    try:                                                                       # ... and both in the reference's ten-layer order
+        eng.set_score_mode("lean_unfolded")
+        eng.set_render_mode(False)
+        s10 = eng.score_views(poses, H, W, *_intr(K))
+        np.testing.assert_allclose(float(s10[0]), render_sum(), rtol=2e-6)
+    finally:
+        eng.set_score_mode("lean")
+        eng.set_render_mode(True)
+    assert 0 < abs(float(s10[0]) - float(s[0])) < 3e-4 * float(s[0])
     pix = torch.randperm(H * W, generator=torch.Generator().manual_seed(1))[:96].to(torch.int32)[None, :].contiguous()
     s_sub = eng.score_views(poses, H, W, *_intr(K), pix_idx=pix.cuda())
     c, f = weights["spread"]
