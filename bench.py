@@ -425,7 +425,7 @@ def run_fullres(args, rank, local_rank, world):
     if rank == 0:
         sampler.start()
     ms_dev, _, launches = timed(step_device, args.steps, args.warmup, profile=True)
-    mlp_ms, mlp_launches, mlp_evals = eng.mlp_time()
+    mlp_ms, mlp_launches, mlp_evals, mlp_flops = eng.mlp_profile()
     eng.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
     _, ms_e2e, _ = timed(step_e2e, max(2, min(args.steps, 3)), 1)
@@ -434,9 +434,10 @@ def run_fullres(args, rank, local_rank, world):
         # the same numbers must come out at every N (rays are independent): fp64 sums of the gathered maps and scores
         check = {"scores": [float(x) for x in scores_pinned[:4]], "maps_sum": float(maps_pinned.sum(dtype=torch.float64)),
                  "depth_sum": float(maps_pinned[..., 3].sum(dtype=torch.float64))}
-        flops_per_launch = FLOP_PER_EVAL * mlp_evals / max(1, mlp_launches)
+        flops_per_launch = mlp_flops / max(1, mlp_launches)        # executed: render() folds feature_linear into the view layer
         avg_launch_ms = mlp_ms / max(1, mlp_launches)
         achieved = flops_per_launch / (avg_launch_ms / 1e3) / 1e12 if avg_launch_ms > 0 else 0.0
+        bpe, _ = measured_traffic_per_eval()
         line = {"metric": "candidate views scored/sec", "value": V / (ms_dev / 1e3), "unit": "views/s",
                 "rays_per_s": V * n_pix / (ms_dev / 1e3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -452,7 +453,7 @@ def run_fullres(args, rank, local_rank, world):
                         "api": "Engine.get_rays + Engine.render_rays (== render()) + dist.render_views_ray_sharded; maps and scores to pinned host memory"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                             "traffic": 11.97 * mlp_evals / max(1, mlp_launches),
+                             "traffic": None,      # (the committed DRAM capture is of the score-only launch: 4 + 4 B per evaluation; render() writes 20 B)
                              "peak_source": f"{src} bf16_tflops_sustained", "kernel": "mlp_tc_kernel",
                              "flop_per_launch": flops_per_launch, "avg_launch_ms": avg_launch_ms,
                              "mlp_share_of_step": mlp_ms / (ms_dev * args.steps) if ms_dev > 0 else None},
