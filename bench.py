@@ -794,7 +794,7 @@ def main():
     mlp_ms, mlp_launches, mlp_evals, mlp_flops = eng.mlp_profile()
     eng.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
-    _, ms_e2e_wall, _, _ = timed(step_e2e, max(2, min(args.steps, 3)), 1)
+    _, ms_e2e_wall, _, _ = timed(step_e2e, max(2, min(args.steps, 3)), min(args.warmup, 3))
     # transparency: the same step with the score-only passes in the reference's ten-layer order (feature_linear NOT folded
     # into the view layer), one untimed + one timed sweep
     ms_unfolded = None

@@ -7,12 +7,13 @@
 //
 // The whole fit is ONE kernel launch: 300 epochs x (8 forward + 7 backward stages) of latency-bound 100 x 64 x 64 products,
 // far too small to spread over the GPU (a grid-wide barrier per stage would cost more than the stage).  The default
-// runs on one cluster of 8 CTAs that split every layer by columns and exchange slices through L2 with one cluster
-// barrier per stage (surrogate_fit_cluster_kernel); the single-CTA twin (surrogate_fit_kernel) does the same arithmetic
-// on one SM and is the fallback.  Parameters, Adam moments and activations live in global memory (L2 resident,
-// < 0.7 MB); every stage stages its weight rows / columns (row stride 65: conflict-free for both the forward and the
-// transposed backward product) and one activation tile in shared memory.  Gradients are never written to global
-// memory: they are applied by the Adam update of the thread (or CTA) that produced them.
+// runs on one cluster of 8 CTAs that split every layer by columns, keep parameters, Adam moments and tiles resident in
+// shared memory and exchange slices through distributed shared memory with one cluster barrier per stage
+// (surrogate_fit_cluster_kernel).  The single-CTA twin (surrogate_fit_kernel) does the same arithmetic on one SM with
+// parameters, moments and activations in global memory (L2 resident, < 0.7 MB) and is the fallback; the two produce
+// bit-identical parameters (tools/surrogate_ab.py).  Weight rows are staged with stride 65: conflict-free for both the
+// forward and the transposed backward product.  Gradients are never written to global memory: they are applied by the
+// Adam update of the thread (or CTA) that produced them.
 #include "surrogate.cuh"
 
 namespace evpp {
@@ -40,14 +41,19 @@ struct AdamStep {
 };
 
 // torch.optim.Adam (single-tensor form, defaults betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad)
+// Every product / sum is spelled out: left to the compiler, `v * beta2 + (1 - beta2) * g * g` contracts into an FMA
+// around either product depending on the surrounding code, and the two fit kernels would differ in the last bit.
+__device__ __forceinline__ float adam_step(float p, float& mi, float& vi, float g, const AdamStep& a) {
+  mi = fmaf(__fsub_rn(g, mi), 1.f - a.beta1, mi);                                     // exp_avg.lerp_(grad, 1 - beta1)
+  vi = fmaf(__fmul_rn(1.f - a.beta2, g), g, __fmul_rn(vi, a.beta2));                  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = fmaf(__fsqrt_rn(vi), a.inv_sqrt_bc2, a.eps);                    // sqrt(v) / sqrt(bias_correction2) + eps
+  return fmaf(-a.lr_over_bc1, __fdiv_rn(mi, denom), p);                               // param.addcdiv_(exp_avg, denom, value=-lr / bias_correction1)
+}
 __device__ __forceinline__ void adam_update(float* p, float* m, float* v, int idx, float g, const AdamStep& a) {
   float mi = m[idx], vi = v[idx];
-  mi = mi + (g - mi) * (1.f - a.beta1);                       // exp_avg.lerp_(grad, 1 - beta1)
-  vi = vi * a.beta2 + (1.f - a.beta2) * g * g;                // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  p[idx] = adam_step(p[idx], mi, vi, g, a);
   m[idx] = mi;
   v[idx] = vi;
-  const float denom = sqrtf(vi) * a.inv_sqrt_bc2 + a.eps;     // sqrt(v) / sqrt(bias_correction2) + eps
-  p[idx] = p[idx] - a.lr_over_bc1 * (mi / denom);             // param.addcdiv_(exp_avg, denom, value=-lr / bias_correction1)
 }
 
 struct __align__(16) Smem {
@@ -111,7 +117,7 @@ __device__ __forceinline__ void last_forward(const float* P, const float* act, i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* w = P + off_l3w();
   for (int r = warp; r < n; r += kSgThreads / 32) {
-    float a = act[r * kH + lane] * w[lane] + act[r * kH + 32 + lane] * w[32 + lane];
+    float a = fmaf(act[r * kH + 32 + lane], w[32 + lane], __fmul_rn(act[r * kH + lane], w[lane]));   // explicit: same bits in every kernel
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) y[r] = a + P[off_l3b()];
@@ -267,28 +273,50 @@ surrogate_fit_kernel(float* P, float* M, float* V, const float* __restrict__ x, 
 // ---------------------------------------------------------------------------------------------------------------------
 // The fit on a CLUSTER of 8 CTAs.  CTA j owns columns 8j .. 8j+7 of every layer: it computes that slice of every
 // forward activation, of every input delta, the gradients of its 8 weight rows, and applies their Adam updates at the
-// end of the epoch (so every weight read of an epoch sees the previous epoch's values).  Slices are exchanged through
-// global memory (L2) with one cluster barrier per stage -- barrier.cluster release / acquire orders the global writes,
-// and the readers bypass L1 (ld.global.cg), whose lines may be stale from the previous epoch.  The 64 -> 1 output
-// layer, the loss and the output delta are computed redundantly (identically) by all CTAs, which saves three barriers.
-// 15 barriers and ~1.5 us of compute per stage instead of ~9 us on one SM.
+// end of the epoch (so every weight read of an epoch sees the previous epoch's values).
+// Everything the epoch loop touches lives in shared memory: the CTA's weight rows with their Adam moments, a copy of
+// the weight COLUMNS it needs for the transposed backward product, ping-pong activation and delta tiles.  Slices are
+// exchanged through DISTRIBUTED SHARED MEMORY: the producer stores its 8 columns of every row straight into the tile
+// of all eight CTAs (st.shared::cluster, 32-byte segments), one barrier.cluster (release / acquire) per stage makes
+// them visible, and the consumer's operands are local when it wakes up -- a stage costs its FMAs, ~0.6 us of remote
+// stores and one cluster barrier instead of two L2 round trips (the first version exchanged through global memory:
+// 83 us per epoch).  Updated weight rows are pushed the same way into the column copies of their readers during the
+// Adam step.  Global memory only receives the forward activations (fire-and-forget; the backward pass prefetches each
+// layer's input tile with cp.async one stage ahead) and the loss curve; parameters are written back once at the end.
+// The 3 -> 64 input layer, the 64 -> 1 output layer, the loss and the output delta are computed redundantly
+// (identically) by all CTAs, which saves four exchanges.  Same arithmetic, operation by operation, as
+// surrogate_fit_kernel: the two produce bit-identical parameters.
 constexpr int kClu = 8;
-constexpr int kCluThreads = 256;
+#ifndef EVPP_SG_CLU_THREADS
+#define EVPP_SG_CLU_THREADS 512
+#endif
+constexpr int kCluThreads = EVPP_SG_CLU_THREADS;
 constexpr int kSl = kH / kClu;          // columns per CTA
+constexpr int kAs = 68;                 // row stride of the activation tiles: the four rows a warp reads as 16-byte broadcasts
+                                        // sit in different banks (stride 64 would be a 4-way conflict)
+constexpr int kRq = kSurrogateMaxN / (kCluThreads / kSl);   // rows per thread in the (column, row group) products
+constexpr int kRg = kCluThreads / kSl;                      // row groups
+constexpr int kCq = kSl / (kCluThreads / kH);               // weight rows per thread in the gradient product
+static_assert(kRq >= 1 && kCq >= 1 && kCluThreads >= 2 * kSurrogateMaxN, "cluster fit: thread mapping");
 
 struct __align__(16) CluSmem {
-  float A[kSurrogateMaxN * kH];         // full input activations of the stage
-  float D[kSurrogateMaxN * kDs];        // full deltas at the stage's output
-  float Wf[kSl * kWs];                  // own weight rows W[cs + c][k]
-  float Wc[kH * kSl];                   // weight columns W[c][ks + kk], stored [c][kk]
-  float bown[kSl];
+  float A[2][kSurrogateMaxN * kAs];     // forward: input / output activations of the stage; backward: layer inputs
+  float D[2][kSurrogateMaxN * kDs];     // deltas at the stage's output / input
+  float Wf[kHid][kSl * kWs];            // own weight rows W[cs + c][k] of every hidden layer (resident, updated in place)
+  float Mo[kHid][kSl * kH];             // their Adam moments
+  float Vo[kHid][kSl * kH];
+  float Wc[kHid][kH * kSl];             // weight columns W[c][cs + kk] of every hidden layer, stored [c][kk]; kept current by
+                                        // the owners of the rows (remote stores in their Adam step)
   float dW[kHid][kSl * kH];             // gradients of the own rows, applied after the backward pass
-  float db[kHid][kSl];
-  float dW1[kSl * 4];                   // first layer: [c][0..2] weight, [c][3] bias
+  float bown[kHid][kSl], mb[kHid][kSl], vb[kHid][kSl], db[kHid][kSl];
+  float w1[kH * 4];                     // input layer, all 64 units: [c][0..2] weight, [c][3] bias (owners push updates)
+  float m1[kSl * 4], v1[kSl * 4], dW1[kSl * 4];
   float w3[kH + 1], m3[kH + 1], v3[kH + 1], g3[kH + 1];   // output layer (+ bias), a private identical copy per CTA
+  float x[kSurrogateMaxN * 3], t[kSurrogateMaxN];
   float y[kSurrogateMaxN];
   float red[8];
 };
+static_assert(sizeof(CluSmem) <= 227 * 1024, "cluster fit: shared memory");
 
 __device__ __forceinline__ uint32_t clu_rank() {
   uint32_t r;
@@ -298,27 +326,32 @@ __device__ __forceinline__ uint32_t clu_rank() {
 __device__ __forceinline__ void clu_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// [n][64] tile L2 -> shared memory (row stride `ds` floats), bypassing L1; all of a thread's 16-byte loads are issued
-// before the first store so that the copy costs one L2 latency, not one per element
-__device__ __forceinline__ void clu_load(float* dst, const float* src, int n, int ds) {
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-  const int n4 = n * (kH / 4);
-  float4 v[kSurrogateMaxN * (kH / 4) / kCluThreads];            // 8
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int idx = threadIdx.x + u * kCluThreads;
-    if (idx < n4) v[u] = __ldcg(s4 + idx);
-  }
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int idx = threadIdx.x + u * kCluThreads;
-    if (idx < n4) *reinterpret_cast<float4*>(dst + (idx >> 4) * ds + (idx & 15) * 4) = v[u];
-  }
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t clu_map(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(rank));
+  return r;
 }
+__device__ __forceinline__ void clu_store(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// v -> the same location in all eight CTAs (this one included)
+__device__ __forceinline__ void clu_store_all(const float* p, float v) {
+#pragma unroll
+  for (uint32_t j = 0; j < kClu; ++j) clu_store(clu_map(p, j), v);
+}
+// [n][64] tile global (L2) -> shared memory, asynchronously (the caller waits with clu_prefetch_wait + a barrier)
+__device__ __forceinline__ void clu_prefetch(float* dst, const float* src, int n) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  for (int idx = threadIdx.x; idx < n * (kH / 4); idx += kCluThreads)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + ((idx >> 4) * kAs + (idx & 15) * 4) * 4), "l"(src + idx * 4) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void clu_prefetch_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __global__ void __cluster_dims__(kClu, 1, 1) __launch_bounds__(kCluThreads, 1)
-surrogate_fit_cluster_kernel(float* P, float* M, float* V, const float* __restrict__ x, const float* __restrict__ target,
-                             int n, int epochs, float lr, float* act, float* dbuf, float* __restrict__ loss_out) {
+surrogate_fit_cluster_kernel(float* P, const float* __restrict__ x, const float* __restrict__ target, int n, int epochs,
+                             float lr, float* act, float* __restrict__ loss_out) {
   extern __shared__ __align__(16) uint8_t sg_smem[];
   CluSmem& s = *reinterpret_cast<CluSmem*>(sg_smem);
   const int tid = threadIdx.x;
@@ -326,59 +359,82 @@ surrogate_fit_cluster_kernel(float* P, float* M, float* V, const float* __restri
   const int act_stride = n * kH;
   const float beta1 = 0.9f, beta2 = 0.999f;
   double b1t = 1.0, b2t = 1.0;
+  // ---- one-time staging: parameters, zero moments (a fresh optimizer per fit, like train_only), inputs
+  for (int i = 0; i < kHid; ++i) {
+    const int j = used_layer(i);
+    for (int q = tid; q < kSl * kH; q += kCluThreads) {
+      s.Wf[i][(q >> 6) * kWs + (q & 63)] = P[off_l2w(j) + (cs + (q >> 6)) * kH + (q & 63)];
+      s.Mo[i][q] = 0.f;
+      s.Vo[i][q] = 0.f;
+      s.Wc[i][q] = P[off_l2w(j) + (q >> 3) * kH + cs + (q & 7)];
+    }
+    if (tid < kSl) { s.bown[i][tid] = P[off_l2b(j) + cs + tid]; s.mb[i][tid] = 0.f; s.vb[i][tid] = 0.f; }
+  }
+  if (tid < kH * 4) s.w1[tid] = (tid & 3) < 3 ? P[off_l1w() + (tid >> 2) * 3 + (tid & 3)] : P[off_l1b() + (tid >> 2)];
+  if (tid < kSl * 4) { s.m1[tid] = 0.f; s.v1[tid] = 0.f; }
   if (tid <= kH) { s.w3[tid] = P[off_l3w() + tid]; s.m3[tid] = 0.f; s.v3[tid] = 0.f; }   // off_l3b() == off_l3w() + 64
-  __syncthreads();
+  for (int i = tid; i < n * 3; i += kCluThreads) s.x[i] = x[i];
+  for (int i = tid; i < n; i += kCluThreads) s.t[i] = target[i];
+  clu_sync();                                    // every CTA of the cluster is resident before the first remote store
   for (int ep = 0; ep < epochs; ++ep) {
     // ================= forward =================
-    for (int i = tid; i < n * kSl; i += kCluThreads) {          // layer 1 (3 -> 64), own columns
-      const int r = i >> 3, c = cs + (i & 7);
-      float a = P[off_l1b() + c];
-      a = fmaf(x[r * 3 + 0], P[off_l1w() + c * 3 + 0], a);
-      a = fmaf(x[r * 3 + 1], P[off_l1w() + c * 3 + 1], a);
-      a = fmaf(x[r * 3 + 2], P[off_l1w() + c * 3 + 2], a);
-      act[r * kH + c] = fmaxf(a, 0.f);
+    for (int i = tid; i < n * kH; i += kCluThreads) {           // layer 1 (3 -> 64): all columns, every CTA the same
+      const int r = i >> 6, c = i & 63;
+      float a = s.w1[c * 4 + 3];
+      a = fmaf(s.x[r * 3 + 0], s.w1[c * 4 + 0], a);
+      a = fmaf(s.x[r * 3 + 1], s.w1[c * 4 + 1], a);
+      a = fmaf(s.x[r * 3 + 2], s.w1[c * 4 + 2], a);
+      a = fmaxf(a, 0.f);
+      s.A[0][r * kAs + c] = a;
+      if ((c >> 3) * kSl == cs) act[i] = a;                     // kept for the backward pass (own columns)
     }
-    clu_sync();
+    __syncthreads();
     for (int i = 0; i < kHid; ++i) {
-      const int j = used_layer(i);
-      clu_load(s.A, act + (size_t)i * act_stride, n, kH);
-      for (int q = tid; q < kSl * kH; q += kCluThreads) s.Wf[(q >> 6) * kWs + (q & 63)] = P[off_l2w(j) + (cs + (q >> 6)) * kH + (q & 63)];
-      if (tid < kSl) s.bown[tid] = P[off_l2b(j) + cs + tid];
-      __syncthreads();
+      const float* Ain = s.A[i & 1];
+      float* Aout = s.A[(i + 1) & 1];
       {
         const int c = tid & 7, rg = tid >> 3;
-        float acc[4];
+        float acc[kRq];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] = s.bown[c];
-        const float* wrow = s.Wf + c * kWs;
+        for (int q = 0; q < kRq; ++q) acc[q] = s.bown[i][c];
+        const float* wrow = s.Wf[i] + c * kWs;
 #pragma unroll 4
         for (int k = 0; k < kH; k += 4) {
           const float w0 = wrow[k], w1 = wrow[k + 1], w2 = wrow[k + 2], w3 = wrow[k + 3];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 a = *reinterpret_cast<const float4*>(s.A + (rg + 32 * q) * kH + k);
+          for (int q = 0; q < kRq; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(Ain + (rg + kRg * q) * kAs + k);
             acc[q] = fmaf(a.x, w0, acc[q]);
             acc[q] = fmaf(a.y, w1, acc[q]);
             acc[q] = fmaf(a.z, w2, acc[q]);
             acc[q] = fmaf(a.w, w3, acc[q]);
           }
         }
-        float* out = act + (size_t)(i + 1) * act_stride;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = rg + 32 * q;
-          if (r < n) out[r * kH + cs + c] = fmaxf(acc[q], 0.f);
+        for (int q = 0; q < kRq; ++q) {
+          const int r = rg + kRg * q;
+          acc[q] = fmaxf(acc[q], 0.f);
+          if (r < n) clu_store_all(Aout + r * kAs + cs + c, acc[q]);
+        }
+        clu_sync();
+        // act[1..5] are re-read by the backward pass (6 and 7 stay in A).  Stored AFTER the barrier: its release would
+        // otherwise wait for these global stores to be acknowledged by L2 in every stage
+        if (i + 1 < kHid - 1) {
+          float* out = act + (size_t)(i + 1) * act_stride;
+#pragma unroll
+          for (int q = 0; q < kRq; ++q) {
+            const int r = rg + kRg * q;
+            if (r < n) out[r * kH + cs + c] = acc[q];
+          }
         }
       }
-      clu_sync();
     }
     // output layer, loss and output delta: every CTA computes all of it from the same data
-    clu_load(s.A, act + (size_t)kHid * act_stride, n, kH);
-    __syncthreads();
+    const float* A7 = s.A[kHid & 1];
     {
       const int warp = tid >> 5, lane = tid & 31;
       for (int r = warp; r < n; r += kCluThreads / 32) {
-        float a = s.A[r * kH + lane] * s.w3[lane] + s.A[r * kH + 32 + lane] * s.w3[32 + lane];
+        float a = fmaf(A7[r * kAs + 32 + lane], s.w3[32 + lane], __fmul_rn(A7[r * kAs + lane], s.w3[lane]));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (lane == 0) s.y[r] = a + s.w3[kH];
@@ -388,7 +444,7 @@ surrogate_fit_cluster_kernel(float* P, float* M, float* V, const float* __restri
     {
       float e = 0.f;
       if (tid < n) {
-        const float d = s.y[tid] - target[tid];
+        const float d = s.y[tid] - s.t[tid];
         s.y[tid] = 2.f * d / (float)n;                          // dy
         e = d * d;
       }
@@ -409,98 +465,127 @@ surrogate_fit_cluster_kernel(float* P, float* M, float* V, const float* __restri
     as.lr_over_bc1 = (float)((double)lr / (1.0 - b1t));
     as.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - b2t));
     // ================= backward =================
-    for (int i = tid; i < n * kH; i += kCluThreads) {
-      const int r = i >> 6, k = i & 63;
-      s.D[r * kDs + k] = s.A[i] > 0.f ? s.y[r] * s.w3[k] : 0.f;
-    }
-    if (tid < kH) {
-      float g = 0.f;
-      for (int r = 0; r < n; ++r) g = fmaf(s.y[r], s.A[r * kH + tid], g);
-      s.g3[tid] = g;
-    } else if (tid == kH) {
-      float g = 0.f;
-      for (int r = 0; r < n; ++r) g += s.y[r];
-      s.g3[kH] = g;
+    // stage i reads the delta at layer i's output from D[(i + 1) & 1] and the layer's input activations from A[i & 1]
+    // (act[6] is still there from the forward pass; act[i - 1] is prefetched into the other buffer during stage i)
+    {
+      float* D7 = s.D[kHid & 1];
+      for (int i = tid; i < n * kH; i += kCluThreads) {
+        const int r = i >> 6, k = i & 63;
+        D7[r * kDs + k] = A7[r * kAs + k] > 0.f ? s.y[r] * s.w3[k] : 0.f;
+      }
+      if (tid < kH) {
+        float g = 0.f;
+        for (int r = 0; r < n; ++r) g = fmaf(s.y[r], A7[r * kAs + tid], g);
+        s.g3[tid] = g;
+      } else if (tid == kH) {
+        float g = 0.f;
+        for (int r = 0; r < n; ++r) g += s.y[r];
+        s.g3[kH] = g;
+      }
     }
     __syncthreads();
     for (int i = kHid - 1; i >= 0; --i) {
-      const int j = used_layer(i);
-      clu_load(s.A, act + (size_t)i * act_stride, n, kH);       // the layer's input activations
-      for (int q = tid; q < kH * kSl; q += kCluThreads) s.Wc[q] = __ldcg(P + off_l2w(j) + (q >> 3) * kH + cs + (q & 7));
-      __syncthreads();
-      {   // gradients of the own rows: dW[c][k] = sum_r D[r][cs + c] A[r][k], two rows per thread
+      const float* Ain = s.A[i & 1];
+      const float* Din = s.D[(i + 1) & 1];
+      float* Dout = s.D[i & 1];
+      if (i > 0) clu_prefetch(s.A[(i - 1) & 1], act + (size_t)(i - 1) * act_stride, n);   // next stage's layer inputs
+      {   // gradients of the own rows: dW[c][k] = sum_r D[r][cs + c] A[r][k], kCq rows per thread; bias gradients
+          // db[c] = sum_r D[r][c] ride along (rows in order, like the single-CTA kernel)
         const int k = tid & 63, cq = tid >> 6;
-        float g0 = 0.f, g1 = 0.f;
+        float gw[kCq], gb[kCq];
+#pragma unroll
+        for (int u = 0; u < kCq; ++u) { gw[u] = 0.f; gb[u] = 0.f; }
 #pragma unroll 4
         for (int r = 0; r < n; ++r) {
-          const float a = s.A[r * kH + k];
-          const float2 d = *reinterpret_cast<const float2*>(s.D + r * kDs + cs + 2 * cq);
-          g0 = fmaf(d.x, a, g0);
-          g1 = fmaf(d.y, a, g1);
-        }
-        s.dW[i][(2 * cq) * kH + k] = g0;
-        s.dW[i][(2 * cq + 1) * kH + k] = g1;
-        {   // bias gradients: warp w sums column cs + w over the rows
-          const int w = tid >> 5, lane = tid & 31;
-          float gb = 0.f;
-          for (int r = lane; r < n; r += 32) gb += s.D[r * kDs + cs + w];
+          const float a = Ain[r * kAs + k];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) gb += __shfl_xor_sync(0xffffffffu, gb, o);
-          if (lane == 0) s.db[i][w] = gb;
+          for (int u = 0; u < kCq; ++u) {
+            const float d = Din[r * kDs + cs + kCq * cq + u];
+            gw[u] = fmaf(d, a, gw[u]);
+            gb[u] += d;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kCq; ++u) {
+          s.dW[i][(kCq * cq + u) * kH + k] = gw[u];
+          if (k == 0) s.db[i][kCq * cq + u] = gb[u];
         }
       }
-      {   // own columns of the input delta: dA[r][ks + kk] = sum_c D[r][c] W[c][ks + kk], masked by the input's ReLU
+      {   // own columns of the input delta: dA[r][cs + kk] = sum_c D[r][c] W[c][cs + kk], masked by the input's ReLU
         const int kk = tid & 7, rg = tid >> 3;
-        float dn[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* Wc = s.Wc[i];
+        float dn[kRq];
+#pragma unroll
+        for (int q = 0; q < kRq; ++q) dn[q] = 0.f;
 #pragma unroll 4
         for (int c = 0; c < kH; c += 4) {
-          const float w0 = s.Wc[c * kSl + kk], w1 = s.Wc[(c + 1) * kSl + kk], w2 = s.Wc[(c + 2) * kSl + kk], w3 = s.Wc[(c + 3) * kSl + kk];
+          const float w0 = Wc[c * kSl + kk], w1 = Wc[(c + 1) * kSl + kk], w2 = Wc[(c + 2) * kSl + kk], w3 = Wc[(c + 3) * kSl + kk];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 d = *reinterpret_cast<const float4*>(s.D + (rg + 32 * q) * kDs + c);
+          for (int q = 0; q < kRq; ++q) {
+            const float4 d = *reinterpret_cast<const float4*>(Din + (rg + kRg * q) * kDs + c);
             dn[q] = fmaf(d.x, w0, dn[q]);
             dn[q] = fmaf(d.y, w1, dn[q]);
             dn[q] = fmaf(d.z, w2, dn[q]);
             dn[q] = fmaf(d.w, w3, dn[q]);
           }
         }
-        float* dst = dbuf + (size_t)(i & 1) * act_stride;       // ping-pong: the other buffer may still be read by a slower CTA
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = rg + 32 * q;
-          if (r < n) dst[r * kH + cs + kk] = s.A[r * kH + cs + kk] > 0.f ? dn[q] : 0.f;
+        for (int q = 0; q < kRq; ++q) {
+          const int r = rg + kRg * q;
+          if (r < n) {
+            const float v = Ain[r * kAs + cs + kk] > 0.f ? dn[q] : 0.f;
+            if (i > 0) clu_store_all(Dout + r * kDs + cs + kk, v);
+            else Dout[r * kDs + cs + kk] = v;                   // the input layer's gradient only needs the own columns
+          }
         }
       }
-      clu_sync();
-      clu_load(s.D, dbuf + (size_t)(i & 1) * act_stride, n, kDs);
-      __syncthreads();
+      clu_prefetch_wait();
+      clu_sync();        // deltas of all CTAs (and this CTA's prefetched tile) are in place; after stage 0: every CTA
+                         // is done with its weight-column copies, which the Adam step below overwrites remotely
     }
     if (tid < kSl * 4) {   // first layer, own rows
       const int c = tid >> 2, d = tid & 3;
+      const float* D0 = s.D[0];
       float g = 0.f;
-      if (d < 3) { for (int r = 0; r < n; ++r) g = fmaf(s.D[r * kDs + cs + c], x[r * 3 + d], g); }
-      else { for (int r = 0; r < n; ++r) g += s.D[r * kDs + cs + c]; }
+      if (d < 3) { for (int r = 0; r < n; ++r) g = fmaf(D0[r * kDs + cs + c], s.x[r * 3 + d], g); }
+      else { for (int r = 0; r < n; ++r) g += D0[r * kDs + cs + c]; }
       s.dW1[tid] = g;
     }
     __syncthreads();
-    // ================= Adam, own parameters =================
+    // ================= Adam, own parameters; new values go to every CTA that reads them =================
     for (int i = 0; i < kHid; ++i) {
-      const int j = used_layer(i);
-      for (int q = tid; q < kSl * kH; q += kCluThreads)
-        adam_update(P, M, V, off_l2w(j) + (cs + (q >> 6)) * kH + (q & 63), s.dW[i][q], as);
-      if (tid < kSl) adam_update(P, M, V, off_l2b(j) + cs + tid, s.db[i][tid], as);
+      for (int q = tid; q < kSl * kH; q += kCluThreads) {
+        const int c = q >> 6, k = q & 63;
+        // the padded row image Wf is the parameter; Mo / Vo use the dense index
+        float* w = s.Wf[i] + c * kWs + k;
+        float mi = s.Mo[i][q], vi = s.Vo[i][q];
+        const float pn = adam_step(*w, mi, vi, s.dW[i][q], as);
+        s.Mo[i][q] = mi;
+        s.Vo[i][q] = vi;
+        *w = pn;
+        // column k of row cs + c belongs to the backward product of CTA k / 8
+        clu_store(clu_map(&s.Wc[i][(cs + c) * kSl + (k & 7)], (uint32_t)(k >> 3)), pn);
+      }
+      if (tid < kSl) adam_update(s.bown[i], s.mb[i], s.vb[i], tid, s.db[i][tid], as);
     }
     if (tid < kSl * 4) {
-      const int c = cs + (tid >> 2), d = tid & 3;
-      adam_update(P, M, V, d < 3 ? off_l1w() + c * 3 + d : off_l1b() + c, s.dW1[tid], as);
+      adam_update(s.w1 + cs * 4, s.m1, s.v1, tid, s.dW1[tid], as);
+      clu_store_all(s.w1 + cs * 4 + tid, s.w1[cs * 4 + tid]);
     }
-    if (tid <= kH) {       // output layer: identical private update in every CTA; CTA 0 publishes it
-      adam_update(s.w3, s.m3, s.v3, tid, s.g3[tid], as);
-      if (cs == 0) P[off_l3w() + tid] = s.w3[tid];
-    }
-    __syncthreads();
+    if (tid <= kH) adam_update(s.w3, s.m3, s.v3, tid, s.g3[tid], as);   // output layer: identical private update in every CTA
+    clu_sync();          // all remote parameter stores have landed before the next epoch reads them
   }
-  clu_sync();
+  // ---- write the fitted parameters back: own rows of the hidden layers and of the input layer; CTA 0 the output layer
+  for (int i = 0; i < kHid; ++i) {
+    const int j = used_layer(i);
+    for (int q = tid; q < kSl * kH; q += kCluThreads) P[off_l2w(j) + (cs + (q >> 6)) * kH + (q & 63)] = s.Wf[i][(q >> 6) * kWs + (q & 63)];
+    if (tid < kSl) P[off_l2b(j) + cs + tid] = s.bown[i][tid];
+  }
+  if (tid < kSl * 4) {
+    const int c = cs + (tid >> 2), d = tid & 3;
+    P[d < 3 ? off_l1w() + c * 3 + d : off_l1b() + c] = s.w1[cs * 4 + tid];
+  }
+  if (tid <= kH && cs == 0) P[off_l3w() + tid] = s.w3[tid];
 }
 
 // Batched queries g_phi(x): one CTA per 128 points, activations ping-pong in shared memory.
@@ -536,7 +621,6 @@ int launch_surrogate_fit(float* params, float* m, float* v, const float* x, cons
   if (cudaFuncSetAttribute(surrogate_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) return -1;
   float* act = workspace;
   float* yws = workspace + (size_t)(kHid + 1) * n * kH;
-  float* dbuf = yws + kSurrogateMaxN;
   static int use_cluster = -1;       // process-wide preference; the attribute itself is set per launch
   if (use_cluster < 0) {
     const char* e = getenv("EVPP_SG_CLUSTER");
@@ -548,7 +632,7 @@ int launch_surrogate_fit(float* params, float* m, float* v, const float* x, cons
     use_cluster = 0;
   }
   if (use_cluster) {
-    surrogate_fit_cluster_kernel<<<kClu, kCluThreads, sizeof(CluSmem), st>>>(params, m, v, x, target, n, epochs, lr, act, dbuf, loss_out);
+    surrogate_fit_cluster_kernel<<<kClu, kCluThreads, sizeof(CluSmem), st>>>(params, x, target, n, epochs, lr, act, loss_out);
     if (cudaPeekAtLastError() == cudaSuccess) return 1;
     cudaGetLastError();          // no 8-CTA cluster available (e.g. a partitioned device): fall back to one CTA
     use_cluster = 0;

@@ -958,6 +958,19 @@ def test_surrogate_fit_and_queries(engine_factory):
         evpp_b200.train_only(mlp, np.zeros((200, 6)), N=200)
 
 
+def test_surrogate_cluster_fit_is_bit_identical_to_the_single_cta_fit():
+    """The default fit runs on a cluster of 8 CTAs that exchange activation / delta slices and updated weights through
+    distributed shared memory (st.shared::cluster + barrier.cluster); EVPP_SG_CLUSTER=0 runs the same arithmetic on one
+    SM.  Who computes what must not change a bit: parameters and loss curves of both are compared for a full 300-epoch
+    fit, the maximum batch (128), a ragged batch (37) and a single point.  The switch is read once per process, so
+    both runs are subprocesses (tools/surrogate_ab.py)."""
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "surrogate_ab.py")], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and "SURROGATE A/B OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
 def test_planning_step_end_to_end(weights):
     """One planning step with every stage on the GPU, through the reference's call shapes: direction fan -> stage-1 TSDF
     scores -> top 3 per location -> stage-2 NeRF uncertainty (Controller.get_uncertainty) -> depth clip / per-location
