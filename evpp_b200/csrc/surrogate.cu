@@ -7,7 +7,7 @@
 //
 // The whole fit is ONE kernel launch: 300 epochs x (8 forward + 7 backward stages) of latency-bound 100 x 64 x 64 products,
 // far too small to spread over the GPU (a grid-wide barrier per stage would cost more than the stage).  The default
-// runs on one cluster of 8 CTAs that split every layer by columns, keep parameters, Adam moments and tiles resident in
+// runs on one cluster of 16 (or 8) CTAs that split every layer by columns, keep parameters, Adam moments and tiles resident in
 // shared memory and exchange slices through distributed shared memory with one cluster barrier per stage
 // (surrogate_fit_cluster_kernel).  The single-CTA twin (surrogate_fit_kernel) does the same arithmetic on one SM with
 // parameters, moments and activations in global memory (L2 resident, < 0.7 MB) and is the fallback; the two produce
@@ -271,7 +271,7 @@ surrogate_fit_kernel(float* P, float* M, float* V, const float* __restrict__ x, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The fit on a CLUSTER of 8 CTAs.  CTA j owns columns 8j .. 8j+7 of every layer: it computes that slice of every
+// The fit on a CLUSTER of CLU = 16 or 8 CTAs (described for 8).  CTA j owns columns 8j .. 8j+7 of every layer: it computes that slice of every
 // forward activation, of every input delta, the gradients of its 8 weight rows, and applies their Adam updates at the
 // end of the epoch (so every weight read of an epoch sees the previous epoch's values).
 // Everything the epoch loop touches lives in shared memory: the CTA's weight rows with their Adam moments, a copy of
@@ -286,20 +286,17 @@ surrogate_fit_kernel(float* P, float* M, float* V, const float* __restrict__ x, 
 // The 3 -> 64 input layer, the 64 -> 1 output layer, the loss and the output delta are computed redundantly
 // (identically) by all CTAs, which saves four exchanges.  Same arithmetic, operation by operation, as
 // surrogate_fit_kernel: the two produce bit-identical parameters.
-constexpr int kClu = 8;
-#ifndef EVPP_SG_CLU_THREADS
-#define EVPP_SG_CLU_THREADS 512
-#endif
-constexpr int kCluThreads = EVPP_SG_CLU_THREADS;
-constexpr int kSl = kH / kClu;          // columns per CTA
+// CLU = 8 CTAs (portable cluster size) x 512 threads, or 16 CTAs (non-portable, preferred when the device can place
+// one) x 256 threads: a CTA is a (columns of the slice) x (64 row groups) grid of threads either way.
 constexpr int kAs = 68;                 // row stride of the activation tiles: the four rows a warp reads as 16-byte broadcasts
                                         // sit in different banks (stride 64 would be a 4-way conflict)
-constexpr int kRq = kSurrogateMaxN / (kCluThreads / kSl);   // rows per thread in the (column, row group) products
-constexpr int kRg = kCluThreads / kSl;                      // row groups
-constexpr int kCq = kSl / (kCluThreads / kH);               // weight rows per thread in the gradient product
-static_assert(kRq >= 1 && kCq >= 1 && kCluThreads >= 2 * kSurrogateMaxN, "cluster fit: thread mapping");
+constexpr int kRg = 64;                 // row groups
+constexpr int kRq = kSurrogateMaxN / kRg;                   // rows per thread in the (column, row group) products
+__host__ __device__ constexpr int clu_threads(int clu) { return kRg * (kH / clu); }
 
+template <int CLU>
 struct __align__(16) CluSmem {
+  static constexpr int kSl = kH / CLU;  // columns per CTA
   float A[2][kSurrogateMaxN * kAs];     // forward: input / output activations of the stage; backward: layer inputs
   float D[2][kSurrogateMaxN * kDs];     // deltas at the stage's output / input
   float Wf[kHid][kSl * kWs];            // own weight rows W[cs + c][k] of every hidden layer (resident, updated in place)
@@ -316,7 +313,7 @@ struct __align__(16) CluSmem {
   float y[kSurrogateMaxN];
   float red[8];
 };
-static_assert(sizeof(CluSmem) <= 227 * 1024, "cluster fit: shared memory");
+static_assert(sizeof(CluSmem<8>) <= 227 * 1024 && sizeof(CluSmem<16>) <= 227 * 1024, "cluster fit: shared memory");
 
 __device__ __forceinline__ uint32_t clu_rank() {
   uint32_t r;
@@ -335,25 +332,29 @@ __device__ __forceinline__ uint32_t clu_map(const void* p, uint32_t rank) {
 __device__ __forceinline__ void clu_store(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-// v -> the same location in all eight CTAs (this one included)
+// v -> the same location in all CTAs of the cluster (this one included)
+template <int CLU>
 __device__ __forceinline__ void clu_store_all(const float* p, float v) {
 #pragma unroll
-  for (uint32_t j = 0; j < kClu; ++j) clu_store(clu_map(p, j), v);
+  for (uint32_t j = 0; j < CLU; ++j) clu_store(clu_map(p, j), v);
 }
 // [n][64] tile global (L2) -> shared memory, asynchronously (the caller waits with clu_prefetch_wait + a barrier)
 __device__ __forceinline__ void clu_prefetch(float* dst, const float* src, int n) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-  for (int idx = threadIdx.x; idx < n * (kH / 4); idx += kCluThreads)
+  for (int idx = threadIdx.x; idx < n * (kH / 4); idx += blockDim.x)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + ((idx >> 4) * kAs + (idx & 15) * 4) * 4), "l"(src + idx * 4) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void clu_prefetch_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__global__ void __cluster_dims__(kClu, 1, 1) __launch_bounds__(kCluThreads, 1)
+template <int CLU>
+__global__ void __launch_bounds__(clu_threads(CLU), 1)
 surrogate_fit_cluster_kernel(float* P, const float* __restrict__ x, const float* __restrict__ target, int n, int epochs,
                              float lr, float* act, float* __restrict__ loss_out) {
   extern __shared__ __align__(16) uint8_t sg_smem[];
-  CluSmem& s = *reinterpret_cast<CluSmem*>(sg_smem);
+  CluSmem<CLU>& s = *reinterpret_cast<CluSmem<CLU>*>(sg_smem);
+  constexpr int kSl = kH / CLU, kCluThreads = clu_threads(CLU);
+  static_assert(kCluThreads >= 4 * kH && kCluThreads % kH == 0 && kSl == kCluThreads / kH, "cluster fit: thread mapping");
   const int tid = threadIdx.x;
   const int cs = (int)clu_rank() * kSl;          // first column of this CTA's slice
   const int act_stride = n * kH;
@@ -366,7 +367,7 @@ surrogate_fit_cluster_kernel(float* P, const float* __restrict__ x, const float*
       s.Wf[i][(q >> 6) * kWs + (q & 63)] = P[off_l2w(j) + (cs + (q >> 6)) * kH + (q & 63)];
       s.Mo[i][q] = 0.f;
       s.Vo[i][q] = 0.f;
-      s.Wc[i][q] = P[off_l2w(j) + (q >> 3) * kH + cs + (q & 7)];
+      s.Wc[i][q] = P[off_l2w(j) + (q / kSl) * kH + cs + (q % kSl)];
     }
     if (tid < kSl) { s.bown[i][tid] = P[off_l2b(j) + cs + tid]; s.mb[i][tid] = 0.f; s.vb[i][tid] = 0.f; }
   }
@@ -386,14 +387,14 @@ surrogate_fit_cluster_kernel(float* P, const float* __restrict__ x, const float*
       a = fmaf(s.x[r * 3 + 2], s.w1[c * 4 + 2], a);
       a = fmaxf(a, 0.f);
       s.A[0][r * kAs + c] = a;
-      if ((c >> 3) * kSl == cs) act[i] = a;                     // kept for the backward pass (own columns)
+      if ((c / kSl) * kSl == cs) act[i] = a;                    // kept for the backward pass (own columns)
     }
     __syncthreads();
     for (int i = 0; i < kHid; ++i) {
       const float* Ain = s.A[i & 1];
       float* Aout = s.A[(i + 1) & 1];
       {
-        const int c = tid & 7, rg = tid >> 3;
+        const int c = tid % kSl, rg = tid / kSl;
         float acc[kRq];
 #pragma unroll
         for (int q = 0; q < kRq; ++q) acc[q] = s.bown[i][c];
@@ -414,7 +415,7 @@ surrogate_fit_cluster_kernel(float* P, const float* __restrict__ x, const float*
         for (int q = 0; q < kRq; ++q) {
           const int r = rg + kRg * q;
           acc[q] = fmaxf(acc[q], 0.f);
-          if (r < n) clu_store_all(Aout + r * kAs + cs + c, acc[q]);
+          if (r < n) clu_store_all<CLU>(Aout + r * kAs + cs + c, acc[q]);
         }
         clu_sync();
         // act[1..5] are re-read by the backward pass (6 and 7 stay in A).  Stored AFTER the barrier: its release would
@@ -489,30 +490,21 @@ surrogate_fit_cluster_kernel(float* P, const float* __restrict__ x, const float*
       const float* Din = s.D[(i + 1) & 1];
       float* Dout = s.D[i & 1];
       if (i > 0) clu_prefetch(s.A[(i - 1) & 1], act + (size_t)(i - 1) * act_stride, n);   // next stage's layer inputs
-      {   // gradients of the own rows: dW[c][k] = sum_r D[r][cs + c] A[r][k], kCq rows per thread; bias gradients
-          // db[c] = sum_r D[r][c] ride along (rows in order, like the single-CTA kernel)
-        const int k = tid & 63, cq = tid >> 6;
-        float gw[kCq], gb[kCq];
-#pragma unroll
-        for (int u = 0; u < kCq; ++u) { gw[u] = 0.f; gb[u] = 0.f; }
+      {   // gradients of the own rows: dW[c][k] = sum_r D[r][cs + c] A[r][k], thread = (k, c); the bias gradient
+          // db[c] = sum_r D[r][c] rides along (rows in order, like the single-CTA kernel)
+        const int k = tid & 63, c = tid >> 6;
+        float gw = 0.f, gb = 0.f;
 #pragma unroll 4
         for (int r = 0; r < n; ++r) {
-          const float a = Ain[r * kAs + k];
-#pragma unroll
-          for (int u = 0; u < kCq; ++u) {
-            const float d = Din[r * kDs + cs + kCq * cq + u];
-            gw[u] = fmaf(d, a, gw[u]);
-            gb[u] += d;
-          }
+          const float d = Din[r * kDs + cs + c];
+          gw = fmaf(d, Ain[r * kAs + k], gw);
+          gb += d;
         }
-#pragma unroll
-        for (int u = 0; u < kCq; ++u) {
-          s.dW[i][(kCq * cq + u) * kH + k] = gw[u];
-          if (k == 0) s.db[i][kCq * cq + u] = gb[u];
-        }
+        s.dW[i][c * kH + k] = gw;
+        if (k == 0) s.db[i][c] = gb;
       }
       {   // own columns of the input delta: dA[r][cs + kk] = sum_c D[r][c] W[c][cs + kk], masked by the input's ReLU
-        const int kk = tid & 7, rg = tid >> 3;
+        const int kk = tid % kSl, rg = tid / kSl;
         const float* Wc = s.Wc[i];
         float dn[kRq];
 #pragma unroll
@@ -534,7 +526,7 @@ surrogate_fit_cluster_kernel(float* P, const float* __restrict__ x, const float*
           const int r = rg + kRg * q;
           if (r < n) {
             const float v = Ain[r * kAs + cs + kk] > 0.f ? dn[q] : 0.f;
-            if (i > 0) clu_store_all(Dout + r * kDs + cs + kk, v);
+            if (i > 0) clu_store_all<CLU>(Dout + r * kDs + cs + kk, v);
             else Dout[r * kDs + cs + kk] = v;                   // the input layer's gradient only needs the own columns
           }
         }
@@ -563,14 +555,14 @@ surrogate_fit_cluster_kernel(float* P, const float* __restrict__ x, const float*
         s.Mo[i][q] = mi;
         s.Vo[i][q] = vi;
         *w = pn;
-        // column k of row cs + c belongs to the backward product of CTA k / 8
-        clu_store(clu_map(&s.Wc[i][(cs + c) * kSl + (k & 7)], (uint32_t)(k >> 3)), pn);
+        // column k of row cs + c belongs to the backward product of CTA k / kSl
+        clu_store(clu_map(&s.Wc[i][(cs + c) * kSl + (k % kSl)], (uint32_t)(k / kSl)), pn);
       }
       if (tid < kSl) adam_update(s.bown[i], s.mb[i], s.vb[i], tid, s.db[i][tid], as);
     }
     if (tid < kSl * 4) {
       adam_update(s.w1 + cs * 4, s.m1, s.v1, tid, s.dW1[tid], as);
-      clu_store_all(s.w1 + cs * 4 + tid, s.w1[cs * 4 + tid]);
+      clu_store_all<CLU>(s.w1 + cs * 4 + tid, s.w1[cs * 4 + tid]);
     }
     if (tid <= kH) adam_update(s.w3, s.m3, s.v3, tid, s.g3[tid], as);   // output layer: identical private update in every CTA
     clu_sync();          // all remote parameter stores have landed before the next epoch reads them
@@ -614,6 +606,40 @@ surrogate_query_kernel(const float* __restrict__ P, const float* __restrict__ x,
 
 size_t surrogate_workspace_floats(int n) { return (size_t)(kHid + 1) * n * kH + kSurrogateMaxN + (size_t)2 * n * kH; }
 
+// One cluster of CLU CTAs; false when the device cannot place it (the caller falls back to a smaller shape)
+template <int CLU>
+static bool launch_fit_cluster(float* params, const float* x, const float* target, int n, int epochs, float lr, float* act,
+                               float* loss_out, cudaStream_t st) {
+  auto kern = surrogate_fit_cluster_kernel<CLU>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CluSmem<CLU>)) != cudaSuccess ||
+      (CLU > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CLU, 1, 1);
+  cfg.blockDim = dim3(clu_threads(CLU), 1, 1);
+  cfg.dynamicSmemBytes = sizeof(CluSmem<CLU>);
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = CLU;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess || clusters < 1) {
+    cudaGetLastError();
+    return false;
+  }
+  if (cudaLaunchKernelEx(&cfg, kern, params, x, target, n, epochs, lr, act, loss_out) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
 int launch_surrogate_fit(float* params, float* m, float* v, const float* x, const float* target, int n, int epochs, float lr,
                          float* workspace, float* loss_out, cudaStream_t st) {
   if (n <= 0 || epochs <= 0) return 0;
@@ -621,22 +647,17 @@ int launch_surrogate_fit(float* params, float* m, float* v, const float* x, cons
   if (cudaFuncSetAttribute(surrogate_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) return -1;
   float* act = workspace;
   float* yws = workspace + (size_t)(kHid + 1) * n * kH;
-  static int use_cluster = -1;       // process-wide preference; the attribute itself is set per launch
-  if (use_cluster < 0) {
+  // EVPP_SG_CLUSTER: 0 = single CTA, 8 / 16 = that cluster size; default: 16 CTAs when the device can co-schedule such a
+  // cluster (non-portable size, 177 KB of shared memory per CTA), else 8, else one CTA.  Process-wide preference; the
+  // kernel attributes are set per launch.
+  static int want = -1;
+  if (want < 0) {
     const char* e = getenv("EVPP_SG_CLUSTER");
-    use_cluster = (e && atoi(e) == 0) ? 0 : 1;
+    want = e && *e ? atoi(e) : 16;
+    if (want != 0 && want != 8 && want != 16) want = 16;
   }
-  if (use_cluster && cudaFuncSetAttribute(surrogate_fit_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(CluSmem)) != cudaSuccess) {
-    cudaGetLastError();
-    use_cluster = 0;
-  }
-  if (use_cluster) {
-    surrogate_fit_cluster_kernel<<<kClu, kCluThreads, sizeof(CluSmem), st>>>(params, x, target, n, epochs, lr, act, loss_out);
-    if (cudaPeekAtLastError() == cudaSuccess) return 1;
-    cudaGetLastError();          // no 8-CTA cluster available (e.g. a partitioned device): fall back to one CTA
-    use_cluster = 0;
-  }
+  if (want == 16 && launch_fit_cluster<16>(params, x, target, n, epochs, lr, act, loss_out, st)) return 1;
+  if (want >= 8 && launch_fit_cluster<8>(params, x, target, n, epochs, lr, act, loss_out, st)) return 1;
   surrogate_fit_kernel<<<1, kSgThreads, sizeof(Smem), st>>>(params, m, v, x, target, n, epochs, lr, act, yws, loss_out);
   return 1;
 }

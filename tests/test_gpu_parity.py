@@ -959,11 +959,12 @@ def test_surrogate_fit_and_queries(engine_factory):
 
 
 def test_surrogate_cluster_fit_is_bit_identical_to_the_single_cta_fit():
-    """The default fit runs on a cluster of 8 CTAs that exchange activation / delta slices and updated weights through
-    distributed shared memory (st.shared::cluster + barrier.cluster); EVPP_SG_CLUSTER=0 runs the same arithmetic on one
-    SM.  Who computes what must not change a bit: parameters and loss curves of both are compared for a full 300-epoch
-    fit, the maximum batch (128), a ragged batch (37) and a single point.  The switch is read once per process, so
-    both runs are subprocesses (tools/surrogate_ab.py)."""
+    """The default fit runs on a cluster of 16 (or 8) CTAs that exchange activation / delta slices and updated weights
+    through distributed shared memory (st.shared::cluster + barrier.cluster); EVPP_SG_CLUSTER=0 runs the same arithmetic
+    on one SM.  Who computes what must not change a bit: parameters and loss curves of the default, the 16-CTA and the
+    8-CTA launch are compared with the single-CTA fit for a full 300-epoch fit, the maximum batch (128), a ragged batch
+    (37) and a single point.  The switch is read once per process, so every run is a subprocess
+    (tools/surrogate_ab.py)."""
     import subprocess
     import sys
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "surrogate_ab.py")], capture_output=True, text=True,

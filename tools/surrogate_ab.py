@@ -1,5 +1,7 @@
-"""GPU-box check of the surrogate fit: the 8-CTA cluster kernel (distributed shared memory) against the single-CTA
-kernel (EVPP_SG_CLUSTER=0, separate process): parameters and loss curve must be bit-identical; prints the fit time."""
+"""GPU-box check of the surrogate fit: the cluster kernels (16 CTAs = the default where the device can place such a
+cluster, 8 CTAs; slices exchanged through distributed shared memory) against the single-CTA kernel (EVPP_SG_CLUSTER=0):
+parameters and loss curves must be bit-identical; prints the fit times.  The switch is read once per process, so
+every variant runs in its own process."""
 import os
 import subprocess
 import sys
@@ -41,14 +43,17 @@ if __name__ == "__main__":
         run(sys.argv[1])
         sys.exit(0)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    for tag, env in (("cluster", {}), ("single", {"EVPP_SG_CLUSTER": "0"})):
-        subprocess.run([sys.executable, os.path.abspath(__file__), tag], env=dict(os.environ, **env), check=True)
-    a = np.load(os.path.join(ROOT, "gpurun_out", "surrogate_cluster.npz"))
+    for tag, env in (("default", {}), ("cluster16", {"EVPP_SG_CLUSTER": "16"}), ("cluster8", {"EVPP_SG_CLUSTER": "8"}),
+                     ("single", {"EVPP_SG_CLUSTER": "0"})):
+        env_ = {k: v for k, v in os.environ.items() if k != "EVPP_SG_CLUSTER"}
+        subprocess.run([sys.executable, os.path.abspath(__file__), tag], env=dict(env_, **env), check=True)
     b = np.load(os.path.join(ROOT, "gpurun_out", "surrogate_single.npz"))
     ok = True
-    for k in a.files:
-        same = np.array_equal(a[k], b[k])
-        ok &= same
-        print(k, "bit-identical" if same else f"DIFFERENT: max abs {np.abs(a[k] - b[k]).max():.3e}")
+    for tag in ("default", "cluster16", "cluster8"):
+        a = np.load(os.path.join(ROOT, "gpurun_out", f"surrogate_{tag}.npz"))
+        for k in a.files:
+            same = np.array_equal(a[k], b[k])
+            ok &= same
+            print(tag, k, "bit-identical" if same else f"DIFFERENT: max abs {np.abs(a[k] - b[k]).max():.3e}")
     print("SURROGATE A/B", "OK" if ok else "MISMATCH")
     sys.exit(0 if ok else 1)
