@@ -166,6 +166,22 @@ def train_only(mlp, data, N=100, epochs=300, lr=0.001):
     return mlp
 
 
+def get_mlp_maxdata(init_test_data, mlp, N_MAX=1):
+    """The query half of ``Viewpath_planner.get_mlp_maxdata`` (vpp.py:223-244): evaluate the fitted surrogate on the
+    sampled candidate locations ``init_test_data[:, 0:3]`` in one batched kernel launch, sort by predicted gain and
+    return ``(data_all [N, 4] = (x, y, z, g), init_node [3] = mean of the N_MAX best locations, init_node_gain)``.
+    Drawing the locations (``sample_location``: the planner's collision state) stays on the caller's side."""
+    xyz = np.ascontiguousarray(np.asarray(init_test_data, dtype=np.float64)[:, 0:3])
+    test_input = torch.tensor(xyz).to(torch.float32)
+    g = mlp(test_input).detach().cpu()
+    data_all = torch.cat((test_input, g), axis=1).numpy()
+    data_sort = data_all[data_all[:, 3].argsort()]
+    n = data_all.shape[0]
+    init_node = np.array([float(np.mean(data_sort[n - N_MAX:, k])) for k in range(3)])
+    init_node_gain = mlp(torch.tensor(init_node).to(torch.float32)).detach().cpu().numpy()[0]
+    return data_all, init_node, init_node_gain
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Viewpath_planner.sample_direction (plannerServer_Object/core/vpp.py:144-210, plannerServer_Room/core/vpp.py:141-200):
 # the two-stage candidate scoring of one planning step, with both stages on the GPU scorers

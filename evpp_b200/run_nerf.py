@@ -1,11 +1,12 @@
 """Drop-in for the renderer seam of the reference: same names, argument meaning and return
-structure as nerfServer/core/run_nerf.py (render, :131-196) and run_nerf_helpers.py (get_rays,
-:173-182), backed by the CUDA engine instead of PyTorch ops.
+structure as nerfServer/core/run_nerf.py (render, :131-196; render_path, :199-241) and run_nerf_helpers.py
+(get_rays, :173-182), backed by the CUDA engine instead of PyTorch ops.
 
 Supported configuration = what the server runs at inference (nerf.py:727-752): ndc=False,
 use_viewdirs=True, perturb=0, raw_noise_std=0.  Anything else raises (no silent fallback).
 """
 import hashlib
+import os
 
 import numpy as np
 import torch
@@ -160,3 +161,29 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
         extras.update({"rgb0": rs(o["rgb0"]), "disp0": rs(o["disp0"]), "acc0": rs(o["acc0"]),
                        "uncertainty_map0": rs(o["unc0"]), "depth_map0": rs(o["depth0"]), "z_std": rs(o["z_std"])})
     return [rs(o["rgb"]), rs(o["disp"]), rs(o["acc"]), rs(o["unc"]), rs(o["depth"]), extras]
+
+
+def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0, dev=None):
+    """Full-image renders of a list of poses: signature and return value of run_nerf.render_path (run_nerf.py:199-241,
+    the caller of BASELINE configs[4]): returns (rgbs, disps, uncers, depths), four lists of per-pose numpy arrays
+    ([H,W,3], [H,W], [H,W,S_f], [H,W]).  ``render_factor`` downsamples H, W and the focal length like the reference
+    (K is used as given, as there); with ``savedir`` every rgb map is also written as ``%03d.png`` (8-bit, the
+    reference's to8b).  ``gt_imgs`` is unused there too (its PSNR print is commented out)."""
+    H, W, focal = hwf
+    if render_factor != 0:
+        H = H // render_factor
+        W = W // render_factor
+        focal = focal / render_factor
+    rgbs, disps, uncers, depths = [], [], [], []
+    for i, c2w in enumerate(render_poses):
+        c2w = torch.as_tensor(np.asarray(c2w.cpu() if torch.is_tensor(c2w) else c2w), dtype=torch.float32)
+        rgb, disp, acc, uncer, depth, _ = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], dev=dev, **render_kwargs)
+        rgbs.append(rgb.cpu().numpy())
+        disps.append(disp.cpu().numpy())
+        uncers.append(uncer.cpu().numpy())
+        depths.append(depth.cpu().numpy())
+        if savedir is not None:
+            import cv2
+            rgb8 = (255 * np.clip(rgbs[-1], 0, 1)).astype(np.uint8)
+            cv2.imwrite(os.path.join(savedir, "{:03d}.png".format(i)), rgb8[..., ::-1])
+    return rgbs, disps, uncers, depths

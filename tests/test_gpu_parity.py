@@ -383,6 +383,36 @@ def test_render_and_controller_drop_in(engine_factory, weights):
     assert pts.ndim == 2 and pts.shape[1] == 3
 
 
+def test_render_path_drop_in(weights, tmp_path):
+    """run_nerf.render_path (run_nerf.py:199-241, the caller of the full-resolution sweep): same arguments and return
+    lists; every pose's maps equal the reference's render() output stored in the golden file, render_factor halves
+    the image like the reference, savedir receives the 8-bit PNGs."""
+    import evpp_b200
+    g = load_golden("render_small_spread.npz")
+    c, f = weights["spread"]
+    kw = evpp_b200.make_render_kwargs(c, f, precision="fp32", near=0.5, far=6.0)
+    kw.update(near=0.5, far=6.0)
+    H, W, focal = int(g["H"]), int(g["W"]), float(g["focal"])
+    K = O.make_K(H, W, focal)
+    poses = torch.Tensor(g["poses"])
+    rgbs, disps, uncers, depths = evpp_b200.render_path(poses, (H, W, focal), K, 1024 * 32, kw, savedir=str(tmp_path))
+    assert len(rgbs) == len(disps) == len(uncers) == len(depths) == poses.shape[0]
+    assert rgbs[0].shape == (H, W, 3) and disps[0].shape == (H, W) and uncers[0].shape == (H, W, 192) and depths[0].shape == (H, W)
+    n = H * W
+    for i in range(poses.shape[0]):
+        # (tolerances of test_render_fp32_matches_reference_golden for rays with a flipped searchsorted index)
+        np.testing.assert_allclose(rgbs[i].reshape(-1, 3), g["rgb"][i * n:(i + 1) * n], atol=2e-3)
+        np.testing.assert_allclose(depths[i].reshape(-1), g["depth"][i * n:(i + 1) * n], rtol=2e-3, atol=2e-3)
+        # the per-sample uncertainty maps reduce to the reference's view score (nerf.py:307-309)
+        np.testing.assert_allclose((uncers[i].astype(np.float64) ** 2).sum() / n, g["uncers"][i], rtol=2e-5)
+    assert sorted(os.listdir(tmp_path)) == ["%03d.png" % i for i in range(poses.shape[0])]
+    import cv2
+    img = cv2.imread(str(tmp_path / "000.png"))[..., ::-1]
+    assert np.array_equal(img, (255 * np.clip(rgbs[0], 0, 1)).astype(np.uint8))
+    half = evpp_b200.render_path(poses[:1], (H, W, focal), K, 1024 * 32, kw, render_factor=2)
+    assert half[0][0].shape == (H // 2, W // 2, 3)
+
+
 # ---------------------------------------------------------------- edge cases -------------------
 def test_edge_cases(engine_factory):
     eng = engine_factory()
@@ -953,6 +983,21 @@ def test_surrogate_fit_and_queries(engine_factory):
     pred = mlp(x).cpu().numpy().reshape(-1)
     assert np.abs(pred - g["pred_trained"]).max() < 0.06
     assert np.sqrt(np.mean((pred - data[:, 5]) ** 2)) < 0.06               # it fits the gains it was given
+    # get_mlp_maxdata (vpp.py:223-244): batched queries over sampled locations, best location and its gain, against the
+    # same lines run on the reference's torch module holding the same weights
+    cand = np.random.RandomState(3).uniform(-4, 4, size=(1000, 3))
+    data_all, init_node, init_gain = evpp_b200.get_mlp_maxdata(cand, mlp)
+    ref = SO.MLP()
+    ref.load_state_dict(mlp.state_dict())
+    ti = torch.tensor(cand).to(torch.float32)
+    gr = ref(ti).detach()
+    ref_all = torch.cat((ti, gr), axis=1).numpy()
+    ref_sort = ref_all[ref_all[:, 3].argsort()]
+    assert data_all.shape == (1000, 4)
+    np.testing.assert_allclose(data_all, ref_all, rtol=0, atol=2e-6)
+    if ref_sort[-1, 3] - ref_sort[-2, 3] > 1e-5:                             # an untied maximum: the same location
+        assert np.array_equal(init_node, ref_sort[-1, 0:3].astype(np.float64))
+        assert abs(float(init_gain) - float(ref(torch.tensor(init_node).to(torch.float32)).detach().numpy()[0])) < 2e-6
     # argument checks
     with pytest.raises(Exception):
         evpp_b200.train_only(mlp, np.zeros((200, 6)), N=200)
