@@ -886,6 +886,15 @@ def main():
                                                  "cmd": f"python bench.py --mode {mode} --steps 3 --warmup 3"}
                 except Exception as e:
                     line["other_modes"][mode] = {"value": None, "note": f"not measured: {e}"}
+            try:    # one planning step of the Object planner (rows f1 + a11 + a12 + f3 behind the reference's call shapes)
+                res = subprocess.run([sys.executable, os.path.abspath(__file__), "--mode", "planner", "--steps", "3", "--warmup", "3"],
+                                     capture_output=True, text=True, timeout=300)
+                ml = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+                line["other_modes"]["planner"] = {"ms_per_planning_step": ml["ms_per_step"], "value": ml["value"], "unit": "views/s",
+                                                  "stage_ms": ml["config"].get("stage_ms"), "workload": ml["config"]["workload"],
+                                                  "cmd": "python bench.py --mode planner --steps 3 --warmup 3"}
+            except Exception as e:
+                line["other_modes"]["planner"] = {"value": None, "note": f"not measured: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
