@@ -1024,6 +1024,35 @@ int evpp_ngp_set_occupancy(evpp_handle* h, const uint8_t* bitfield, int64_t nbyt
   if (h->ngp_bits.ensure((size_t)nbytes)) return fail(EVPP_ERR_CUDA, "bitfield alloc failed");
   CUDA_TRY(cudaMemcpy(h->ngp_bits.p, bitfield, (size_t)nbytes, cudaMemcpyDefault));
   h->ngp.bitfield = h->ngp_bits.as<uint8_t>();
+  for (int c = 0; c < 3; ++c) { h->ngp.occ_lo[c] = 1.f; h->ngp.occ_hi[c] = 0.f; }       // "nothing occupied"
+  if (h->ngp.march_mode == 0) {
+    // Box of the occupied cells (cell (x*G+y)*G+z <-> bit (cell & 7) of byte cell >> 3), grown by one cell: the marcher
+    // only tests the steps of a ray that fall inside it (ngp.cu:ray_span).  One pass over the bitfield on the host.
+    std::vector<uint8_t> host((size_t)nbytes);
+    CUDA_TRY(cudaMemcpy(host.data(), h->ngp_bits.p, (size_t)nbytes, cudaMemcpyDeviceToHost));
+    int64_t lo[3] = {G, G, G}, hi[3] = {-1, -1, -1};
+    for (int64_t x = 0; x < G; ++x)
+      for (int64_t y = 0; y < G; ++y) {
+        const int64_t row = (x * G + y) * G;            // G is a multiple of 8 (checked by evpp_ngp_configure): whole bytes
+        int64_t z0 = -1, z1 = -1;
+        for (int64_t b = 0; b < G / 8; ++b) {
+          const uint8_t v = host[(size_t)(row / 8 + b)];
+          if (!v) continue;
+          for (int k = 0; k < 8; ++k)
+            if (v >> k & 1) { if (z0 < 0) z0 = b * 8 + k; z1 = b * 8 + k; }
+        }
+        if (z0 < 0) continue;
+        lo[0] = std::min(lo[0], x); hi[0] = std::max(hi[0], x);
+        lo[1] = std::min(lo[1], y); hi[1] = std::max(hi[1], y);
+        lo[2] = std::min(lo[2], z0); hi[2] = std::max(hi[2], z1);
+      }
+    if (hi[0] >= 0)
+      for (int c = 0; c < 3; ++c) {
+        const double cell = ((double)h->ngp.amax[c] - (double)h->ngp.amin[c]) / (double)G;
+        h->ngp.occ_lo[c] = (float)((double)h->ngp.amin[c] + (double)(lo[c] - 1) * cell);
+        h->ngp.occ_hi[c] = (float)((double)h->ngp.amin[c] + (double)(hi[c] + 2) * cell);
+      }
+  }
   h->ngp_has_occ = true;
   return 0;
 }

@@ -85,10 +85,11 @@ __global__ void ngp_encode_kernel(NgpParams P, const float* __restrict__ u, long
 }
 
 // ---------------------------------------------------------------- marching ------------------------
-struct RaySpan { float t0; int n_steps; };
+struct RaySpan { float t0; int n_steps; int i_begin, i_end; };
 
 __device__ __forceinline__ RaySpan ray_span(const NgpParams& P, const float* o, const float* d) {
   float lo = P.near_plane, hi = P.far_plane;
+  float blo = -3.0e38f, bhi = 3.0e38f;      // the ray inside the (grown) box of the occupied cells
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float inv = __fdiv_rn(1.f, d[c]);
@@ -96,13 +97,27 @@ __device__ __forceinline__ RaySpan ray_span(const NgpParams& P, const float* o, 
     const float tb = __fmul_rn(__fsub_rn(P.amax[c], o[c]), inv);
     lo = fmaxf(lo, fminf(ta, tb));      // fminf / fmaxf drop NaNs (0 * inf on axis-parallel rays)
     hi = fminf(hi, fmaxf(ta, tb));
+    const float oa = (P.occ_lo[c] - o[c]) * inv, ob = (P.occ_hi[c] - o[c]) * inv;
+    blo = fmaxf(blo, fminf(oa, ob));
+    bhi = fminf(bhi, fmaxf(oa, ob));
+    if (d[c] == 0.f && (o[c] < P.occ_lo[c] || o[c] > P.occ_hi[c])) bhi = -3.0e38f;   // parallel to the slab and outside it
   }
   RaySpan s;
   s.t0 = lo;
   s.n_steps = 0;
+  s.i_begin = s.i_end = 0;
   if (hi > lo) {
     const int n = (int)ceilf(__fdiv_rn(__fsub_rn(hi, lo), P.dt));
     s.n_steps = n < P.max_steps ? n : P.max_steps;
+    // Steps that can possibly be kept: those whose sample lies inside the grown occupied box, with two steps of slack
+    // for the rounding of this estimate (the box itself is one whole cell larger than the occupied cells on every
+    // side).  Everything outside has an empty cell by construction, so skipping it changes no count and no sample.
+    if (bhi >= blo && P.occ_lo[0] <= P.occ_hi[0]) {
+      const float fb = floorf((blo - lo) / P.dt) - 2.f, fe = ceilf((bhi - lo) / P.dt) + 2.f;
+      s.i_begin = fb > 0.f ? (fb < (float)s.n_steps ? (int)fb : s.n_steps) : 0;
+      s.i_end = fe < (float)s.n_steps ? (fe > 0.f ? (int)fe : 0) : s.n_steps;
+      if (s.i_end < s.i_begin) s.i_end = s.i_begin;
+    }
   }
   return s;
 }
@@ -122,16 +137,18 @@ __global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, 
   const RaySpan sp = ray_span(P, o, d);
   uint32_t* mrow = masks + (long long)ray * words_per_ray;
   int count = 0;
+  const int first = (sp.i_begin >> 5) << 5;       // the walk starts at the ballot word that holds the first candidate step
+  for (int w = lane; w < (first >> 5) && w < words_per_ray; w += 32) mrow[w] = 0u;   // skipped leading words: nothing kept
   // Four 32-step batches per iteration: their cell computations and bitfield loads are independent, so they are
   // issued together; the sequential rule "stop once the sample budget is reached" is applied afterwards, batch by
   // batch, exactly as a one-batch-at-a-time walk would.
-  for (int base0 = 0; base0 < sp.n_steps && count < P.max_samples; base0 += 128) {
+  for (int base0 = first; base0 < sp.i_end && count < P.max_samples; base0 += 128) {
     unsigned bal[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = base0 + j * 32 + lane;
       bool keep = false;
-      if (i < sp.n_steps) {
+      if (i < sp.i_end) {
         const float t = __fadd_rn(sp.t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
         // cell = floor(u * G) per axis, inside the grid iff 0 <= cell < G: one round-down conversion and one
         // unsigned compare per axis (grid_res <= 1024, so the linear index fits 32 bits)
@@ -154,7 +171,7 @@ __global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int base = base0 + j * 32;
-      if (base < sp.n_steps && count < P.max_samples) {
+      if (base < sp.i_end && count < P.max_samples) {
         if (lane == 0 && (base >> 5) < words_per_ray) mrow[base >> 5] = bal[j];
         count += __popc(bal[j]);
       }

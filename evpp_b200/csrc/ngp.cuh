@@ -30,6 +30,8 @@ struct NgpParams {      // device pointers + configuration, passed to kernels by
   const uint16_t* table;        // fp16 [entries][2]
   const float* mlp;             // kNgpMlpFloats
   const uint8_t* bitfield;      // grid_res^3 / 8 bytes, cell (x*G+y)*G+z -> bit (cell & 7) of byte cell >> 3
+  float occ_lo[3], occ_hi[3];   // march_mode 0: world-space box of the occupied cells grown by one cell (evpp_ngp_set_occupancy);
+                                // steps outside it cannot be kept, so the marcher does not test them.  occ_lo > occ_hi: nothing occupied
   NgpLevel levels[kNgpMaxLevels];
   int n_levels;
   int grid_res;

@@ -763,6 +763,57 @@ def test_ngp_march_step_and_budget_variants(ngp_setup, dt, max_steps, max_sample
     assert np.array_equal(out["t"].cpu().numpy(), np.concatenate(ts))
 
 
+@pytest.mark.parametrize("occupancy", ["empty", "corners", "shell", "slab"])
+def test_ngp_march_skips_only_steps_outside_the_occupied_box(ngp_setup, occupancy):
+    """The marcher only tests the steps of a ray that fall inside the box of the occupied cells (grown by one cell;
+    computed by evpp_ngp_set_occupancy).  Every skipped step has an empty cell, so counts, offsets and kept t values
+    must stay bit-exact against the restatement, which walks every step: nothing occupied, single cells in the grid's
+    corners (the grown box sticks out of the scene box), the room shell of the benchmark (no specks: a tight box that
+    most rays leave early) and a thin slab that most rays miss or cross obliquely; rays from inside and outside the
+    box, axis-parallel rays, rays that miss it."""
+    import evpp_b200
+    from evpp_b200 import synthetic as S
+    from oracle import ngp_oracle as N
+    _, p, levels, _ = ngp_setup
+    G = 128
+    occ = np.zeros((G, G, G), dtype=bool)
+    if occupancy == "corners":
+        occ[0, 0, 0] = occ[G - 1, G - 1, G - 1] = occ[0, G - 1, 0] = True
+    elif occupancy == "shell":
+        occ = np.unpackbits(S.room_occupancy_bitfield(G), bitorder="little").reshape(G, G, G).astype(bool)
+    elif occupancy == "slab":
+        occ[70:73, 5:40, 60:90] = True
+    bits = np.packbits(occ.reshape(-1), bitorder="little")
+    sc = evpp_b200.NGPScorer(device=0, H=60, W=80, focal=60.0, dt=0.02, max_steps=1024, max_samples=256)
+    sc.set_occupancy(bits)
+    sc.load_params(p)
+    views = O.hemisphere_views(3, seed=6, center=(0., 1., 0.5), rmin=0.8, rmax=4.2)       # cameras inside and outside the room
+    ro, rd = O.build_view_rays(O.views_to_poses(views), 60, 80, O.make_K(60, 80, 60.0))
+    extra_o = torch.tensor([[0., 1., -4.9], [0.2, 1.0, 0.5], [20., 1., 0.], [0., 1., 0.5], [-4.99, 0.02, -4.99], [4.9, 4.9, 5.9],
+                            [0.55, 0.3, 0.6], [-4.0, 4.5, -4.0]])
+    extra_d = torch.tensor([[0., 0., 1.], [1., 0., 0.], [1., 0., 0.], [0., -1., 0.], [1., 1., 1.], [-1., -1., -1.],
+                            [0., 1., 0.], [1., 0., 0.]])
+    # axis-parallel rays through the centres of the three corner cells, 0.7 m from their origins
+    amin, amax = np.array(NGP_CFG["aabb_min"]), np.array(NGP_CFG["aabb_max"])
+    vox = (amax - amin) / G
+    c000, c111, c010 = amin + 0.5 * vox, amax - 0.5 * vox, np.array([amin[0] + 0.5 * vox[0], amax[1] - 0.5 * vox[1], amin[2] + 0.5 * vox[2]])
+    aim_d = np.array([[-1., 0., 0.], [0., 0., 1.], [0., 1., 0.]])
+    aim_o = np.stack([c000, c111, c010]) - 0.7 * aim_d
+    ro = torch.cat([ro, extra_o, torch.tensor(aim_o, dtype=torch.float32)])
+    rd = torch.cat([rd, extra_d, torch.tensor(aim_d, dtype=torch.float32)])
+    out = sc.render_rays(ro, rd, want_samples=True)
+    counts, ts = N.march(ro.numpy(), rd.numpy(), bits, G, NGP_CFG["aabb_min"], NGP_CFG["aabb_max"], 0.5, 6.0, 0.02, 1024, 256)
+    if occupancy == "corners":
+        assert (counts[-3:] > 0).all()
+    assert np.array_equal(out["counts"].cpu().numpy(), counts)
+    assert out["total"] == int(counts.sum())
+    assert np.array_equal(out["t"].cpu().numpy(), np.concatenate(ts) if len(ts) else np.zeros(0, np.float32))
+    if occupancy == "empty":
+        assert out["total"] == 0
+    else:
+        assert out["total"] > 0
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("fp16", 4e-3)])
 def test_ngp_render_and_scores_vs_restatement(precision, tol):
     """fp32 = FFMA field kernel; fp16 = tensor-core field kernel (fp16 operands, fp32 accumulate): the marching is
