@@ -271,9 +271,9 @@ surrogate_fit_kernel(float* P, float* M, float* V, const float* __restrict__ x, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The fit on a CLUSTER of CLU = 16 or 8 CTAs (described for 8).  CTA j owns columns 8j .. 8j+7 of every layer: it computes that slice of every
-// forward activation, of every input delta, the gradients of its 8 weight rows, and applies their Adam updates at the
-// end of the epoch (so every weight read of an epoch sees the previous epoch's values).
+// The fit on a CLUSTER of CLU = 16 or 8 CTAs (described for 8).  CTA j owns columns 8j .. 8j+7 of every layer: it
+// computes that slice of every forward activation, of every input delta, the gradients of its 8 weight rows, and
+// applies their Adam updates at the end of the epoch (so every weight read of an epoch sees the previous epoch's values).
 // Everything the epoch loop touches lives in shared memory: the CTA's weight rows with their Adam moments, a copy of
 // the weight COLUMNS it needs for the transposed backward product, ping-pong activation and delta tiles.  Slices are
 // exchanged through DISTRIBUTED SHARED MEMORY: the producer stores its 8 columns of every row straight into the tile
