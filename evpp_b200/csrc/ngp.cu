@@ -8,10 +8,12 @@
 // w = alpha * prod(1 - alpha + 1e-10) (run_nerf.py:376-378), score = sum(beta^2) / rays (nerf.py:307-309).
 //
 // Kernels
-//   ngp_march_kernel<false>  one warp per ray: 32 steps per iteration, occupancy bit test, ballot + popc
-//                            prefix -> per-ray sample count (integer, bit-exact with the restatement)
-//   ngp_scan_kernel          exclusive scan of the counts -> sample offsets
-//   ngp_march_kernel<true>   same walk, writes the kept t values at offset + rank (compaction)
+//   ngp_march_kernel         count pass, a warp per 32 rays: span per ray on its own lane, then the warp walks each ray
+//                            32 steps per batch inside the box of the occupied cells: occupancy bit test, ballot +
+//                            popc -> per-ray sample count (integer, bit-exact with the restatement), ballots stored
+//   ngp_tile_sum/scan        exclusive scan of the counts -> sample offsets
+//   ngp_fill_kernel          replays the stored ballots, writes the kept t values at offset + rank (compaction)
+//   tngp_march_kernel        the torch-ngp marching rule (cascades, Morton bitfield, dt_gamma), thread per ray
 //   ngp_encode_kernel        hash-grid encoding alone (parity + gather-bandwidth measurement)
 //   ngp_field_kernel         per sample: encode (16 levels x 8 corners, half2 gathers from the L2-resident
 //                            table) + density net + colour net + uncertainty head, fp32 FFMA (exact mode)
@@ -113,7 +115,8 @@ __device__ __forceinline__ RaySpan ray_span(const NgpParams& P, const float* o, 
     // for the rounding of this estimate (the box itself is one whole cell larger than the occupied cells on every
     // side).  Everything outside has an empty cell by construction, so skipping it changes no count and no sample.
     if (bhi >= blo && P.occ_lo[0] <= P.occ_hi[0]) {
-      const float fb = floorf((blo - lo) / P.dt) - 2.f, fe = ceilf((bhi - lo) / P.dt) + 2.f;
+      const float inv_dt = __frcp_rn(P.dt);
+      const float fb = floorf((blo - lo) * inv_dt) - 2.f, fe = ceilf((bhi - lo) * inv_dt) + 2.f;
       s.i_begin = fb > 0.f ? (fb < (float)s.n_steps ? (int)fb : s.n_steps) : 0;
       s.i_end = fe < (float)s.n_steps ? (fe > 0.f ? (int)fe : 0) : s.n_steps;
       if (s.i_end < s.i_begin) s.i_end = s.i_begin;
@@ -122,64 +125,82 @@ __device__ __forceinline__ RaySpan ray_span(const NgpParams& P, const float* o, 
   return s;
 }
 
-// Count pass.  One warp per ray walks 32 steps per iteration, tests the occupancy bit of each step's cell and
-// ballots the kept lanes.  The ballots are stored (masks[ray][word]) so that the fill pass replays them instead of
-// recomputing cells and bitfield lookups.
+// Count pass.  A warp owns 32 consecutive rays: lane L loads ray L and computes its span (six divisions and two slab
+// tests per ray -- done once per ray instead of 32 times, with coalesced loads), then the whole warp walks the rays one
+// after the other, 32 steps per lane batch: it tests the occupancy bit of each step's cell and ballots the kept lanes.
+// The ballots are stored (masks[ray][word]) so that the fill pass replays them instead of recomputing cells and
+// bitfield lookups.
 __global__ void ngp_march_kernel(NgpParams P, const float* __restrict__ rays_o, const float* __restrict__ rays_d, int n,
                                  int32_t* __restrict__ counts, uint32_t* __restrict__ masks, int words_per_ray,
                                  float* __restrict__ t0_out) {
-  const int ray = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const long long ray0 = ((((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) << 5;
   const int lane = threadIdx.x & 31;
-  if (ray >= n) return;
-  float o[3], d[3];
+  if (ray0 >= n) return;
+  const long long mine = ray0 + lane;
+  float mo[3] = {0.f, 0.f, 0.f}, md[3] = {1.f, 1.f, 1.f};
+  RaySpan msp;
+  msp.t0 = 0.f;
+  msp.n_steps = msp.i_begin = msp.i_end = 0;
+  if (mine < n) {
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { o[c] = rays_o[(long long)ray * 3 + c]; d[c] = rays_d[(long long)ray * 3 + c]; }
-  const RaySpan sp = ray_span(P, o, d);
-  uint32_t* mrow = masks + (long long)ray * words_per_ray;
-  int count = 0;
-  const int first = (sp.i_begin >> 5) << 5;       // the walk starts at the ballot word that holds the first candidate step
-  for (int w = lane; w < (first >> 5) && w < words_per_ray; w += 32) mrow[w] = 0u;   // skipped leading words: nothing kept
-  // Four 32-step batches per iteration: their cell computations and bitfield loads are independent, so they are
-  // issued together; the sequential rule "stop once the sample budget is reached" is applied afterwards, batch by
-  // batch, exactly as a one-batch-at-a-time walk would.
-  for (int base0 = first; base0 < sp.i_end && count < P.max_samples; base0 += 128) {
-    unsigned bal[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = base0 + j * 32 + lane;
-      bool keep = false;
-      if (i < sp.i_end) {
-        const float t = __fadd_rn(sp.t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
-        // cell = floor(u * G) per axis, inside the grid iff 0 <= cell < G: one round-down conversion and one
-        // unsigned compare per axis (grid_res <= 1024, so the linear index fits 32 bits)
-        uint32_t cell[3];
-        bool ok = true;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float p = __fadd_rn(o[c], __fmul_rn(d[c], t));
-          const float u = __fmul_rn(__fsub_rn(p, P.amin[c]), P.inv_size[c]);
-          cell[c] = (uint32_t)__float2int_rd(__fmul_rn(u, (float)P.grid_res));
-          ok = ok && cell[c] < (uint32_t)P.grid_res;
-        }
-        if (ok) {
-          const uint32_t lin = (cell[0] * (uint32_t)P.grid_res + cell[1]) * (uint32_t)P.grid_res + cell[2];
-          keep = (P.bitfield[lin >> 3] >> (lin & 7u)) & 1;
-        }
-      }
-      bal[j] = __ballot_sync(0xffffffffu, keep);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int base = base0 + j * 32;
-      if (base < sp.i_end && count < P.max_samples) {
-        if (lane == 0 && (base >> 5) < words_per_ray) mrow[base >> 5] = bal[j];
-        count += __popc(bal[j]);
-      }
-    }
+    for (int c = 0; c < 3; ++c) { mo[c] = rays_o[mine * 3 + c]; md[c] = rays_d[mine * 3 + c]; }
+    msp = ray_span(P, mo, md);
   }
-  if (lane == 0) {
-    counts[ray] = count < P.max_samples ? count : P.max_samples;
-    t0_out[ray] = sp.t0;
+  int my_count = 0;
+  const int nr = (int)(n - ray0 < 32 ? n - ray0 : 32);
+  for (int r = 0; r < nr; ++r) {
+    float o[3], d[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { o[c] = __shfl_sync(0xffffffffu, mo[c], r); d[c] = __shfl_sync(0xffffffffu, md[c], r); }
+    const float t0 = __shfl_sync(0xffffffffu, msp.t0, r);
+    const int i_begin = __shfl_sync(0xffffffffu, msp.i_begin, r), i_end = __shfl_sync(0xffffffffu, msp.i_end, r);
+    uint32_t* mrow = masks + (ray0 + r) * words_per_ray;
+    int count = 0;
+    const int first = (i_begin >> 5) << 5;       // the walk starts at the ballot word that holds the first candidate step
+    for (int w = lane; w < (first >> 5) && w < words_per_ray; w += 32) mrow[w] = 0u;   // skipped leading words: nothing kept
+    // Four 32-step batches per iteration: their cell computations and bitfield loads are independent, so they are
+    // issued together; the sequential rule "stop once the sample budget is reached" is applied afterwards, batch by
+    // batch, exactly as a one-batch-at-a-time walk would.
+    for (int base0 = first; base0 < i_end && count < P.max_samples; base0 += 128) {
+      unsigned bal[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = base0 + j * 32 + lane;
+        bool keep = false;
+        if (i < i_end) {
+          const float t = __fadd_rn(t0, __fmul_rn(__fadd_rn((float)i, 0.5f), P.dt));
+          // cell = floor(u * G) per axis, inside the grid iff 0 <= cell < G: one round-down conversion and one
+          // unsigned compare per axis (grid_res <= 1024, so the linear index fits 32 bits)
+          uint32_t cell[3];
+          bool ok = true;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float p = __fadd_rn(o[c], __fmul_rn(d[c], t));
+            const float u = __fmul_rn(__fsub_rn(p, P.amin[c]), P.inv_size[c]);
+            cell[c] = (uint32_t)__float2int_rd(__fmul_rn(u, (float)P.grid_res));
+            ok = ok && cell[c] < (uint32_t)P.grid_res;
+          }
+          if (ok) {
+            const uint32_t lin = (cell[0] * (uint32_t)P.grid_res + cell[1]) * (uint32_t)P.grid_res + cell[2];
+            keep = (P.bitfield[lin >> 3] >> (lin & 7u)) & 1;
+          }
+        }
+        bal[j] = __ballot_sync(0xffffffffu, keep);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int base = base0 + j * 32;
+        if (base < i_end && count < P.max_samples) {
+          if (lane == 0 && (base >> 5) < words_per_ray) mrow[base >> 5] = bal[j];
+          count += __popc(bal[j]);
+        }
+      }
+    }
+    if (lane == r) my_count = count;
+  }
+  if (mine < n) {
+    counts[mine] = my_count < P.max_samples ? my_count : P.max_samples;
+    t0_out[mine] = msp.t0;
   }
 }
 
@@ -1078,7 +1099,8 @@ int ngp_scan_tiles(int n) { return (n + kScanTile - 1) / kScanTile; }
 int launch_ngp_march_count(const NgpParams& P, const float* ro, const float* rd, int n, int32_t* counts, uint32_t* masks,
                            float* t0, cudaStream_t st) {
   if (n <= 0) return 0;
-  ngp_march_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(P, ro, rd, n, counts, masks, ngp_mask_words(P), t0);
+  const long long warps = ((long long)n + 31) / 32;       // a warp per 32 rays
+  ngp_march_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(P, ro, rd, n, counts, masks, ngp_mask_words(P), t0);
   return 1;
 }
 
