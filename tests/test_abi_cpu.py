@@ -74,3 +74,36 @@ def test_render_rejects_unsupported_modes():
         render(4, 4, K, rays=(torch.zeros(1, 3), torch.ones(1, 3)), ndc=False, use_viewdirs=False)
     with pytest.raises(NotImplementedError):
         render(4, 4, K, rays=(torch.zeros(1, 3), torch.ones(1, 3)), ndc=False, use_viewdirs=True, perturb=1.0)
+
+
+def test_get_mlp_maxdata_host_logic_matches_reference_lines():
+    """planner.get_mlp_maxdata (vpp.py:223-244) over a stand-in module on the CPU: the same lines as the reference's
+    method (sort by predicted gain, mean of the N_MAX best locations, gain of that location)."""
+    from evpp_b200 import planner
+    from oracle import surrogate_oracle as SO
+    torch.manual_seed(3)
+    mlp = SO.MLP()
+    cand = np.random.RandomState(1).uniform(-4, 4, size=(200, 6))
+    data_all, init_node, init_gain = planner.get_mlp_maxdata(cand, mlp)
+    # the reference's lines
+    N_test = cand.shape[0]
+    xyz = np.concatenate((cand[:, 0].reshape(N_test, 1), cand[:, 1].reshape(N_test, 1), cand[:, 2].reshape(N_test, 1)), axis=1)
+    test_input = torch.tensor(xyz).to(torch.float32)
+    g = mlp(test_input).detach()
+    ref_all = torch.cat((test_input, g), axis=1).cpu().numpy()
+    ref_sort = ref_all[ref_all[:, 3].argsort()]
+    ref_node = np.array([float(np.mean(ref_sort[N_test - 1:, k])) for k in range(3)])
+    ref_gain = mlp(torch.tensor(ref_node).to(torch.float32)).detach().cpu().numpy()[0]
+    assert np.array_equal(data_all, ref_all) and np.array_equal(init_node, ref_node) and init_gain == ref_gain
+    _, node3, _ = planner.get_mlp_maxdata(cand, mlp, N_MAX=3)
+    np.testing.assert_allclose(node3, ref_sort[N_test - 3:, 0:3].mean(0), rtol=1e-6)
+
+
+def test_render_path_passes_the_reference_arguments_through():
+    """render_path (run_nerf.py:199-241) forwards to render(): unsupported modes are refused the same way, before any
+    device work."""
+    from evpp_b200 import render_path
+    K = O.make_K(4, 4, 3.0)
+    with pytest.raises(NotImplementedError):
+        render_path([np.eye(4)], (4, 4, 3.0), K, 1024, {"ndc": True, "use_viewdirs": True})
+    assert render_path([], (4, 4, 3.0), K, 1024, {"ndc": False, "use_viewdirs": True}) == ([], [], [], [])
