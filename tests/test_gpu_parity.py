@@ -763,7 +763,7 @@ def test_ngp_march_step_and_budget_variants(ngp_setup, dt, max_steps, max_sample
     assert np.array_equal(out["t"].cpu().numpy(), np.concatenate(ts))
 
 
-@pytest.mark.parametrize("occupancy", ["empty", "corners", "shell", "slab"])
+@pytest.mark.parametrize("occupancy", ["empty", "corners", "shell", "slab", "specks"])
 def test_ngp_march_skips_only_steps_outside_the_occupied_box(ngp_setup, occupancy):
     """The marcher only tests the steps of a ray that fall inside the box of the occupied cells (grown by one cell;
     computed by evpp_ngp_set_occupancy).  Every skipped step has an empty cell, so counts, offsets and kept t values
@@ -783,6 +783,9 @@ def test_ngp_march_skips_only_steps_outside_the_occupied_box(ngp_setup, occupanc
         occ = np.unpackbits(S.room_occupancy_bitfield(G), bitorder="little").reshape(G, G, G).astype(bool)
     elif occupancy == "slab":
         occ[70:73, 5:40, 60:90] = True
+    elif occupancy == "specks":          # isolated cells all over the box: the occupied box is the whole grid
+        occ = np.random.RandomState(11).rand(G, G, G) < 2e-4
+        occ[3::16, 4::16, 7::16] = True
     bits = np.packbits(occ.reshape(-1), bitorder="little")
     sc = evpp_b200.NGPScorer(device=0, H=60, W=80, focal=60.0, dt=0.02, max_steps=1024, max_samples=256)
     sc.set_occupancy(bits)
@@ -799,12 +802,16 @@ def test_ngp_march_skips_only_steps_outside_the_occupied_box(ngp_setup, occupanc
     c000, c111, c010 = amin + 0.5 * vox, amax - 0.5 * vox, np.array([amin[0] + 0.5 * vox[0], amax[1] - 0.5 * vox[1], amin[2] + 0.5 * vox[2]])
     aim_d = np.array([[-1., 0., 0.], [0., 0., 1.], [0., 1., 0.]])
     aim_o = np.stack([c000, c111, c010]) - 0.7 * aim_d
-    ro = torch.cat([ro, extra_o, torch.tensor(aim_o, dtype=torch.float32)])
-    rd = torch.cat([rd, extra_d, torch.tensor(aim_d, dtype=torch.float32)])
+    # un-normalised directions change the world length of a step (x 0.25, x 3, x 12): the span estimate that clips the
+    # walk works in steps, so it must hold for any step length
+    sub = slice(0, ro.shape[0], 7)
+    ro = torch.cat([ro, extra_o, torch.tensor(aim_o, dtype=torch.float32), ro[sub], ro[sub], ro[sub]])
+    rd = torch.cat([rd, extra_d, torch.tensor(aim_d, dtype=torch.float32), rd[sub] * 0.25, rd[sub] * 3.0, rd[sub] * 12.0])
+    n_aim = 3 + 3 * len(range(*sub.indices(60 * 80 * 3)))
     out = sc.render_rays(ro, rd, want_samples=True)
     counts, ts = N.march(ro.numpy(), rd.numpy(), bits, G, NGP_CFG["aabb_min"], NGP_CFG["aabb_max"], 0.5, 6.0, 0.02, 1024, 256)
     if occupancy == "corners":
-        assert (counts[-3:] > 0).all()
+        assert (counts[-n_aim:][:3] > 0).all()
     assert np.array_equal(out["counts"].cpu().numpy(), counts)
     assert out["total"] == int(counts.sum())
     assert np.array_equal(out["t"].cpu().numpy(), np.concatenate(ts) if len(ts) else np.zeros(0, np.float32))
