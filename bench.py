@@ -330,7 +330,7 @@ def run_ngp(args, rank, local_rank, world):
                              "kernel": "tensorf_field_kernel" if tensorf else "ngp_field_tc_kernel (hash-grid gathers + small MLP on warp-level tensor-core MMA)",
                              "achieved_whole_step": gather_gbs, "achieved_field_kernel_only": field_gbs,
                              "field_kernel_ms_per_step": field_ms_per_step, "field_share_of_step": field_ms_per_step / ms_dev if ms_dev > 0 else None,
-                             "peak_definition": ("measured HBM copy bandwidth (MEASURED_PEAKS.json): 128-byte-line reads of L2-resident grids, see the note in bench.py" if tensorf else
+                             "peak_definition": ("measured HBM copy bandwidth (MEASURED_PEAKS.json), for scale only: the 34.6 MB of grids are L2-resident and neighbouring samples share their 128-byte lines through L1 (ncu, profiles/r2_tensorf_ncu_metrics.txt: L1 hit rate 87 %, L2 throughput 4 %, DRAM < 1 %), so the algorithmic rate can exceed it; the kernel is bound by instruction latency at 16 warps per SM (issue-active 48 %), not by memory" if tensorf else
                                                  "memory-system bound, but by the L2 gather rate, not HBM: measured rate of the stand-alone encode kernel on "
                                                  "ray-coherent points (the access pattern of this step)"), "peaks_measured": peaks_g,
                              "frac_of_random_pair_rate": (field_gbs if field_gbs else gather_gbs) / peaks_g["random_pairs_GBs"],
