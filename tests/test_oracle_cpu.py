@@ -416,3 +416,29 @@ def test_weight_fingerprint_tracks_content_not_identity():
     assert a == R._weights_fingerprint(sd) == R._weights_fingerprint({k: v.clone() for k, v in sd.items()})
     sd["alpha_linear.bias"].add_(1.0)
     assert R._weights_fingerprint(sd) != a
+
+
+def test_contenders_band_always_holds_the_true_argmax():
+    """The guarantee behind the identical next-best view (precision and arg-max identity): if every fast
+    score is within tol = margin / 2 (relative) of its true score, the true arg-max lies inside
+    contenders(fast, margin) -- for near-tied, widely spread and weighted score vectors alike.  2000 random cases with
+    adversarial error signs (the leader pushed down, a rival pushed up)."""
+    from evpp_b200.planner import contenders
+    rng = np.random.RandomState(7)
+    tol = 1e-3
+    for case in range(2000):
+        n = int(rng.randint(1, 300))
+        spread = 10.0 ** rng.uniform(-6, 0)                      # from 1e-6 relative ties to 100 % spread
+        true = 100.0 * (1.0 + spread * rng.rand(n))
+        err = rng.uniform(-tol, tol, size=n)
+        lead = int(np.argmax(true))
+        err[lead] = -tol                                         # worst case for the leader ...
+        if n > 1:
+            err[int(rng.randint(0, n))] = tol                    # ... and a rival at its most flattering
+            err[lead] = -tol
+        fast = true * (1.0 + err)
+        w = None if case % 3 else rng.uniform(0.2, 1.0, size=n)
+        t_w = true if w is None else true * w
+        band = contenders(fast, w, 2 * tol)
+        assert int(np.argmax(t_w)) in band.tolist(), (case, n, spread)
+        assert np.all(np.diff(band) > 0)                         # sorted, unique
